@@ -1,0 +1,18 @@
+"""bazinga_b200 -- B200 (sm_100a) implementation of the PANOC+/ALPS hot path of aldma/Bazinga.jl.
+
+The directory is named ``bazinga.jl_b200`` after the reference; import it as ``bazinga_b200`` (the
+shim ``bazinga_b200.py`` at the repository root registers this directory under that name).
+
+Host code here is a thin mirror of the reference's operator/plugin interface over the C ABI in
+``include/bazinga_b200.h``; all arithmetic runs in the CUDA kernels under ``csrc/``.
+"""
+from ._capi import BazingaError, LIB_PATH, STATUS_SYMBOLS, load_library  # noqa: F401
+from .oracles import (  # noqa: F401
+    ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, FreeSet, IdentityFunction, IndBox, IndFree,
+    IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NormL0, NormL0Box, NormL1, NormL1Box,
+    NormL1Nonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
+)
+from .solver import (  # noqa: F401
+    BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, alps_batch, comm_unique_id,
+    default_context, default_subsolver,
+)

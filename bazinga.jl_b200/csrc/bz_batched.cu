@@ -1,0 +1,438 @@
+// Batched tiny instances: the demos' sequential
+// `for i = 1:ntests ... alps(...)` loop (demo/eitheror.jl:238-271, demo/mpvca.jl:241-281,
+// demo/rosenbrock.jl:154-177) becomes one kernel launch in which every thread runs one complete
+// `alps` solve -- outer augmented-Lagrangian loop (src/algorithms/alps.jl:59-102), PANOC+ inner loop
+// with L-BFGS(<=8) and the closed-form oracles -- entirely in registers.
+// No collectives, no host syncs inside a solve.  Not HBM-bound: I/O is 16 B in and ~100 B out per
+// solve; the bound is fp64 dependent-issue latency and the iteration-count tail (H8).
+//
+// Compiled with -fmad=false: the arithmetic (order of operations, no contraction) is the same as
+// oracle/tiny_oracle.c, so results and iteration counts are bit-identical to the oracle.
+#include "bz_internal.cuh"
+
+#define TB_MAXMEM 8
+#define TB_THREADS 64
+
+namespace {
+
+struct TbOpts {
+    double tol_prim, tol_dual, inner_tol;
+    int maxit;
+    double theta_penalty, kappa_penalty, kappa_tol;
+    long long subsolver_maxit;
+    double alpha, beta, minimum_gamma;
+    int max_backtracks, mem;
+    long long sub_maxit;
+};
+
+__device__ __forceinline__ double jmax(double a, double b) {
+    return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, b);
+}
+
+// ---- problem definitions: KIND 0 rosenbrock, 1 either-or, 2 xor, 3 mpvca ------------------------
+template <int KIND> struct Prob;
+
+template <> struct Prob<0> {   // demo/rosenbrock.jl:39-80 (w = 10, lambda = 1)
+    static constexpr int NY = 2;
+    __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
+        const double w = 10.0;
+        const double tmp = x[1] + 1 - (x[0] + 1) * (x[0] + 1);
+        dfx[0] = -4 * w * tmp * (x[0] + 1);
+        dfx[1] = 2 * w * tmp;
+        return w * (tmp * tmp);
+    }
+    __device__ static void c_eval(const double (&x)[2], double (&cx)[NY]) {
+        cx[0] = -x[0] - x[1];
+        cx[1] = x[1] - x[0];
+    }
+    __device__ static void c_jt(const double (&x)[2], const double (&v)[NY], double (&jtv)[2]) {
+        jtv[0] = -v[0] - v[1];
+        jtv[1] = v[1] - v[0];
+    }
+    __device__ static void proj(const double (&v)[NY], double (&z)[NY]) {
+        bz_proj_pair(BZ_D_EITHEROR, v[0], v[1], z[0], z[1]);
+    }
+    __device__ static double prox(const double (&x)[2], double gamma, double (&z)[2]) {
+        const double gl = gamma * 1.0;
+        if (fabs(x[0]) <= gl) z[0] = 0.0;
+        else z[0] = (x[0] > 0 ? 1.0 : -1.0) * (fabs(x[0]) - gl);
+        z[1] = x[1];
+        return 1.0 * fabs(z[0]);
+    }
+};
+
+template <int DK> struct ProbOr {   // demo/eitheror.jl:58-132 (c = (8,-3))
+    static constexpr int NY = 4;
+    __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
+        const double d0 = x[0] - 8.0, d1 = x[1] - (-3.0);
+        dfx[0] = 2 * d0;
+        dfx[1] = 2 * d1;
+        const double nr = sqrt(d0 * d0 + d1 * d1);
+        return nr * nr;
+    }
+    __device__ static void c_eval(const double (&x)[2], double (&cx)[NY]) {
+        cx[0] = 2 * x[1] - x[0] - 4;
+        cx[1] = 2 - x[0];
+        cx[2] = 4 * x[1] - x[0] * x[0];
+        cx[3] = 10 - (x[0] - 3) * (x[0] - 3) - (x[1] - 1) * (x[1] - 1);
+    }
+    __device__ static void c_jt(const double (&x)[2], const double (&v)[NY], double (&jtv)[2]) {
+        jtv[0] = -v[0] - v[1] - 2 * x[0] * v[2] + 2 * (3 - x[0]) * v[3];
+        jtv[1] = 2 * v[0] + 4 * v[2] + 2 * (1 - x[1]) * v[3];
+    }
+    __device__ static void proj(const double (&v)[NY], double (&z)[NY]) {
+        bz_proj_pair(DK, v[0], v[1], z[0], z[1]);
+        bz_proj_pair(DK, v[2], v[3], z[2], z[3]);
+    }
+    __device__ static double prox(const double (&x)[2], double, double (&z)[2]) {
+        z[0] = x[0];
+        z[1] = x[1];
+        return 0.0;
+    }
+};
+template <> struct Prob<1> : ProbOr<BZ_D_EITHEROR> {};
+template <> struct Prob<2> : ProbOr<BZ_D_XOR> {};
+
+template <> struct Prob<3> {   // demo/mpvca.jl:77-150 (c = (4,2))
+    static constexpr int NY = 4;
+    __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
+        dfx[0] = 4.0;
+        dfx[1] = 2.0;
+        return 4.0 * x[0] + 2.0 * x[1];
+    }
+    __device__ static void c_eval(const double (&x)[2], double (&cx)[NY]) {
+        cx[0] = x[0];
+        cx[1] = x[0] + x[1] - 5.0 * sqrt(2.0);
+        cx[2] = x[1];
+        cx[3] = x[0] + x[1] - 5.0;
+    }
+    __device__ static void c_jt(const double (&)[2], const double (&v)[NY], double (&jtv)[2]) {
+        jtv[0] = v[0] + v[1] + v[3];
+        jtv[1] = v[1] + v[2] + v[3];
+    }
+    __device__ static void proj(const double (&v)[NY], double (&z)[NY]) {
+        bz_proj_pair(BZ_D_VC, v[0], v[1], z[0], z[1]);
+        bz_proj_pair(BZ_D_VC, v[2], v[3], z[2], z[3]);
+    }
+    __device__ static double prox(const double (&x)[2], double, double (&z)[2]) {
+        z[0] = fmax(0.0, x[0]);
+        z[1] = fmax(0.0, x[1]);
+        return 0.0;
+    }
+};
+
+// ---- per-thread augmented-Lagrangian state (auglagfun.jl:11-26) -----------------------------------
+template <int KIND> struct Al {
+    static constexpr int NY = Prob<KIND>::NY;
+    double mu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;
+
+    __device__ void update() {   // AugLagUpdate!
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) { muy[i] = mu[i] * y[i]; acc += muy[i] * y[i]; }
+        musqy = 0.5 * acc;
+    }
+    __device__ double gradient(const double (&x)[2], double (&dlx)[2]) {   // gradient!(dlx, al, x)
+        double dfx[2], jtv[2], acc = 0.0;
+        Prob<KIND>::c_eval(x, cx);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) yupd[i] = cx[i] + muy[i];
+        Prob<KIND>::proj(yupd, s);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) yupd[i] -= s[i];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) acc += (yupd[i] * yupd[i]) / mu[i];
+        double lx = 0.5 * acc;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) yupd[i] /= mu[i];
+        fx = Prob<KIND>::f_grad(x, dfx);
+        lx += fx;
+        lx -= musqy;
+        Prob<KIND>::c_jt(x, yupd, jtv);
+        dlx[0] = dfx[0] + jtv[0];
+        dlx[1] = dfx[1] + jtv[1];
+        return lx;
+    }
+};
+
+__device__ __forceinline__ double dot2(const double (&a)[2], const double (&b)[2]) {
+    return a[0] * b[0] + a[1] * b[1];
+}
+__device__ __forceinline__ double f_model(double fx, const double (&g)[2], const double (&res)[2],
+                                          double L) {
+    const double nr = sqrt(dot2(res, res));
+    return fx - dot2(g, res) + (L / 2) * (nr * nr);
+}
+
+// L-BFGS history kept newest-first and shifted on update, so every index is static (registers);
+// the visiting order (loop1 newest->oldest, loop2 oldest->newest) is that of the upstream ring.
+struct Lbfgs {
+    int M, currmem;
+    double H, s[TB_MAXMEM][2], y[TB_MAXMEM][2], ys[TB_MAXMEM];
+    __device__ void reset() { currmem = 0; H = 1.0; }
+    __device__ void update(const double (&sv)[2], const double (&yv)[2]) {
+        if (M == 0) return;
+        const double ysv = dot2(sv, yv);
+        if (ysv > 0) {
+#pragma unroll
+            for (int i = TB_MAXMEM - 1; i > 0; --i) {
+                s[i][0] = s[i - 1][0]; s[i][1] = s[i - 1][1];
+                y[i][0] = y[i - 1][0]; y[i][1] = y[i - 1][1];
+                ys[i] = ys[i - 1];
+            }
+            s[0][0] = sv[0]; s[0][1] = sv[1];
+            y[0][0] = yv[0]; y[0][1] = yv[1];
+            ys[0] = ysv;
+            currmem = currmem + 1 > M ? M : currmem + 1;
+            H = ysv / dot2(yv, yv);
+        }
+    }
+    __device__ void mul(const double (&v)[2], double (&d)[2]) const {
+        double al[TB_MAXMEM];
+        d[0] = v[0]; d[1] = v[1];
+#pragma unroll
+        for (int i = 0; i < TB_MAXMEM; ++i) {
+            if (i < currmem) {
+                al[i] = dot2(s[i], d) / ys[i];
+                d[0] -= al[i] * y[i][0];
+                d[1] -= al[i] * y[i][1];
+            }
+        }
+        d[0] = H * d[0]; d[1] = H * d[1];
+#pragma unroll
+        for (int i = TB_MAXMEM - 1; i >= 0; --i) {
+            if (i < currmem) {
+                const double beta = dot2(y[i], d) / ys[i];
+                const double coef = al[i] - beta;
+                d[0] += coef * s[i][0];
+                d[1] += coef * s[i][1];
+            }
+        }
+    }
+};
+
+// PANOCplus (Appendix A.2-A.5); returns k, solution in z
+template <int KIND>
+__device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts& o, double tol,
+                               double (&z)[2]) {
+    const double a = o.alpha;
+    double x[2] = {x0[0], x0[1]}, grad_x[2], grad_z[2], tmpg[2], y[2], res[2];
+    double x_prev[2], res_prev[2], x_d[2], z_curr[2], d[2];
+    double f_x = al.gradient(x, grad_x);
+    {
+        const double xe[2] = {x[0] + 1.0, x[1] + 1.0};
+        al.gradient(xe, tmpg);
+    }
+    const double df[2] = {tmpg[0] - grad_x[0], tmpg[1] - grad_x[1]};
+    const double Lest = sqrt(dot2(df, df)) / sqrt(2.0);
+    double gamma = a / Lest;
+    y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+    double g_z = Prob<KIND>::prox(y, gamma, z);
+    res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+    Lbfgs H;
+    H.M = o.mem;
+    H.reset();
+    double f_up = f_model(f_x, grad_x, res, a / gamma);
+    double f_z = al.gradient(z, grad_z);
+    while (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
+        gamma /= 2;
+        y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+        g_z = Prob<KIND>::prox(y, gamma, z);
+        res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+        f_up = f_model(f_x, grad_x, res, a / gamma);
+        f_z = al.gradient(z, grad_z);
+    }
+    double tau = 1.0;
+    long long k = 1;
+    for (;;) {
+        const double v0 = (res[0] / gamma - grad_x[0]) + grad_z[0];
+        const double v1 = (res[1] / gamma - grad_x[1]) + grad_z[1];
+        const double stopnorm = jmax(fabs(v0), fabs(v1));
+        if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
+        x_prev[0] = x[0]; x_prev[1] = x[1];
+        res_prev[0] = res[0]; res_prev[1] = res[1];
+        const double FBE_x = f_model(f_x, grad_x, res, a / gamma) + g_z;
+        const double nres[2] = {-res[0], -res[1]};
+        H.mul(nres, d);
+        x_d[0] = x[0] + d[0]; x_d[1] = x[1] + d[1];
+        f_x = al.gradient(x_d, grad_x);
+        x[0] = x_d[0]; x[1] = x_d[1];
+        z_curr[0] = z[0]; z_curr[1] = z[1];
+        tau = 1.0;
+        const double sigma = o.beta * (0.5 / gamma) * (1 - a);
+        const double nr = sqrt(dot2(res, res));
+        const double thresh = FBE_x - sigma * (nr * nr) + 10 * BZ_EPS * (1 + fabs(FBE_x));
+        for (int kb = 1; kb <= o.max_backtracks; ++kb) {
+            y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+            g_z = Prob<KIND>::prox(y, gamma, z);
+            res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+            f_up = f_model(f_x, grad_x, res, a / gamma);
+            f_z = al.gradient(z, grad_z);
+            if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
+                gamma *= 0.5;
+                H.reset();
+                continue;
+            }
+            if (f_up + g_z <= thresh || kb >= o.max_backtracks) break;
+            tau = (kb >= o.max_backtracks - 1) ? 0.0 : tau / 2;
+            x[0] = tau * x_d[0] + (1 - tau) * z_curr[0];
+            x[1] = tau * x_d[1] + (1 - tau) * z_curr[1];
+            f_x = al.gradient(x, grad_x);
+        }
+        const double sv[2] = {x[0] - x_prev[0], x[1] - x_prev[1]};
+        const double yv[2] = {res[0] - res_prev[0], res[1] - res_prev[1]};
+        H.update(sv, yv);
+        k += 1;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TB_THREADS)
+    k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
+                 TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
+                 long long* __restrict__ tot_inners, int* __restrict__ statuses,
+                 double* __restrict__ nrps) {
+    constexpr int NY = Prob<KIND>::NY;
+    const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    Al<KIND> al;
+    double x[2], z[2], cx[NY], s[NY];
+    {   // alps.jl:37-45
+        const double x0[2] = {x0s[inst * 2], x0s[inst * 2 + 1]};
+        al.gz = Prob<KIND>::prox(x0, BZ_EPS, x);
+    }
+    double dtmp[2];
+    double objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;
+    Prob<KIND>::c_eval(x, cx);
+    Prob<KIND>::proj(cx, s);
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {   // default_penalty_parameter!, safeguards.jl:13-18
+        const double df = cx[i] - s[i];
+        double m = jmax(1.0, 0.5 * (df * df)) / jmax(1.0, objx);
+        m *= 0.1;
+        al.mu[i] = jmax(1e-8, (m != m) ? m : fmin(m, 1e8));
+        al.y[i] = y0s[inst * NY + i];
+    }
+    double inner_tol = o.inner_tol;
+    int tot_it = 0;
+    bool solved = false, tired = tot_it >= o.maxit, broken = objx != objx, have_old = false;
+    long long tot_inner = 0;
+    double nrp = __longlong_as_double(0x7ff8000000000000LL), nrp_old = nrp;
+    while (!(solved || tired || broken)) {
+        tot_it++;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20));   // safeguards.jl:2-5
+        al.update();
+        const long long sub_it = panocplus<KIND>(al, x, o, inner_tol, z);
+        x[0] = z[0]; x[1] = z[1];
+        objx = al.fx + al.gz;
+        tot_inner += sub_it;
+        const bool sub_solved = sub_it < o.subsolver_maxit;
+        Prob<KIND>::c_eval(x, cx);
+        double t[NY];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) t[i] = cx[i] + al.muy[i];
+        Prob<KIND>::proj(t, s);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) al.y[i] = (t[i] - s[i]) / al.mu[i];
+        nrp_old = nrp;
+        nrp = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) nrp = jmax(nrp, fabs(cx[i] - s[i]));
+        solved = (inner_tol <= o.tol_dual && sub_solved) && (nrp <= o.tol_prim);
+        tired = tot_it >= o.maxit;
+        broken = objx != objx;
+        if (!(solved || tired || broken)) {
+            if (have_old && nrp > jmax(o.theta_penalty * nrp_old, o.tol_prim)) {
+#pragma unroll
+                for (int i = 0; i < NY; ++i) al.mu[i] *= o.kappa_penalty;
+            }
+            inner_tol = jmax(o.kappa_tol * inner_tol, o.tol_dual);
+        }
+        have_old = true;
+    }
+    xs[inst * 2] = x[0];
+    xs[inst * 2 + 1] = x[1];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) ys[inst * NY + i] = al.y[i];
+    tot_its[inst] = tot_it;
+    tot_inners[inst] = tot_inner;
+    statuses[inst] = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+    nrps[inst] = nrp;
+}
+
+}  // namespace
+
+extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
+                              const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                              int64_t* tot_inner_it, int32_t* status, double* norm_res_prim,
+                              double* kernel_ms) {
+    if (!ctx || !x0 || !y0 || !opt || !x || !y || !tot_it || !tot_inner_it || !status || !norm_res_prim)
+        return bz_fail(ctx, BZ_ERR_ARG, "bz_batch_solve: NULL argument");
+    if (kind < 0 || kind > 3) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_batch_solve: unknown problem kind");
+    if (batch < 0) return bz_fail(ctx, BZ_ERR_ARG, "batch must be nonnegative");
+    if (opt->lbfgs_memory < 0 || opt->lbfgs_memory > TB_MAXMEM)
+        return bz_fail(ctx, BZ_ERR_ARG, "batched path supports lbfgs_memory in [0, 8]");
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (kernel_ms) *kernel_ms = 0.0;
+    if (batch == 0) return BZ_OK;
+    const int ny = kind == 0 ? 2 : 4;
+    TbOpts o;
+    o.tol_prim = opt->tol_prim >= 0 ? opt->tol_prim : opt->tol;
+    o.tol_dual = opt->tol_dual >= 0 ? opt->tol_dual : opt->tol;
+    o.inner_tol = opt->inner_tol >= 0 ? opt->inner_tol : cbrt(o.tol_dual);
+    o.maxit = opt->maxit;
+    o.theta_penalty = opt->theta_penalty; o.kappa_penalty = opt->kappa_penalty; o.kappa_tol = opt->kappa_tol;
+    o.subsolver_maxit = opt->subsolver_maxit;
+    o.alpha = opt->alpha; o.beta = opt->beta; o.minimum_gamma = opt->minimum_gamma;
+    o.max_backtracks = opt->max_backtracks; o.mem = opt->lbfgs_memory;
+    o.sub_maxit = opt->sub_maxit;
+
+    double *dx0 = nullptr, *dy0 = nullptr, *dx = nullptr, *dy = nullptr, *dnrp = nullptr;
+    int* dit = nullptr; int* dst = nullptr; long long* din = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(dx0); cudaFree(dy0); cudaFree(dx); cudaFree(dy); cudaFree(dnrp);
+        cudaFree(dit); cudaFree(dst); cudaFree(din);
+    };
+#define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
+        return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
+    BTRY(cudaMalloc((void**)&dx0, batch * 2 * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dy0, batch * ny * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dx, batch * 2 * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dy, batch * ny * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dnrp, batch * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dit, batch * sizeof(int)));
+    BTRY(cudaMalloc((void**)&dst, batch * sizeof(int)));
+    BTRY(cudaMalloc((void**)&din, batch * sizeof(long long)));
+    BTRY(cudaMemcpyAsync(dx0, x0, batch * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BTRY(cudaMemcpyAsync(dy0, y0, batch * ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    BTRY(cudaEventCreate(&e0));
+    BTRY(cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
+    cudaEventRecord(e0, ctx->stream);
+    switch (kind) {
+    case 0: k_batch_alps<0><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
+    case 1: k_batch_alps<1><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
+    case 2: k_batch_alps<2><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
+    default: k_batch_alps<3><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    ctx->n_launches++;
+    BTRY(cudaGetLastError());
+    BTRY(cudaMemcpyAsync(x, dx, batch * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(y, dy, batch * ny * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(norm_res_prim, dnrp, batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(tot_it, dit, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(tot_inner_it, din, batch * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cleanup();
+#undef BTRY
+    return BZ_OK;
+}

@@ -1,0 +1,375 @@
+// Dense kernels: the fused single-pass augmented-Lagrangian gradient for c(x) = A x - b
+// (demo/basispursuit.jl:38-49 inside src/utilities/auglagfun.jl:73-86), the same pass reused for
+// f = LeastSquares(A,b), a plain GEMV for f = Quadratic(Q,q), plus layout / generator helpers.
+//
+// Fused pass (k_dense_algrad): A is row-major m x n and is read from HBM exactly ONCE per
+// evaluation.  A cluster of two CTAs owns a block of rows; CTA `rank` owns the column half
+// [rank*Wh, ...).  Row slices stream through a shared-memory ring filled by cp.async.bulk (TMA
+// bulk copies, mbarrier complete_tx).  For row i: phase A forms the slice dot product with x
+// (x lives in registers), the two halves are exchanged through distributed shared memory and one
+// split-phase cluster barrier, the constraint-space elementwise stage
+//     t = r_i - b_i + mu_i*y_i ;  s = proj_D(t) ;  w = (t - s)/mu_i ;  lx += (t-s)^2/mu_i
+// is evaluated redundantly by every thread, and phase B accumulates w * A[i, :] into per-thread
+// column accumulators from the SAME shared-memory slots.  Per-cluster partial gradients go to
+// P[cluster][n]; the consumer kernels (bz_vec.cu) sum them in fixed order, so the result is
+// deterministic (no float atomics).
+#include "bz_internal.cuh"
+#include "bz_dense.cuh"
+#include "bz_rng.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer_f64(void* local_smem_ptr, uint32_t peer_rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                 : "=r"(remote)
+                 : "r"(smem_u32(local_smem_ptr)), "r"(peer_rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused AL-gradient pass
+// ---------------------------------------------------------------------------------------------
+template <bool BULK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
+    k_dense_algrad(BzDenseArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)DA_SLOTS * DA_CHUNK);
+    double* wsum = reinterpret_cast<double*>(full + DA_SLOTS);   // [2][16] warp partials
+    double* xchg = wsum + 32;                                     // [2]: peer's row dots
+
+    const int tid = threadIdx.x;
+    int target = a.force_target;
+    if (target < 0) {
+        if (__ldcg(&a.st->next_op) != OP_G) return;   // both CTAs of a cluster take the same branch
+        target = __ldcg(&a.st->grad_target);
+    }
+    const double* __restrict__ xsrc = a.src[target];
+
+    const uint32_t rank = cluster_ctarank();
+    const int q = blockIdx.x >> 1;
+    const long long n = a.n;
+    const long long Wh = (((n + 1) >> 1) + 1) & ~1LL;   // even split point
+    const long long col0 = rank ? Wh : 0;
+    long long Wl = rank ? (n - Wh) : (Wh < n ? Wh : n);
+    if (Wl < 0) Wl = 0;
+    const int W = (int)Wl;                               // slice width <= DA_MAXCH*DA_CHUNK
+    const int nch = (W + DA_CHUNK - 1) / DA_CHUNK;
+    const long long r0 = (long long)q * a.rows_per_cluster;
+    long long r1 = r0 + a.rows_per_cluster;
+    if (r1 > a.m) r1 = a.m;
+    const int nrows = (int)(r1 - r0);
+    const int total = nrows * nch;                       // chunks this CTA streams
+
+    // x slice and accumulators in registers; lane validity is per (chunk, element)
+    const int lc0 = 2 * tid;
+    double2 xr[DA_MAXCH], acc[DA_MAXCH];
+#pragma unroll
+    for (int c = 0; c < DA_MAXCH; ++c) {
+        const int lc = c * DA_CHUNK + lc0;
+        xr[c].x = (lc < W) ? xsrc[col0 + lc] : 0.0;
+        xr[c].y = (lc + 1 < W) ? xsrc[col0 + lc + 1] : 0.0;
+        acc[c] = make_double2(0.0, 0.0);
+    }
+
+    if (BULK) {
+        if (tid == 0) {
+            for (int s = 0; s < DA_SLOTS; ++s) mbar_init(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    // issue (BULK: thread 0, asynchronous) or fill (all threads, synchronous) chunks [g0, g1)
+    auto issue_range = [&](int g0, int g1) {
+        if (BULK) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                int row = g0 / nch, c = g0 % nch, slot = g0 % DA_SLOTS;
+                for (int g = g0; g < g1; ++g) {
+                    int len = W - c * DA_CHUNK;
+                    if (len > DA_CHUNK) len = DA_CHUNK;
+                    const double* src = a.A + (r0 + row) * a.lda + col0 + (long long)c * DA_CHUNK;
+                    mbar_expect_tx(&full[slot], (uint32_t)(len * 8));
+                    bulk_g2s(ring + (size_t)slot * DA_CHUNK, src, (uint32_t)(len * 8), &full[slot]);
+                    if (++c == nch) { c = 0; ++row; }
+                    if (++slot == DA_SLOTS) slot = 0;
+                }
+            }
+            __syncwarp();
+        } else {
+            int row = g0 / (nch > 0 ? nch : 1), c = g0 % (nch > 0 ? nch : 1), slot = g0 % DA_SLOTS;
+            for (int g = g0; g < g1; ++g) {
+                int len = W - c * DA_CHUNK;
+                if (len > DA_CHUNK) len = DA_CHUNK;
+                const double* src = a.A + (r0 + row) * a.lda + col0 + (long long)c * DA_CHUNK;
+                double* dst = ring + (size_t)slot * DA_CHUNK;
+                for (int k = tid; k < len; k += DA_THREADS) dst[k] = __ldg(src + k);
+                if (++c == nch) { c = 0; ++row; }
+                if (++slot == DA_SLOTS) slot = 0;
+            }
+            __syncthreads();
+        }
+    };
+
+    int issued = total < DA_SLOTS ? total : DA_SLOTS;
+    issue_range(0, issued);
+
+    double lx = 0.0;
+    double own_prev = 0.0;           // this CTA's slice dot of the previous row
+    double b_prev = 0.0, mu_prev = 1.0, muy_prev = 0.0;
+    int sb = 0, par = 0;             // ring slot / mbarrier parity of the current row's first chunk
+    int sb_prev = 0;
+
+    // constraint-space stage + phase B for local row `rowp`, given both slice dots
+    auto finish_row = [&](int rowp, int sbp, double own, double peer, double bi, double mui,
+                          double muyi) {
+        const double p0 = rank ? peer : own, p1 = rank ? own : peer;
+        const double cxv = (p0 + p1) - bi;                           // cx = A*x - b
+        const double t = cxv + muyi;                                 // auglagfun.jl:75
+        const double sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);    // :76
+        const double u = t - sv;                                     // :77
+        lx += (u * u) / mui;                                         // :78 (0.5 applied later)
+        const double w = u / mui;                                    // :79
+        if (rank == 0 && tid == 0) {
+            const long long gi = r0 + rowp;
+            if (a.cx) a.cx[gi] = cxv;
+            if (a.s) a.s[gi] = sv;
+            if (a.yupd) a.yupd[gi] = w;
+        }
+#pragma unroll
+        for (int c = 0; c < DA_MAXCH; ++c) {
+            if (c < nch) {
+                int slot = sbp + c;
+                if (slot >= DA_SLOTS) slot -= DA_SLOTS;
+                const double2 av =
+                    reinterpret_cast<const double2*>(ring + (size_t)slot * DA_CHUNK)[tid];
+                const int lc = c * DA_CHUNK + lc0;
+                if (lc < W) acc[c].x = fma(av.x, w, acc[c].x);
+                if (lc + 1 < W) acc[c].y = fma(av.y, w, acc[c].y);
+            }
+        }
+    };
+
+    for (int i = 0; i < nrows; ++i) {
+        const long long gi = r0 + i;
+        const double b_i = __ldg(a.b + gi), mu_i = __ldg(a.mu + gi), muy_i = __ldg(a.muy + gi);
+        // ---- phase A: slice dot of row i
+        double pa = 0.0, pb = 0.0;
+#pragma unroll
+        for (int c = 0; c < DA_MAXCH; ++c) {
+            if (c < nch) {
+                int slot = sb + c, p = par;
+                if (slot >= DA_SLOTS) { slot -= DA_SLOTS; p ^= 1; }
+                if (BULK) mbar_wait(&full[slot], (uint32_t)p);
+                const double2 av =
+                    reinterpret_cast<const double2*>(ring + (size_t)slot * DA_CHUNK)[tid];
+                const int lc = c * DA_CHUNK + lc0;
+                if (lc < W) pa = fma(av.x, xr[c].x, pa);
+                if (lc + 1 < W) pb = fma(av.y, xr[c].y, pb);
+            }
+        }
+        const double part = bz_warp_sum(pa + pb);
+        // ---- finish row i-1 (its peer dot arrived with the previous cluster-barrier phase)
+        if (i > 0) {
+            cluster_wait();
+            const double peer = xchg[(i - 1) & 1];
+            finish_row(i - 1, sb_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
+        }
+        double* ws = wsum + (i & 1) * 16;
+        if ((tid & 31) == 0) ws[tid >> 5] = part;
+        __syncthreads();   // row i-1's slots are free; warp sums of row i are visible
+        if (i > 0 && issued < total) {
+            int g1 = issued + nch;
+            if (g1 > total) g1 = total;
+            issue_range(issued, g1);
+            issued = g1;
+        }
+        double own = 0.0;
+#pragma unroll
+        for (int w = 0; w < DA_THREADS / 32; ++w) own += ws[w];
+        if (tid == 0) st_peer_f64(&xchg[i & 1], rank ^ 1u, own);
+        __syncwarp();
+        cluster_arrive();
+        own_prev = own; b_prev = b_i; mu_prev = mu_i; muy_prev = muy_i;
+        sb_prev = sb;
+        sb += nch;
+        if (sb >= DA_SLOTS) { sb -= DA_SLOTS; par ^= 1; }
+    }
+    if (nrows > 0) {
+        cluster_wait();
+        const double peer = xchg[(nrows - 1) & 1];
+        finish_row(nrows - 1, sb_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
+    }
+
+    // ---- write this cluster's partial gradient slice and its lx partial
+    double* Pq = a.P + (size_t)q * n;
+#pragma unroll
+    for (int c = 0; c < DA_MAXCH; ++c) {
+        const int lc = c * DA_CHUNK + lc0;
+        if (lc < W) Pq[col0 + lc] = acc[c].x;
+        if (lc + 1 < W) Pq[col0 + lc + 1] = acc[c].y;
+    }
+    if (rank == 0 && tid == 0) a.lxpart[q] = lx;
+
+    if (bz_last_cta(a.counter, gridDim.x)) {
+        if (tid == 0 && a.set_after) {
+            a.st->next_op = a.st->after_g;
+            __threadfence();
+        }
+    }
+}
+
+int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) {
+    static bool attr_set = false;
+    const size_t smem = (size_t)DA_SLOTS * DA_CHUNK * 8 + DA_SLOTS * 8 + 32 * 8 + 4 * 8;
+    if (!attr_set) {
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
+    if (bulk)
+        k_dense_algrad<true><<<2 * nclusters, DA_THREADS, smem, ctx->stream>>>(args);
+    else
+        k_dense_algrad<false><<<2 * nclusters, DA_THREADS, smem, ctx->stream>>>(args);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f = Quadratic(Q, q): dfx = Q x + q, fx = 0.5 x'Qx + q'x.  One warp per row, rows strided over the
+// grid; per-CTA fx partials (fixed order).  Only used by the reference's small QP tests.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_quad_grad(const double* __restrict__ Q,
+                                                   const double* __restrict__ qv, BzState* st,
+                                                   int force_target, const double* x0,
+                                                   const double* x1, const double* x2, long long n,
+                                                   double* __restrict__ Ef, double* fxpart) {
+    __shared__ double scratch[32];
+    int target = force_target;
+    if (target < 0) {
+        if (__ldcg(&st->next_op) != OP_G) return;
+        target = __ldcg(&st->grad_target);
+    }
+    const double* x = target == 0 ? x0 : (target == 1 ? x1 : x2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    double v[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * wpb + warp; i < n; i += (long long)gridDim.x * wpb) {
+        double sacc = 0.0;
+        for (long long j = lane; j < n; j += 32) sacc = fma(Q[i * n + j], x[j], sacc);
+        sacc = bz_warp_sum(sacc);
+        if (lane == 0) {
+            Ef[i] = sacc + qv[i];
+            v[0] += 0.5 * x[i] * sacc + qv[i] * x[i];
+        }
+    }
+    bz_block_sum<1>(v, scratch);
+    if (threadIdx.x == 0) fxpart[blockIdx.x] = v[0];
+}
+
+int bz_launch_quad_grad(bz_ctx* ctx, const double* Q, const double* q, BzState* st, int force_target,
+                        const double* const* src, long long n, double* Ef, double* fxpart,
+                        int nblocks) {
+    k_quad_grad<<<nblocks, 256, 0, ctx->stream>>>(Q, q, st, force_target, src[0], src[1], src[2], n,
+                                                   Ef, fxpart);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout / generator helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, long long rows,
+                            long long cols) {
+    // in: column-major rows x cols (Julia) == row-major cols x rows; out: row-major rows x cols
+    __shared__ double tile[32][33];
+    long long bx = (long long)blockIdx.x * 32, by = (long long)blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        long long r = bx + threadIdx.x, c = by + k;   // in(r, c) at in[c*rows + r]
+        tile[k][threadIdx.x] = (r < rows && c < cols) ? in[c * rows + r] : 0.0;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        long long r = bx + k, c = by + threadIdx.x;
+        if (r < rows && c < cols) out[r * cols + c] = tile[threadIdx.x][k];
+    }
+}
+
+int bz_launch_transpose(bz_ctx* ctx, const double* in_colmajor, double* out_rowmajor, long long rows,
+                        long long cols) {
+    dim3 block(32, 8), grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    k_transpose<<<grid, block, 0, ctx->stream>>>(in_colmajor, out_rowmajor, rows, cols);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
+__global__ void k_randn_fill(unsigned long long seed, unsigned long long stream,
+                             unsigned long long start, long long count, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = bz_randn_at(seed, stream, start + (unsigned long long)i);
+}
+
+int bz_launch_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, long long count,
+                         double* out_dev) {
+    if (count <= 0) return BZ_OK;
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    k_randn_fill<<<(unsigned)blocks, 256, 0, ctx->stream>>>(seed, stream, start, count, out_dev);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}

@@ -1,0 +1,40 @@
+// Launch interfaces of bz_dense.cu
+#pragma once
+#include "bz_internal.cuh"
+
+#define DA_THREADS 512
+#define DA_CHUNK 1024   // doubles per ring slot (8 KB)
+#define DA_MAXCH 8      // ring slots per row slice -> slice width <= 8192, n <= 16384
+#define DA_SLOTS 26     // 208 KB ring
+#define DA_MAX_N (2 * DA_MAXCH * DA_CHUNK)
+
+struct BzDenseArgs {
+    const double* A;       // row-major m x n (local rows)
+    long long lda;
+    const double* b;       // m
+    const double* mu;      // m (ones for the LeastSquares pass)
+    const double* muy;     // m (zeros for the LeastSquares pass)
+    const double* src[3];  // candidate input vectors: x, z, xeps
+    BzState* st;
+    int force_target;      // >= 0: ignore the state machine, read src[force_target]
+    long long m, n;
+    int rows_per_cluster;
+    int dkind;
+    double dlo, dhi;
+    double* cx;            // outputs over rows (may be null)
+    double* s;
+    double* yupd;
+    double* P;             // nclusters x n partial rows of A' w
+    double* lxpart;        // nclusters partial sums of (t-s)^2/mu
+    unsigned int* counter;
+    int set_after;         // last CTA sets st->next_op = st->after_g
+};
+
+int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);
+int bz_launch_quad_grad(bz_ctx* ctx, const double* Q, const double* q, BzState* st, int force_target,
+                        const double* const* src, long long n, double* Ef, double* fxpart,
+                        int nblocks);
+int bz_launch_transpose(bz_ctx* ctx, const double* in_colmajor, double* out_rowmajor, long long rows,
+                        long long cols);
+int bz_launch_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, long long count,
+                         double* out_dev);

@@ -1,0 +1,309 @@
+// Internal declarations shared by the translation units of libbazinga_b200.so.
+// Device-side state machine, reduction helpers and the prox / projection functors.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bazinga_b200.h"
+
+#define BZ_MAXMEM BZ_LBFGS_MAX_MEMORY
+#define BZ_MAX_PARTS 1024          // max per-CTA scalar partial slots of any kernel
+#define BZ_EPS 2.220446049250313e-16
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident solver state.  All control flow of the PANOC+ inner loop lives here so that the
+// host can enqueue the fixed kernel cycle [L, G, F, G, D] without knowing which branch is taken
+// (<= 1 host sync per inner iteration; we need far fewer).
+// ---------------------------------------------------------------------------------------------
+enum BzOp : int { OP_L = 0, OP_G = 1, OP_F = 2, OP_D = 3, OP_DONE = 4 };
+enum BzMode : int { MODE_INIT0 = 0, MODE_INIT1 = 1, MODE_INITFB = 2, MODE_ITER = 3 };
+enum BzLRole : int { LROLE_NEWITER = 0, LROLE_INTERP = 1 };
+enum BzTarget : int { TGT_X = 0, TGT_Z = 1, TGT_XEPS = 2 };
+enum BzInnerStatus : int { IST_RUNNING = 0, IST_CONVERGED = 1, IST_MAXIT = 2 };
+
+struct BzState {
+    // ---- control words
+    int next_op;
+    int after_g;
+    int mode;
+    int l_role;
+    int grad_target;
+    int grad_x_fresh;   // F must assemble grad_x from the provider outputs (else reuse stored grad_x)
+    int skip_update;    // first L of an inner solve: no L-BFGS update (A.4 -> A.5)
+    int inner_status;
+    int k_bt;
+    int max_backtracks;
+    int mem;            // L-BFGS memory M
+    int currmem, curridx;  // curridx is 1-based like upstream, 0 = empty
+    int err_flag;       // nonpositive mu etc.
+    long long iter;     // k of the IterativeAlgorithm driver (initial state counts as 1)
+    long long maxit;
+    long long n_grad, n_prox;
+    // ---- PANOC+ scalars
+    double gamma, tau, tol, alpha, beta, gamma_min;
+    double f_x, f_z, g_z, f_up, dot_gr, res_nrm2sq, FBE_x, sigma, thresh, stopnorm, Lest;
+    double H;
+    double ys[BZ_MAXMEM];
+    double alphas[BZ_MAXMEM];
+    // ---- augmented-Lagrangian scalars (auglagfun.jl cached state)
+    double musqy;       // 0.5*sum(mu.*y.^2)
+    double al_fx;       // alFun.fx of the last gradient! call
+    double al_lx;       // value of the last gradient! call
+    // ---- outer loop scalars (alps.jl:59-102), updated by the multiplier kernel
+    double objx, norm_res_prim, norm_res_prim_old, inner_tol, tol_prim, tol_dual;
+    double theta_penalty, kappa_penalty, kappa_tol;
+    int have_old, solved, tired, broken, scale_mu;
+    int tot_it, outer_maxit;
+    long long tot_inner_it, subsolver_maxit;
+    // generic scalar outputs of the parity entry points
+    double out[8];
+};
+
+// Where the assembled gradient comes from:  grad = dfx_term + jtv_term  (auglagfun.jl:84), each
+// term being 0, a vector, or a sum of per-CTA partial rows written by a dense pass.
+struct BzGradSrc {
+    const double* Pf; int npf;   // partial rows of dfx (LeastSquares pass), npf x n
+    const double* Ef;            // dfx as a vector (Quadratic), or nullptr
+    const double* Pc; int npc;   // partial rows of jtv (dense-affine constraint pass)
+    const double* Ec;            // jtv as a vector (identity / stencil constraints)
+    const double* lxpart; int nlx;    // sum -> sum(yupd.^2 ./ mu) (before the 0.5)
+    const double* fxpart; int nfx;    // f(x) = fx_scale * sum(fxpart) + fx_scale2 * sum(fxpart2)
+    double fx_scale;
+    const double* fxpart2; int nfx2;
+    double fx_scale2;
+};
+
+// g / D parameter blocks passed by value to kernels
+struct BzGParams {
+    int kind;
+    double lambda, lo, hi;
+    const double* u;
+    long long N;   // obstacle block size
+};
+struct BzDParams {
+    int kind;
+    double lo, hi;
+    long long stride;  // pair stride (1 = adjacent)
+};
+
+// ---------------------------------------------------------------------------------------------
+// Projections onto the 2-element sets, exact branch order of src/projections/*.jl
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void bz_proj_pair(int kind, double x1, double x2, double& z1, double& z2) {
+    switch (kind) {
+    case BZ_D_EITHEROR:  // orConstraints.jl:7-17
+        z1 = x1; z2 = x2;
+        if (x1 < 0 && x2 < 0) { if (x1 > x2) z1 = 0.0; else z2 = 0.0; }
+        break;
+    case BZ_D_XOR:       // orConstraints.jl:24-36
+        z1 = x1; z2 = x2;
+        if (x1 * x2 > 0) {
+            if (x1 > x2) { z1 = fmax(0.0, x1); z2 = fmin(0.0, x2); }
+            else         { z1 = fmin(0.0, x1); z2 = fmax(0.0, x2); }
+        }
+        break;
+    case BZ_D_VC:        // vanishingConstraints.jl:27-46
+        z1 = 0.0; z2 = 0.0;
+        if (x1 <= 0) { z2 = x2; }
+        else if (x2 >= 0) { z1 = x1; z2 = x2; }
+        else {
+            double sm = x1 + x2;
+            if (sm > 0) z1 = x1; else z2 = x2;   // sm < 0 and the set-valued tie both keep z2
+        }
+        break;
+    case BZ_D_CC:        // complementarityConstraints.jl:8-20
+        if (x1 > 0 && x2 > 0) { z1 = x1; z2 = x2; if (x2 > x1) z1 = 0.0; else z2 = 0.0; }
+        else { z1 = fmax(0.0, x1); z2 = fmax(0.0, x2); }
+        break;
+    default: z1 = x1; z2 = x2;
+    }
+}
+
+// elementwise sets (zeroSet.jl:17-20, freeSet.jl:17-20, indicatorSet.jl:8-11 -> IndBox clamp)
+__host__ __device__ inline double bz_proj_elem(int kind, double lo, double hi, double v) {
+    if (kind == BZ_D_ZERO) return 0.0;
+    if (kind == BZ_D_BOX) return fmin(hi, fmax(lo, v));
+    return v;
+}
+__host__ __device__ inline bool bz_d_is_pair(int kind) { return kind >= BZ_D_EITHEROR; }
+
+// Elementwise prox of the g kinds that do not couple entries.  Returns z and adds this entry's
+// contribution to the value accumulator `acc` (sum |z|, sum z, or a nonzero count).
+__device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma, long long j,
+                                      double& acc) {
+    switch (g.kind) {
+    case BZ_G_NORM_L1: {  // sign(x)*max(|x|-gamma*lambda,0)
+        double gl = gamma * g.lambda;
+        double a = fabs(x) - gl;
+        double z = (a > 0.0 ? a : 0.0);
+        z = (x > 0.0) ? z : ((x < 0.0) ? -z : 0.0 * z);
+        acc += fabs(z);
+        return z;
+    }
+    case BZ_G_NORM_L0: {  // keep iff |x| > sqrt(2*gamma*lambda)
+        double thr = sqrt(2.0 * gamma * g.lambda);
+        double z = (fabs(x) > thr) ? x : 0.0;
+        acc += (z != 0.0) ? 1.0 : 0.0;
+        return z;
+    }
+    case BZ_G_IND_BOX: return fmin(g.hi, fmax(g.lo, x));
+    case BZ_G_NORML1_BOX: {  // normL1Box.jl:34-37
+        double gl = gamma * g.lambda;
+        double z = fmax(0.0, fmin(x - gl, g.u[j]));
+        acc += z;
+        return z;
+    }
+    case BZ_G_NORML1_NONNEG: {  // normL1Nonneg.jl:33-40
+        double gl = gamma * g.lambda;
+        if (x >= gl) { double z = x - gl; acc += z; return z; }
+        return 0.0;
+    }
+    case BZ_G_NORML0_BOX: {  // normL0Box.jl:36-56 (threshold sqrt(gamma*lambda), returns x not u)
+        double gl2 = gamma * g.lambda;
+        double u = g.u[j];
+        if (u == 0.0) return 0.0;
+        if (x > sqrt(gl2)) {
+            if (x > u) {
+                double du = u - x;
+                if (x * x > gl2 + du * du) { acc += 1.0; return x; }
+                return 0.0;
+            }
+            acc += 1.0;
+            return x;
+        }
+        return 0.0;
+    }
+    case BZ_G_ROSENBROCK: {  // demo/rosenbrock.jl:55-64: soft threshold on entry 1 only
+        if (j != 0) return x;
+        double gl = gamma * g.lambda;
+        double z;
+        if (fabs(x) <= gl) z = 0.0;
+        else z = ((x > 0.0) ? 1.0 : -1.0) * (fabs(x) - gl);
+        acc += fabs(z);
+        return z;
+    }
+    case BZ_G_NONNEG: return fmax(0.0, x);   // demo/mpvca.jl:90-93
+    default: return x;  // BZ_G_ZERO
+    }
+}
+// scale that turns the accumulated sum into g(z)
+__host__ __device__ inline double bz_g_value_scale(const BzGParams& g) {
+    switch (g.kind) {
+    case BZ_G_NORM_L1: case BZ_G_NORM_L0: case BZ_G_NORML1_BOX: case BZ_G_NORML1_NONNEG:
+    case BZ_G_NORML0_BOX: case BZ_G_ROSENBROCK: return g.lambda;
+    case BZ_G_OBSTACLE_L1: return 1.0;
+    default: return 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reductions.  Everything is order-fixed (no float atomics): warp butterfly, then a fixed-order
+// sum over warp partials, then a fixed-order sum over CTA partials by the last CTA to finish.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bz_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double bz_warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of K values per thread; result valid in every thread.  `scratch` needs
+// K * 32 doubles of shared memory.  Contains two __syncthreads.
+template <int K>
+__device__ __forceinline__ void bz_block_sum(double (&v)[K], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = bz_warp_sum(v[k]);
+    __syncthreads();   // protect scratch reuse
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += scratch[k * 32 + w];
+        v[k] = s;
+    }
+}
+template <int K>
+__device__ __forceinline__ void bz_block_max(double (&v)[K], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = bz_warp_max(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) scratch[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = scratch[k * 32];
+        for (int w = 1; w < nwarps; ++w) s = fmax(s, scratch[k * 32 + w]);
+        v[k] = s;
+    }
+}
+
+// "last CTA done" ticket: returns true in every thread of the CTA that finishes last.  The caller
+// must have written its per-CTA partials to global memory before calling.  The counter is reset
+// by the last CTA so the kernel can be launched again.
+__device__ __forceinline__ bool bz_last_cta(unsigned int* counter, unsigned int nctas) {
+    __shared__ int s_is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        s_is_last = (t == nctas - 1u);
+        if (s_is_last) { *counter = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    return s_is_last != 0;
+}
+
+__device__ __forceinline__ double bz_ldcg(const double* p) { return __ldcg(p); }
+
+// fixed-order sum of a global partial array (read through L2, the writers were other CTAs)
+__device__ inline double bz_sum_parts(const double* part, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += __ldcg(part + i);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side objects
+// ---------------------------------------------------------------------------------------------
+struct bz_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool profiling = false;
+    // NCCL (loaded lazily with dlopen; see bz_comm.cu)
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+    // event pool for the dominant-kernel timing
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    long long n_launches = 0;
+};
+
+int bz_fail(bz_ctx* ctx, int code, const std::string& msg);
+#define BZ_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return bz_fail((ctx), BZ_ERR_CUDA,                                               \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));             \
+    } while (0)

@@ -1,0 +1,858 @@
+// Host side of libbazinga_b200.so: contexts, problems, the AL-gradient provider dispatch, the
+// PANOC+ / ALPS drivers and the C-ABI entry points declared in include/bazinga_b200.h.
+//
+// Host responsibilities are deliberately thin: enqueue the fixed kernel cycle, poll one status
+// word, and run the handful of per-OUTER-iteration decisions that need a host round trip
+// (alps.jl:59-102 -- one sync per outer iteration).
+#include "bz_internal.cuh"
+#include "bz_dense.cuh"
+#include "bz_vec.cuh"
+#include "bz_comm.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+
+static std::string g_last_error;
+
+int bz_fail(bz_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+struct bz_problem {
+    bz_ctx* ctx = nullptr;
+    bz_problem_desc desc{};
+    long long n = 0, m = 0, ml = 0;   // nx, global ny, local rows
+    // oracle data
+    double* cA = nullptr; bool own_cA = false; double* cb = nullptr;
+    double* fA = nullptr; double* fb = nullptr; long long fm = 0;
+    double* f_ones = nullptr; double* f_zeros = nullptr;
+    double* g_u = nullptr;
+    // AL m-vectors (local rows)
+    double *mu = nullptr, *y = nullptr, *muy = nullptr, *cx = nullptr, *s = nullptr, *yupd = nullptr;
+    double *tm1 = nullptr, *tm2 = nullptr, *tm3 = nullptr;
+    // n-vectors
+    BzVecs v{};
+    double *Ec = nullptr, *Ef = nullptr;
+    // provider partial buffers
+    double *Pc = nullptr, *Pf = nullptr, *lxpart = nullptr, *fxpart = nullptr;
+    int c_clusters = 0, c_rpc = 0, f_clusters = 0, f_rpc = 0, nlx = 0, nfx = 0, nfx2 = 0;
+    double* part = nullptr;
+    unsigned int* counters = nullptr;   // [8]
+    BzTeam team{};
+    BzState* st = nullptr;
+    BzState* st_host = nullptr;         // pinned
+    int* status_host = nullptr;         // pinned, [2]
+    cudaEvent_t poll_ev[2]{};
+    BzGParams g{};
+    BzDParams D{};
+    BzObstacle ob{};
+    bool sharded = false;
+    BzShard shard{};
+    // dominant-kernel timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dom_events;
+};
+
+static const double* const* src_ptrs(bz_problem* p, const double* (&buf)[3]) {
+    buf[0] = p->v.x; buf[1] = p->v.z; buf[2] = p->v.xeps;
+    return buf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int bz_abi_version(void) { return BZ_ABI_VERSION; }
+
+extern "C" const char* bz_last_error(bz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int bz_device_count(int* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return bz_fail(nullptr, BZ_ERR_CUDA, cudaGetErrorString(e)); }
+    *n = c;
+    return BZ_OK;
+}
+
+extern "C" int bz_ctx_create(int device, bz_ctx** out) {
+    if (!out) return bz_fail(nullptr, BZ_ERR_ARG, "bz_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return bz_fail(nullptr, BZ_ERR_CUDA,
+                       std::string("no CUDA device (this library has no CPU path): ") +
+                           cudaGetErrorString(e));
+    if (device < 0 || device >= count) return bz_fail(nullptr, BZ_ERR_ARG, "bad device index");
+    bz_ctx* ctx = new bz_ctx();
+    ctx->device = device;
+    BZ_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BZ_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        std::string msg = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                          "; this library is built for sm_100a only";
+        delete ctx;
+        return bz_fail(nullptr, BZ_ERR_CUDA, msg);
+    }
+    BZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return BZ_OK;
+}
+
+extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
+    if (!ctx) return BZ_OK;
+    cudaSetDevice(ctx->device);
+    bz_comm_destroy(ctx);
+    for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return BZ_OK;
+}
+
+extern "C" int bz_ctx_set_profiling(bz_ctx* ctx, int on) {
+    if (!ctx) return BZ_ERR_ARG;
+    ctx->profiling = on != 0;
+    return BZ_OK;
+}
+
+extern "C" int bz_ctx_sync(bz_ctx* ctx) {
+    if (!ctx) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" void bz_default_options(bz_options* o) {
+    // alps.jl:14-25 and SURVEY Appendix A.1
+    o->tol = 1e-6; o->tol_prim = -1.0; o->tol_dual = -1.0; o->inner_tol = -1.0;
+    o->maxit = 100;
+    o->theta_penalty = 0.8; o->kappa_penalty = 0.5; o->kappa_tol = 0.1;
+    o->subsolver_maxit = 1000000000LL;
+    o->alpha = 0.95; o->beta = 0.5; o->minimum_gamma = 1e-7;
+    o->max_backtracks = 20; o->lbfgs_memory = 5;
+    o->sub_maxit = 1000;
+    o->max_inner_total = 0;
+    o->verbose = 0;
+}
+
+static cudaEvent_t ctx_event(bz_ctx* ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        ctx->ev_pool.push_back(ev);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+
+// ---------------------------------------------------------------------------------------------
+// problems
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int dev_alloc(bz_ctx* ctx, T** ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    BZ_CUDA(ctx, cudaMalloc((void**)ptr, count * sizeof(T)));
+    BZ_CUDA(ctx, cudaMemsetAsync(*ptr, 0, count * sizeof(T), ctx->stream));
+    return BZ_OK;
+}
+#define BZ_TRY(x) do { int rc__ = (x); if (rc__ != BZ_OK) return rc__; } while (0)
+
+static int upload_matrix(bz_ctx* ctx, const double* host, int layout, long long rows, long long cols,
+                         double* dst_rowmajor) {
+    const size_t bytes = (size_t)rows * cols * sizeof(double);
+    if (layout == BZ_ROW_MAJOR) {
+        BZ_CUDA(ctx, cudaMemcpyAsync(dst_rowmajor, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        double* tmp = nullptr;
+        BZ_CUDA(ctx, cudaMalloc((void**)&tmp, bytes));
+        BZ_CUDA(ctx, cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        BZ_TRY(bz_launch_transpose(ctx, tmp, dst_rowmajor, rows, cols));
+        BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    return BZ_OK;
+}
+
+static void dense_partition(bz_ctx* ctx, long long rows, int* clusters, int* rpc) {
+    int maxc = ctx->num_sms / 2;
+    if (maxc < 1) maxc = 1;
+    long long r = (rows + maxc - 1) / maxc;
+    if (r < 1) r = 1;
+    *rpc = (int)r;
+    *clusters = (int)((rows + r - 1) / r);
+    if (*clusters < 1) *clusters = 1;
+}
+
+extern "C" int bz_problem_destroy(bz_problem* p) {
+    if (!p) return BZ_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->own_cA) cudaFree(p->cA);
+    double* frees[] = {p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
+                       p->s, p->yupd, p->tm1, p->tm2, p->tm3, p->v.x, p->v.z, p->v.xeps, p->v.x_prev,
+                       p->v.x_d, p->v.z_curr, p->v.res, p->v.res_prev, p->v.grad_x, p->v.grad_z,
+                       p->v.d, p->v.sM, p->v.yM, p->Ec, p->Ef, p->Pc, p->Pf, p->lxpart, p->fxpart,
+                       p->part, p->team.slots};
+    for (double* f : frees) if (f) cudaFree(f);
+    if (p->counters) cudaFree(p->counters);
+    if (p->team.bars) cudaFree(p->team.bars);
+    if (p->st) cudaFree(p->st);
+    if (p->st_host) cudaFreeHost(p->st_host);
+    if (p->status_host) cudaFreeHost(p->status_host);
+    for (auto& e : p->poll_ev) if (e) cudaEventDestroy(e);
+    bz_shard_free(p->ctx, &p->shard);
+    delete p;
+    return BZ_OK;
+}
+
+extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_problem** out) {
+    if (!ctx || !d || !out) return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_create: NULL argument");
+    *out = nullptr;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d->nx <= 0 || d->ny <= 0) return bz_fail(ctx, BZ_ERR_ARG, "nx and ny must be positive");
+    bz_problem* p = new bz_problem();
+    p->ctx = ctx;
+    p->desc = *d;
+    p->n = d->nx;
+    p->m = d->ny;
+    p->ml = d->ny_local > 0 ? d->ny_local : d->ny;
+    p->sharded = d->ny_local > 0 && ctx->nranks > 1;
+    auto fail = [&](int code, const std::string& msg) {
+        bz_problem_destroy(p);
+        return bz_fail(ctx, code, msg);
+    };
+    const long long n = p->n, ml = p->ml;
+
+    // ---- catalogue check (H2: closed catalogue, unknown combinations raise; no CPU fallback)
+    const bool d_pair = bz_d_is_pair(d->d_kind);
+    switch (d->c_kind) {
+    case BZ_C_DENSE_AFFINE:
+        if (d_pair) return fail(BZ_ERR_UNSUPPORTED, "pair sets with a dense affine c are not in the fused path yet");
+        if (n > DA_MAX_N) return fail(BZ_ERR_UNSUPPORTED, "dense affine c: nx > 16384 needs the column-split path (not built yet)");
+        if (!(d->f_kind == BZ_F_ZERO || d->f_kind == BZ_F_LEAST_SQUARES || d->f_kind == BZ_F_QUADRATIC))
+            return fail(BZ_ERR_UNSUPPORTED, "f kind not available with a dense affine c");
+        break;
+    case BZ_C_IDENTITY:
+        if (d->ny != d->nx) return fail(BZ_ERR_ARG, "identity c needs ny == nx");
+        if (!(d->f_kind == BZ_F_ZERO || d->f_kind == BZ_F_LEAST_SQUARES || d->f_kind == BZ_F_QUADRATIC))
+            return fail(BZ_ERR_UNSUPPORTED, "f kind not available with the identity c");
+        if (d_pair && d->d_pair_stride != 1 && d->d_pair_stride * 2 != d->ny)
+            return fail(BZ_ERR_ARG, "pair stride must be 1 or ny/2");
+        break;
+    case BZ_C_OBSTACLE:
+        if (d->f_kind != BZ_F_OBSTACLE_L1 || d->g_kind != BZ_G_OBSTACLE_L1 || d->d_kind != BZ_D_ZERO)
+            return fail(BZ_ERR_UNSUPPORTED, "obstacle c is built for the obstacle_l1 variant only");
+        if (d->nx != 3 * d->ny) return fail(BZ_ERR_ARG, "obstacle: nx must be 3*ny");
+        if (d->grid_y * d->grid_x != 0 && d->grid_y * d->grid_x != d->ny)
+            return fail(BZ_ERR_ARG, "obstacle: grid_y*grid_x must equal ny");
+        break;
+    default:
+        return fail(BZ_ERR_UNSUPPORTED,
+                    "c kind is only available in the batched tiny-instance path (bz_batch_solve)");
+    }
+    if (d->f_kind == BZ_F_LEAST_SQUARES && n > DA_MAX_N)
+        return fail(BZ_ERR_UNSUPPORTED, "LeastSquares f: nx > 16384 not built yet");
+    if (d->g_kind == BZ_G_OBSTACLE_L1 && d->c_kind != BZ_C_OBSTACLE)
+        return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
+    if ((d->g_kind == BZ_G_NORML1_BOX || d->g_kind == BZ_G_NORML0_BOX)) {
+        if (!d->g_u) return fail(BZ_ERR_ARG, "g_u is required for the *_BOX prox kinds");
+        if (d->g_lambda < 0) return fail(BZ_ERR_ARG, "parameter λ must be nonnegative");
+        for (long long j = 0; j < n; ++j)
+            if (d->g_u[j] < 0) return fail(BZ_ERR_ARG, "vector u must have nonnegative entries");
+    }
+    if (d->g_kind == BZ_G_NORML1_NONNEG && d->g_lambda < 0)
+        return fail(BZ_ERR_ARG, "λ must be nonnegative");
+
+    int rc = BZ_OK;
+#define PTRY(x) do { rc = (x); if (rc != BZ_OK) { bz_problem_destroy(p); return rc; } } while (0)
+    // ---- parameters
+    p->g.kind = d->g_kind; p->g.lambda = d->g_lambda; p->g.lo = d->g_lo; p->g.hi = d->g_hi;
+    p->g.u = nullptr; p->g.N = d->ny;
+    p->D.kind = d->d_kind; p->D.lo = d->d_lo; p->D.hi = d->d_hi;
+    p->D.stride = d->d_pair_stride > 0 ? d->d_pair_stride : 1;
+    p->ob.N = d->ny; p->ob.gy = d->grid_y; p->ob.gx = d->grid_x;
+    if (d->g_u) {
+        PTRY(dev_alloc(ctx, &p->g_u, n));
+        cudaMemcpyAsync(p->g_u, d->g_u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        p->g.u = p->g_u;
+    }
+    // ---- vectors
+    double** nvecs[] = {&p->v.x, &p->v.z, &p->v.xeps, &p->v.x_prev, &p->v.x_d, &p->v.z_curr, &p->v.res,
+                        &p->v.res_prev, &p->v.grad_x, &p->v.grad_z, &p->v.d, &p->Ec, &p->Ef};
+    for (double** q : nvecs) PTRY(dev_alloc(ctx, q, n));
+    PTRY(dev_alloc(ctx, &p->v.sM, (size_t)BZ_MAXMEM * n));
+    PTRY(dev_alloc(ctx, &p->v.yM, (size_t)BZ_MAXMEM * n));
+    p->v.n = n;
+    double** mvecs[] = {&p->mu, &p->y, &p->muy, &p->cx, &p->s, &p->yupd, &p->tm1, &p->tm2, &p->tm3};
+    for (double** q : mvecs) PTRY(dev_alloc(ctx, q, ml));
+    const int maxgrid = ctx->num_sms * 8;
+    PTRY(dev_alloc(ctx, &p->part, (size_t)4 * maxgrid));
+    PTRY(dev_alloc(ctx, &p->lxpart, (size_t)maxgrid));
+    PTRY(dev_alloc(ctx, &p->fxpart, (size_t)2 * maxgrid));
+    PTRY(dev_alloc(ctx, &p->counters, 8));
+    PTRY(dev_alloc(ctx, &p->team.bars, 2 * BZ_MAXBAR));
+    p->team.max_ctas = ctx->num_sms;
+    PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * ctx->num_sms * 2));
+    p->team.parity = 0;
+    PTRY(dev_alloc(ctx, &p->st, 1));
+    BZ_CUDA(ctx, cudaMallocHost((void**)&p->st_host, sizeof(BzState)));
+    BZ_CUDA(ctx, cudaMallocHost((void**)&p->status_host, 2 * sizeof(int)));
+    for (auto& e : p->poll_ev) BZ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+    // ---- f data
+    if (d->f_kind == BZ_F_LEAST_SQUARES) {
+        if (!d->f_A || !d->f_b || d->f_m <= 0) return fail(BZ_ERR_ARG, "LeastSquares needs f_A, f_b, f_m");
+        p->fm = d->f_m;
+        PTRY(dev_alloc(ctx, &p->fA, (size_t)p->fm * n));
+        PTRY(upload_matrix(ctx, d->f_A, d->f_layout, p->fm, n, p->fA));
+        PTRY(dev_alloc(ctx, &p->fb, p->fm));
+        cudaMemcpyAsync(p->fb, d->f_b, p->fm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        PTRY(dev_alloc(ctx, &p->f_ones, p->fm));
+        PTRY(dev_alloc(ctx, &p->f_zeros, p->fm));
+        PTRY(bz_launch_fill(ctx, p->f_ones, p->fm, 1.0));
+        dense_partition(ctx, p->fm, &p->f_clusters, &p->f_rpc);
+        PTRY(dev_alloc(ctx, &p->Pf, (size_t)p->f_clusters * n));
+    } else if (d->f_kind == BZ_F_QUADRATIC) {
+        if (!d->f_A || !d->f_b) return fail(BZ_ERR_ARG, "Quadratic needs f_A (Q) and f_b (q)");
+        PTRY(dev_alloc(ctx, &p->fA, (size_t)n * n));
+        PTRY(upload_matrix(ctx, d->f_A, d->f_layout, n, n, p->fA));
+        PTRY(dev_alloc(ctx, &p->fb, n));
+        cudaMemcpyAsync(p->fb, d->f_b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    // ---- c data
+    if (d->c_kind == BZ_C_DENSE_AFFINE) {
+        if (!d->c_b) return fail(BZ_ERR_ARG, "dense affine c needs c_b");
+        PTRY(dev_alloc(ctx, &p->cb, ml));
+        cudaMemcpyAsync(p->cb, d->c_b, ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (d->c_A_is_device) {
+            if (!d->c_A) return fail(BZ_ERR_ARG, "c_A_is_device set but c_A is NULL");
+            p->cA = const_cast<double*>(d->c_A);
+            p->own_cA = false;
+        } else {
+            PTRY(dev_alloc(ctx, &p->cA, (size_t)ml * n));
+            p->own_cA = true;
+            if (d->c_gen) {
+                PTRY(bz_launch_randn_fill(ctx, d->c_gen_seed, 0,
+                                          (uint64_t)d->row_begin * (uint64_t)n, ml * n, p->cA));
+            } else {
+                if (!d->c_A) return fail(BZ_ERR_ARG, "dense affine c needs c_A");
+                PTRY(upload_matrix(ctx, d->c_A, d->c_layout, ml, n, p->cA));
+            }
+        }
+        dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc);
+        PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
+        if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
+    }
+#undef PTRY
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = p;
+    return BZ_OK;
+}
+
+extern "C" int bz_problem_upload_dense(bz_problem* p, const double* c_A, const double* c_b) {
+    if (!p || !c_A || !c_b) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (p->desc.c_kind != BZ_C_DENSE_AFFINE || !p->own_cA)
+        return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_upload_dense: problem does not own a dense A");
+    BZ_TRY(upload_matrix(ctx, c_A, p->desc.c_layout, p->ml, p->n, p->cA));
+    BZ_CUDA(ctx, cudaMemcpyAsync(p->cb, c_b, p->ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AL-gradient provider: enqueue the kernels that evaluate gradient!(dlx, alFun, .) at the target
+// vector (auglagfun.jl:73-86).  `force_target` < 0: predicated on the state machine.
+// ---------------------------------------------------------------------------------------------
+static BzGradSrc grad_src(bz_problem* p) {
+    BzGradSrc gs{};
+    const bz_problem_desc& d = p->desc;
+    gs.fx_scale = 1.0; gs.fx_scale2 = 0.0;
+    if (d.f_kind == BZ_F_LEAST_SQUARES) {
+        gs.Pf = p->Pf; gs.npf = p->f_clusters;
+        gs.fxpart = p->fxpart; gs.nfx = p->f_clusters; gs.fx_scale = 0.5;
+    } else if (d.f_kind == BZ_F_QUADRATIC) {
+        gs.Ef = p->Ef;
+        gs.fxpart = p->fxpart; gs.nfx = p->nfx; gs.fx_scale = 1.0;
+    } else if (d.f_kind == BZ_F_OBSTACLE_L1) {
+        gs.fxpart = p->fxpart; gs.nfx = p->nfx; gs.fx_scale = 0.5;
+        gs.fxpart2 = p->fxpart + p->nfx; gs.nfx2 = p->nfx; gs.fx_scale2 = -1.0;
+    }
+    if (d.c_kind == BZ_C_DENSE_AFFINE) {
+        if (p->sharded) { gs.Ec = p->shard.reduced; gs.lxpart = p->shard.reduced + p->n; gs.nlx = 1; }
+        else { gs.Pc = p->Pc; gs.npc = p->c_clusters; gs.lxpart = p->lxpart; gs.nlx = p->c_clusters; }
+    } else if (d.c_kind == BZ_C_IDENTITY) {
+        gs.Ec = p->yupd; gs.lxpart = p->lxpart; gs.nlx = p->nlx;
+    } else {
+        gs.Ec = p->Ec; gs.lxpart = p->lxpart; gs.nlx = p->nlx;
+    }
+    return gs;
+}
+
+static int launch_provider(bz_problem* p, int force_target) {
+    bz_ctx* ctx = p->ctx;
+    const bz_problem_desc& d = p->desc;
+    const double* srcbuf[3];
+    const double* const* src = src_ptrs(p, srcbuf);
+    // ---- smooth cost f
+    if (d.f_kind == BZ_F_LEAST_SQUARES) {
+        BzDenseArgs a{};
+        a.A = p->fA; a.lda = p->n; a.b = p->fb; a.mu = p->f_ones; a.muy = p->f_zeros;
+        a.src[0] = src[0]; a.src[1] = src[1]; a.src[2] = src[2];
+        a.st = p->st; a.force_target = force_target; a.m = p->fm; a.n = p->n;
+        a.rows_per_cluster = p->f_rpc; a.dkind = BZ_D_ZERO; a.dlo = 0; a.dhi = 0;
+        a.cx = nullptr; a.s = nullptr; a.yupd = nullptr;
+        a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
+        BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
+    } else if (d.f_kind == BZ_F_QUADRATIC) {
+        p->nfx = std::min<long long>(ctx->num_sms, (p->n + 7) / 8);
+        if (p->nfx < 1) p->nfx = 1;
+        BZ_TRY(bz_launch_quad_grad(ctx, p->fA, p->fb, p->st, force_target, src, p->n, p->Ef,
+                                   p->fxpart, p->nfx));
+    }
+    // ---- constraint part
+    if (d.c_kind == BZ_C_DENSE_AFFINE) {
+        BzDenseArgs a{};
+        a.A = p->cA; a.lda = p->n; a.b = p->cb; a.mu = p->mu; a.muy = p->muy;
+        a.src[0] = src[0]; a.src[1] = src[1]; a.src[2] = src[2];
+        a.st = p->st; a.force_target = force_target; a.m = p->ml; a.n = p->n;
+        a.rows_per_cluster = p->c_rpc; a.dkind = p->D.kind; a.dlo = p->D.lo; a.dhi = p->D.hi;
+        a.cx = p->cx; a.s = p->s; a.yupd = p->yupd;
+        a.P = p->Pc; a.lxpart = p->lxpart; a.counter = p->counters + 1; a.set_after = 1;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->profiling) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
+        BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
+        if (ctx->profiling) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
+        if (p->sharded)
+            BZ_TRY(bz_shard_allreduce(ctx, &p->shard, p->Pc, p->c_clusters, p->lxpart, p->n));
+    } else if (d.c_kind == BZ_C_IDENTITY) {
+        p->nlx = bz_vec_grid(ctx, bz_d_is_pair(p->D.kind) ? p->n / 2 : p->n);
+        BZ_TRY(bz_launch_identity_c(ctx, p->st, force_target, src, p->n, p->mu, p->muy, p->D, p->cx,
+                                    p->s, p->yupd, p->lxpart, p->counters + 1, 1));
+    } else if (d.c_kind == BZ_C_OBSTACLE) {
+        p->nlx = p->nfx = bz_vec_grid(ctx, p->ob.N);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (ctx->profiling) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
+        BZ_TRY(bz_launch_obstacle(ctx, p->st, force_target, src, p->ob, p->mu, p->muy, p->cx, p->s,
+                                  p->yupd, p->Ec, p->lxpart, p->fxpart, p->counters + 1, 1));
+        if (ctx->profiling) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
+    }
+    return BZ_OK;
+}
+
+// one pass of the fixed cycle [L, G, F, G, D]
+static int launch_cycle(bz_problem* p) {
+    bz_ctx* ctx = p->ctx;
+    BzGradSrc gs = grad_src(p);
+    BzTeam tm = p->team;
+    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1));
+    p->team.parity ^= 1;
+    BZ_TRY(launch_provider(p, -1));
+    gs = grad_src(p);
+    BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs, p->g, p->part, p->counters + 3, -1));
+    BZ_TRY(launch_provider(p, -1));
+    BZ_TRY(bz_launch_dstep(ctx, p->st, p->v, gs, p->part, p->counters + 4));
+    return BZ_OK;
+}
+
+// PANOCplus on the current (mu, y): x must be in p->v.x.  Returns with the solution in p->v.z and
+// the AugLagFun side-effect state at z (Appendix A.7).
+static int panoc_run(bz_problem* p, const bz_options* o, double tol, long long maxit) {
+    bz_ctx* ctx = p->ctx;
+    if (o->lbfgs_memory < 0 || o->lbfgs_memory > BZ_MAXMEM)
+        return bz_fail(ctx, BZ_ERR_ARG, "lbfgs_memory must be in [0, 16]");
+    if (maxit < 1) maxit = 1;
+    BZ_TRY(bz_launch_panoc_begin(ctx, p->st, tol, maxit, o->alpha, o->beta, o->minimum_gamma,
+                                 o->max_backtracks, o->lbfgs_memory));
+    const int cycles_per_batch = 4;
+    int slot = 0, inflight = 0;
+    p->status_host[0] = p->status_host[1] = IST_RUNNING;
+    for (;;) {
+        for (int c = 0; c < cycles_per_batch; ++c) BZ_TRY(launch_cycle(p));
+        BZ_CUDA(ctx, cudaMemcpyAsync(&p->status_host[slot], &p->st->inner_status, sizeof(int),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        BZ_CUDA(ctx, cudaEventRecord(p->poll_ev[slot], ctx->stream));
+        inflight++;
+        slot ^= 1;
+        if (inflight == 2) {
+            BZ_CUDA(ctx, cudaEventSynchronize(p->poll_ev[slot]));   // the older batch
+            inflight--;
+            if (p->status_host[slot] != IST_RUNNING) break;
+        }
+    }
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+static int fetch_state(bz_problem* p) {
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaMemcpyAsync(p->st_host, p->st, sizeof(BzState), cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+static int push_state(bz_problem* p) {
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaMemcpyAsync(p->st, p->st_host, sizeof(BzState), cudaMemcpyHostToDevice, ctx->stream));
+    return BZ_OK;
+}
+static int h2d(bz_problem* p, double* dst, const double* src, long long count) {
+    BZ_CUDA(p->ctx, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, p->ctx->stream));
+    return BZ_OK;
+}
+static int d2h(bz_problem* p, double* dst, const double* src, long long count) {
+    if (!dst) return BZ_OK;
+    BZ_CUDA(p->ctx, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToHost, p->ctx->stream));
+    return BZ_OK;
+}
+static int d2d(bz_problem* p, double* dst, const double* src, long long count) {
+    BZ_CUDA(p->ctx, cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToDevice, p->ctx->stream));
+    return BZ_OK;
+}
+
+static void collect_dominant(bz_problem* p, long long n_real, bz_result* res) {
+    // the top `n_real` durations are the launches that actually ran (the rest returned at the
+    // state-machine check); sum them
+    std::vector<float> ms;
+    ms.reserve(p->dom_events.size());
+    for (auto& e : p->dom_events) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) ms.push_back(t);
+    }
+    std::sort(ms.begin(), ms.end(), [](float a, float b) { return a > b; });
+    long long k = std::min<long long>(n_real, (long long)ms.size());
+    double sum = 0.0;
+    for (long long i = 0; i < k; ++i) sum += ms[i];
+    res->dominant_kernel_ms = sum;
+    res->dominant_kernel_launches = k;
+    p->dom_events.clear();
+    p->ctx->ev_used = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// alps (src/algorithms/alps.jl:7-117)
+// ---------------------------------------------------------------------------------------------
+extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
+                             double* x, double* y, double* s, double* mu, bz_result* res) {
+    if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_alps_solve: NULL argument");
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long launches0 = ctx->n_launches;
+    p->dom_events.clear();
+    ctx->ev_used = 0;
+    const double tol = o->tol;
+    const double tol_prim = o->tol_prim >= 0 ? o->tol_prim : tol;
+    const double tol_dual = o->tol_dual >= 0 ? o->tol_dual : tol;
+    double inner_tol = o->inner_tol >= 0 ? o->inner_tol : std::cbrt(tol_dual);
+    const long long n = p->n, ml = p->ml;
+
+    // ---- initialise (alps.jl:31-46)
+    BZ_TRY(h2d(p, p->v.z_curr, x0, n));
+    BZ_TRY(h2d(p, p->y, y0 + (p->sharded ? p->desc.row_begin : 0), ml));
+    BzState* h = p->st_host;
+    memset(h, 0, sizeof(BzState));
+    h->next_op = OP_DONE;
+    h->H = 1.0;
+    h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
+    h->theta_penalty = o->theta_penalty; h->kappa_penalty = o->kappa_penalty; h->kappa_tol = o->kappa_tol;
+    h->outer_maxit = o->maxit; h->subsolver_maxit = o->subsolver_maxit;
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_prox(ctx, p->st, p->v.z_curr, BZ_EPS, p->v.x, n, p->g, p->part, p->counters + 5));
+    BZ_TRY(bz_launch_fill(ctx, p->mu, ml, 1.0));
+    BZ_TRY(bz_launch_fill(ctx, p->muy, ml, 0.0));
+    BZ_TRY(launch_provider(p, TGT_X));       // cx = c(x), f(x)
+    {
+        BzGradSrc gs = grad_src(p);
+        BZ_TRY(bz_launch_assemble(ctx, p->st, gs, n, p->v.grad_x, p->part, p->counters + 6));
+    }
+    BZ_TRY(fetch_state(p));
+    double objx = h->al_fx + h->g_z;         // objx = f(x) + gFun.gz
+    h->objx = objx;
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->cx, p->s, p->mu, ml, p->D, 1, nullptr));
+
+    int tot_it = 0;
+    long long tot_inner = 0;
+    bool solved = false, tired = tot_it >= o->maxit, broken = std::isnan(objx);
+    double norm_res_prim = NAN;
+    long long n_grad = 0, n_prox = 0;
+    bool can_stop = solved || tired || broken;
+    while (!can_stop) {
+        tot_it++;
+        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, 1, 1, p->part, p->counters + 5));
+        if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));
+        long long maxit_inner = o->sub_maxit;
+        if (o->max_inner_total > 0)
+            maxit_inner = std::max<long long>(1, std::min<long long>(maxit_inner, o->max_inner_total - tot_inner));
+        BZ_TRY(panoc_run(p, o, inner_tol, maxit_inner));
+        BZ_TRY(d2d(p, p->v.x, p->v.z, n));                  // x .= sub_sol
+        BZ_TRY(bz_launch_multiplier(ctx, p->st, p->cx, p->muy, p->mu, p->y, p->s, ml, p->D,
+                                    p->sharded ? 0 : 1, p->part, p->counters + 5));
+        if (p->sharded) {   // ||cx - s||_inf over all row blocks, then the same scalar logic on every rank
+            BZ_TRY(bz_comm_allreduce(ctx, &p->st->out[0], 1, BZ_COMM_MAX));
+            BZ_TRY(bz_launch_outer_logic(ctx, p->st));
+        }
+        BZ_TRY(fetch_state(p));                               // the one sync per outer iteration
+        if (h->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
+        objx = h->objx;
+        tot_inner = h->tot_inner_it;
+        norm_res_prim = h->norm_res_prim;
+        solved = h->solved; tired = h->tired; broken = h->broken;
+        n_grad = h->n_grad; n_prox = h->n_prox;
+        can_stop = solved || tired || broken;
+        if (o->max_inner_total > 0 && tot_inner >= o->max_inner_total) can_stop = true;
+        if (!can_stop && h->scale_mu) BZ_TRY(bz_launch_scale(ctx, p->mu, ml, o->kappa_penalty));
+        inner_tol = h->inner_tol;
+    }
+    BZ_TRY(d2h(p, x, p->v.x, n));
+    BZ_TRY(d2h(p, y, p->y, ml));
+    BZ_TRY(d2h(p, s, p->s, ml));
+    BZ_TRY(d2h(p, mu, p->mu, ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    res->tot_it = tot_it;
+    res->tot_inner_it = tot_inner;
+    res->status = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+    res->inner_tol = inner_tol;
+    res->norm_res_prim = norm_res_prim;
+    res->objective = objx;
+    res->n_grad = n_grad;
+    res->n_prox = n_prox;
+    res->n_launches = ctx->n_launches - launches0;
+    res->dominant_kernel_ms = 0.0;
+    res->dominant_kernel_launches = 0;
+    if (ctx->profiling) collect_dominant(p, n_grad + 1, res);
+    res->elapsed_time =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// subsolver slot and parity entry points
+// ---------------------------------------------------------------------------------------------
+static int set_mu_y(bz_problem* p, const double* mu, const double* y) {
+    bz_ctx* ctx = p->ctx;
+    BZ_TRY(h2d(p, p->mu, mu, p->ml));
+    BZ_TRY(h2d(p, p->y, y, p->ml));
+    BZ_TRY(fetch_state(p));
+    p->st_host->err_flag = 0;
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, p->ml, 0, 0, p->part, p->counters + 5));
+    BZ_TRY(fetch_state(p));
+    if (p->st_host->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
+    return BZ_OK;
+}
+
+extern "C" int bz_auglag_update(bz_problem* p, const double* mu, const double* y) {
+    if (!p || !mu || !y) return BZ_ERR_ARG;
+    BZ_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    return set_mu_y(p, mu, y);
+}
+
+extern "C" int bz_auglag_grad(bz_problem* p, const double* x, double* dlx, double* lx, double* fx,
+                              double* cx, double* s, double* yupd) {
+    if (!p || !x) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(h2d(p, p->v.xeps, x, p->n));
+    BZ_TRY(launch_provider(p, TGT_XEPS));
+    BzGradSrc gs = grad_src(p);
+    BZ_TRY(bz_launch_assemble(ctx, p->st, gs, p->n, p->v.d, p->part, p->counters + 6));
+    BZ_TRY(fetch_state(p));
+    if (lx) *lx = p->st_host->out[0];
+    if (fx) *fx = p->st_host->out[1];
+    BZ_TRY(d2h(p, dlx, p->v.d, p->n));
+    BZ_TRY(d2h(p, cx, p->cx, p->ml));
+    BZ_TRY(d2h(p, s, p->s, p->ml));
+    BZ_TRY(d2h(p, yupd, p->yupd, p->ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_auglag_state(bz_problem* p, double* cx, double* s, double* yupd, double* muy,
+                               double* musqy) {
+    if (!p) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(fetch_state(p));
+    if (musqy) *musqy = p->st_host->musqy;
+    BZ_TRY(d2h(p, cx, p->cx, p->ml));
+    BZ_TRY(d2h(p, s, p->s, p->ml));
+    BZ_TRY(d2h(p, yupd, p->yupd, p->ml));
+    BZ_TRY(d2h(p, muy, p->muy, p->ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_panocplus_solve(bz_problem* p, const double* mu, const double* y, const double* x0,
+                                  const bz_options* o, double tol, double* x_out, int64_t* sub_it,
+                                  double* fx, double* gz) {
+    if (!p || !mu || !y || !x0 || !o) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(set_mu_y(p, mu, y));
+    BZ_TRY(h2d(p, p->v.x, x0, p->n));
+    BZ_TRY(panoc_run(p, o, tol, o->sub_maxit));
+    BZ_TRY(fetch_state(p));
+    if (sub_it) *sub_it = p->st_host->iter;
+    if (fx) *fx = p->st_host->al_fx;
+    if (gz) *gz = p->st_host->g_z;
+    BZ_TRY(d2h(p, x_out, p->v.z, p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_prox(bz_problem* p, const double* x, double gamma, double* z, double* gz) {
+    if (!p || !x) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(h2d(p, p->v.xeps, x, p->n));
+    BZ_TRY(bz_launch_prox(ctx, p->st, p->v.xeps, gamma, p->v.d, p->n, p->g, p->part, p->counters + 5));
+    BZ_TRY(fetch_state(p));
+    if (gz) *gz = p->st_host->out[0];
+    BZ_TRY(d2h(p, z, p->v.d, p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_proj(bz_problem* p, const double* v, double* z) {
+    if (!p || !v) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(h2d(p, p->tm1, v, p->ml));
+    BZ_TRY(bz_launch_proj(ctx, p->tm1, p->tm2, p->ml, p->D));
+    BZ_TRY(d2h(p, z, p->tm2, p->ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_fb_step(bz_problem* p, const double* x, const double* grad, double gamma, double* z,
+                          double* res, double* gz, double* dot_grad_res, double* res_sq) {
+    if (!p || !x || !grad) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(h2d(p, p->v.x, x, p->n));
+    BZ_TRY(h2d(p, p->v.grad_x, grad, p->n));
+    BZ_TRY(fetch_state(p));
+    p->st_host->gamma = gamma;
+    p->st_host->grad_x_fresh = 0;
+    p->st_host->alpha = 0.95;
+    BZ_TRY(push_state(p));
+    BzGradSrc gs = grad_src(p);
+    BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs, p->g, p->part, p->counters + 3, MODE_ITER));
+    BZ_TRY(fetch_state(p));
+    if (gz) *gz = p->st_host->out[0];
+    if (dot_grad_res) *dot_grad_res = p->st_host->out[1];
+    if (res_sq) *res_sq = p->st_host->out[2];
+    BZ_TRY(d2h(p, z, p->v.z, p->n));
+    BZ_TRY(d2h(p, res, p->v.res, p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_lbfgs_reset(bz_problem* p, int memory) {
+    if (!p || memory < 0 || memory > BZ_MAXMEM) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(fetch_state(p));
+    BzState* h = p->st_host;
+    h->mem = memory; h->currmem = 0; h->curridx = 0; h->H = 1.0;
+    h->gamma = 1.0; h->alpha = 0.95; h->beta = 0.5;
+    BZ_TRY(push_state(p));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+static int lbfgs_call(bz_problem* p, int skip_update) {
+    bz_ctx* ctx = p->ctx;
+    BZ_TRY(fetch_state(p));
+    p->st_host->skip_update = skip_update;
+    BZ_TRY(push_state(p));
+    BzTeam tm = p->team;
+    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, LROLE_NEWITER));
+    p->team.parity ^= 1;
+    return BZ_OK;
+}
+
+extern "C" int bz_lbfgs_update(bz_problem* p, const double* s, const double* y) {
+    if (!p || !s || !y) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    // update!(H, s, y) with s = x - x_prev, y = res - res_prev: feed x_prev = res_prev = 0
+    BZ_TRY(h2d(p, p->v.x, s, p->n));
+    BZ_TRY(h2d(p, p->v.res, y, p->n));
+    BZ_CUDA(ctx, cudaMemsetAsync(p->v.x_prev, 0, p->n * sizeof(double), ctx->stream));
+    BZ_CUDA(ctx, cudaMemsetAsync(p->v.res_prev, 0, p->n * sizeof(double), ctx->stream));
+    BZ_TRY(lbfgs_call(p, 0));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_lbfgs_apply(bz_problem* p, const double* v, double* d) {
+    if (!p || !v) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    // d = H * v: the kernel computes H * (-res), so feed res = -v
+    std::vector<double> neg(p->n);
+    for (long long j = 0; j < p->n; ++j) neg[j] = -v[j];
+    BZ_TRY(h2d(p, p->v.res, neg.data(), p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BZ_TRY(lbfgs_call(p, 1));
+    BZ_TRY(d2h(p, d, p->v.d, p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_multiplier_update(bz_problem* p, const double* cx, const double* mu,
+                                    const double* y_in, double* y_out, double* s_out,
+                                    double* norm_res_prim) {
+    if (!p || !cx || !mu || !y_in) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(set_mu_y(p, mu, y_in));
+    BZ_TRY(h2d(p, p->cx, cx, p->ml));
+    BZ_TRY(bz_launch_multiplier(ctx, p->st, p->cx, p->muy, p->mu, p->y, p->s, p->ml, p->D, 0, p->part,
+                                p->counters + 5));
+    BZ_TRY(fetch_state(p));
+    if (norm_res_prim) *norm_res_prim = p->st_host->out[0];
+    BZ_TRY(d2h(p, y_out, p->y, p->ml));
+    BZ_TRY(d2h(p, s_out, p->s, p->ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_default_penalty(bz_problem* p, const double* cx, const double* proj_cx, double objx,
+                                  double* mu) {
+    if (!p || !cx || !proj_cx || !mu) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_TRY(h2d(p, p->tm1, cx, p->ml));
+    BZ_TRY(h2d(p, p->tm2, proj_cx, p->ml));
+    BZ_TRY(fetch_state(p));
+    p->st_host->out[7] = objx;
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->tm1, p->tm2, p->tm3, p->ml, p->D, 0, &p->st->out[7]));
+    BZ_TRY(d2h(p, mu, p->tm3, p->ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, int64_t count,
+                             double* out) {
+    if (!ctx || !out || count < 0) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    BZ_CUDA(ctx, cudaMalloc((void**)&d, (size_t)std::max<int64_t>(count, 1) * sizeof(double)));
+    int rc = bz_launch_randn_fill(ctx, seed, stream, start, count, d);
+    if (rc == BZ_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}

@@ -1,0 +1,62 @@
+// Launch interfaces of bz_vec.cu (n-space / m-space vector kernels of the PANOC+ state machine)
+#pragma once
+#include "bz_internal.cuh"
+
+#define BZ_MAXBAR 48          // team barriers per L launch (1 + 2*memory + slack)
+#define BZ_VEC_THREADS 256
+#define BZ_L_THREADS 512
+
+struct BzVecs {
+    double *x, *z, *xeps, *x_prev, *x_d, *z_curr, *res, *res_prev, *grad_x, *grad_z, *d;
+    double *sM, *yM;   // mem x n ring buffers
+    long long n;
+};
+
+// software grid barrier + all-CTA reduction used by the cooperative L kernel
+struct BzTeam {
+    unsigned int* bars;   // [2][BZ_MAXBAR]
+    double* slots;        // [2][BZ_MAXBAR][max_ctas][2]
+    int max_ctas;
+    int parity;
+};
+
+struct BzObstacle {      // demo/obstacle.jl ConstraintObstacle (+ 2-D extension)
+    long long N, gy, gx; // gy = gx = 0: 1-D SymTridiagonal(2,-1)
+};
+
+int bz_vec_grid(const bz_ctx* ctx, long long n);
+int bz_l_grid(const bz_ctx* ctx, long long n);
+
+int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
+                    const BzGParams& g, double* part, unsigned int* counter, int force_mode);
+int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
+                    unsigned int* counter);
+int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
+                    unsigned int* counter, int force_role);
+int bz_launch_assemble(bz_ctx* ctx, BzState* st, const BzGradSrc& gs, long long n, double* out,
+                       double* part, unsigned int* counter);
+
+int bz_launch_identity_c(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
+                         long long n, const double* mu, const double* muy, const BzDParams& D,
+                         double* cx, double* s, double* yupd, double* lxpart, unsigned int* counter,
+                         int set_after);
+int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
+                       const BzObstacle& ob, const double* mu, const double* muy, double* cx,
+                       double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
+                       unsigned int* counter, int set_after);
+
+int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, double* out, long long n,
+                   const BzGParams& g, double* part, unsigned int* counter);
+int bz_launch_proj(bz_ctx* ctx, const double* in, double* out, long long m, const BzDParams& D);
+int bz_launch_al_update(bz_ctx* ctx, BzState* st, double* mu, double* y, double* muy, long long m,
+                        int safeguard, int count_outer, double* part, unsigned int* counter);
+int bz_launch_multiplier(bz_ctx* ctx, BzState* st, const double* cx, const double* muy,
+                         const double* mu, double* y, double* s, long long m, const BzDParams& D,
+                         int outer_logic, double* part, unsigned int* counter);
+int bz_launch_init_mu(bz_ctx* ctx, BzState* st, const double* cx, double* s, double* mu, long long m,
+                      const BzDParams& D, int compute_s, const double* objx_ptr);
+int bz_launch_outer_logic(bz_ctx* ctx, BzState* st);
+int bz_launch_scale(bz_ctx* ctx, double* v, long long m, double factor);
+int bz_launch_fill(bz_ctx* ctx, double* v, long long m, double value);
+int bz_launch_panoc_begin(bz_ctx* ctx, BzState* st, double tol, long long maxit, double alpha,
+                          double beta, double gamma_min, int max_backtracks, int mem);

@@ -1,0 +1,221 @@
+"""The oracle catalogue: Python mirrors of the Julia types that ``Bazinga.alps(f, g, c, D, x0, y0)``
+dispatches on.  These objects only *describe* a problem; every method that
+computes (``prox!``, ``proj!``, ``gradient!`` ...) goes through the C-ABI to the CUDA kernels, see
+solver.py.  Constructor guards raise the reference's messages.
+
+Arbitrary user-defined Julia methods cannot cross a C ABI: the GPU path accepts this
+closed catalogue and raises ``BazingaError(BZ_ERR_UNSUPPORTED)`` for anything else -- never a CPU
+fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi as K
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+# ------------------------------------------------------------------ smooth costs f
+class Zero:
+    """ProximalOperators.Zero() / Bazinga.Zero (src/proxoperators/zero.jl): as f or as g."""
+    f_kind = K.F_ZERO
+    g_kind = K.G_ZERO
+
+
+class LeastSquares:
+    """ProximalOperators.LeastSquares(A, b): 0.5||Ax-b||^2 (test/problems/test_verbose.jl:22)."""
+    f_kind = K.F_LEAST_SQUARES
+
+    def __init__(self, A, b):
+        self.A, self.b = _f64(A), _f64(b)
+        if self.A.shape[0] != self.b.shape[0]:
+            raise ValueError("LeastSquares: size mismatch")
+
+
+class Quadratic:
+    """ProximalOperators.Quadratic(Q, q): 0.5x'Qx + q'x (test/problems/test_nonconvex_qp.jl:14)."""
+    f_kind = K.F_QUADRATIC
+
+    def __init__(self, Q, q):
+        self.Q, self.q = _f64(Q), _f64(q)
+
+
+class SmoothCostObstacleL1:
+    """demo/obstacle.jl:37-47."""
+    f_kind = K.F_OBSTACLE_L1
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
+# ------------------------------------------------------------------ nonsmooth costs g
+class IndFree(Zero):
+    """ProximalOperators.IndFree() (test/problems/test_nonconvex_qp.jl:39)."""
+
+
+class NormL1:
+    """ProximalOperators.NormL1(lambda) (demo/basispursuit.jl:63)."""
+    g_kind = K.G_NORM_L1
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        self.lam = float(lam)
+
+
+class NormL0:
+    """ProximalOperators.NormL0(lambda) (demo/basispursuit.jl:64)."""
+    g_kind = K.G_NORM_L0
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        self.lam = float(lam)
+
+
+class IndBox:
+    """ProximalOperators.IndBox(lo, hi) (test/problems/test_nonconvex_qp.jl:15); also usable as
+    ``ClosedSet(IndBox(lo, hi))``."""
+    g_kind = K.G_IND_BOX
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = float(lo), float(hi)
+
+
+class NormL1Box:
+    """src/proxoperators/normL1Box.jl:11-39."""
+    g_kind = K.G_NORML1_BOX
+
+    def __init__(self, lam=1.0, *, u):
+        u = _f64(u)
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        if np.any(u < 0):
+            raise ValueError("vector u must have nonnegative entries")
+        self.lam, self.u = float(lam), u
+
+
+class NormL1Nonneg:
+    """src/proxoperators/normL1Nonneg.jl:11-42."""
+    g_kind = K.G_NORML1_NONNEG
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("λ must be nonnegative")
+        self.lam = float(lam)
+
+
+class NormL0Box:
+    """src/proxoperators/normL0Box.jl:12-58."""
+    g_kind = K.G_NORML0_BOX
+
+    def __init__(self, lam=1.0, *, u):
+        u = _f64(u)
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        if np.any(u < 0):
+            raise ValueError("vector u must have nonnegative entries")
+        self.lam, self.u = float(lam), u
+
+
+class NonsmoothCostObstacleL1:
+    """demo/obstacle.jl:64-81."""
+    g_kind = K.G_OBSTACLE_L1
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
+# ------------------------------------------------------------------ constraint functions c
+class IdentityFunction:
+    """test/definitions/identityFunction.jl:3-13."""
+    c_kind = K.C_IDENTITY
+
+
+class ConstraintBasisPursuit:
+    """demo/basispursuit.jl:38-49: cx = A*x - b, jtv = A'*v.  ``A`` may be C-contiguous
+    (row-major) or Fortran-contiguous (Julia's layout); or pass ``gen_seed`` to have the library
+    generate A on the device."""
+    c_kind = K.C_DENSE_AFFINE
+
+    def __init__(self, A, b, *, gen_seed=None, shape=None, row_begin=0, ny_global=None):
+        self.b = _f64(b)
+        self.gen_seed = gen_seed
+        self.row_begin = int(row_begin)
+        self.ny_global = ny_global
+        if A is None:
+            if gen_seed is None or shape is None:
+                raise ValueError("ConstraintBasisPursuit: need A, or gen_seed and shape")
+            self.A, self.shape, self.layout = None, tuple(shape), K.ROW_MAJOR
+        else:
+            A = np.asarray(A, dtype=np.float64)
+            if A.flags.c_contiguous:
+                self.A, self.layout = A, K.ROW_MAJOR
+            elif A.flags.f_contiguous:
+                self.A, self.layout = A, K.COL_MAJOR
+            else:
+                self.A, self.layout = np.ascontiguousarray(A), K.ROW_MAJOR
+            self.shape = A.shape
+        if self.shape[0] != self.b.shape[0]:
+            raise ValueError("ConstraintBasisPursuit: size mismatch")
+
+
+class ConstraintObstacle:
+    """demo/obstacle.jl:92-113; ``grid=(gy, gx)`` selects the 2-D 5-point extension (config C4)."""
+    c_kind = K.C_OBSTACLE
+
+    def __init__(self, N, grid=None):
+        self.N = int(N)
+        self.grid = grid
+
+
+# ------------------------------------------------------------------ closed sets D
+class ZeroSet:
+    """src/projections/zeroSet.jl (also demo/obstacle.jl SetObstacle)."""
+    d_kind = K.D_ZERO
+
+
+class FreeSet:
+    """src/projections/freeSet.jl."""
+    d_kind = K.D_FREE
+
+
+class IndicatorSet:
+    """src/projections/indicatorSet.jl: ClosedSet(f) = IndicatorSet(f) (src/Bazinga.jl:18).
+    Only IndBox is in the catalogue."""
+    d_kind = K.D_BOX
+
+    def __init__(self, f):
+        if not isinstance(f, IndBox):
+            raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "IndicatorSet: only IndBox is supported on the GPU path")
+        self.lo, self.hi = f.lo, f.hi
+
+
+def ClosedSet(f):
+    return IndicatorSet(f)
+
+
+class PairSet:
+    """Pairs projected by project_onto_{EITHEROR,XOR,VC,CC}_set! (src/projections/orConstraints.jl,
+    vanishingConstraints.jl, complementarityConstraints.jl), adjacent (stride 1) as in SetEOR /
+    SetXOR / SetMPVCA, or (i, i+N) as in SetObstacleRed."""
+    _KINDS = {"eitheror": K.D_EITHEROR, "xor": K.D_XOR, "vc": K.D_VC, "cc": K.D_CC}
+
+    def __init__(self, kind, stride=1):
+        self.d_kind = self._KINDS[kind]
+        self.stride = int(stride)
+
+
+def SetEOR():
+    return PairSet("eitheror")
+
+
+def SetXOR():
+    return PairSet("xor")
+
+
+def SetMPVCA():
+    return PairSet("vc")

@@ -1,0 +1,225 @@
+/*
+ * bazinga_b200.h -- C ABI of libbazinga_b200.so, the B200 (sm_100a) implementation of the
+ * PANOC+/ALPS hot path of aldma/Bazinga.jl.
+ *
+ * This is the drop-in boundary: every entry point is what a Julia `ccall` (or the ctypes harness
+ * in bazinga.jl_b200/) binds in place of the reference function cited next to it.  Plain pointers
+ * and sizes only; all arrays are caller-owned HOST buffers of IEEE fp64 unless a parameter says
+ * "device".  Every function returns 0 on success and a negative bz_status on failure; the message
+ * is available from bz_last_error().  Nothing unwinds across this boundary.  There is no CPU
+ * fallback: a machine without a CUDA device gets BZ_ERR_CUDA from bz_ctx_create.
+ *
+ * Threading: a bz_ctx is not thread-safe (the reference is single-threaded and mutates its oracle
+ * structs, src/utilities/auglagfun.jl:11-26).  Use one ctx per host thread / per GPU.
+ */
+#ifndef BAZINGA_B200_H
+#define BAZINGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BZ_ABI_VERSION 1
+#define BZ_LBFGS_MAX_MEMORY 16
+
+typedef struct bz_ctx bz_ctx;
+typedef struct bz_problem bz_problem;
+typedef struct bz_batch bz_batch;
+
+typedef enum {
+    BZ_OK = 0,
+    BZ_ERR_ARG = -1,         /* bad argument (the reference's `error(...)` guards) */
+    BZ_ERR_CUDA = -2,        /* CUDA runtime failure, or no device */
+    BZ_ERR_UNSUPPORTED = -3, /* oracle combination not in the catalogue: no CPU fallback exists */
+    BZ_ERR_COMM = -4,        /* NCCL failure */
+    BZ_ERR_NONPOSITIVE_MU = -5 /* "parameters `mu` must be positive", auglagfun.jl:33-34,92-93 */
+} bz_status;
+
+/* ---- oracle catalogue: the dispatch keys of the drop-in ------------------- */
+typedef enum { /* smooth cost f: f(x), gradient!(dfx,f,x)->fx */
+    BZ_F_ZERO = 0,          /* ProximalOperators.Zero / src/proxoperators/zero.jl:12-20 */
+    BZ_F_LEAST_SQUARES = 1, /* ProximalOperators.LeastSquares(A,b), test/problems/test_verbose.jl:22 */
+    BZ_F_QUADRATIC = 2,     /* ProximalOperators.Quadratic(Q,q), test/problems/test_nonconvex_qp.jl:14 */
+    BZ_F_ROSENBROCK = 3,    /* demo/rosenbrock.jl:39-50 (f_p[0] = w) */
+    BZ_F_SQDIST2 = 4,       /* demo/eitheror.jl:58-68 SmoothCostOR (f_p[0..1] = c) */
+    BZ_F_LINEAR2 = 5,       /* demo/mpvca.jl:77-87 SmoothCostMPVCA (f_p[0..1] = c) */
+    BZ_F_OBSTACLE_L1 = 6    /* demo/obstacle.jl:37-47 SmoothCostObstacleL1 */
+} bz_f_kind;
+
+typedef enum { /* nonsmooth cost g: prox!(z,g,x,gamma)->g(z) */
+    BZ_G_ZERO = 0,          /* zero.jl:22-25; ProximalOperators.IndFree/Zero; demo/eitheror.jl:71-74 */
+    BZ_G_NORM_L1 = 1,       /* ProximalOperators.NormL1(lambda), demo/basispursuit.jl:63 */
+    BZ_G_NORM_L0 = 2,       /* ProximalOperators.NormL0(lambda), demo/basispursuit.jl:64 */
+    BZ_G_IND_BOX = 3,       /* ProximalOperators.IndBox(lo,hi), test_nonconvex_qp.jl:15 */
+    BZ_G_NORML1_BOX = 4,    /* src/proxoperators/normL1Box.jl:30-39 (u vector) */
+    BZ_G_NORML1_NONNEG = 5, /* src/proxoperators/normL1Nonneg.jl:29-42 */
+    BZ_G_NORML0_BOX = 6,    /* src/proxoperators/normL0Box.jl:33-58 (u vector) */
+    BZ_G_ROSENBROCK = 7,    /* demo/rosenbrock.jl:52-64 */
+    BZ_G_NONNEG = 8,        /* demo/mpvca.jl:89-93 */
+    BZ_G_OBSTACLE_L1 = 9    /* demo/obstacle.jl:64-81 */
+} bz_g_kind;
+
+typedef enum { /* constraint function c: eval!(cx,c,x), jtprod!(jtv,c,x,v) */
+    BZ_C_IDENTITY = 0,      /* test/definitions/identityFunction.jl:3-13 */
+    BZ_C_DENSE_AFFINE = 1,  /* demo/basispursuit.jl:38-49: cx = A*x - b, jtv = A'*v */
+    BZ_C_ROSENBROCK = 2,    /* demo/rosenbrock.jl:66-74 */
+    BZ_C_EITHEROR = 3,      /* demo/eitheror.jl:92-104 ConstraintOR */
+    BZ_C_MPVCA = 4,         /* demo/mpvca.jl:110-118 ConstraintMPVCA */
+    BZ_C_OBSTACLE = 5       /* demo/obstacle.jl:92-113 ConstraintObstacle (1-D, or 2-D grid) */
+} bz_c_kind;
+
+typedef enum { /* closed set D: proj!(z,D,v) */
+    BZ_D_ZERO = 0,     /* src/projections/zeroSet.jl:17-20 */
+    BZ_D_FREE = 1,     /* src/projections/freeSet.jl:17-20 */
+    BZ_D_BOX = 2,      /* ClosedSet(IndBox) = IndicatorSet, src/projections/indicatorSet.jl:8-11 */
+    BZ_D_EITHEROR = 3, /* pairs, src/projections/orConstraints.jl:7-17 */
+    BZ_D_XOR = 4,      /* pairs, src/projections/orConstraints.jl:24-36 */
+    BZ_D_VC = 5,       /* pairs, src/projections/vanishingConstraints.jl:27-46 */
+    BZ_D_CC = 6        /* pairs, src/projections/complementarityConstraints.jl:8-20 */
+} bz_d_kind;
+
+typedef enum { BZ_ROW_MAJOR = 0, BZ_COL_MAJOR = 1 /* Julia's native layout */ } bz_layout;
+
+/* Problem description: the four oracles of `alps(f, g, c, D, x0, y0; ...)`, alps.jl:7-13. */
+typedef struct {
+    int32_t f_kind, g_kind, c_kind, d_kind;
+    int64_t nx, ny;
+    /* f parameters.  LEAST_SQUARES: f_A is f_m x nx, f_b has f_m entries.  QUADRATIC: f_A = Q
+     * (nx x nx), f_b = q.  Closed forms use f_p. */
+    const double* f_A;
+    const double* f_b;
+    int64_t f_m;
+    int32_t f_layout;
+    double f_p[4];
+    /* g parameters */
+    double g_lambda;
+    double g_lo, g_hi;
+    const double* g_u; /* nx entries for the *_BOX kinds */
+    /* c parameters.  DENSE_AFFINE: c_A is ny_local x nx (see sharding), c_b has ny_local entries.
+     * If c_gen != 0 the library generates A = bz_randn(c_gen_seed, global element index) on the
+     * device instead of reading c_A (the 68.7 GB instance cannot live on the host);
+     * c_b must still be supplied. */
+    const double* c_A;
+    const double* c_b;
+    int32_t c_layout;
+    int32_t c_A_is_device; /* adopt a device pointer (row-major only), caller keeps it alive */
+    int32_t c_gen;
+    uint64_t c_gen_seed;
+    int64_t grid_y, grid_x; /* OBSTACLE: 0,0 = 1-D SymTridiagonal(2,-1); else 2-D 5-point grid */
+    /* D parameters */
+    double d_lo, d_hi;
+    int64_t d_pair_stride; /* pair sets: 1 = adjacent (2k,2k+1); N = (i, i+N) */
+    /* Row sharding of a DENSE_AFFINE instance over ranks.  ny is the GLOBAL row
+     * count; this rank owns rows [row_begin, row_begin + ny_local).  ny_local = 0 means unsharded. */
+    int64_t row_begin, ny_local;
+} bz_problem_desc;
+
+/* Options of `alps` (alps.jl:14-25) plus the PANOCplus closure options the demos bake in
+ * (demo/basispursuit.jl:69-78). Use bz_default_options() and override. */
+typedef struct {
+    double tol, tol_prim, tol_dual, inner_tol; /* inner_tol < 0 means cbrt(tol_dual) */
+    int32_t maxit;
+    double theta_penalty, kappa_penalty, kappa_tol;
+    int64_t subsolver_maxit; /* alps.jl:25,70 */
+    /* PANOCplus */
+    double alpha, beta, minimum_gamma;
+    int32_t max_backtracks, lbfgs_memory;
+    int64_t sub_maxit;       /* PANOCplus(maxit = ...) */
+    int64_t max_inner_total; /* >0: stop after this many inner iterations in total (bench sampling) */
+    int32_t verbose;
+} bz_options;
+
+typedef struct {
+    int32_t tot_it;
+    int64_t tot_inner_it;
+    double elapsed_time;
+    int32_t status; /* 0 :first_order, 1 :max_iter, 2 :exception, 3 :unknown (alps.jl:105-113) */
+    double inner_tol;
+    double norm_res_prim;
+    double objective;
+    int64_t n_grad, n_prox;       /* AL-gradient evaluations and prox calls */
+    int64_t n_launches;           /* kernels launched by the library for this call */
+    double dominant_kernel_ms;    /* CUDA-event time summed over the dominant kernel's launches */
+    int64_t dominant_kernel_launches;
+} bz_result;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int bz_abi_version(void);
+int bz_ctx_create(int device, bz_ctx** out);
+int bz_ctx_destroy(bz_ctx* ctx);
+const char* bz_last_error(bz_ctx* ctx); /* ctx may be NULL: last error of a failed bz_ctx_create */
+int bz_ctx_set_profiling(bz_ctx* ctx, int on); /* CUDA events around the dominant kernel */
+int bz_ctx_sync(bz_ctx* ctx);
+int bz_device_count(int* n);
+void bz_default_options(bz_options* opt);
+
+/* ---- problems -------------------------------------------------------------------------------------
+ * bz_problem_create copies the oracle data to the device (or adopts / generates it) and allocates
+ * all solver state.  Replaces constructing the Julia oracle structs + AugLagFun (auglagfun.jl:32-54). */
+int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* desc, bz_problem** out);
+int bz_problem_destroy(bz_problem* p);
+/* Re-upload the dense constraint data of an existing problem (host -> device), for end-to-end timing. */
+int bz_problem_upload_dense(bz_problem* p, const double* c_A, const double* c_b);
+
+/* alps(f,g,c,D,x0,y0; ...) -> (x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol,
+ * norm_res_prim, s, mu), src/algorithms/alps.jl:7-117.  x0,y0 are read-only. */
+int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* opt,
+                  double* x, double* y, double* s, double* mu, bz_result* res);
+
+/* The `subsolver` plugin slot, alps.jl:64,66: PANOCplus on (alFun, gFun) from x0 with fixed mu, y.
+ * Leaves the AugLagFun / NonsmoothCostFun side-effect state (fx, gz, cx, s, yupd) at the returned
+ * point, readable with bz_auglag_state. */
+int bz_panocplus_solve(bz_problem* p, const double* mu, const double* y, const double* x0,
+                       const bz_options* opt, double tol, double* x_out, int64_t* sub_it,
+                       double* fx, double* gz);
+int bz_auglag_state(bz_problem* p, double* cx, double* s, double* yupd, double* muy, double* musqy);
+
+/* ---- per-kernel parity entry points ---------------------------------------------------------------- */
+/* AugLagUpdate!(al, mu, y), auglagfun.jl:91-101 (returns BZ_ERR_NONPOSITIVE_MU like the reference) */
+int bz_auglag_update(bz_problem* p, const double* mu, const double* y);
+/* lx = gradient!(dlx, al, x), auglagfun.jl:73-86; also returns the cached cx, s, yupd, fx
+ * (any output pointer may be NULL) */
+int bz_auglag_grad(bz_problem* p, const double* x, double* dlx, double* lx, double* fx,
+                   double* cx, double* s, double* yupd);
+/* gz = prox!(z, g, x, gamma), nonsmoothcostfun.jl:17-22 + the g kinds above */
+int bz_prox(bz_problem* p, const double* x, double gamma, double* z, double* gz);
+/* proj!(z, D, v) */
+int bz_proj(bz_problem* p, const double* v, double* z);
+/* forward-backward step: y = x - gamma*grad; z = prox(y); res = x - z; returns g(z), <grad,res>,
+ * ||res||^2 */
+int bz_fb_step(bz_problem* p, const double* x, const double* grad, double gamma, double* z,
+               double* res, double* gz, double* dot_grad_res, double* res_sq);
+/* L-BFGS operator: reset / update!(s, y) / d = H*v */
+int bz_lbfgs_reset(bz_problem* p, int memory);
+int bz_lbfgs_update(bz_problem* p, const double* s, const double* y);
+int bz_lbfgs_apply(bz_problem* p, const double* v, double* d);
+/* multiplier update y = (c(x)+mu*y - proj_D(c(x)+mu*y))/mu and ||c(x)-s||_inf, alps.jl:72-84 */
+int bz_multiplier_update(bz_problem* p, const double* cx, const double* mu, const double* y_in,
+                         double* y_out, double* s_out, double* norm_res_prim);
+/* default_penalty_parameter!, safeguards.jl:13-18 */
+int bz_default_penalty(bz_problem* p, const double* cx, const double* proj_cx, double objx,
+                       double* mu);
+/* synthetic data generator shared bit-for-bit with the oracle (bz_randn_like): fills out[0..count)
+ * with entries for element indices [start, start+count) */
+int bz_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, int64_t count,
+                  double* out);
+
+/* ---- batched tiny instances (the demos' `for i = 1:ntests` loop) --------------------
+ * kind: 0 rosenbrock (demo/rosenbrock.jl), 1 either-or, 2 xor (demo/eitheror.jl), 3 mpvca
+ * (demo/mpvca.jl).  x0 is batch x nx (instance-major), y0 batch x ny.  One full alps solve per
+ * instance, on the device, no collectives. */
+int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
+                   const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                   int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
+
+/* ---- row-sharded multi-GPU: one process per GPU --------------------------------------- */
+int bz_comm_unique_id(void* id128); /* 128-byte NCCL unique id, generate on rank 0 and broadcast */
+int bz_comm_init(bz_ctx* ctx, const void* id128, int nranks, int rank);
+int bz_comm_destroy(bz_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAZINGA_B200_H */

@@ -1,0 +1,363 @@
+/*
+ * CPU ORACLE (test infrastructure -- NOT a product path): plain-C restatement of one full
+ * `Bazinga.alps` solve for the tiny closed-form problems the demos run over grids of starting
+ * points.  It follows oracle/bazinga_oracle.py statement by statement (which in
+ * turn follows src/algorithms/alps.jl:7-117, src/utilities/auglagfun.jl:73-101,
+ * src/utilities/safeguards.jl:2-18, src/projections/orConstraints.jl:7-36,
+ * src/projections/vanishingConstraints.jl:27-46 and SURVEY.md Appendix A for the third-party
+ * PANOCplus / LBFGS), with sums evaluated left to right and no FMA contraction
+ * (build with -ffp-contract=off), so the batched CUDA kernel can be checked against it bit for bit.
+ *
+ * Problem kinds (same numbering as bz_batch_solve in include/bazinga_b200.h):
+ *   0 rosenbrock  demo/rosenbrock.jl:39-80   nx=2 ny=2  f=w(x2+1-(x1+1)^2)^2, g=lambda|x1|, D=EITHEROR
+ *   1 either-or   demo/eitheror.jl:58-126    nx=2 ny=4  D = 2 EITHEROR pairs
+ *   2 xor         demo/eitheror.jl:128-132   nx=2 ny=4  D = 2 XOR pairs
+ *   3 mpvca       demo/mpvca.jl:77-150       nx=2 ny=4  g = max(0,x), D = 2 VC pairs
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this file's shared object.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define TNX 2
+#define TNY 4
+#define TMEM 16
+#define T_EPS 2.220446049250313e-16
+
+typedef struct {
+    double tol, tol_prim, tol_dual, inner_tol;
+    int maxit;
+    double theta_penalty, kappa_penalty, kappa_tol;
+    long long subsolver_maxit;
+    double alpha, beta, minimum_gamma;
+    int max_backtracks, lbfgs_memory;
+    long long sub_maxit;
+} tiny_opts;
+
+typedef struct {
+    int kind, ny;
+    double mu[TNY], y[TNY], muy[TNY], musqy;
+    double cx[TNY], s[TNY], yupd[TNY], fx;
+    double gz;
+    long long n_grad, n_prox;
+} tiny_al;
+
+/* ---- 2-element projections ------------------------------------------------------------------ */
+static void proj_eitheror(const double* x, double* z) { /* orConstraints.jl:7-17 */
+    z[0] = x[0]; z[1] = x[1];
+    if (x[0] < 0 && x[1] < 0) { if (x[0] > x[1]) z[0] = 0.0; else z[1] = 0.0; }
+}
+static void proj_xor(const double* x, double* z) { /* orConstraints.jl:24-36 */
+    z[0] = x[0]; z[1] = x[1];
+    if (x[0] * x[1] > 0) {
+        if (x[0] > x[1]) { z[0] = fmax(0.0, x[0]); z[1] = fmin(0.0, x[1]); }
+        else { z[0] = fmin(0.0, x[0]); z[1] = fmax(0.0, x[1]); }
+    }
+}
+static void proj_vc(const double* x, double* z) { /* vanishingConstraints.jl:27-46 */
+    z[0] = 0.0; z[1] = 0.0;
+    if (x[0] <= 0) z[1] = x[1];
+    else if (x[1] >= 0) { z[0] = x[0]; z[1] = x[1]; }
+    else {
+        double sm = x[0] + x[1];
+        if (sm > 0) z[0] = x[0];
+        else if (sm < 0) z[1] = x[1];
+        else z[1] = x[1];
+    }
+}
+static void projD(int kind, const double* v, double* z) {
+    switch (kind) {
+    case 0: proj_eitheror(v, z); break;                               /* demo/rosenbrock.jl:77-80 */
+    case 1: proj_eitheror(v, z); proj_eitheror(v + 2, z + 2); break;  /* demo/eitheror.jl:122-126 */
+    case 2: proj_xor(v, z); proj_xor(v + 2, z + 2); break;            /* demo/eitheror.jl:128-132 */
+    default: proj_vc(v, z); proj_vc(v + 2, z + 2); break;             /* demo/mpvca.jl:146-150 */
+    }
+}
+
+/* ---- oracles --------------------------------------------------------------------------------- */
+static double f_grad(int kind, const double* x, double* dfx) {
+    if (kind == 0) { /* demo/rosenbrock.jl:45-50, w = 10 */
+        const double w = 10.0;
+        double tmp = x[1] + 1 - (x[0] + 1) * (x[0] + 1);
+        dfx[0] = -4 * w * tmp * (x[0] + 1);
+        dfx[1] = 2 * w * tmp;
+        return w * (tmp * tmp);
+    } else if (kind == 1 || kind == 2) { /* demo/eitheror.jl:64-68, c = (8,-3): norm(.)^2 */
+        double d0 = x[0] - 8.0, d1 = x[1] - (-3.0);
+        dfx[0] = 2 * d0; dfx[1] = 2 * d1;
+        double nr = sqrt(d0 * d0 + d1 * d1);
+        return nr * nr;
+    } else { /* demo/mpvca.jl:83-87, c = (4,2) */
+        dfx[0] = 4.0; dfx[1] = 2.0;
+        return 4.0 * x[0] + 2.0 * x[1];
+    }
+}
+static double f_value(int kind, const double* x) { double t[TNX]; return f_grad(kind, x, t); }
+
+static void c_eval(int kind, const double* x, double* cx) {
+    if (kind == 0) { cx[0] = -x[0] - x[1]; cx[1] = x[1] - x[0]; }       /* rosenbrock.jl:67-70 */
+    else if (kind == 1 || kind == 2) {                                   /* eitheror.jl:93-99 */
+        cx[0] = 2 * x[1] - x[0] - 4;
+        cx[1] = 2 - x[0];
+        cx[2] = 4 * x[1] - x[0] * x[0];
+        cx[3] = 10 - (x[0] - 3) * (x[0] - 3) - (x[1] - 1) * (x[1] - 1);
+    } else {                                                             /* mpvca.jl:111-114 */
+        cx[0] = x[0];
+        cx[1] = x[0] + x[1] - 5.0 * sqrt(2.0);
+        cx[2] = x[1];
+        cx[3] = x[0] + x[1] - 5.0;
+    }
+}
+static void c_jtprod(int kind, const double* x, const double* v, double* jtv) {
+    if (kind == 0) { jtv[0] = -v[0] - v[1]; jtv[1] = v[1] - v[0]; }     /* rosenbrock.jl:71-74 */
+    else if (kind == 1 || kind == 2) {                                   /* eitheror.jl:100-104 */
+        jtv[0] = -v[0] - v[1] - 2 * x[0] * v[2] + 2 * (3 - x[0]) * v[3];
+        jtv[1] = 2 * v[0] + 4 * v[2] + 2 * (1 - x[1]) * v[3];
+    } else {                                                             /* mpvca.jl:115-118 */
+        jtv[0] = v[0] + v[1] + v[3];
+        jtv[1] = v[1] + v[2] + v[3];
+    }
+}
+static double g_prox(int kind, const double* x, double gamma, double* z) {
+    if (kind == 0) { /* rosenbrock.jl:55-64, lambda = 1 */
+        const double lambda = 1.0;
+        double gl = gamma * lambda;
+        if (fabs(x[0]) <= gl) z[0] = 0.0;
+        else z[0] = (x[0] > 0 ? 1.0 : -1.0) * (fabs(x[0]) - gl);
+        z[1] = x[1];
+        return lambda * fabs(z[0]);
+    } else if (kind == 1 || kind == 2) { z[0] = x[0]; z[1] = x[1]; return 0.0; } /* eitheror.jl:71-74 */
+    else { z[0] = fmax(0.0, x[0]); z[1] = fmax(0.0, x[1]); return 0.0; }         /* mpvca.jl:90-93 */
+}
+
+/* ---- AugLagFun (auglagfun.jl:73-101) ------------------------------------------------------------- */
+static void al_update(tiny_al* al) {
+    double acc = 0.0;
+    for (int i = 0; i < al->ny; ++i) { al->muy[i] = al->mu[i] * al->y[i]; acc += al->muy[i] * al->y[i]; }
+    al->musqy = 0.5 * acc;
+}
+static double al_gradient(tiny_al* al, const double* x, double* dlx) {
+    double dfx[TNX], jtv[TNX], acc = 0.0;
+    al->n_grad++;
+    c_eval(al->kind, x, al->cx);
+    for (int i = 0; i < al->ny; ++i) al->yupd[i] = al->cx[i] + al->muy[i];
+    projD(al->kind, al->yupd, al->s);
+    for (int i = 0; i < al->ny; ++i) al->yupd[i] -= al->s[i];
+    for (int i = 0; i < al->ny; ++i) acc += (al->yupd[i] * al->yupd[i]) / al->mu[i];
+    double lx = 0.5 * acc;
+    for (int i = 0; i < al->ny; ++i) al->yupd[i] /= al->mu[i];
+    al->fx = f_grad(al->kind, x, dfx);
+    lx += al->fx;
+    lx -= al->musqy;
+    c_jtprod(al->kind, x, al->yupd, jtv);
+    for (int j = 0; j < TNX; ++j) dlx[j] = dfx[j] + jtv[j];
+    return lx;
+}
+static double al_prox(tiny_al* al, const double* x, double gamma, double* z) {
+    al->n_prox++;
+    al->gz = g_prox(al->kind, x, gamma, z);
+    return al->gz;
+}
+
+/* ---- LBFGS + PANOCplus ------------------------------------------------------- */
+typedef struct {
+    int M, currmem, curridx;
+    double H, s[TMEM][TNX], y[TMEM][TNX], ys[TMEM], alphas[TMEM];
+} tiny_lbfgs;
+
+static double dot2(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1]; }
+
+static void lbfgs_update(tiny_lbfgs* L, const double* s, const double* yv) {
+    if (L->M == 0) return;
+    double ys = dot2(s, yv);
+    if (ys > 0) {
+        L->curridx += 1;
+        if (L->curridx > L->M) L->curridx = 1;
+        L->currmem = L->currmem + 1 > L->M ? L->M : L->currmem + 1;
+        int i = L->curridx - 1;
+        L->ys[i] = ys;
+        L->s[i][0] = s[0]; L->s[i][1] = s[1];
+        L->y[i][0] = yv[0]; L->y[i][1] = yv[1];
+        L->H = ys / dot2(yv, yv);
+    }
+}
+static void lbfgs_mul(tiny_lbfgs* L, const double* v, double* d) {
+    d[0] = v[0]; d[1] = v[1];
+    int idx = L->curridx;
+    for (int t = 0; t < L->currmem; ++t) {
+        int i = idx - 1;
+        L->alphas[i] = dot2(L->s[i], d) / L->ys[i];
+        d[0] -= L->alphas[i] * L->y[i][0];
+        d[1] -= L->alphas[i] * L->y[i][1];
+        idx -= 1;
+        if (idx == 0) idx = L->M;
+    }
+    d[0] = L->H * d[0]; d[1] = L->H * d[1];
+    for (int t = 0; t < L->currmem; ++t) {
+        idx += 1;
+        if (idx > L->M) idx = 1;
+        int i = idx - 1;
+        double beta = dot2(L->y[i], d) / L->ys[i];
+        double coef = L->alphas[i] - beta;
+        d[0] += coef * L->s[i][0];
+        d[1] += coef * L->s[i][1];
+    }
+}
+static double f_model(double fx, const double* grad, const double* res, double L) {
+    double nr = sqrt(dot2(res, res));
+    return fx - dot2(grad, res) + (L / 2) * (nr * nr);
+}
+
+/* returns k; solution in z */
+static long long panocplus(tiny_al* al, const double* x0, const tiny_opts* o, double tol,
+                           long long maxit, double* z) {
+    const double a = o->alpha;
+    double x[TNX] = {x0[0], x0[1]}, grad_x[TNX], grad_z[TNX], tmpg[TNX], xe[TNX];
+    double y[TNX], res[TNX], x_prev[TNX], res_prev[TNX], x_d[TNX], z_curr[TNX], d[TNX], nres[TNX];
+    double f_x = al_gradient(al, x, grad_x);
+    xe[0] = x[0] + 1.0; xe[1] = x[1] + 1.0;
+    al_gradient(al, xe, tmpg);
+    double df[TNX] = {tmpg[0] - grad_x[0], tmpg[1] - grad_x[1]};
+    double Lest = sqrt(dot2(df, df)) / sqrt((double)TNX);
+    double gamma = a / Lest;
+    y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+    double g_z = al_prox(al, y, gamma, z);
+    res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+    tiny_lbfgs H;
+    memset(&H, 0, sizeof H);
+    H.M = o->lbfgs_memory; H.H = 1.0;
+    double f_up = f_model(f_x, grad_x, res, a / gamma);
+    double f_z = al_gradient(al, z, grad_z);
+    while (f_z > f_up + 10 * T_EPS * (1 + fabs(f_z)) && gamma >= o->minimum_gamma) {
+        gamma /= 2;
+        y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+        g_z = al_prox(al, y, gamma, z);
+        res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+        f_up = f_model(f_x, grad_x, res, a / gamma);
+        f_z = al_gradient(al, z, grad_z);
+    }
+    double tau = 1.0;
+    long long k = 1;
+    for (;;) {
+        double v0 = (res[0] / gamma - grad_x[0]) + grad_z[0], v1 = (res[1] / gamma - grad_x[1]) + grad_z[1];
+        double stopnorm;
+        if (v0 != v0 || v1 != v1) stopnorm = NAN; else stopnorm = fmax(fabs(v0), fabs(v1));
+        if (k >= maxit || stopnorm <= tol) return k;
+        x_prev[0] = x[0]; x_prev[1] = x[1];
+        res_prev[0] = res[0]; res_prev[1] = res[1];
+        double FBE_x = f_model(f_x, grad_x, res, a / gamma) + g_z;
+        nres[0] = -res[0]; nres[1] = -res[1];
+        lbfgs_mul(&H, nres, d);
+        x_d[0] = x[0] + d[0]; x_d[1] = x[1] + d[1];
+        f_x = al_gradient(al, x_d, grad_x);
+        x[0] = x_d[0]; x[1] = x_d[1];
+        z_curr[0] = z[0]; z_curr[1] = z[1];
+        tau = 1.0;
+        double sigma = o->beta * (0.5 / gamma) * (1 - a);
+        double nr = sqrt(dot2(res, res));
+        double thresh = FBE_x - sigma * (nr * nr) + 10 * T_EPS * (1 + fabs(FBE_x));
+        for (int kb = 1; kb <= o->max_backtracks; ++kb) {
+            y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+            g_z = al_prox(al, y, gamma, z);
+            res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+            f_up = f_model(f_x, grad_x, res, a / gamma);
+            f_z = al_gradient(al, z, grad_z);
+            if (f_z > f_up + 10 * T_EPS * (1 + fabs(f_z)) && gamma >= o->minimum_gamma) {
+                gamma *= 0.5;
+                H.currmem = 0; H.curridx = 0; H.H = 1.0;
+                continue;
+            }
+            if (f_up + g_z <= thresh || kb >= o->max_backtracks) break;
+            tau = (kb >= o->max_backtracks - 1) ? 0.0 : tau / 2;
+            x[0] = tau * x_d[0] + (1 - tau) * z_curr[0];
+            x[1] = tau * x_d[1] + (1 - tau) * z_curr[1];
+            f_x = al_gradient(al, x, grad_x);
+        }
+        double sv[TNX] = {x[0] - x_prev[0], x[1] - x_prev[1]};
+        double yv[TNX] = {res[0] - res_prev[0], res[1] - res_prev[1]};
+        lbfgs_update(&H, sv, yv);
+        k += 1;
+    }
+}
+
+static double jl_max(double a, double b) { return (a != a || b != b) ? NAN : fmax(a, b); }
+
+/* one alps solve (alps.jl:7-117); status: 0 first_order, 1 max_iter, 2 exception, 3 unknown */
+int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, double* x_out,
+              double* y_out, int* tot_it_out, long long* tot_inner_out, int* status_out,
+              double* nrp_out, long long* ngrad_out) {
+    const int ny = kind == 0 ? 2 : 4;
+    double tol_prim = o->tol_prim >= 0 ? o->tol_prim : o->tol;
+    double tol_dual = o->tol_dual >= 0 ? o->tol_dual : o->tol;
+    double inner_tol = o->inner_tol >= 0 ? o->inner_tol : cbrt(tol_dual);
+    tiny_al al;
+    memset(&al, 0, sizeof al);
+    al.kind = kind; al.ny = ny;
+    double x[TNX], cx[TNY], s[TNY], z[TNX];
+    al_prox(&al, x0, T_EPS, x);
+    double objx = f_value(kind, x) + al.gz;
+    c_eval(kind, x, cx);
+    projD(kind, cx, s);
+    for (int i = 0; i < ny; ++i) { /* safeguards.jl:13-18 */
+        double df = cx[i] - s[i];
+        double m = jl_max(1.0, 0.5 * (df * df)) / jl_max(1.0, objx);
+        m *= 0.1;
+        al.mu[i] = jl_max(1e-8, (m != m) ? NAN : fmin(m, 1e8));
+        al.y[i] = y0[i];
+    }
+    int tot_it = 0, solved = 0, tired = tot_it >= o->maxit, broken = objx != objx, have_old = 0;
+    long long tot_inner = 0;
+    double nrp = NAN, nrp_old = NAN;
+    while (!(solved || tired || broken)) {
+        tot_it++;
+        for (int i = 0; i < ny; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20)); /* safeguards.jl:2-5 */
+        al_update(&al);
+        long long sub_it = panocplus(&al, x, o, inner_tol, o->sub_maxit, z);
+        x[0] = z[0]; x[1] = z[1];
+        objx = al.fx + al.gz;
+        tot_inner += sub_it;
+        int sub_solved = sub_it < o->subsolver_maxit;
+        c_eval(kind, x, cx);
+        double t[TNY];
+        for (int i = 0; i < ny; ++i) t[i] = cx[i] + al.muy[i];
+        projD(kind, t, s);
+        for (int i = 0; i < ny; ++i) al.y[i] = (t[i] - s[i]) / al.mu[i];
+        nrp_old = nrp;
+        nrp = 0.0;
+        for (int i = 0; i < ny; ++i) {
+            double v = fabs(cx[i] - s[i]);
+            nrp = (v != v || nrp != nrp) ? NAN : fmax(nrp, v);
+        }
+        solved = (inner_tol <= tol_dual && sub_solved) && (nrp <= tol_prim);
+        tired = tot_it >= o->maxit;
+        broken = objx != objx;
+        if (!(solved || tired || broken)) {
+            if (have_old && nrp > jl_max(o->theta_penalty * nrp_old, tol_prim))
+                for (int i = 0; i < ny; ++i) al.mu[i] *= o->kappa_penalty;
+            inner_tol = jl_max(o->kappa_tol * inner_tol, tol_dual);
+        }
+        have_old = 1;
+    }
+    x_out[0] = x[0]; x_out[1] = x[1];
+    for (int i = 0; i < ny; ++i) y_out[i] = al.y[i];
+    *tot_it_out = tot_it;
+    *tot_inner_out = tot_inner;
+    *status_out = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+    *nrp_out = nrp;
+    if (ngrad_out) *ngrad_out = al.n_grad;
+    return 0;
+}
+
+/* the demos' `for i = 1:ntests` loop; OpenMP over instances when built with -fopenmp */
+int tiny_alps_batch(int kind, long long batch, const double* x0, const double* y0,
+                    const tiny_opts* o, double* x, double* y, int* tot_it, long long* tot_inner,
+                    int* status, double* nrp) {
+    const int ny = kind == 0 ? 2 : 4;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < batch; ++i)
+        tiny_alps(kind, x0 + i * TNX, y0 + i * ny, o, x + i * TNX, y + i * ny, tot_it + i,
+                  tot_inner + i, status + i, nrp + i, 0);
+    return 0;
+}

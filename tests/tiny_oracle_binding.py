@@ -1,0 +1,41 @@
+"""ctypes binding of oracle/tiny_oracle.c (test infrastructure).  Builds the shared object on first
+use with gcc -O2 -ffp-contract=off (no FMA contraction, see the file header)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "oracle", "tiny_oracle.c")
+SO = os.path.join(ROOT, "oracle", "_build", "libtiny_oracle.so")
+
+
+def build_tiny_oracle(force=False):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-fopenmp", "-o", SO, SRC, "-lm"])
+    return SO
+
+
+class TinyOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("tol_prim", C.c_double), ("tol_dual", C.c_double), ("inner_tol", C.c_double),
+                ("maxit", C.c_int), ("theta_penalty", C.c_double), ("kappa_penalty", C.c_double),
+                ("kappa_tol", C.c_double), ("subsolver_maxit", C.c_longlong), ("alpha", C.c_double),
+                ("beta", C.c_double), ("minimum_gamma", C.c_double), ("max_backtracks", C.c_int),
+                ("lbfgs_memory", C.c_int), ("sub_maxit", C.c_longlong)]
+
+
+def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inner_tol=1.0, maxit=100, memory=5):
+    lib = C.CDLL(build_tiny_oracle())
+    X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, 2)
+    B = X0.shape[0]
+    ny = 2 if kind == 0 else 4
+    o = TinyOpts(tol, -1.0, -1.0, inner_tol, maxit, 0.8, 0.5, 0.1, subsolver_maxit, 0.95, 0.5, min_gamma, 20, memory, sub_maxit)
+    Y0 = np.zeros((B, ny))
+    x, y = np.zeros((B, 2)), np.zeros((B, ny))
+    it, st = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    inn, nrp = np.zeros(B, np.int64), np.zeros(B)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.tiny_alps_batch(C.c_int(kind), C.c_longlong(B), P(X0), P(Y0), C.byref(o), P(x), P(y), P(it), P(inn), P(st), P(nrp))
+    return dict(x=x, y=y, iters=it, sub_iters=inn, status=st, norm_res_prim=nrp)
