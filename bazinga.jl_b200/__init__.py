@@ -14,5 +14,5 @@ from .oracles import (  # noqa: F401
 )
 from .solver import (  # noqa: F401
     BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, alps_batch, comm_unique_id,
-    default_context, default_subsolver,
+    default_context, default_subsolver, row_shard,
 )

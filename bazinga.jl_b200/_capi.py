@@ -71,6 +71,8 @@ SYMBOLS = {
     "bz_last_error": (C.c_char_p, [_vp]),
     "bz_ctx_set_profiling": (C.c_int, [_vp, C.c_int]),
     "bz_ctx_sync": (C.c_int, [_vp]),
+    "bz_ctx_timer_start": (C.c_int, [_vp]),
+    "bz_ctx_timer_stop": (C.c_int, [_vp, _dp]),
     "bz_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "bz_default_options": (None, [C.POINTER(Options)]),
     "bz_problem_create": (C.c_int, [_vp, C.POINTER(ProblemDesc), C.POINTER(_vp)]),

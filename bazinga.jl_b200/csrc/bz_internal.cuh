@@ -297,6 +297,7 @@ struct bz_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     long long n_launches = 0;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 };
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);

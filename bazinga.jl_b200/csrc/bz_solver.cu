@@ -109,6 +109,7 @@ extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
     cudaSetDevice(ctx->device);
     bz_comm_destroy(ctx);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BZ_OK;
@@ -124,6 +125,24 @@ extern "C" int bz_ctx_sync(bz_ctx* ctx) {
     if (!ctx) return BZ_ERR_ARG;
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
+extern "C" int bz_ctx_timer_start(bz_ctx* ctx) {
+    if (!ctx) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->timer0) { BZ_CUDA(ctx, cudaEventCreate(&ctx->timer0)); BZ_CUDA(ctx, cudaEventCreate(&ctx->timer1)); }
+    BZ_CUDA(ctx, cudaEventRecord(ctx->timer0, ctx->stream));
+    return BZ_OK;
+}
+extern "C" int bz_ctx_timer_stop(bz_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->timer0) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    BZ_CUDA(ctx, cudaEventRecord(ctx->timer1, ctx->stream));
+    BZ_CUDA(ctx, cudaEventSynchronize(ctx->timer1));
+    float t = 0.f;
+    BZ_CUDA(ctx, cudaEventElapsedTime(&t, ctx->timer0, ctx->timer1));
+    *ms = t;
     return BZ_OK;
 }
 
@@ -561,6 +580,7 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
     h->theta_penalty = o->theta_penalty; h->kappa_penalty = o->kappa_penalty; h->kappa_tol = o->kappa_tol;
     h->outer_maxit = o->maxit; h->subsolver_maxit = o->subsolver_maxit;
+    h->n_prox = 1;   // the prox!(x, gFun, x0, eps(T)) of alps.jl:38
     BZ_TRY(push_state(p));
     BZ_TRY(bz_launch_prox(ctx, p->st, p->v.z_curr, BZ_EPS, p->v.x, n, p->g, p->part, p->counters + 5));
     BZ_TRY(bz_launch_fill(ctx, p->mu, ml, 1.0));

@@ -41,6 +41,14 @@ class Context:
     def sync(self):
         K.check(self.lib.bz_ctx_sync(self.handle), self.handle)
 
+    def timer_start(self):
+        K.check(self.lib.bz_ctx_timer_start(self.handle), self.handle)
+
+    def timer_stop(self):
+        ms = C.c_double()
+        K.check(self.lib.bz_ctx_timer_stop(self.handle, C.byref(ms)), self.handle)
+        return ms.value
+
     def comm_init(self, unique_id: bytes, nranks: int, rank: int):
         buf = C.create_string_buffer(unique_id, 128)
         K.check(self.lib.bz_comm_init(self.handle, buf, nranks, rank), self.handle)
@@ -77,6 +85,18 @@ def comm_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     K.check(lib.bz_comm_unique_id(buf))
     return buf.raw
+
+
+def row_shard(ny: int, nranks: int, rank: int):
+    """Row block of rank `rank` when a dense-affine instance is row-sharded over `nranks` GPUs
+    (SURVEY.md §8e): contiguous blocks, sizes differing by at most one row, even-sized except possibly
+    the last so that adjacent pairs never straddle shards.  Returns (row_begin, ny_local)."""
+    if not (0 <= rank < nranks) or ny < nranks:
+        raise ValueError("row_shard: need 0 <= rank < nranks <= ny")
+    base = (ny // nranks) & ~1 if ny // nranks >= 2 else ny // nranks
+    begin = rank * base
+    local = base if rank < nranks - 1 else ny - begin
+    return begin, local
 
 
 class LBFGS:
@@ -142,16 +162,17 @@ class Problem:
     plus ``AugLagFun`` / ``NonsmoothCostFun`` (src/utilities/auglagfun.jl, nonsmoothcostfun.jl)."""
 
     def __init__(self, f, g, c, D, nx=None, ny=None, ctx: Context | None = None):
-        self.ctx = ctx or default_context()
-        self.lib = self.ctx.lib
-        self.f, self.g, self.c, self.D = f, g, c, D
-        d = K.ProblemDesc()
-        self._keep = []
+        self.handle = C.c_void_p()
         for name, obj, attr in (("f", f, "f_kind"), ("g", g, "g_kind"), ("c", c, "c_kind"), ("D", D, "d_kind")):
             if not hasattr(obj, attr):
                 raise K.BazingaError(K.BZ_ERR_UNSUPPORTED,
                                      f"{name} = {type(obj).__name__} is not in the GPU oracle catalogue "
                                      "(no CPU fallback)")
+        self.ctx = ctx or default_context()
+        self.lib = self.ctx.lib
+        self.f, self.g, self.c, self.D = f, g, c, D
+        d = K.ProblemDesc()
+        self._keep = []
         d.f_kind, d.g_kind, d.c_kind, d.d_kind = f.f_kind, g.g_kind, c.c_kind, D.d_kind
         # ---- c
         if isinstance(c, O.ConstraintBasisPursuit):

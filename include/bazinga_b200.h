@@ -152,6 +152,9 @@ int bz_ctx_destroy(bz_ctx* ctx);
 const char* bz_last_error(bz_ctx* ctx); /* ctx may be NULL: last error of a failed bz_ctx_create */
 int bz_ctx_set_profiling(bz_ctx* ctx, int on); /* CUDA events around the dominant kernel */
 int bz_ctx_sync(bz_ctx* ctx);
+/* device-side stopwatch on the library's stream (CUDA events): start, then stop returns ms */
+int bz_ctx_timer_start(bz_ctx* ctx);
+int bz_ctx_timer_stop(bz_ctx* ctx, double* ms);
 int bz_device_count(int* n);
 void bz_default_options(bz_options* opt);
 

@@ -361,3 +361,29 @@ int tiny_alps_batch(int kind, long long batch, const double* x0, const double* y
                   tot_inner + i, status + i, nrp + i, 0);
     return 0;
 }
+
+/* ---- synthetic data generator (C form of bazinga_oracle.bz_randn_like; Philox-4x32-10, counter =
+ * element index, key = (seed, stream)); used by bench.py's CPU legs to build the 4096x16384 instance
+ * quickly.  tests/test_oracle_pins.py checks it against the numpy definition. ------------------------- */
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t* out) {
+    uint32_t c2 = 0, c3 = 0;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+int oracle_randn_fill(uint64_t seed, uint64_t stream, uint64_t start, long long count, double* out) {
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < count; ++i) {
+        uint32_t u[4];
+        uint64_t idx = start + (uint64_t)i;
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)seed, (uint32_t)stream, u);
+        int64_t ssum = (int64_t)((uint64_t)u[0] + u[1] + u[2] + u[3]) - (int64_t)(2ull * 0xFFFFFFFFull);
+        out[i] = (double)ssum * 0x1.bb67ae8584caap-32;
+    }
+    return 0;
+}

@@ -1,0 +1,412 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI
+(include/bazinga_b200.h via bazinga.jl_b200/_capi.py) and is compared with the CPU oracle on the
+same seeded inputs.  Tolerances (BASELINE.json north_star): per-kernel outputs 1e-12 relative in
+fp64 (normwise for results of dense products); final objective / constraint violation
+/ multipliers 1e-6 relative; iteration counts within +-2 % where the trajectory is not chaotic."""
+import numpy as np
+import pytest
+
+import bazinga_b200 as bz
+import bazinga_oracle as bo
+from tiny_oracle_binding import tiny_batch
+
+pytestmark = pytest.mark.gpu
+KTOL = 1e-12
+
+
+def _bp_problem(ctx, m, n, g=None, D=None, seed=0):
+    A = bo.bz_randn_like(seed, 0, m * n).reshape(m, n)
+    xt = bo.bz_sparse_randn(seed + 1, n, 0.1)
+    b = A @ xt
+    p = bz.Problem(bz.Zero(), g or bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), D or bz.ZeroSet(), ctx=ctx)
+    return A, b, p
+
+
+# ------------------------------------------------------------------------------- generator
+def test_generator_bit_exact(gpu_ctx):
+    for seed, start, count in [(0, 0, 10000), (5, (1 << 32) - 17, 4096), (9, 1 << 40, 1000)]:
+        assert np.array_equal(gpu_ctx.randn_fill(seed, start, count), bo.bz_randn_like(seed, start, count))
+    assert gpu_ctx.randn_fill(0, 0, 0).size == 0
+
+
+# ------------------------------------------------------------------------------- fused dense AL-gradient
+@pytest.mark.parametrize("m,n", [(1, 2), (3, 5), (20, 100), (64, 256), (75, 1001), (200, 4096),
+                                 (33, 16384), (150, 2050), (300, 6), (74, 8192)])
+@pytest.mark.parametrize("dname", ["zero", "free", "box"])
+def test_dense_auglag_gradient_parity(gpu_ctx, m, n, dname):
+    """k_dense_algrad (single pass over A) vs auglagfun.jl:73-86 restated; ragged and odd shapes use
+    the non-bulk loader, even ones the cp.async.bulk ring."""
+    Dg = {"zero": bz.ZeroSet(), "free": bz.FreeSet(), "box": bz.ClosedSet(bz.IndBox(-0.5, 0.7))}[dname]
+    Do = {"zero": bo.ZeroSet(), "free": bo.FreeSet(), "box": bo.BoxSet(-0.5, 0.7)}[dname]
+    A, b, p = _bp_problem(gpu_ctx, m, n, D=Dg, seed=m + n)
+    rng = np.random.default_rng(m * 7 + n)
+    mu, y, x = rng.uniform(0.05, 3.0, m), rng.standard_normal(m), rng.standard_normal(n)
+    p.auglag_update(mu, y)
+    g = p.gradient(x)
+    al = bo.AugLagFun(bo.FZero(), bo.CDenseAffine(A, b), Do, mu.copy(), y.copy(), x)
+    dl = np.empty(n)
+    lx = al.gradient(dl, x)
+    nA = np.linalg.norm(A, 2)
+    cscale = nA * np.linalg.norm(x) + np.linalg.norm(b)
+    assert np.max(np.abs(g["cx"] - al.cx)) <= KTOL * cscale
+    assert np.max(np.abs(g["s"] - al.s)) <= KTOL * cscale
+    assert np.max(np.abs(g["yupd"] - al.yupd)) <= KTOL * cscale / mu.min()
+    gscale = nA * max(np.linalg.norm(al.yupd), 1e-300) + 1e-300
+    assert np.max(np.abs(g["dlx"] - dl)) <= KTOL * gscale
+    assert abs(g["lx"] - lx) <= KTOL * max(abs(lx), np.sum(al.yupd**2 * mu))
+    assert g["fx"] == 0.0
+    st = p.auglag_state()
+    assert np.array_equal(st["muy"], mu * y) and abs(st["musqy"] - 0.5 * np.sum(mu * y * y)) <= KTOL * abs(st["musqy"])
+    p.close()
+
+
+def test_column_major_input_matches_row_major(gpu_ctx):
+    # Julia hands over column-major matrices: the library transposes once on the device
+    m, n = 37, 130
+    A = bo.bz_randn_like(3, 0, m * n).reshape(m, n)
+    b = bo.bz_randn_like(4, 0, m)
+    rng = np.random.default_rng(1)
+    mu, y, x = rng.uniform(0.5, 2.0, m), rng.standard_normal(m), rng.standard_normal(n)
+    outs = []
+    for Ain in (A, np.asfortranarray(A)):
+        p = bz.Problem(bz.Zero(), bz.Zero(), bz.ConstraintBasisPursuit(Ain, b), bz.ZeroSet(), ctx=gpu_ctx)
+        p.auglag_update(mu, y)
+        outs.append(p.gradient(x)["dlx"])
+        p.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_nonpositive_mu_raises_like_reference(gpu_ctx):
+    # auglagfun.jl:33-34,92-93: error("parameters `mu` must be positive")
+    _, _, p = _bp_problem(gpu_ctx, 8, 16)
+    with pytest.raises(bz.BazingaError, match="must be positive"):
+        p.auglag_update(np.array([1.0] * 7 + [0.0]), np.zeros(8))
+    p.auglag_update(np.ones(8), np.zeros(8))   # and recovers
+    p.close()
+
+
+def test_unsupported_combinations_raise(gpu_ctx):
+    A = np.ones((4, 6))
+    with pytest.raises(bz.BazingaError):   # pair set + dense affine: not in the fused path yet
+        bz.Problem(bz.Zero(), bz.Zero(), bz.ConstraintBasisPursuit(A, np.ones(4)), bz.SetEOR(), ctx=gpu_ctx)
+    with pytest.raises(bz.BazingaError):   # identity needs ny == nx
+        bz.Problem(bz.Zero(), bz.Zero(), bz.IdentityFunction(), bz.FreeSet(), nx=4, ny=6, ctx=gpu_ctx)
+
+
+# ------------------------------------------------------------------------------- prox / proj families
+def _prox_cases(n, rng):
+    u = np.where(rng.random(n) < 0.2, 0.0, rng.uniform(0.1, 2.0, n))
+    return [
+        (bz.NormL1(0.7), bo.GNormL1(0.7)), (bz.NormL0(0.3), bo.GNormL0(0.3)), (bz.IndBox(-0.4, 0.9), bo.GIndBox(-0.4, 0.9)),
+        (bz.Zero(), bo.GZero()), (bz.NormL1Box(0.5, u=u), bo.GNormL1Box(0.5, u)),
+        (bz.NormL1Nonneg(0.6), bo.GNormL1Nonneg(0.6)), (bz.NormL0Box(0.8, u=u), bo.GNormL0Box(0.8, u)),
+    ]
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 70001])
+def test_prox_family_bit_exact(gpu_ctx, n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) * 2.0
+    x[:: max(1, n // 11)] = 0.0
+    for gamma in (0.3, 1.7):
+        for gg, go in _prox_cases(n, rng):
+            p = bz.Problem(bz.Zero(), gg, bz.IdentityFunction(), bz.FreeSet(), nx=n, ny=n, ctx=gpu_ctx)
+            z, gz = p.prox(x, gamma)
+            zz = np.empty(n)
+            gzz = go.prox(zz, x, gamma)
+            assert np.array_equal(z, zz), type(gg).__name__          # elementwise: bit-exact
+            assert abs(gz - gzz) <= KTOL * max(1.0, abs(gzz)), type(gg).__name__
+            p.close()
+
+
+def test_prox_thresholds_and_ties(gpu_ctx):
+    # values sitting exactly on the thresholds: > vs >= is part of the contract
+    gamma, lam = 0.5, 2.0
+    gl = gamma * lam
+    x = np.array([gl, -gl, np.nextafter(gl, 2), np.sqrt(2 * gl), np.nextafter(np.sqrt(2 * gl), 9), 0.0, -0.0, np.sqrt(gl)])
+    n = x.size
+    u = np.full(n, 0.9)
+    for gg, go in [(bz.NormL1(lam), bo.GNormL1(lam)), (bz.NormL0(lam), bo.GNormL0(lam)),
+                   (bz.NormL1Nonneg(lam), bo.GNormL1Nonneg(lam)), (bz.NormL0Box(lam, u=u), bo.GNormL0Box(lam, u)),
+                   (bz.NormL1Box(lam, u=u), bo.GNormL1Box(lam, u))]:
+        p = bz.Problem(bz.Zero(), gg, bz.IdentityFunction(), bz.FreeSet(), nx=n, ny=n, ctx=gpu_ctx)
+        z, gz = p.prox(x, gamma)
+        zz = np.empty(n)
+        gzz = go.prox(zz, x, gamma)
+        assert np.array_equal(z, zz) and gz == gzz, type(gg).__name__
+        p.close()
+
+
+def test_obstacle_prox_bit_exact(gpu_ctx):
+    N = 257
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(3 * N)
+    x[N + 5] = x[2 * N + 5] = 0.75        # the set-valued tie (demo/obstacle.jl:76-79)
+    p = bz.Problem(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleL1(N), bz.ConstraintObstacle(N), bz.ZeroSet(), ctx=gpu_ctx)
+    z, gz = p.prox(x, 0.2)
+    zz = np.empty(3 * N)
+    gzz = bo.GObstacleL1(N).prox(zz, x, 0.2)
+    assert np.array_equal(z, zz) and abs(gz - gzz) <= KTOL * abs(gzz)
+    assert z[N + 5] == 0.0 and z[2 * N + 5] == 0.75
+    p.close()
+
+
+@pytest.mark.parametrize("kind", ["eitheror", "xor", "vc", "cc"])
+@pytest.mark.parametrize("stride", [1, "half"])
+def test_pair_projections_bit_exact(gpu_ctx, kind, stride):
+    v1 = np.arange(-2.0, 2.01, 0.25)
+    a, b = np.meshgrid(v1, v1)
+    a, b = a.ravel(), b.ravel()            # contains every tie x1 == x2, x1 + x2 == 0, zeros
+    m = 2 * a.size
+    st = 1 if stride == 1 else m // 2
+    v = np.empty(m)
+    if st == 1:
+        v[0::2], v[1::2] = a, b
+    else:
+        v[: m // 2], v[m // 2:] = a, b
+    p = bz.Problem(bz.Zero(), bz.Zero(), bz.IdentityFunction(), bz.PairSet(kind, st), nx=m, ny=m, ctx=gpu_ctx)
+    z = p.proj(v)
+    zz = np.empty(m)
+    bo.PairSet(kind, st).proj(zz, v)
+    assert np.array_equal(z, zz)
+    p.close()
+
+
+def test_elementwise_projections(gpu_ctx):
+    v = np.linspace(-3, 3, 1001)
+    for Dg, Do in [(bz.ZeroSet(), bo.ZeroSet()), (bz.FreeSet(), bo.FreeSet()),
+                   (bz.ClosedSet(bz.IndBox(-1.0, 0.5)), bo.BoxSet(-1.0, 0.5))]:
+        p = bz.Problem(bz.Zero(), bz.Zero(), bz.IdentityFunction(), Dg, nx=v.size, ny=v.size, ctx=gpu_ctx)
+        zz = np.empty_like(v)
+        Do.proj(zz, v)
+        assert np.array_equal(p.proj(v), zz)
+        p.close()
+
+
+# ------------------------------------------------------------------------------- fb step / L-BFGS / outer step
+@pytest.mark.parametrize("n", [5, 4096, 100003])
+def test_forward_backward_step(gpu_ctx, n):
+    rng = np.random.default_rng(n)
+    x, grad = rng.standard_normal(n), rng.standard_normal(n)
+    p = bz.Problem(bz.Zero(), bz.NormL1(1.0), bz.IdentityFunction(), bz.FreeSet(), nx=n, ny=n, ctx=gpu_ctx)
+    for gamma in (0.05, 0.8):
+        fb = p.fb_step(x, grad, gamma)
+        y = x - gamma * grad
+        z = np.empty(n)
+        gz = bo.GNormL1(1.0).prox(z, y, gamma)
+        res = x - z
+        assert np.array_equal(fb["z"], z) and np.array_equal(fb["res"], res)
+        assert abs(fb["gz"] - gz) <= KTOL * abs(gz)
+        assert abs(fb["dot_grad_res"] - grad @ res) <= KTOL * np.linalg.norm(grad) * np.linalg.norm(res)
+        assert abs(fb["res_sq"] - res @ res) <= KTOL * (res @ res)
+    p.close()
+
+
+@pytest.mark.parametrize("n,mem", [(3, 5), (1000, 5), (16384, 5), (50000, 3), (257, 0), (4099, 16)])
+def test_lbfgs_operator(gpu_ctx, n, mem):
+    """update!/mul!/reset! of the L-BFGS operator, incl. ring wrap-around and the
+    `ys > 0` rejection."""
+    rng = np.random.default_rng(n + mem)
+    p = bz.Problem(bz.Zero(), bz.Zero(), bz.IdentityFunction(), bz.FreeSet(), nx=n, ny=n, ctx=gpu_ctx)
+    p.lbfgs_reset(mem)
+    L = bo.LBFGS(n, mem)
+    for k in range(2 * mem + 3):
+        s = rng.standard_normal(n)
+        yv = s * rng.uniform(0.5, 1.5, n) + 0.01 * rng.standard_normal(n)
+        if k == 2:
+            yv = -yv                     # <s, y> <= 0: the pair must be rejected
+        p.lbfgs_update(s, yv)
+        L.update(s, yv)
+        v = rng.standard_normal(n)
+        d, dd = p.lbfgs_apply(v), L.mul(v)
+        assert np.max(np.abs(d - dd)) <= 1e-11 * np.max(np.abs(dd)), k
+    p.lbfgs_reset(mem)
+    v = rng.standard_normal(n)
+    assert np.array_equal(p.lbfgs_apply(v), v)    # H = I after reset!
+    p.close()
+
+
+@pytest.mark.parametrize("dname", ["zero", "box", "eitheror", "vc"])
+def test_multiplier_update_and_default_penalty(gpu_ctx, dname):
+    m = 1000
+    rng = np.random.default_rng(5)
+    cx, mu, y = rng.standard_normal(m), rng.uniform(0.1, 2.0, m), rng.standard_normal(m) * 3
+    Dg = {"zero": bz.ZeroSet(), "box": bz.ClosedSet(bz.IndBox(-0.3, 0.3)), "eitheror": bz.SetEOR(), "vc": bz.SetMPVCA()}[dname]
+    Do = {"zero": bo.ZeroSet(), "box": bo.BoxSet(-0.3, 0.3), "eitheror": bo.PairSet("eitheror"), "vc": bo.PairSet("vc")}[dname]
+    p = bz.Problem(bz.Zero(), bz.Zero(), bz.IdentityFunction(), Dg, nx=m, ny=m, ctx=gpu_ctx)
+    yo, so, nrp = p.multiplier_update(cx, mu, y)
+    t = cx + mu * y                      # alps.jl:74-81
+    s = np.empty(m)
+    Do.proj(s, t)
+    yy = (t - s) / mu
+    assert np.array_equal(so, s) and np.array_equal(yo, yy)
+    assert nrp == np.max(np.abs(cx - s))
+    pc = np.empty(m)
+    Do.proj(pc, cx)
+    for objx in (0.3, 17.0, -4.0):
+        mug = p.default_penalty(cx, pc, objx)
+        muo = np.empty(m)
+        bo.default_penalty_parameter(muo, cx, pc, objx)
+        assert np.array_equal(mug, muo)
+    p.close()
+
+
+# ------------------------------------------------------------------------------- whole solves
+def _check_final(out, r, rel=1e-6):
+    x, y = out[0], out[1]
+    assert out[5] == r.status
+    assert np.max(np.abs(x - r.x)) <= rel * max(1.0, np.max(np.abs(r.x)))
+    assert np.max(np.abs(y - r.y)) <= rel * max(1.0, np.max(np.abs(r.y)))
+    if r.norm_res_prim is not None:
+        assert abs(out[7] - r.norm_res_prim) <= rel * max(1.0, abs(r.norm_res_prim))
+
+
+def test_reference_test_verbose_on_gpu(gpu_ctx):
+    # test/problems/test_verbose.jl, same assertions, through the GPU path
+    A = np.array([[1, -2, 3, -4, 5], [2, -1, 0, -1, 3], [-1, 0, 4, -3, 2], [-1, -1, -1, 1, 3]], float)
+    b = np.array([1.0, 2.0, 3.0, 4.0])
+    lam = 0.1 * np.max(np.abs(A.T @ b))
+    x_star = np.array([-3.877278911564627e-01, 0, 0, 2.174149659863943e-02, 6.168435374149660e-01])
+    x0, y0 = np.zeros(5), np.zeros(5)
+    out = bz.alps(bz.LeastSquares(A, b), bz.NormL1(lam), bz.IdentityFunction(), bz.FreeSet(), x0, y0, verbose=True, ctx=gpu_ctx)
+    x, it, subit = out[0], out[2], out[3]
+    assert x.dtype == np.float64
+    assert np.max(np.abs(x - x_star)) <= 1e-4
+    assert it < 10 and subit < 50
+    assert not x0.any() and not y0.any()
+    r = bo.alps(bo.FLeastSquares(A, b), bo.GNormL1(lam), bo.CIdentity(), bo.FreeSet(), x0, y0)
+    assert (it, subit) == (r.tot_it, r.tot_inner_it)       # exact iteration-count parity
+    _check_final(out, r, 1e-9)
+
+
+@pytest.mark.parametrize("gname", ["box", "free"])
+def test_reference_nonconvex_qp_on_gpu(gpu_ctx, gname):
+    # test/problems/test_nonconvex_qp.jl tiny + five n=100 instances
+    cases = [(np.diag([-0.5, 1.0]), np.array([0.3, 0.5]), 1.0)]
+    for k in range(1, 6):
+        rng = np.random.default_rng(k)
+        U, _ = np.linalg.qr(rng.standard_normal((100, 100)))
+        ev = 2.0 * rng.random(100) - 1.0
+        Q = U @ np.diag(ev) @ U.T
+        cases.append((0.5 * (Q + Q.T), rng.standard_normal(100), np.max(np.abs(ev))))
+    for Q, q, lip in cases:
+        n = q.size
+        gamma = 0.95 / lip
+        x0 = np.zeros(n)
+        gg, go = (bz.IndBox(-1.0, 1.0), bo.GIndBox(-1.0, 1.0)) if gname == "box" else (bz.IndFree(), bo.GZero())
+        out = bz.alps(bz.Quadratic(Q, q), gg, bz.IdentityFunction(), bz.ClosedSet(bz.IndBox(-1.0, 1.0)), x0, np.zeros(n), ctx=gpu_ctx)
+        x = out[0]
+        z = np.clip(x - gamma * (Q @ x + q), -1.0, 1.0)
+        assert np.max(np.abs(x - z)) / gamma <= 1e-4
+        assert not x0.any()
+        r = bo.alps(bo.FQuadratic(Q, q), go, bo.CIdentity(), bo.BoxSet(-1.0, 1.0), x0, np.zeros(n))
+        assert out[2] == r.tot_it
+        assert abs(out[3] - r.tot_inner_it) <= max(1, 0.02 * r.tot_inner_it)
+        _check_final(out, r)
+
+
+def test_basis_pursuit_demo_size(gpu_ctx):
+    # demo/basispursuit.jl at its own size (20 x 100), L1 and L0
+    A, _, b = bo.make_basis_pursuit(20, 100)
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
+    for gg, gname in ((bz.NormL1(1.0), "l1"), (bz.NormL0(1.0), "l0")):
+        out = bz.alps(bz.Zero(), gg, bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100), np.zeros(20),
+                      subsolver=sub, subsolver_maxit=100_000, ctx=gpu_ctx)
+        r = bo.solve(bo.problem_basis_pursuit(A, b, gname), np.zeros(100))
+        assert out[5] == r.status == "first_order"
+        assert np.max(np.abs(A @ out[0] - b)) <= 1e-5
+        if gname == "l1":
+            # convex: same minimiser; trajectories differ by reduction order only
+            assert abs(np.sum(np.abs(out[0])) - np.sum(np.abs(r.x))) <= 1e-5 * np.sum(np.abs(r.x))
+            assert np.max(np.abs(out[0] - r.x)) <= 1e-4
+            assert abs(out[3] - r.tot_inner_it) <= 0.1 * r.tot_inner_it
+
+
+def test_subsolver_slot_postconditions(gpu_ctx):
+    # alps.jl:66-68 reads alFun.fx / gFun.gz after the subsolver returns: they must refer to the
+    # returned point
+    A, _, b = bo.make_basis_pursuit(20, 100)
+    p = bz.Problem(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), ctx=gpu_ctx)
+    mu, y, x0 = np.full(20, 0.1), np.zeros(20), np.zeros(100)
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=10_000, minimum_gamma=bo.EPS, tol=1e-3)
+    z, it, fx, gz = p.panocplus(mu, y, x0, sub)
+    st = p.auglag_state()
+    assert np.max(np.abs(st["cx"] - (A @ z - b))) <= KTOL * (np.linalg.norm(A, 2) * np.linalg.norm(z) + np.linalg.norm(b))
+    assert abs(gz - np.sum(np.abs(z))) <= KTOL * gz and fx == 0.0
+    al = bo.AugLagFun(bo.FZero(), bo.CDenseAffine(A, b), bo.ZeroSet(), mu.copy(), y.copy(), x0)
+    zo, ito = bo.panocplus(al, bo.NonsmoothCostFun(bo.GNormL1(1.0)), x0, bo.PanocOptions(minimum_gamma=bo.EPS, maxit=10_000, tol=1e-3))
+    assert abs(it - ito) <= max(1, 0.02 * ito)
+    assert np.max(np.abs(z - zo)) <= 1e-6
+    p.close()
+
+
+def test_obstacle_1d(gpu_ctx):
+    N = 16
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=1_000_000, minimum_gamma=bo.EPS)
+    out = bz.alps(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleL1(N), bz.ConstraintObstacle(N), bz.ZeroSet(),
+                  2 * np.ones(3 * N), np.zeros(N), tol=1e-3, subsolver=sub, subsolver_maxit=1_000_000, ctx=gpu_ctx)
+    r = bo.solve(bo.problem_obstacle(N), 2 * np.ones(3 * N), tol=1e-3)
+    assert out[5] == r.status == "first_order" and out[2] == r.tot_it
+    assert out[7] <= 1e-3
+    x = out[0]
+    assert np.all(x >= 0) and np.all(np.minimum(x[N:2 * N], x[2 * N:]) == 0)      # complementarity holds exactly
+
+
+def test_obstacle_2d_gradient(gpu_ctx):
+    gy, gx = 24, 40
+    N = gy * gx
+    rng = np.random.default_rng(0)
+    x, mu, y = rng.standard_normal(3 * N), rng.uniform(0.1, 2.0, N), rng.standard_normal(N)
+    p = bz.Problem(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleL1(N), bz.ConstraintObstacle(N, (gy, gx)), bz.ZeroSet(), ctx=gpu_ctx)
+    p.auglag_update(mu, y)
+    g = p.gradient(x)
+    al = bo.AugLagFun(bo.FObstacleL1(N), bo.CObstacle(N, (gy, gx)), bo.ZeroSet(), mu.copy(), y.copy(), x)
+    dl = np.empty(3 * N)
+    lx = al.gradient(dl, x)
+    assert np.max(np.abs(g["dlx"] - dl)) <= KTOL * np.max(np.abs(dl))
+    assert abs(g["lx"] - lx) <= KTOL * abs(lx) and abs(g["fx"] - al.fx) <= KTOL * abs(al.fx)
+    assert np.max(np.abs(g["cx"] - al.cx)) <= KTOL * np.max(np.abs(al.cx))
+    p.close()
+
+
+# ------------------------------------------------------------------------------- batched tiny instances
+def _grid(lo, hi, step):
+    v = np.arange(lo, hi + 1e-9, step)
+    return np.array([(i, j) for j in v for i in v])     # column-major like the demos (i fastest)
+
+
+@pytest.mark.parametrize("kind,name,grid,mg,sm", [
+    (1, "eitheror", (-4.0, 8.0, 0.25), bo.EPS, 1000),      # demo/eitheror.jl:229-236
+    (2, "xor", (-4.0, 8.0, 0.5), bo.EPS, 1000),
+    (3, "mpvca", (-5.0, 20.0, 0.5), bo.EPS, 1000),         # demo/mpvca.jl:232-239
+])
+def test_batched_demo_grids_bit_exact(gpu_ctx, kind, name, grid, mg, sm):
+    X0 = _grid(*grid)
+    out = bz.alps_batch(name, X0, ctx=gpu_ctx)
+    ref = tiny_batch(kind, X0, min_gamma=mg, sub_maxit=sm, subsolver_maxit=sm)
+    assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["sub_iters"], ref["sub_iters"])
+    assert np.array_equal(out["status"], ref["status"])
+    assert np.array_equal(out["x"], ref["x"], equal_nan=True) and np.array_equal(out["y"], ref["y"], equal_nan=True)
+    assert np.array_equal(out["norm_res_prim"], ref["norm_res_prim"], equal_nan=True)
+
+
+def test_batched_rosenbrock_c1(gpu_ctx):
+    # config C1: demo/rosenbrock.jl (w=10, lambda=1, minimum_gamma=1e-32, maxit=1e9); a coarse grid keeps the
+    # 2e5-iteration tail instances out of the test
+    X0 = _grid(-5.0, 5.0, 1.25)
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=10**9, minimum_gamma=1e-32)
+    out = bz.alps_batch("rosenbrock", X0, subsolver=sub, subsolver_maxit=10**9, ctx=gpu_ctx)
+    ref = tiny_batch(0, X0, min_gamma=1e-32, sub_maxit=10**9, subsolver_maxit=10**9)
+    assert np.array_equal(out["sub_iters"], ref["sub_iters"]) and np.array_equal(out["x"], ref["x"], equal_nan=True)
+    assert (out["status"] == 0).all() and np.max(np.abs(out["x"])) <= 1e-6       # all -> (0, 0)
+
+
+def test_batched_edge_cases(gpu_ctx):
+    out = bz.alps_batch("mpvca", np.zeros((0, 2)), ctx=gpu_ctx)              # empty batch
+    assert out["x"].shape == (0, 2)
+    out = bz.alps_batch("mpvca", np.array([[1.0, 1.0]]), maxit=0, ctx=gpu_ctx)   # tired before the first iteration
+    assert out["iters"][0] == 0 and out["status"][0] == 1
+    out = bz.alps_batch("eitheror", np.array([[np.nan, 0.0]]), ctx=gpu_ctx)  # NaN objective -> :exception
+    assert out["status"][0] == 2
+    ref = tiny_batch(1, np.array([[np.nan, 0.0]]), min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000)
+    assert ref["status"][0] == 2

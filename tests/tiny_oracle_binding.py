@@ -39,3 +39,11 @@ def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inn
     P = lambda a: a.ctypes.data_as(C.c_void_p)
     lib.tiny_alps_batch(C.c_int(kind), C.c_longlong(B), P(X0), P(Y0), C.byref(o), P(x), P(y), P(it), P(inn), P(st), P(nrp))
     return dict(x=x, y=y, iters=it, sub_iters=inn, status=st, norm_res_prim=nrp)
+
+
+def oracle_randn_fill(seed, start, count, stream=0):
+    lib = C.CDLL(build_tiny_oracle())
+    out = np.empty(int(count))
+    lib.oracle_randn_fill(C.c_uint64(seed), C.c_uint64(stream), C.c_uint64(start), C.c_longlong(int(count)),
+                          out.ctypes.data_as(C.c_void_p))
+    return out
