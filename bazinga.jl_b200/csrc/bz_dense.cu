@@ -75,14 +75,18 @@ __device__ __forceinline__ void st_peer_f64(void* local_smem_ptr, uint32_t peer_
 // ---------------------------------------------------------------------------------------------
 // fused AL-gradient pass
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 template <bool BULK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     k_dense_algrad(BzDenseArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* ring = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)DA_SLOTS * DA_CHUNK);
-    double* wsum = reinterpret_cast<double*>(full + DA_SLOTS);   // [2][16] warp partials
-    double* xchg = wsum + 32;                                     // [2]: peer's row dots
+    double* ring = reinterpret_cast<double*>(smem_raw);                      // DA_RING_DOUBLES
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + DA_RING_DOUBLES);    // [DA_MAXSLOTS]
+    double* wsum = reinterpret_cast<double*>(full + DA_MAXSLOTS);            // [2][16] warp partials
+    double* xchg = wsum + 32;                                                 // [2]: peer's row dots
 
     const int tid = threadIdx.x;
     int target = a.force_target;
@@ -105,7 +109,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     long long r1 = r0 + a.rows_per_cluster;
     if (r1 > a.m) r1 = a.m;
     const int nrows = (int)(r1 - r0);
-    const int total = nrows * nch;                       // chunks this CTA streams
+
+    // ring of whole row slices: slot stride rounded to an even number of doubles (16 B)
+    const int stride = ((W + 1) & ~1) > 0 ? ((W + 1) & ~1) : 2;
+    int nslots = DA_RING_DOUBLES / stride;
+    if (nslots > DA_MAXSLOTS) nslots = DA_MAXSLOTS;
+    const uint32_t row_bytes = (uint32_t)W * 8u;
 
     // x slice and accumulators in registers; lane validity is per (chunk, element)
     const int lc0 = 2 * tid;
@@ -120,55 +129,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
 
     if (BULK) {
         if (tid == 0) {
-            for (int s = 0; s < DA_SLOTS; ++s) mbar_init(&full[s], 1);
+            for (int s = 0; s < DA_MAXSLOTS; ++s) mbar_init(&full[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
     __syncthreads();
 
-    // issue (BULK: thread 0, asynchronous) or fill (all threads, synchronous) chunks [g0, g1)
-    auto issue_range = [&](int g0, int g1) {
+    // bring local row `row` into ring slot `slot`: one bulk copy + one mbarrier phase (BULK), or a
+    // cooperative synchronous fill (ragged / odd shapes)
+    auto issue_row = [&](int row, int slot) {
+        const double* src = a.A + (r0 + row) * a.lda + col0;
         if (BULK) {
-            if (tid == 0) {
+            if (tid == 0 && W > 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                int row = g0 / nch, c = g0 % nch, slot = g0 % DA_SLOTS;
-                for (int g = g0; g < g1; ++g) {
-                    int len = W - c * DA_CHUNK;
-                    if (len > DA_CHUNK) len = DA_CHUNK;
-                    const double* src = a.A + (r0 + row) * a.lda + col0 + (long long)c * DA_CHUNK;
-                    mbar_expect_tx(&full[slot], (uint32_t)(len * 8));
-                    bulk_g2s(ring + (size_t)slot * DA_CHUNK, src, (uint32_t)(len * 8), &full[slot]);
-                    if (++c == nch) { c = 0; ++row; }
-                    if (++slot == DA_SLOTS) slot = 0;
-                }
+                mbar_expect_tx(&full[slot], row_bytes);
+                bulk_g2s(ring + (size_t)slot * stride, src, row_bytes, &full[slot]);
+                const int pf = row + a.l2_prefetch_rows;
+                if (a.l2_prefetch_rows > 0 && pf < nrows)
+                    l2_prefetch(a.A + (r0 + pf) * a.lda + col0, row_bytes);
             }
             __syncwarp();
         } else {
-            int row = g0 / (nch > 0 ? nch : 1), c = g0 % (nch > 0 ? nch : 1), slot = g0 % DA_SLOTS;
-            for (int g = g0; g < g1; ++g) {
-                int len = W - c * DA_CHUNK;
-                if (len > DA_CHUNK) len = DA_CHUNK;
-                const double* src = a.A + (r0 + row) * a.lda + col0 + (long long)c * DA_CHUNK;
-                double* dst = ring + (size_t)slot * DA_CHUNK;
-                for (int k = tid; k < len; k += DA_THREADS) dst[k] = __ldg(src + k);
-                if (++c == nch) { c = 0; ++row; }
-                if (++slot == DA_SLOTS) slot = 0;
-            }
+            double* dst = ring + (size_t)slot * stride;
+            for (int k = tid; k < W; k += DA_THREADS) dst[k] = __ldg(src + k);
             __syncthreads();
         }
     };
 
-    int issued = total < DA_SLOTS ? total : DA_SLOTS;
-    issue_range(0, issued);
+    const int npre = nrows < nslots ? nrows : nslots;
+    for (int r = 0; r < npre; ++r) issue_row(r, r);
 
     double lx = 0.0;
     double own_prev = 0.0;           // this CTA's slice dot of the previous row
     double b_prev = 0.0, mu_prev = 1.0, muy_prev = 0.0;
-    int sb = 0, par = 0;             // ring slot / mbarrier parity of the current row's first chunk
-    int sb_prev = 0;
+    int slot = 0, par = 0, slot_prev = 0;
 
     // constraint-space stage + phase B for local row `rowp`, given both slice dots
-    auto finish_row = [&](int rowp, int sbp, double own, double peer, double bi, double mui,
+    auto finish_row = [&](int rowp, int slotp, double own, double peer, double bi, double mui,
                           double muyi) {
         const double p0 = rank ? peer : own, p1 = rank ? own : peer;
         const double cxv = (p0 + p1) - bi;                           // cx = A*x - b
@@ -183,14 +180,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
             if (a.s) a.s[gi] = sv;
             if (a.yupd) a.yupd[gi] = w;
         }
+        const double2* rowv = reinterpret_cast<const double2*>(ring + (size_t)slotp * stride);
 #pragma unroll
         for (int c = 0; c < DA_MAXCH; ++c) {
             if (c < nch) {
-                int slot = sbp + c;
-                if (slot >= DA_SLOTS) slot -= DA_SLOTS;
-                const double2 av =
-                    reinterpret_cast<const double2*>(ring + (size_t)slot * DA_CHUNK)[tid];
                 const int lc = c * DA_CHUNK + lc0;
+                const double2 av = rowv[c * (DA_CHUNK / 2) + tid];
                 if (lc < W) acc[c].x = fma(av.x, w, acc[c].x);
                 if (lc + 1 < W) acc[c].y = fma(av.y, w, acc[c].y);
             }
@@ -201,16 +196,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         const long long gi = r0 + i;
         const double b_i = __ldg(a.b + gi), mu_i = __ldg(a.mu + gi), muy_i = __ldg(a.muy + gi);
         // ---- phase A: slice dot of row i
+        if (BULK && W > 0) mbar_wait(&full[slot], (uint32_t)par);
+        const double2* rowv = reinterpret_cast<const double2*>(ring + (size_t)slot * stride);
         double pa = 0.0, pb = 0.0;
 #pragma unroll
         for (int c = 0; c < DA_MAXCH; ++c) {
             if (c < nch) {
-                int slot = sb + c, p = par;
-                if (slot >= DA_SLOTS) { slot -= DA_SLOTS; p ^= 1; }
-                if (BULK) mbar_wait(&full[slot], (uint32_t)p);
-                const double2 av =
-                    reinterpret_cast<const double2*>(ring + (size_t)slot * DA_CHUNK)[tid];
                 const int lc = c * DA_CHUNK + lc0;
+                const double2 av = rowv[c * (DA_CHUNK / 2) + tid];
                 if (lc < W) pa = fma(av.x, xr[c].x, pa);
                 if (lc + 1 < W) pb = fma(av.y, xr[c].y, pb);
             }
@@ -220,32 +213,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         if (i > 0) {
             cluster_wait();
             const double peer = xchg[(i - 1) & 1];
-            finish_row(i - 1, sb_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
+            finish_row(i - 1, slot_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
         }
         double* ws = wsum + (i & 1) * 16;
         if ((tid & 31) == 0) ws[tid >> 5] = part;
-        __syncthreads();   // row i-1's slots are free; warp sums of row i are visible
-        if (i > 0 && issued < total) {
-            int g1 = issued + nch;
-            if (g1 > total) g1 = total;
-            issue_range(issued, g1);
-            issued = g1;
-        }
-        double own = 0.0;
+        __syncthreads();   // row i-1's slot is free; warp sums of row i are visible
+        if (i > 0 && i - 1 + nslots < nrows) issue_row(i - 1 + nslots, slot_prev);
+        // fixed-order pairwise tree over the 16 warp partials (identical in every thread / both CTAs)
+        double t8[8];
 #pragma unroll
-        for (int w = 0; w < DA_THREADS / 32; ++w) own += ws[w];
+        for (int w = 0; w < 8; ++w) t8[w] = ws[2 * w] + ws[2 * w + 1];
+        const double own = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
         if (tid == 0) st_peer_f64(&xchg[i & 1], rank ^ 1u, own);
         __syncwarp();
         cluster_arrive();
         own_prev = own; b_prev = b_i; mu_prev = mu_i; muy_prev = muy_i;
-        sb_prev = sb;
-        sb += nch;
-        if (sb >= DA_SLOTS) { sb -= DA_SLOTS; par ^= 1; }
+        slot_prev = slot;
+        if (++slot == nslots) { slot = 0; par ^= 1; }
     }
     if (nrows > 0) {
         cluster_wait();
         const double peer = xchg[(nrows - 1) & 1];
-        finish_row(nrows - 1, sb_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
+        finish_row(nrows - 1, slot_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
     }
 
     // ---- write this cluster's partial gradient slice and its lx partial
@@ -268,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) {
     static bool attr_set = false;
-    const size_t smem = (size_t)DA_SLOTS * DA_CHUNK * 8 + DA_SLOTS * 8 + 32 * 8 + 4 * 8;
+    const size_t smem = (size_t)DA_RING_DOUBLES * 8 + DA_MAXSLOTS * 8 + 32 * 8 + 4 * 8;
     if (!attr_set) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -286,6 +275,7 @@ int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) 
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // f = Quadratic(Q, q): dfx = Q x + q, fx = 0.5 x'Qx + q'x.  One warp per row, rows strided over the

@@ -5,7 +5,8 @@
 #define DA_THREADS 512
 #define DA_CHUNK 1024   // doubles per ring slot (8 KB)
 #define DA_MAXCH 8      // ring slots per row slice -> slice width <= 8192, n <= 16384
-#define DA_SLOTS 26     // 208 KB ring
+#define DA_RING_DOUBLES (26 * 1024)   // 208 KB ring of whole row slices
+#define DA_MAXSLOTS 16
 #define DA_MAX_N (2 * DA_MAXCH * DA_CHUNK)
 
 struct BzDenseArgs {
@@ -28,6 +29,7 @@ struct BzDenseArgs {
     double* lxpart;        // nclusters partial sums of (t-s)^2/mu
     unsigned int* counter;
     int set_after;         // last CTA sets st->next_op = st->after_g
+    int l2_prefetch_rows;  // >0: cp.async.bulk.prefetch.L2 this many rows ahead of each issue
 };
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);

@@ -1,0 +1,306 @@
+// F and D kernels of the PANOC+ state machine (see bz_vec.cu for the cycle [L, G, F, G, D]).
+//   F  k_fstep   assemble grad_x, forward-backward step  y = x - gamma*grad; z = prox_g(y); res = x - z,
+//                fused with <grad,res>, ||res||^2 and g(z)      (+ the two init modes of Appendix A.4)
+//   D  k_dstep   assemble grad_z and f(z); stop norm; gamma-halving / sufficient-decrease decisions
+// Both finish with the "last CTA done" pattern: per-CTA partials in fixed slots, the last CTA sums
+// them in fixed order and runs the scalar logic -- deterministic, no float atomics.
+// When the provider left per-cluster partial rows (dense passes) the assembly is the blocked one of
+// bz_vecdev.cuh (64 columns per CTA pass, 4 partial groups); otherwise plain grid-stride.
+// Compiled with -fmad=false (the reference's Julia broadcasts are not contracted).
+#include "bz_vecdev.cuh"
+
+static int fbd_grid(const bz_ctx* ctx, const BzGradSrc& gs, long long items) {
+    if (gs.Pf || gs.Pc) {
+        long long nb = (items + BZ_ASM_COLS - 1) / BZ_ASM_COLS;
+        const long long cap = (long long)ctx->num_sms * 8;
+        if (nb < 1) nb = 1;
+        return (int)(nb > cap ? cap : nb);
+    }
+    return bz_vec_grid(ctx, items);
+}
+
+// ---------------------------------------------------------------------------------------------
+// F
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_VEC_THREADS)
+    k_fstep(BzState* st, BzVecs v, BzGradSrc gs, BzGParams g, double* part, unsigned int* counter,
+            int force_mode) {
+    __shared__ double scratch[4 * 32];
+    __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    int mode = force_mode;
+    if (mode < 0) {
+        if (__ldcg(&st->next_op) != OP_F) return;
+        mode = __ldcg(&st->mode);
+    }
+    const long long n = v.n;
+    const bool blocked = bz_gs_blocked(gs);
+    const double gamma = __ldcg(&st->gamma);
+    const int fresh = (mode >= MODE_INITFB) ? __ldcg(&st->grad_x_fresh) : 0;
+    double a[3] = {0.0, 0.0, 0.0};
+
+    // elementwise work for entry j given the assembled gradient value (or the stored grad_x)
+    auto elem = [&](long long j, double gr) {
+        if (mode == MODE_INIT0) {
+            v.grad_x[j] = gr;
+            v.xeps[j] = v.x[j] + 1.0;            // lower_bound_smoothness_constant: x .+ 1
+        } else if (mode == MODE_INIT1) {
+            const double df = gr - v.grad_x[j];
+            a[0] += df * df;
+        } else {
+            if (fresh) v.grad_x[j] = gr;
+            const double xj = v.x[j];
+            const double y = xj - gamma * gr;
+            const double z = bz_prox_elem(g, y, gamma, j, a[2]);
+            const double r = xj - z;
+            v.z[j] = z;
+            v.res[j] = r;
+            a[0] += gr * r;
+            a[1] += r * r;
+        }
+    };
+
+    const bool need_assembly = (mode == MODE_INIT0) || (mode == MODE_INIT1) || fresh;
+    if (mode >= MODE_INITFB && g.kind == BZ_G_OBSTACLE_L1) {
+        // demo/obstacle.jl:67-81: soft threshold block 1 by gamma, max(0,.) on blocks 2-3, then
+        // complementarity zeroing between blocks 2 and 3 (tie zeroes the block-2 entry)
+        const long long N = g.N;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+            double gr[3], xv[3], zv[3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const long long j = i + b * N;
+                gr[b] = fresh ? bz_assemble_grad(gs, j, n) : v.grad_x[j];
+                if (fresh) v.grad_x[j] = gr[b];
+                xv[b] = v.x[j];
+            }
+            zv[0] = fmax(0.0, (xv[0] - gamma * gr[0]) - gamma);
+            zv[1] = fmax(0.0, xv[1] - gamma * gr[1]);
+            zv[2] = fmax(0.0, xv[2] - gamma * gr[2]);
+            if (zv[1] > zv[2]) zv[2] = 0.0; else zv[1] = 0.0;
+            a[2] += zv[0];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const long long j = i + b * N;
+                const double r = xv[b] - zv[b];
+                v.z[j] = zv[b];
+                v.res[j] = r;
+                a[0] += gr[b] * r;
+                a[1] += r * r;
+            }
+        }
+    } else if (blocked) {
+        for (long long jb = (long long)blockIdx.x * BZ_ASM_COLS; jb < n; jb += (long long)gridDim.x * BZ_ASM_COLS) {
+            const double gr = need_assembly ? bz_assemble_blocked(gs, jb, n, asm_sm) : 0.0;
+            const long long j = jb + threadIdx.x;
+            if (threadIdx.x < BZ_ASM_COLS && j < n) elem(j, need_assembly ? gr : v.grad_x[j]);
+        }
+    } else {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+            elem(j, need_assembly ? bz_assemble_grad(gs, j, n) : v.grad_x[j]);
+    }
+    bz_block_sum<3>(a, scratch);
+    const int nb = gridDim.x;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = a[0];
+        part[nb + blockIdx.x] = a[1];
+        part[2 * nb + blockIdx.x] = a[2];
+    }
+    if (!bz_last_cta(counter, nb)) return;
+
+    // ---- last CTA: scalar bookkeeping
+    const double s0 = bz_final_sum(part, nb, scratch);
+    const double s1 = bz_final_sum(part + nb, nb, scratch);
+    const double s2 = bz_final_sum(part + 2 * nb, nb, scratch);
+    double fx = 0.0, lx = 0.0;
+    const bool need_value = (mode == MODE_INIT0) || (mode >= MODE_INITFB && fresh);
+    if (need_value) lx = bz_assemble_value(gs, st, scratch, fx);
+    if (threadIdx.x != 0) return;
+    if (mode == MODE_INIT0) {
+        st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
+        st->n_grad += 1;
+        st->grad_target = TGT_XEPS;
+        st->after_g = OP_F;
+        st->mode = MODE_INIT1;
+        st->next_op = OP_G;
+    } else if (mode == MODE_INIT1) {
+        const double Lest = sqrt(s0) / sqrt((double)n);
+        st->Lest = Lest;
+        st->gamma = st->alpha / Lest;     // L = 0 -> gamma = Inf, IEEE semantics as upstream
+        st->n_grad += 1;
+        st->mode = MODE_INITFB;
+        st->grad_x_fresh = 0;
+        st->next_op = OP_F;
+    } else {
+        if (fresh) {
+            st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
+            st->n_grad += 1;
+        }
+        const double nrm = sqrt(s1);
+        const double nrm2 = nrm * nrm;                       // norm(res)^2
+        st->dot_gr = s0;
+        st->res_nrm2sq = nrm2;
+        st->f_up = st->f_x - s0 + ((st->alpha / gamma) / 2) * nrm2;   // f_model
+        st->g_z = bz_g_value_scale(g) * s2;
+        st->n_prox += 1;
+        st->grad_x_fresh = 0;
+        st->grad_target = TGT_Z;
+        st->after_g = OP_D;
+        st->next_op = OP_G;
+        st->out[0] = st->g_z; st->out[1] = s0; st->out[2] = s1;
+    }
+    __threadfence();
+}
+
+int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
+                    const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
+    const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
+    k_fstep<<<fbd_grid(ctx, gs, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, g, part, counter,
+                                                                          force_mode);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// D: gradient at z is in; decide (A.4 backtrack_stepsize!, A.5 loop body, A.3 stop rule)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_VEC_THREADS)
+    k_dstep(BzState* st, BzVecs v, BzGradSrc gs, double* part, unsigned int* counter) {
+    __shared__ double scratch[4 * 32];
+    __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    if (__ldcg(&st->next_op) != OP_D) return;
+    const long long n = v.n;
+    const double gamma = __ldcg(&st->gamma);
+    const double gamma_h = gamma * 0.5;
+    double m1 = 0.0, m2 = 0.0;
+    auto elem = [&](long long j, double gz) {
+        v.grad_z[j] = gz;
+        const double r = v.res[j], gx = v.grad_x[j];
+        m1 = bz_nanmax(m1, (r / gamma - gx) + gz);      // norm(res/gamma - grad_x + grad_z, Inf)
+        m2 = bz_nanmax(m2, (r / gamma_h - gx) + gz);    // same with the halved gamma (edge case below)
+    };
+    if (bz_gs_blocked(gs)) {
+        for (long long jb = (long long)blockIdx.x * BZ_ASM_COLS; jb < n; jb += (long long)gridDim.x * BZ_ASM_COLS) {
+            const double gz = bz_assemble_blocked(gs, jb, n, asm_sm);
+            const long long j = jb + threadIdx.x;
+            if (threadIdx.x < BZ_ASM_COLS && j < n) elem(j, gz);
+        }
+    } else {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+            elem(j, bz_assemble_grad(gs, j, n));
+    }
+    // NaN-propagating block max: the NaN flag travels in a second lane
+    double a[2] = {m1 != m1 ? 0.0 : m1, m2 != m2 ? 0.0 : m2};
+    double f[2] = {m1 != m1 ? 1.0 : 0.0, m2 != m2 ? 1.0 : 0.0};
+    bz_block_max<2>(a, scratch);
+    bz_block_max<2>(f, scratch);
+    const int nb = gridDim.x;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = f[0] > 0.0 ? NANQ : a[0];
+        part[nb + blockIdx.x] = f[1] > 0.0 ? NANQ : a[1];
+    }
+    if (!bz_last_cta(counter, nb)) return;
+
+    const double stop1 = bz_final_nanmax(part, nb, scratch);
+    const double stop2 = bz_final_nanmax(part + nb, nb, scratch);
+    double fx;
+    const double f_z = bz_assemble_value(gs, st, scratch, fx);
+    if (threadIdx.x != 0) return;
+
+    st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
+    st->n_grad += 1;
+    const int mode = st->mode;
+    const bool cond = (f_z > st->f_up + 10 * BZ_EPS * (1 + fabs(f_z))) && (gamma >= st->gamma_min);
+    bool end_iter = false;
+    double stopn = stop1;
+    if (mode == MODE_INITFB) {          // backtrack_stepsize! (A.4)
+        if (cond) {
+            st->gamma = gamma / 2;
+            st->grad_x_fresh = 0;
+            st->next_op = OP_F;
+        } else {
+            end_iter = true;
+            st->skip_update = 1;
+            st->mode = MODE_ITER;
+        }
+    } else {                            // A.5 loop body at backtrack index k
+        const int k = st->k_bt;
+        if (cond) {
+            st->gamma = gamma * 0.5;
+            st->currmem = 0; st->curridx = 0; st->H = 1.0;       // reset_direction_state!
+            if (k + 1 > st->max_backtracks) {                    // `continue` ran off the loop
+                end_iter = true;
+                stopn = stop2;
+            } else {
+                st->k_bt = k + 1;
+                st->grad_x_fresh = 0;
+                st->next_op = OP_F;
+            }
+        } else if (st->f_up + st->g_z <= st->thresh || k >= st->max_backtracks) {
+            end_iter = true;
+        } else {
+            st->tau = (k >= st->max_backtracks - 1) ? 0.0 : st->tau / 2;
+            st->k_bt = k + 1;
+            st->l_role = LROLE_INTERP;
+            st->next_op = OP_L;
+        }
+        if (end_iter) st->skip_update = 0;
+    }
+    if (end_iter) {
+        st->iter += 1;
+        st->stopnorm = stopn;
+        if (st->iter >= st->maxit || stopn <= st->tol) {
+            st->inner_status = (stopn <= st->tol) ? IST_CONVERGED : IST_MAXIT;
+            st->next_op = OP_DONE;
+        } else {
+            st->l_role = LROLE_NEWITER;
+            st->next_op = OP_L;
+        }
+    }
+    __threadfence();
+}
+
+int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
+                    unsigned int* counter) {
+    k_dstep<<<fbd_grid(ctx, gs, v.n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, part, counter);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
+// assemble a gradient + value for the parity entry point bz_auglag_grad
+__global__ void __launch_bounds__(BZ_VEC_THREADS)
+    k_assemble(BzState* st, BzGradSrc gs, long long n, double* out, double* part,
+               unsigned int* counter) {
+    __shared__ double scratch[4 * 32];
+    __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    if (bz_gs_blocked(gs)) {
+        for (long long jb = (long long)blockIdx.x * BZ_ASM_COLS; jb < n; jb += (long long)gridDim.x * BZ_ASM_COLS) {
+            const double gr = bz_assemble_blocked(gs, jb, n, asm_sm);
+            const long long j = jb + threadIdx.x;
+            if (threadIdx.x < BZ_ASM_COLS && j < n) out[j] = gr;
+        }
+    } else {
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+            out[j] = bz_assemble_grad(gs, j, n);
+    }
+    if (!bz_last_cta(counter, gridDim.x)) return;
+    double fx;
+    const double lx = bz_assemble_value(gs, st, scratch, fx);
+    if (threadIdx.x == 0) {
+        st->al_fx = fx; st->al_lx = lx;
+        st->out[0] = lx; st->out[1] = fx;
+        __threadfence();
+    }
+}
+int bz_launch_assemble(bz_ctx* ctx, BzState* st, const BzGradSrc& gs, long long n, double* out,
+                       double* part, unsigned int* counter) {
+    k_assemble<<<fbd_grid(ctx, gs, n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, gs, n, out, part, counter);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}

@@ -298,6 +298,7 @@ struct bz_ctx {
     size_t ev_used = 0;
     long long n_launches = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu
 };
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);

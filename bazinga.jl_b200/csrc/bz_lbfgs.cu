@@ -1,0 +1,465 @@
+// L kernels of the PANOC+ state machine: L-BFGS update!(H, x - x_prev, res - res_prev), the two-loop
+// direction d = H*(-res) (ProximalAlgorithms LBFGS operator), x_d = x + d,
+// and the tau-interpolation x = tau*x_d + (1-tau)*z_curr.  Two implementations with the same
+// arithmetic per element and the same order of the 2*currmem (+1) sequential dot products:
+//   k_lstep_cluster  n <= 8 CTAs x 256 threads x 16: ONE thread-block cluster; d and the vectors
+//                    of the current step live in registers, every dot product is a warp-shuffle +
+//                    shared-memory block sum followed by an all-to-all through distributed shared
+//                    memory and one hardware cluster barrier (north_star: "warp-shuffle and
+//                    cluster-level reductions").
+//   k_lstep          any n: cooperative launch over up to one CTA per SM with a software grid
+//                    barrier; each axpy pass is fused with the next dot product.
+// All sums are order-fixed (no float atomics).  Compiled with -fmad=false.
+#include "bz_vecdev.cuh"
+#include <cooperative_groups.h>
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct TeamCtx {
+    BzTeam tm;
+    int idx;
+    double* scratch;   // >= 2*32 + 2 doubles of shared memory
+};
+
+template <int K>
+__device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
+    bz_block_sum<K>(v, tc.scratch);
+    const int nb = gridDim.x;
+    if (nb == 1) return;
+    const int j = tc.idx++;
+    unsigned int* bar = tc.tm.bars + tc.tm.parity * BZ_MAXBAR + j;
+    double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 2;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sl[blockIdx.x * 2 + k] = v[k];
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (ld_acquire_u32(bar) < (unsigned int)nb) { }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double s = 0.0;
+            for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 2 + k);
+            s = bz_warp_sum(s);
+            if (threadIdx.x == 0) tc.scratch[64 + k] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(BZ_L_THREADS)
+    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
+    __shared__ double scratch[2 * 32 + 4];
+    // the other parity's barrier words are free again: reset them for the launch after this one
+    if (blockIdx.x == 0 && threadIdx.x < BZ_MAXBAR)
+        tm.bars[(1 - tm.parity) * BZ_MAXBAR + threadIdx.x] = 0u;
+    int role = force_role;
+    if (role < 0) {
+        if (__ldcg(&st->next_op) != OP_L) return;
+        role = __ldcg(&st->l_role);
+    }
+    const long long n = v.n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
+        const double tau = __ldcg(&st->tau);
+        for (long long j = j0; j < n; j += stride)
+            v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
+        if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
+            st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
+            st->next_op = OP_G;
+            __threadfence();
+        }
+        return;
+    }
+
+    TeamCtx tc{tm, 0, scratch};
+    const int M = __ldcg(&st->mem);
+    int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
+    double H = __ldcg(&st->H);
+    const int skip = __ldcg(&st->skip_update);
+    double ys[BZ_MAXMEM], al[BZ_MAXMEM];
+    for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; }
+
+    // ---- update!(H, x - x_prev, res - res_prev)
+    if (!skip && M > 0) {
+        double a[2] = {0.0, 0.0};
+        for (long long j = j0; j < n; j += stride) {
+            const double s = v.x[j] - v.x_prev[j], yv = v.res[j] - v.res_prev[j];
+            a[0] += s * yv;
+            a[1] += yv * yv;
+        }
+        team_sum<2>(tc, a);
+        if (a[0] > 0) {
+            curridx += 1;
+            if (curridx > M) curridx = 1;
+            currmem = currmem + 1 > M ? M : currmem + 1;
+            ys[curridx - 1] = a[0];
+            double* sm = v.sM + (size_t)(curridx - 1) * n;
+            double* ym = v.yM + (size_t)(curridx - 1) * n;
+            for (long long j = j0; j < n; j += stride) {
+                sm[j] = v.x[j] - v.x_prev[j];
+                ym[j] = v.res[j] - v.res_prev[j];
+            }
+            H = a[0] / a[1];
+        }
+    }
+
+    // ---- d = H * (-res): two-loop recursion, each axpy fused with the next dot product
+    int idx = curridx;
+    {
+        double a[1] = {0.0};
+        if (currmem > 0) {
+            const double* sm = v.sM + (size_t)(idx - 1) * n;
+            for (long long j = j0; j < n; j += stride) {
+                const double dj = -v.res[j];
+                v.d[j] = dj;
+                a[0] += sm[j] * dj;
+            }
+        } else {
+            for (long long j = j0; j < n; j += stride) v.d[j] = H * (-v.res[j]);
+        }
+        for (int t = 0; t < currmem; ++t) {       // loop1!: newest -> oldest
+            team_sum<1>(tc, a);
+            const int i = idx - 1;
+            const double alpha_i = a[0] / ys[i];
+            al[i] = alpha_i;
+            int idx2 = idx - 1;
+            if (idx2 == 0) idx2 = M;
+            const double* ym = v.yM + (size_t)i * n;
+            a[0] = 0.0;
+            if (t < currmem - 1) {
+                const double* sm2 = v.sM + (size_t)(idx2 - 1) * n;
+                for (long long j = j0; j < n; j += stride) {
+                    const double dj = v.d[j] - alpha_i * ym[j];
+                    v.d[j] = dj;
+                    a[0] += sm2[j] * dj;
+                }
+            } else {                               // last: also d .= H .* d, then first dot of loop2!
+                int idn = idx2 + 1;
+                if (idn > M) idn = 1;
+                const double* ymn = v.yM + (size_t)(idn - 1) * n;
+                for (long long j = j0; j < n; j += stride) {
+                    double dj = v.d[j] - alpha_i * ym[j];
+                    dj = H * dj;
+                    v.d[j] = dj;
+                    a[0] += ymn[j] * dj;
+                }
+            }
+            idx = idx2;
+        }
+        for (int t = 0; t < currmem; ++t) {       // loop2!: oldest -> newest
+            idx += 1;
+            if (idx > M) idx = 1;
+            team_sum<1>(tc, a);
+            const int i = idx - 1;
+            const double beta = a[0] / ys[i];
+            const double coef = al[i] - beta;
+            const double* sm = v.sM + (size_t)i * n;
+            a[0] = 0.0;
+            if (t < currmem - 1) {
+                int idn = idx + 1;
+                if (idn > M) idn = 1;
+                const double* ymn = v.yM + (size_t)(idn - 1) * n;
+                for (long long j = j0; j < n; j += stride) {
+                    const double dj = v.d[j] + coef * sm[j];
+                    v.d[j] = dj;
+                    a[0] += ymn[j] * dj;
+                }
+            } else {
+                for (long long j = j0; j < n; j += stride) v.d[j] = v.d[j] + coef * sm[j];
+            }
+        }
+    }
+    // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
+    for (long long j = j0; j < n; j += stride) {
+        const double xj = v.x[j];
+        v.x_prev[j] = xj;
+        v.res_prev[j] = v.res[j];
+        const double xd = xj + v.d[j];
+        v.x_d[j] = xd;
+        v.x[j] = xd;
+        v.z_curr[j] = v.z[j];
+    }
+    if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
+        const double gamma = st->gamma;
+        const double FBE_x =
+            (st->f_x - st->dot_gr + ((st->alpha / gamma) / 2) * st->res_nrm2sq) + st->g_z;
+        const double sigma = st->beta * (0.5 / gamma) * (1 - st->alpha);
+        st->FBE_x = FBE_x;
+        st->sigma = sigma;
+        st->thresh = FBE_x - sigma * st->res_nrm2sq + 10 * BZ_EPS * (1 + fabs(FBE_x));
+        st->tau = 1.0;
+        st->k_bt = 1;
+        st->currmem = currmem; st->curridx = curridx; st->H = H;
+        for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; }
+        st->skip_update = 0;
+        st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
+        st->next_op = OP_G;
+        __threadfence();
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// cluster version
+// ---------------------------------------------------------------------------------------------
+#define LC_THREADS 256
+#define LC_EPT 16          // max elements per thread
+#define LC_MAXCS 8         // portable cluster size
+
+__device__ __forceinline__ uint32_t lc_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t lc_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t lc_cluster_size() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void lc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void lc_st_remote(void* local_ptr, uint32_t rank, double v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(lc_smem_u32(local_ptr)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+struct ClusterRed {
+    double* wpart;     // [2][8] warp partials (K <= 2)
+    double* slots;     // [2 parities][LC_MAXCS][2]
+    uint32_t rank, cs;
+    int round;
+};
+
+// all-cluster sum of K values per thread; result in every thread of every CTA, identical bits
+template <int K>
+__device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = bz_warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) cr.wpart[k * 8 + warp] = v[k];
+    }
+    __syncthreads();
+    const int par = cr.round & 1;
+    cr.round++;
+    double* sl = cr.slots + par * (LC_MAXCS * 2);
+    if (threadIdx.x < cr.cs) {     // thread t sends this CTA's block sums to CTA t
+        double bs[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double* w = cr.wpart + k * 8;
+            bs[k] = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) lc_st_remote(&sl[cr.rank * 2 + k], threadIdx.x, bs[k]);
+    }
+    lc_cluster_sync();             // release/acquire: remote stores are visible; also a CTA barrier
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        for (uint32_t c = 0; c < cr.cs; ++c) s += sl[c * 2 + k];
+        v[k] = s;
+    }
+}
+
+template <int EPT>
+__global__ void __launch_bounds__(LC_THREADS)
+    k_lstep_cluster(BzState* st, BzVecs v, int force_role) {
+    __shared__ double wpart[2 * 8];
+    __shared__ double slots[2 * LC_MAXCS * 2];
+    int role = force_role;
+    if (role < 0) {
+        if (__ldcg(&st->next_op) != OP_L) return;     // uniform over the cluster
+        role = __ldcg(&st->l_role);
+    }
+    ClusterRed cr{wpart, slots, lc_cluster_rank(), lc_cluster_size(), 0};
+    const long long n = v.n;
+    const int stride = (int)(cr.cs * LC_THREADS);
+    const int j0 = (int)(cr.rank * LC_THREADS + threadIdx.x);
+    // element k of this thread is j0 + k*stride; valid iff < n
+#define LC_FOR(k) _Pragma("unroll") for (int k = 0; k < EPT; ++k)
+#define LC_J(k) ((long long)j0 + (long long)(k) * stride)
+
+    if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
+        const double tau = __ldcg(&st->tau);
+        LC_FOR(k) {
+            const long long j = LC_J(k);
+            if (j < n) v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
+        }
+        lc_cluster_sync();
+        if (cr.rank == 0 && threadIdx.x == 0) {
+            st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
+            st->next_op = OP_G;
+            __threadfence();
+        }
+        return;
+    }
+
+    const int M = __ldcg(&st->mem);
+    int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
+    double H = __ldcg(&st->H);
+    const int skip = __ldcg(&st->skip_update);
+    double ys[BZ_MAXMEM], al[BZ_MAXMEM];
+    for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; }
+
+    double xv[EPT], rv[EPT], d[EPT];
+    LC_FOR(k) {
+        const long long j = LC_J(k);
+        xv[k] = j < n ? v.x[j] : 0.0;
+        rv[k] = j < n ? v.res[j] : 0.0;
+    }
+    // ---- update!(H, x - x_prev, res - res_prev)
+    if (!skip && M > 0) {
+        double sv[EPT], yv[EPT];
+        double a[2] = {0.0, 0.0};
+        LC_FOR(k) {
+            const long long j = LC_J(k);
+            sv[k] = j < n ? xv[k] - v.x_prev[j] : 0.0;
+            yv[k] = j < n ? rv[k] - v.res_prev[j] : 0.0;
+        }
+        LC_FOR(k) { a[0] += sv[k] * yv[k]; a[1] += yv[k] * yv[k]; }
+        cluster_sum<2>(cr, a);
+        if (a[0] > 0) {
+            curridx += 1;
+            if (curridx > M) curridx = 1;
+            currmem = currmem + 1 > M ? M : currmem + 1;
+            ys[curridx - 1] = a[0];
+            double* sm = v.sM + (size_t)(curridx - 1) * n;
+            double* ym = v.yM + (size_t)(curridx - 1) * n;
+            LC_FOR(k) {
+                const long long j = LC_J(k);
+                if (j < n) { sm[j] = sv[k]; ym[j] = yv[k]; }
+            }
+            H = a[0] / a[1];
+        }
+    }
+    // ---- d = H * (-res): two-loop recursion, d in registers
+    LC_FOR(k) d[k] = -rv[k];
+    int idx = curridx;
+    for (int t = 0; t < currmem; ++t) {           // loop1!: newest -> oldest
+        const int i = idx - 1;
+        const double* sm = v.sM + (size_t)i * n;
+        const double* ym = v.yM + (size_t)i * n;
+        double yreg[EPT];
+        double a[1] = {0.0};
+        LC_FOR(k) {
+            const long long j = LC_J(k);
+            const double sj = j < n ? __ldcg(sm + j) : 0.0;
+            yreg[k] = j < n ? __ldcg(ym + j) : 0.0;
+            a[0] += sj * d[k];
+        }
+        cluster_sum<1>(cr, a);
+        const double alpha_i = a[0] / ys[i];
+        al[i] = alpha_i;
+        LC_FOR(k) d[k] = d[k] - alpha_i * yreg[k];
+        idx -= 1;
+        if (idx == 0) idx = M;
+    }
+    LC_FOR(k) d[k] = H * d[k];
+    for (int t = 0; t < currmem; ++t) {           // loop2!: oldest -> newest
+        idx += 1;
+        if (idx > M) idx = 1;
+        const int i = idx - 1;
+        const double* sm = v.sM + (size_t)i * n;
+        const double* ym = v.yM + (size_t)i * n;
+        double sreg[EPT];
+        double a[1] = {0.0};
+        LC_FOR(k) {
+            const long long j = LC_J(k);
+            const double yj = j < n ? __ldcg(ym + j) : 0.0;
+            sreg[k] = j < n ? __ldcg(sm + j) : 0.0;
+            a[0] += yj * d[k];
+        }
+        cluster_sum<1>(cr, a);
+        const double beta = a[0] / ys[i];
+        const double coef = al[i] - beta;
+        LC_FOR(k) d[k] = d[k] + coef * sreg[k];
+    }
+    // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
+    LC_FOR(k) {
+        const long long j = LC_J(k);
+        if (j < n) {
+            v.d[j] = d[k];
+            v.x_prev[j] = xv[k];
+            v.res_prev[j] = rv[k];
+            const double xd = xv[k] + d[k];
+            v.x_d[j] = xd;
+            v.x[j] = xd;
+            v.z_curr[j] = v.z[j];
+        }
+    }
+    lc_cluster_sync();
+    if (cr.rank == 0 && threadIdx.x == 0) {
+        const double gamma = st->gamma;
+        const double FBE_x =
+            (st->f_x - st->dot_gr + ((st->alpha / gamma) / 2) * st->res_nrm2sq) + st->g_z;
+        const double sigma = st->beta * (0.5 / gamma) * (1 - st->alpha);
+        st->FBE_x = FBE_x;
+        st->sigma = sigma;
+        st->thresh = FBE_x - sigma * st->res_nrm2sq + 10 * BZ_EPS * (1 + fabs(FBE_x));
+        st->tau = 1.0;
+        st->k_bt = 1;
+        st->currmem = currmem; st->curridx = curridx; st->H = H;
+        for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; }
+        st->skip_update = 0;
+        st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
+        st->next_op = OP_G;
+        __threadfence();
+    }
+#undef LC_FOR
+#undef LC_J
+}
+
+int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
+                    unsigned int* counter, int force_role) {
+    const long long per_cta = (long long)LC_THREADS * LC_EPT;
+    if (v.n <= per_cta * LC_MAXCS) {
+        // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
+        int cs = 1;
+        while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(LC_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if ((long long)cs * LC_THREADS * 8 >= v.n)
+            BZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstep_cluster<8>, st, v, force_role));
+        else
+            BZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstep_cluster<LC_EPT>, st, v, force_role));
+        ctx->n_launches++;
+        return BZ_OK;
+    }
+    const int nb = bz_l_grid(ctx, v.n);
+    BzVecs vv = v;
+    BzTeam tt = tm;
+    void* args[] = {(void*)&st, (void*)&vv, (void*)&tt, (void*)&counter, (void*)&force_role};
+    BZ_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_lstep, dim3(nb), dim3(BZ_L_THREADS), args, 0,
+                                             ctx->stream));
+    ctx->n_launches++;
+    return BZ_OK;
+}

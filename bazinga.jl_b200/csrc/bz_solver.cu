@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <cstdlib>
 
 static std::string g_last_error;
 
@@ -100,6 +101,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
         return bz_fail(nullptr, BZ_ERR_CUDA, msg);
     }
     BZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("BZ_L2_PREFETCH_ROWS")) ctx->l2_prefetch_rows = atoi(e);
     *out = ctx;
     return BZ_OK;
 }
@@ -427,6 +429,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.rows_per_cluster = p->f_rpc; a.dkind = BZ_D_ZERO; a.dlo = 0; a.dhi = 0;
         a.cx = nullptr; a.s = nullptr; a.yupd = nullptr;
         a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
+        a.l2_prefetch_rows = ctx->l2_prefetch_rows;
         BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         p->nfx = std::min<long long>(ctx->num_sms, (p->n + 7) / 8);
@@ -443,6 +446,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.rows_per_cluster = p->c_rpc; a.dkind = p->D.kind; a.dlo = p->D.lo; a.dhi = p->D.hi;
         a.cx = p->cx; a.s = p->s; a.yupd = p->yupd;
         a.P = p->Pc; a.lxpart = p->lxpart; a.counter = p->counters + 1; a.set_after = 1;
+        a.l2_prefetch_rows = ctx->l2_prefetch_rows;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->profiling) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
         BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));

@@ -11,18 +11,9 @@
 //
 // This file is compiled with -fmad=false: the reference's Julia broadcasts are not contracted
 // into FMAs, and the discontinuous operators (H4) make that matter.
-#include "bz_vec.cuh"
+#include "bz_vecdev.cuh"
 #include <cooperative_groups.h>
 
-#define NANQ __longlong_as_double(0x7ff8000000000000LL)
-
-__device__ __forceinline__ double bz_nanmax(double m, double v) {
-    v = fabs(v);
-    return (v != v || m != m) ? NANQ : fmax(m, v);
-}
-__device__ __forceinline__ double jl_max(double a, double b) {   // Julia max propagates NaN
-    return (a != a || b != b) ? NANQ : fmax(a, b);
-}
 
 int bz_vec_grid(const bz_ctx* ctx, long long n) {
     long long nb = (n + BZ_VEC_THREADS - 1) / BZ_VEC_THREADS;
@@ -36,538 +27,6 @@ int bz_l_grid(const bz_ctx* ctx, long long n) {
     if (nb < 1) nb = 1;
     if (nb > ctx->num_sms) nb = ctx->num_sms;
     return (int)nb;
-}
-
-// ---------------------------------------------------------------------------------------------
-// gradient / value assembly from the provider outputs (auglagfun.jl:78-84)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double bz_assemble_grad(const BzGradSrc& gs, long long j, long long n) {
-    double dfx = 0.0, jtv = 0.0;
-    if (gs.Pf) {
-        double s = 0.0;
-        for (int p = 0; p < gs.npf; ++p) s += __ldcg(gs.Pf + (size_t)p * n + j);
-        dfx = s;
-    } else if (gs.Ef) {
-        dfx = __ldcg(gs.Ef + j);
-    }
-    if (gs.Pc) {
-        double s = 0.0;
-        for (int p = 0; p < gs.npc; ++p) s += __ldcg(gs.Pc + (size_t)p * n + j);
-        jtv = s;
-    } else if (gs.Ec) {
-        jtv = __ldcg(gs.Ec + j);
-    }
-    return dfx + jtv;   // dlx .= al.dfx .+ al.jtv
-}
-
-// fixed-order parallel sum of a global partial array by one whole CTA; result in every thread
-__device__ inline double bz_final_sum(const double* part, int n, double* scratch) {
-    double v[1] = {0.0};
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += __ldcg(part + i);
-    bz_block_sum<1>(v, scratch);
-    return v[0];
-}
-__device__ inline double bz_final_nanmax(const double* part, int n, double* scratch) {
-    double m = 0.0;
-    int isnan_ = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double v = __ldcg(part + i);
-        if (v != v) isnan_ = 1; else m = fmax(m, v);
-    }
-    double a[1] = {m};
-    bz_block_max<1>(a, scratch);
-    double b[1] = {(double)isnan_};
-    bz_block_max<1>(b, scratch);
-    return b[0] > 0.0 ? NANQ : a[0];
-}
-
-// AL value from the provider partials:  lx = 0.5*sum(..) ; lx += fx ; lx -= musqy   (:78-82)
-__device__ inline double bz_assemble_value(const BzGradSrc& gs, BzState* st, double* scratch,
-                                           double& fx_out) {
-    const double slx = gs.lxpart ? bz_final_sum(gs.lxpart, gs.nlx, scratch) : 0.0;
-    const double sfx = gs.fxpart ? bz_final_sum(gs.fxpart, gs.nfx, scratch) : 0.0;
-    const double sfx2 = gs.fxpart2 ? bz_final_sum(gs.fxpart2, gs.nfx2, scratch) : 0.0;
-    double lx = 0.5 * slx;
-    double fx = gs.fxpart ? gs.fx_scale * sfx : 0.0;
-    if (gs.fxpart2) fx = fx + gs.fx_scale2 * sfx2;
-    lx += fx;
-    lx -= st->musqy;
-    fx_out = fx;
-    return lx;
-}
-
-// ---------------------------------------------------------------------------------------------
-// F: forward-backward step (also the two init modes of Appendix A.4)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
-    k_fstep(BzState* st, BzVecs v, BzGradSrc gs, BzGParams g, double* part, unsigned int* counter,
-            int force_mode) {
-    __shared__ double scratch[4 * 32];
-    int mode = force_mode;
-    if (mode < 0) {
-        if (__ldcg(&st->next_op) != OP_F) return;
-        mode = __ldcg(&st->mode);
-    }
-    const long long n = v.n;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double a[3] = {0.0, 0.0, 0.0};
-    int fresh = 0;
-
-    if (mode == MODE_INIT0) {
-        for (long long j = j0; j < n; j += stride) {
-            const double gr = bz_assemble_grad(gs, j, n);
-            v.grad_x[j] = gr;
-            v.xeps[j] = v.x[j] + 1.0;   // lower_bound_smoothness_constant: x .+ 1
-        }
-    } else if (mode == MODE_INIT1) {
-        for (long long j = j0; j < n; j += stride) {
-            const double df = bz_assemble_grad(gs, j, n) - v.grad_x[j];
-            a[0] += df * df;
-        }
-    } else {
-        const double gamma = __ldcg(&st->gamma);
-        fresh = __ldcg(&st->grad_x_fresh);
-        if (g.kind == BZ_G_OBSTACLE_L1) {
-            // demo/obstacle.jl:67-81: soft threshold block 1 by gamma, max(0,.) on blocks 2-3, then
-            // complementarity zeroing between blocks 2 and 3 (tie zeroes the block-2 entry)
-            const long long N = g.N;
-            for (long long i = j0; i < N; i += stride) {
-                double gr[3], xv[3], zv[3];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const long long j = i + b * N;
-                    gr[b] = fresh ? bz_assemble_grad(gs, j, n) : v.grad_x[j];
-                    if (fresh) v.grad_x[j] = gr[b];
-                    xv[b] = v.x[j];
-                }
-                zv[0] = fmax(0.0, (xv[0] - gamma * gr[0]) - gamma);
-                zv[1] = fmax(0.0, xv[1] - gamma * gr[1]);
-                zv[2] = fmax(0.0, xv[2] - gamma * gr[2]);
-                if (zv[1] > zv[2]) zv[2] = 0.0; else zv[1] = 0.0;
-                a[2] += zv[0];
-#pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const long long j = i + b * N;
-                    const double r = xv[b] - zv[b];
-                    v.z[j] = zv[b];
-                    v.res[j] = r;
-                    a[0] += gr[b] * r;
-                    a[1] += r * r;
-                }
-            }
-        } else {
-            for (long long j = j0; j < n; j += stride) {
-                const double gr = fresh ? bz_assemble_grad(gs, j, n) : v.grad_x[j];
-                if (fresh) v.grad_x[j] = gr;
-                const double xj = v.x[j];
-                const double y = xj - gamma * gr;
-                const double z = bz_prox_elem(g, y, gamma, j, a[2]);
-                const double r = xj - z;
-                v.z[j] = z;
-                v.res[j] = r;
-                a[0] += gr * r;
-                a[1] += r * r;
-            }
-        }
-    }
-    bz_block_sum<3>(a, scratch);
-    const int nb = gridDim.x;
-    if (threadIdx.x == 0) {
-        part[blockIdx.x] = a[0];
-        part[nb + blockIdx.x] = a[1];
-        part[2 * nb + blockIdx.x] = a[2];
-    }
-    if (!bz_last_cta(counter, nb)) return;
-
-    // ---- last CTA: scalar bookkeeping
-    const double s0 = bz_final_sum(part, nb, scratch);
-    const double s1 = bz_final_sum(part + nb, nb, scratch);
-    const double s2 = bz_final_sum(part + 2 * nb, nb, scratch);
-    double fx = 0.0, lx = 0.0;
-    const bool need_value = (mode == MODE_INIT0) || (mode >= MODE_INITFB && fresh);
-    if (need_value) lx = bz_assemble_value(gs, st, scratch, fx);
-    if (threadIdx.x != 0) return;
-    if (mode == MODE_INIT0) {
-        st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
-        st->n_grad += 1;
-        st->grad_target = TGT_XEPS;
-        st->after_g = OP_F;
-        st->mode = MODE_INIT1;
-        st->next_op = OP_G;
-    } else if (mode == MODE_INIT1) {
-        const double Lest = sqrt(s0) / sqrt((double)n);
-        st->Lest = Lest;
-        st->gamma = st->alpha / Lest;     // L = 0 -> gamma = Inf, IEEE semantics as upstream
-        st->n_grad += 1;
-        st->mode = MODE_INITFB;
-        st->grad_x_fresh = 0;
-        st->next_op = OP_F;
-    } else {
-        if (fresh) {
-            st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
-            st->n_grad += 1;
-        }
-        const double gamma = st->gamma;
-        const double nrm = sqrt(s1);
-        const double nrm2 = nrm * nrm;                       // norm(res)^2
-        st->dot_gr = s0;
-        st->res_nrm2sq = nrm2;
-        st->f_up = st->f_x - s0 + ((st->alpha / gamma) / 2) * nrm2;   // f_model
-        st->g_z = bz_g_value_scale(g) * s2;
-        st->n_prox += 1;
-        st->grad_x_fresh = 0;
-        st->grad_target = TGT_Z;
-        st->after_g = OP_D;
-        st->next_op = OP_G;
-        st->out[0] = st->g_z; st->out[1] = s0; st->out[2] = s1;
-    }
-    __threadfence();
-}
-
-int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
-                    const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
-    const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
-    k_fstep<<<bz_vec_grid(ctx, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, g, part, counter,
-                                                                         force_mode);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// D: gradient at z is in; decide (A.4 backtrack_stepsize!, A.5 loop body, A.3 stop rule)
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
-    k_dstep(BzState* st, BzVecs v, BzGradSrc gs, double* part, unsigned int* counter) {
-    __shared__ double scratch[4 * 32];
-    if (__ldcg(&st->next_op) != OP_D) return;
-    const long long n = v.n;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const double gamma = __ldcg(&st->gamma);
-    const double gamma_h = gamma * 0.5;
-    double m1 = 0.0, m2 = 0.0;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const double gz = bz_assemble_grad(gs, j, n);
-        v.grad_z[j] = gz;
-        const double r = v.res[j], gx = v.grad_x[j];
-        m1 = bz_nanmax(m1, (r / gamma - gx) + gz);      // norm(res/gamma - grad_x + grad_z, Inf)
-        m2 = bz_nanmax(m2, (r / gamma_h - gx) + gz);
-    }
-    // NaN-propagating block max: encode NaN as +inf marker in a second lane
-    double a[2] = {m1 != m1 ? 0.0 : m1, m2 != m2 ? 0.0 : m2};
-    double f[2] = {m1 != m1 ? 1.0 : 0.0, m2 != m2 ? 1.0 : 0.0};
-    bz_block_max<2>(a, scratch);
-    bz_block_max<2>(f, scratch);
-    const int nb = gridDim.x;
-    if (threadIdx.x == 0) {
-        part[blockIdx.x] = f[0] > 0.0 ? NANQ : a[0];
-        part[nb + blockIdx.x] = f[1] > 0.0 ? NANQ : a[1];
-    }
-    if (!bz_last_cta(counter, nb)) return;
-
-    const double stop1 = bz_final_nanmax(part, nb, scratch);
-    const double stop2 = bz_final_nanmax(part + nb, nb, scratch);
-    double fx;
-    const double f_z = bz_assemble_value(gs, st, scratch, fx);
-    if (threadIdx.x != 0) return;
-
-    st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
-    st->n_grad += 1;
-    const int mode = st->mode;
-    const bool cond = (f_z > st->f_up + 10 * BZ_EPS * (1 + fabs(f_z))) && (gamma >= st->gamma_min);
-    bool end_iter = false;
-    double stopn = stop1;
-    if (mode == MODE_INITFB) {          // backtrack_stepsize! (A.4)
-        if (cond) {
-            st->gamma = gamma / 2;
-            st->grad_x_fresh = 0;
-            st->next_op = OP_F;
-        } else {
-            end_iter = true;
-            st->skip_update = 1;
-            st->mode = MODE_ITER;
-        }
-    } else {                            // A.5 loop body at backtrack index k
-        const int k = st->k_bt;
-        if (cond) {
-            st->gamma = gamma * 0.5;
-            st->currmem = 0; st->curridx = 0; st->H = 1.0;       // reset_direction_state!
-            if (k + 1 > st->max_backtracks) {                    // `continue` ran off the loop
-                end_iter = true;
-                stopn = stop2;
-            } else {
-                st->k_bt = k + 1;
-                st->grad_x_fresh = 0;
-                st->next_op = OP_F;
-            }
-        } else if (st->f_up + st->g_z <= st->thresh || k >= st->max_backtracks) {
-            end_iter = true;
-        } else {
-            st->tau = (k >= st->max_backtracks - 1) ? 0.0 : st->tau / 2;
-            st->k_bt = k + 1;
-            st->l_role = LROLE_INTERP;
-            st->next_op = OP_L;
-        }
-        if (end_iter) st->skip_update = 0;
-    }
-    if (end_iter) {
-        st->iter += 1;
-        st->stopnorm = stopn;
-        if (st->iter >= st->maxit || stopn <= st->tol) {
-            st->inner_status = (stopn <= st->tol) ? IST_CONVERGED : IST_MAXIT;
-            st->next_op = OP_DONE;
-        } else {
-            st->l_role = LROLE_NEWITER;
-            st->next_op = OP_L;
-        }
-    }
-    __threadfence();
-}
-
-int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
-                    unsigned int* counter) {
-    k_dstep<<<bz_vec_grid(ctx, v.n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, part, counter);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
-}
-
-// assemble a gradient + value for the parity entry point bz_auglag_grad
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
-    k_assemble(BzState* st, BzGradSrc gs, long long n, double* out, double* part,
-               unsigned int* counter) {
-    __shared__ double scratch[4 * 32];
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-        out[j] = bz_assemble_grad(gs, j, n);
-    if (!bz_last_cta(counter, gridDim.x)) return;
-    double fx;
-    const double lx = bz_assemble_value(gs, st, scratch, fx);
-    if (threadIdx.x == 0) {
-        st->al_fx = fx; st->al_lx = lx;
-        st->out[0] = lx; st->out[1] = fx;
-        __threadfence();
-    }
-}
-int bz_launch_assemble(bz_ctx* ctx, BzState* st, const BzGradSrc& gs, long long n, double* out,
-                       double* part, unsigned int* counter) {
-    k_assemble<<<bz_vec_grid(ctx, n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, gs, n, out, part, counter);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// L: L-BFGS update + two-loop + x_d (cooperative launch; all-CTA reductions in fixed order)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-struct TeamCtx {
-    BzTeam tm;
-    int idx;
-    double* scratch;   // >= 2*32 + 2 doubles of shared memory
-};
-
-template <int K>
-__device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
-    bz_block_sum<K>(v, tc.scratch);
-    const int nb = gridDim.x;
-    if (nb == 1) return;
-    const int j = tc.idx++;
-    unsigned int* bar = tc.tm.bars + tc.tm.parity * BZ_MAXBAR + j;
-    double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 2;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) sl[blockIdx.x * 2 + k] = v[k];
-        __threadfence();
-        atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < (unsigned int)nb) { }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 2 + k);
-            s = bz_warp_sum(s);
-            if (threadIdx.x == 0) tc.scratch[64 + k] = s;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(BZ_L_THREADS)
-    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
-    __shared__ double scratch[2 * 32 + 4];
-    // the other parity's barrier words are free again: reset them for the launch after this one
-    if (blockIdx.x == 0 && threadIdx.x < BZ_MAXBAR)
-        tm.bars[(1 - tm.parity) * BZ_MAXBAR + threadIdx.x] = 0u;
-    int role = force_role;
-    if (role < 0) {
-        if (__ldcg(&st->next_op) != OP_L) return;
-        role = __ldcg(&st->l_role);
-    }
-    const long long n = v.n;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-
-    if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
-        const double tau = __ldcg(&st->tau);
-        for (long long j = j0; j < n; j += stride)
-            v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
-        if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
-            st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-            st->next_op = OP_G;
-            __threadfence();
-        }
-        return;
-    }
-
-    TeamCtx tc{tm, 0, scratch};
-    const int M = __ldcg(&st->mem);
-    int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
-    double H = __ldcg(&st->H);
-    const int skip = __ldcg(&st->skip_update);
-    double ys[BZ_MAXMEM], al[BZ_MAXMEM];
-    for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; }
-
-    // ---- update!(H, x - x_prev, res - res_prev)
-    if (!skip && M > 0) {
-        double a[2] = {0.0, 0.0};
-        for (long long j = j0; j < n; j += stride) {
-            const double s = v.x[j] - v.x_prev[j], yv = v.res[j] - v.res_prev[j];
-            a[0] += s * yv;
-            a[1] += yv * yv;
-        }
-        team_sum<2>(tc, a);
-        if (a[0] > 0) {
-            curridx += 1;
-            if (curridx > M) curridx = 1;
-            currmem = currmem + 1 > M ? M : currmem + 1;
-            ys[curridx - 1] = a[0];
-            double* sm = v.sM + (size_t)(curridx - 1) * n;
-            double* ym = v.yM + (size_t)(curridx - 1) * n;
-            for (long long j = j0; j < n; j += stride) {
-                sm[j] = v.x[j] - v.x_prev[j];
-                ym[j] = v.res[j] - v.res_prev[j];
-            }
-            H = a[0] / a[1];
-        }
-    }
-
-    // ---- d = H * (-res): two-loop recursion, each axpy fused with the next dot product
-    int idx = curridx;
-    {
-        double a[1] = {0.0};
-        if (currmem > 0) {
-            const double* sm = v.sM + (size_t)(idx - 1) * n;
-            for (long long j = j0; j < n; j += stride) {
-                const double dj = -v.res[j];
-                v.d[j] = dj;
-                a[0] += sm[j] * dj;
-            }
-        } else {
-            for (long long j = j0; j < n; j += stride) v.d[j] = H * (-v.res[j]);
-        }
-        for (int t = 0; t < currmem; ++t) {       // loop1!: newest -> oldest
-            team_sum<1>(tc, a);
-            const int i = idx - 1;
-            const double alpha_i = a[0] / ys[i];
-            al[i] = alpha_i;
-            int idx2 = idx - 1;
-            if (idx2 == 0) idx2 = M;
-            const double* ym = v.yM + (size_t)i * n;
-            a[0] = 0.0;
-            if (t < currmem - 1) {
-                const double* sm2 = v.sM + (size_t)(idx2 - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
-                    const double dj = v.d[j] - alpha_i * ym[j];
-                    v.d[j] = dj;
-                    a[0] += sm2[j] * dj;
-                }
-            } else {                               // last: also d .= H .* d, then first dot of loop2!
-                int idn = idx2 + 1;
-                if (idn > M) idn = 1;
-                const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
-                    double dj = v.d[j] - alpha_i * ym[j];
-                    dj = H * dj;
-                    v.d[j] = dj;
-                    a[0] += ymn[j] * dj;
-                }
-            }
-            idx = idx2;
-        }
-        for (int t = 0; t < currmem; ++t) {       // loop2!: oldest -> newest
-            idx += 1;
-            if (idx > M) idx = 1;
-            team_sum<1>(tc, a);
-            const int i = idx - 1;
-            const double beta = a[0] / ys[i];
-            const double coef = al[i] - beta;
-            const double* sm = v.sM + (size_t)i * n;
-            a[0] = 0.0;
-            if (t < currmem - 1) {
-                int idn = idx + 1;
-                if (idn > M) idn = 1;
-                const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
-                    const double dj = v.d[j] + coef * sm[j];
-                    v.d[j] = dj;
-                    a[0] += ymn[j] * dj;
-                }
-            } else {
-                for (long long j = j0; j < n; j += stride) v.d[j] = v.d[j] + coef * sm[j];
-            }
-        }
-    }
-    // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
-    for (long long j = j0; j < n; j += stride) {
-        const double xj = v.x[j];
-        v.x_prev[j] = xj;
-        v.res_prev[j] = v.res[j];
-        const double xd = xj + v.d[j];
-        v.x_d[j] = xd;
-        v.x[j] = xd;
-        v.z_curr[j] = v.z[j];
-    }
-    if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
-        const double gamma = st->gamma;
-        const double FBE_x =
-            (st->f_x - st->dot_gr + ((st->alpha / gamma) / 2) * st->res_nrm2sq) + st->g_z;
-        const double sigma = st->beta * (0.5 / gamma) * (1 - st->alpha);
-        st->FBE_x = FBE_x;
-        st->sigma = sigma;
-        st->thresh = FBE_x - sigma * st->res_nrm2sq + 10 * BZ_EPS * (1 + fabs(FBE_x));
-        st->tau = 1.0;
-        st->k_bt = 1;
-        st->currmem = currmem; st->curridx = curridx; st->H = H;
-        for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; }
-        st->skip_update = 0;
-        st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-        st->next_op = OP_G;
-        __threadfence();
-    }
-}
-
-int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
-                    unsigned int* counter, int force_role) {
-    const int nb = bz_l_grid(ctx, v.n);
-    BzVecs vv = v;
-    BzTeam tt = tm;
-    void* args[] = {(void*)&st, (void*)&vv, (void*)&tt, (void*)&counter, (void*)&force_role};
-    BZ_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_lstep, dim3(nb), dim3(BZ_L_THREADS), args, 0,
-                                             ctx->stream));
-    ctx->n_launches++;
-    return BZ_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

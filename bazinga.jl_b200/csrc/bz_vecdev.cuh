@@ -1,0 +1,127 @@
+// Device helpers shared by the vector kernels (bz_vec.cu, bz_fbd.cu, bz_lbfgs.cu).
+#pragma once
+#include "bz_vec.cuh"
+
+#define NANQ __longlong_as_double(0x7ff8000000000000LL)
+
+__device__ __forceinline__ double bz_nanmax(double m, double v) {
+    v = fabs(v);
+    return (v != v || m != m) ? NANQ : fmax(m, v);
+}
+__device__ __forceinline__ double jl_max(double a, double b) {   // Julia max propagates NaN
+    return (a != a || b != b) ? NANQ : fmax(a, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient / value assembly from the provider outputs (auglagfun.jl:78-84)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double bz_assemble_grad(const BzGradSrc& gs, long long j, long long n) {
+    double dfx = 0.0, jtv = 0.0;
+    if (gs.Pf) {
+        double s = 0.0;
+        for (int p = 0; p < gs.npf; ++p) s += __ldcg(gs.Pf + (size_t)p * n + j);
+        dfx = s;
+    } else if (gs.Ef) {
+        dfx = __ldcg(gs.Ef + j);
+    }
+    if (gs.Pc) {
+        double s = 0.0;
+        for (int p = 0; p < gs.npc; ++p) s += __ldcg(gs.Pc + (size_t)p * n + j);
+        jtv = s;
+    } else if (gs.Ec) {
+        jtv = __ldcg(gs.Ec + j);
+    }
+    return dfx + jtv;   // dlx .= al.dfx .+ al.jtv
+}
+
+// fixed-order parallel sum of a global partial array by one whole CTA; result in every thread
+__device__ inline double bz_final_sum(const double* part, int n, double* scratch) {
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[0] += __ldcg(part + i);
+    bz_block_sum<1>(v, scratch);
+    return v[0];
+}
+__device__ inline double bz_final_nanmax(const double* part, int n, double* scratch) {
+    double m = 0.0;
+    int isnan_ = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = __ldcg(part + i);
+        if (v != v) isnan_ = 1; else m = fmax(m, v);
+    }
+    double a[1] = {m};
+    bz_block_max<1>(a, scratch);
+    double b[1] = {(double)isnan_};
+    bz_block_max<1>(b, scratch);
+    return b[0] > 0.0 ? NANQ : a[0];
+}
+
+// AL value from the provider partials:  lx = 0.5*sum(..) ; lx += fx ; lx -= musqy   (:78-82)
+__device__ inline double bz_assemble_value(const BzGradSrc& gs, BzState* st, double* scratch,
+                                           double& fx_out) {
+    const double slx = gs.lxpart ? bz_final_sum(gs.lxpart, gs.nlx, scratch) : 0.0;
+    const double sfx = gs.fxpart ? bz_final_sum(gs.fxpart, gs.nfx, scratch) : 0.0;
+    const double sfx2 = gs.fxpart2 ? bz_final_sum(gs.fxpart2, gs.nfx2, scratch) : 0.0;
+    double lx = 0.5 * slx;
+    double fx = gs.fxpart ? gs.fx_scale * sfx : 0.0;
+    if (gs.fxpart2) fx = fx + gs.fx_scale2 * sfx2;
+    lx += fx;
+    lx -= st->musqy;
+    fx_out = fx;
+    return lx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blocked assembly for providers that leave per-cluster partial rows (the dense passes): all
+// BZ_VEC_THREADS threads of the CTA cooperate on BZ_ASM_COLS consecutive columns -- thread
+// (grp, col) sums a contiguous quarter of the partial rows with its loads batched 8 deep, the four
+// group sums are combined in fixed order.  The value is returned in threads tid < BZ_ASM_COLS (for
+// column jb + tid); other threads get 0.  Deterministic, no atomics.  `sm` needs 2*256 doubles.
+// ---------------------------------------------------------------------------------------------
+#define BZ_ASM_COLS 64
+#define BZ_ASM_GROUPS (BZ_VEC_THREADS / BZ_ASM_COLS)
+
+__device__ __forceinline__ double bz_sum_group(const double* __restrict__ P, int np, int grp,
+                                               long long j, long long n) {
+    const int cnt = (np + BZ_ASM_GROUPS - 1) / BZ_ASM_GROUPS;
+    int p = grp * cnt;
+    int p1 = p + cnt;
+    if (p1 > np) p1 = np;
+    double s = 0.0;
+    const double* q = P + (size_t)p * n + j;
+    for (; p + 8 <= p1; p += 8, q += 8 * (size_t)n) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcg(q + (size_t)k * n);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; p < p1; ++p, q += n) s += __ldcg(q);
+    return s;
+}
+
+__device__ __forceinline__ bool bz_gs_blocked(const BzGradSrc& gs) { return gs.Pf || gs.Pc; }
+
+__device__ inline double bz_assemble_blocked(const BzGradSrc& gs, long long jb, long long n, double* sm) {
+    const int col = threadIdx.x & (BZ_ASM_COLS - 1), grp = threadIdx.x / BZ_ASM_COLS;
+    const long long j = jb + col;
+    double sf = 0.0, sc = 0.0;
+    if (j < n) {
+        if (gs.Pf) sf = bz_sum_group(gs.Pf, gs.npf, grp, j, n);
+        if (gs.Pc) sc = bz_sum_group(gs.Pc, gs.npc, grp, j, n);
+    }
+    sm[grp * BZ_ASM_COLS + col] = sf;
+    sm[BZ_VEC_THREADS + grp * BZ_ASM_COLS + col] = sc;
+    __syncthreads();
+    double out = 0.0;
+    if (grp == 0 && j < n) {
+        double dfx = 0.0, jtv = 0.0;
+        if (gs.Pf) dfx = (sm[col] + sm[BZ_ASM_COLS + col]) + (sm[2 * BZ_ASM_COLS + col] + sm[3 * BZ_ASM_COLS + col]);
+        else if (gs.Ef) dfx = __ldcg(gs.Ef + j);
+        const double* sc4 = sm + BZ_VEC_THREADS;
+        if (gs.Pc) jtv = (sc4[col] + sc4[BZ_ASM_COLS + col]) + (sc4[2 * BZ_ASM_COLS + col] + sc4[3 * BZ_ASM_COLS + col]);
+        else if (gs.Ec) jtv = __ldcg(gs.Ec + j);
+        out = dfx + jtv;   // dlx .= al.dfx .+ al.jtv
+    }
+    __syncthreads();
+    return out;
+}

