@@ -59,6 +59,7 @@ class Result(C.Structure):
         ("objective", C.c_double), ("n_grad", C.c_int64), ("n_prox", C.c_int64),
         ("n_launches", C.c_int64), ("dominant_kernel_ms", C.c_double),
         ("dominant_kernel_launches", C.c_int64),
+        ("kind_ms", C.c_double * 4), ("kind_launches", C.c_int64 * 4),
     ]
 
 

@@ -93,6 +93,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     if (target < 0) {
         if (__ldcg(&a.st->next_op) != OP_G) return;   // both CTAs of a cluster take the same branch
         target = __ldcg(&a.st->grad_target);
+        if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
     }
     const double* __restrict__ xsrc = a.src[target];
 
@@ -250,6 +251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     if (bz_last_cta(a.counter, gridDim.x)) {
         if (tid == 0 && a.set_after) {
             a.st->next_op = a.st->after_g;
+            if (a.force_target < 0) bz_toc(a.st, 0);
             __threadfence();
         }
     }

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (mode < 0) {
         if (__ldcg(&st->next_op) != OP_F) return;
         mode = __ldcg(&st->mode);
+        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 2);
     }
     const long long n = v.n;
     const bool blocked = bz_gs_blocked(gs);
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
         st->next_op = OP_G;
         st->out[0] = st->g_z; st->out[1] = s0; st->out[2] = s1;
     }
+    if (force_mode < 0) bz_toc(st, 2);
     __threadfence();
 }
 
@@ -171,6 +173,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     __shared__ double scratch[4 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
     if (__ldcg(&st->next_op) != OP_D) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 3);
     const long long n = v.n;
     const double gamma = __ldcg(&st->gamma);
     const double gamma_h = gamma * 0.5;
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
             st->next_op = OP_L;
         }
     }
+    bz_toc(st, 3);
     __threadfence();
 }
 

@@ -61,7 +61,22 @@ struct BzState {
     long long tot_inner_it, subsolver_maxit;
     // generic scalar outputs of the parity entry points
     double out[8];
+    // device-side stopwatch per kernel kind (0 G dense, 1 L, 2 F, 3 D): %globaltimer at the start of a
+    // launch that really runs and at its last-CTA epilogue (diagnostic breakdown; the roofline number
+    // of the dominant kernel uses CUDA events, see bz_solver.cu)
+    unsigned long long t0[4], tsum[4], tcnt[4];
 };
+
+__device__ __forceinline__ unsigned long long bz_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void bz_tic(BzState* st, int kind) { st->t0[kind] = bz_globaltimer(); }
+__device__ __forceinline__ void bz_toc(BzState* st, int kind) {
+    st->tsum[kind] += bz_globaltimer() - st->t0[kind];
+    st->tcnt[kind] += 1;
+}
 
 // Where the assembled gradient comes from:  grad = dfx_term + jtv_term  (auglagfun.jl:84), each
 // term being 0, a vector, or a sum of per-CTA partial rows written by a dense pass.

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
     if (role < 0) {
         if (__ldcg(&st->next_op) != OP_L) return;
         role = __ldcg(&st->l_role);
+        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 1);
     }
     const long long n = v.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
         if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
             st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
             st->next_op = OP_G;
+            if (force_role < 0) bz_toc(st, 1);
             __threadfence();
         }
         return;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
         st->skip_update = 0;
         st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
         st->next_op = OP_G;
+        if (force_role < 0) bz_toc(st, 1);
         __threadfence();
     }
 }
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(LC_THREADS)
     if (role < 0) {
         if (__ldcg(&st->next_op) != OP_L) return;     // uniform over the cluster
         role = __ldcg(&st->l_role);
+        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 1);
     }
     ClusterRed cr{wpart, slots, lc_cluster_rank(), lc_cluster_size(), 0};
     const long long n = v.n;
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(LC_THREADS)
         if (cr.rank == 0 && threadIdx.x == 0) {
             st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
             st->next_op = OP_G;
+            if (force_role < 0) bz_toc(st, 1);
             __threadfence();
         }
         return;
@@ -422,6 +427,7 @@ __global__ void __launch_bounds__(LC_THREADS)
         st->skip_update = 0;
         st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
         st->next_op = OP_G;
+        if (force_role < 0) bz_toc(st, 1);
         __threadfence();
     }
 #undef LC_FOR

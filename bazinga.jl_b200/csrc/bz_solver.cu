@@ -650,6 +650,10 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     res->dominant_kernel_ms = 0.0;
     res->dominant_kernel_launches = 0;
     if (ctx->profiling) collect_dominant(p, n_grad + 1, res);
+    for (int k = 0; k < 4; ++k) {
+        res->kind_ms[k] = 1e-6 * (double)h->tsum[k];
+        res->kind_launches[k] = (int64_t)h->tcnt[k];
+    }
     res->elapsed_time =
         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return BZ_OK;

@@ -224,6 +224,7 @@ def run_b200(args):
     ctx.timer_start()
     its = grads = launches = dom_launches = 0
     dom_ms = 0.0
+    kind_ms, kind_n = [0.0] * 4, [0] * 4
     last = None
     for _ in range(args.steps):
         x, y, s, mu, res = prob.alps(x0, y0, opts)
@@ -232,6 +233,9 @@ def run_b200(args):
         launches += res.n_launches
         dom_ms += res.dominant_kernel_ms
         dom_launches += res.dominant_kernel_launches
+        for k in range(4):
+            kind_ms[k] += res.kind_ms[k]
+            kind_n[k] += res.kind_launches[k]
         last = res
     ms = ctx.timer_stop()
     barrier()
@@ -294,7 +298,10 @@ def run_b200(args):
             "inner_iterations": its_all, "al_gradients_per_iteration": grads / max(1, its),
             "outer_iterations_last_step": last.tot_it, "status_last_step": bz.STATUS_SYMBOLS[last.status],
             "e2e": {"value": e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches,
+            "kernel_breakdown_us": {nm: (1e3 * kind_ms[k] / kind_n[k] if kind_n[k] else None) for k, nm in
+                                    enumerate(["al_gradient", "lbfgs_step", "fb_step", "decision_step"])},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     prob.close()

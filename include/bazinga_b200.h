@@ -143,6 +143,10 @@ typedef struct {
     int64_t n_launches;           /* kernels launched by the library for this call */
     double dominant_kernel_ms;    /* CUDA-event time summed over the dominant kernel's launches */
     int64_t dominant_kernel_launches;
+    /* device-stopwatch breakdown per kernel kind: 0 AL-gradient provider, 1 L-BFGS step, 2 forward-
+     * backward step, 3 decision step -- summed over the launches that really ran */
+    double kind_ms[4];
+    int64_t kind_launches[4];
 } bz_result;
 
 /* ---- context ------------------------------------------------------------------------------------ */
