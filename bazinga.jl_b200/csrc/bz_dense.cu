@@ -64,6 +64,32 @@ __device__ __forceinline__ void cluster_arrive() {
 __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// remote store of one double into the peer CTA's shared memory that completes (8 bytes of tx) on the
+// peer's mbarrier: the DSMEM-native signal, no cluster barrier / membar in the row loop
+__device__ __forceinline__ void st_async_peer_f64(void* local_data_ptr, uint64_t* local_bar_ptr,
+                                                  uint32_t peer_rank, double v) {
+    uint32_t rdata, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdata) : "r"(smem_u32(local_data_ptr)), "r"(peer_rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(local_bar_ptr)), "r"(peer_rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(rdata),
+                 "d"(v), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void st_peer_f64(void* local_smem_ptr, uint32_t peer_rank, double v) {
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
@@ -87,6 +113,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + DA_RING_DOUBLES);    // [DA_MAXSLOTS]
     double* wsum = reinterpret_cast<double*>(full + DA_MAXSLOTS);            // [2][16] warp partials
     double* xchg = wsum + 32;                                                 // [2]: peer's row dots
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(xchg + 2);                   // [2]: their arrival barriers
 
     const int tid = threadIdx.x;
     int target = a.force_target;
@@ -128,13 +155,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         acc[c] = make_double2(0.0, 0.0);
     }
 
-    if (BULK) {
-        if (tid == 0) {
+    if (tid == 0) {
+        if (BULK)
             for (int s = 0; s < DA_MAXSLOTS; ++s) mbar_init(&full[s], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+        mbar_init(&xbar[0], 1);
+        mbar_init(&xbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    cluster_arrive();   // the peer's barriers exist before anything is sent to them
+    cluster_wait();
 
     // bring local row `row` into ring slot `slot`: one bulk copy + one mbarrier phase (BULK), or a
     // cooperative synchronous fill (ragged / odd shapes)
@@ -212,7 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         const double part = bz_warp_sum(pa + pb);
         // ---- finish row i-1 (its peer dot arrived with the previous cluster-barrier phase)
         if (i > 0) {
-            cluster_wait();
+            mbar_wait_cluster(&xbar[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
             const double peer = xchg[(i - 1) & 1];
             finish_row(i - 1, slot_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
         }
@@ -225,15 +255,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
 #pragma unroll
         for (int w = 0; w < 8; ++w) t8[w] = ws[2 * w] + ws[2 * w + 1];
         const double own = ((t8[0] + t8[1]) + (t8[2] + t8[3])) + ((t8[4] + t8[5]) + (t8[6] + t8[7]));
-        if (tid == 0) st_peer_f64(&xchg[i & 1], rank ^ 1u, own);
+        if (tid == 0) {
+            mbar_expect_tx(&xbar[i & 1], 8);                                  // arm my receive of row i
+            st_async_peer_f64(&xchg[i & 1], &xbar[i & 1], rank ^ 1u, own);   // send my half to the peer
+        }
         __syncwarp();
-        cluster_arrive();
         own_prev = own; b_prev = b_i; mu_prev = mu_i; muy_prev = muy_i;
         slot_prev = slot;
         if (++slot == nslots) { slot = 0; par ^= 1; }
     }
     if (nrows > 0) {
-        cluster_wait();
+        mbar_wait_cluster(&xbar[(nrows - 1) & 1], (uint32_t)(((nrows - 1) >> 1) & 1));
         const double peer = xchg[(nrows - 1) & 1];
         finish_row(nrows - 1, slot_prev, own_prev, peer, b_prev, mu_prev, muy_prev);
     }
@@ -247,6 +279,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         if (lc + 1 < W) Pq[col0 + lc + 1] = acc[c].y;
     }
     if (rank == 0 && tid == 0) a.lxpart[q] = lx;
+    cluster_arrive();   // neither CTA exits while the other may still address its shared memory
+    cluster_wait();
 
     if (bz_last_cta(a.counter, gridDim.x)) {
         if (tid == 0 && a.set_after) {
@@ -259,7 +293,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) {
     static bool attr_set = false;
-    const size_t smem = (size_t)DA_RING_DOUBLES * 8 + DA_MAXSLOTS * 8 + 32 * 8 + 4 * 8;
+    const size_t smem = (size_t)DA_RING_DOUBLES * 8 + DA_MAXSLOTS * 8 + 32 * 8 + 4 * 8 + 2 * 8;
     if (!attr_set) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

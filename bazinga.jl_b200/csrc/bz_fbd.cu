@@ -25,7 +25,7 @@ static int fbd_grid(const bz_ctx* ctx, const BzGradSrc& gs, long long items) {
 __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_fstep(BzState* st, BzVecs v, BzGradSrc gs, BzGParams g, double* part, unsigned int* counter,
             int force_mode) {
-    __shared__ double scratch[4 * 32];
+    __shared__ double scratch[6 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
     int mode = force_mode;
     if (mode < 0) {
@@ -111,13 +111,16 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (!bz_last_cta(counter, nb)) return;
 
     // ---- last CTA: scalar bookkeeping
-    const double s0 = bz_final_sum(part, nb, scratch);
-    const double s1 = bz_final_sum(part + nb, nb, scratch);
-    const double s2 = bz_final_sum(part + 2 * nb, nb, scratch);
-    double fx = 0.0, lx = 0.0;
     const bool need_value = (mode == MODE_INIT0) || (mode >= MODE_INITFB && fresh);
-    if (need_value) lx = bz_assemble_value(gs, st, scratch, fx);
+    const double* const ptrs[6] = {part, part + nb, part + 2 * nb, need_value ? gs.lxpart : nullptr,
+                                   need_value ? gs.fxpart : nullptr, need_value ? gs.fxpart2 : nullptr};
+    const int counts[6] = {nb, nb, nb, gs.nlx, gs.nfx, gs.nfx2};
+    double sums[6];
+    bz_final_sums<6>(ptrs, counts, sums, scratch);
     if (threadIdx.x != 0) return;
+    const double s0 = sums[0], s1 = sums[1], s2 = sums[2];
+    double fx = 0.0, lx = 0.0;
+    if (need_value) lx = bz_value_from_sums(gs, st->musqy, sums[3], sums[4], sums[5], fx);
     if (mode == MODE_INIT0) {
         st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
         st->n_grad += 1;
@@ -170,7 +173,7 @@ int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_dstep(BzState* st, BzVecs v, BzGradSrc gs, double* part, unsigned int* counter) {
-    __shared__ double scratch[4 * 32];
+    __shared__ double scratch[6 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
     if (__ldcg(&st->next_op) != OP_D) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 3);
@@ -209,9 +212,13 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 
     const double stop1 = bz_final_nanmax(part, nb, scratch);
     const double stop2 = bz_final_nanmax(part + nb, nb, scratch);
-    double fx;
-    const double f_z = bz_assemble_value(gs, st, scratch, fx);
+    const double* const ptrs[3] = {gs.lxpart, gs.fxpart, gs.fxpart2};
+    const int counts[3] = {gs.nlx, gs.nfx, gs.nfx2};
+    double sums[3];
+    bz_final_sums<3>(ptrs, counts, sums, scratch);
     if (threadIdx.x != 0) return;
+    double fx;
+    const double f_z = bz_value_from_sums(gs, st->musqy, sums[0], sums[1], sums[2], fx);
 
     st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
     st->n_grad += 1;

@@ -356,48 +356,50 @@ __global__ void __launch_bounds__(LC_THREADS)
             H = a[0] / a[1];
         }
     }
-    // ---- d = H * (-res): two-loop recursion, d in registers
+    // ---- d = H * (-res): two-loop recursion, d in registers.  The 2*currmem steps are run as one
+    // sequence (loop1!: newest -> oldest with (dot, axpy) vectors (s_i, y_i); loop2!: oldest -> newest
+    // with (y_i, s_i)); the vectors of step k+1 are loaded BEFORE the cluster reduction of step k so
+    // their L2 latency hides behind it.
     LC_FOR(k) d[k] = -rv[k];
-    int idx = curridx;
-    for (int t = 0; t < currmem; ++t) {           // loop1!: newest -> oldest
-        const int i = idx - 1;
-        const double* sm = v.sM + (size_t)i * n;
-        const double* ym = v.yM + (size_t)i * n;
-        double yreg[EPT];
-        double a[1] = {0.0};
-        LC_FOR(k) {
-            const long long j = LC_J(k);
-            const double sj = j < n ? __ldcg(sm + j) : 0.0;
-            yreg[k] = j < n ? __ldcg(ym + j) : 0.0;
-            a[0] += sj * d[k];
+    const int nsteps = 2 * currmem;
+    auto hist_index = [&](int kk) {      // ring slot visited by step kk
+        const int k1 = kk < currmem ? kk : nsteps - 1 - kk;
+        return ((curridx - 1 - k1) % M + M) % M;
+    };
+    auto load_step = [&](int kk, double (&A)[EPT], double (&B)[EPT]) {
+        if (kk >= nsteps) return;
+        const int i = hist_index(kk);
+        const double* pa = (kk < currmem ? v.sM : v.yM) + (size_t)i * n;
+        const double* pb = (kk < currmem ? v.yM : v.sM) + (size_t)i * n;
+        LC_FOR(e) {
+            const long long j = LC_J(e);
+            A[e] = j < n ? __ldcg(pa + j) : 0.0;
+            B[e] = j < n ? __ldcg(pb + j) : 0.0;
         }
-        cluster_sum<1>(cr, a);
-        const double alpha_i = a[0] / ys[i];
-        al[i] = alpha_i;
-        LC_FOR(k) d[k] = d[k] - alpha_i * yreg[k];
-        idx -= 1;
-        if (idx == 0) idx = M;
-    }
-    LC_FOR(k) d[k] = H * d[k];
-    for (int t = 0; t < currmem; ++t) {           // loop2!: oldest -> newest
-        idx += 1;
-        if (idx > M) idx = 1;
-        const int i = idx - 1;
-        const double* sm = v.sM + (size_t)i * n;
-        const double* ym = v.yM + (size_t)i * n;
-        double sreg[EPT];
+    };
+    double ra[EPT], rb[EPT];
+    load_step(0, ra, rb);
+    for (int kk = 0; kk < nsteps; ++kk) {
+        if (kk == currmem) { LC_FOR(e) d[e] = H * d[e]; }      // d .= L.H .* d between the loops
         double a[1] = {0.0};
-        LC_FOR(k) {
-            const long long j = LC_J(k);
-            const double yj = j < n ? __ldcg(ym + j) : 0.0;
-            sreg[k] = j < n ? __ldcg(sm + j) : 0.0;
-            a[0] += yj * d[k];
-        }
+        LC_FOR(e) a[0] += ra[e] * d[e];
+        double na[EPT], nb[EPT];
+        LC_FOR(e) { na[e] = 0.0; nb[e] = 0.0; }
+        load_step(kk + 1, na, nb);
         cluster_sum<1>(cr, a);
-        const double beta = a[0] / ys[i];
-        const double coef = al[i] - beta;
-        LC_FOR(k) d[k] = d[k] + coef * sreg[k];
+        const int i = hist_index(kk);
+        if (kk < currmem) {
+            const double alpha_i = a[0] / ys[i];
+            al[i] = alpha_i;
+            LC_FOR(e) d[e] = d[e] - alpha_i * rb[e];
+        } else {
+            const double beta = a[0] / ys[i];
+            const double coef = al[i] - beta;
+            LC_FOR(e) d[e] = d[e] + coef * rb[e];
+        }
+        LC_FOR(e) { ra[e] = na[e]; rb[e] = nb[e]; }
     }
+    if (currmem == 0) { LC_FOR(e) d[e] = H * d[e]; }
     // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
     LC_FOR(k) {
         const long long j = LC_J(k);

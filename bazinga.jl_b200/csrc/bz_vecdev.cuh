@@ -55,6 +55,31 @@ __device__ inline double bz_final_nanmax(const double* part, int n, double* scra
     return b[0] > 0.0 ? NANQ : a[0];
 }
 
+// several fixed-order partial-array sums with ONE block reduction (last-CTA epilogues)
+template <int K>
+__device__ inline void bz_final_sums(const double* const (&ptrs)[K], const int (&counts)[K],
+                                     double (&out)[K], double* scratch) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double s = 0.0;
+        if (ptrs[k])
+            for (int i = threadIdx.x; i < counts[k]; i += blockDim.x) s += __ldcg(ptrs[k] + i);
+        out[k] = s;
+    }
+    bz_block_sum<K>(out, scratch);
+}
+// AL value given the three provider sums (auglagfun.jl:78-82)
+__device__ __forceinline__ double bz_value_from_sums(const BzGradSrc& gs, double musqy, double slx,
+                                                     double sfx, double sfx2, double& fx_out) {
+    double lx = 0.5 * slx;
+    double fx = gs.fxpart ? gs.fx_scale * sfx : 0.0;
+    if (gs.fxpart2) fx = fx + gs.fx_scale2 * sfx2;
+    lx += fx;
+    lx -= musqy;
+    fx_out = fx;
+    return lx;
+}
+
 // AL value from the provider partials:  lx = 0.5*sum(..) ; lx += fx ; lx -= musqy   (:78-82)
 __device__ inline double bz_assemble_value(const BzGradSrc& gs, BzState* st, double* scratch,
                                            double& fx_out) {
