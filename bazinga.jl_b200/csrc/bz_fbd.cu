@@ -9,6 +9,13 @@
 // Compiled with -fmad=false (the reference's Julia broadcasts are not contracted).
 #include "bz_vecdev.cuh"
 
+// The dense passes run with the maximum shared-memory carve-out; asking for the same carve-out here
+// keeps the SMs from being reconfigured at every kernel boundary of the cycle.
+template <typename Kern>
+static void prefer_max_smem(Kern kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 static int fbd_grid(const bz_ctx* ctx, const BzGradSrc& gs, long long items) {
     if (gs.Pf || gs.Pc) {
         long long nb = (items + BZ_ASM_COLS - 1) / BZ_ASM_COLS;
@@ -161,6 +168,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
                     const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
     const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
+    static bool once = false;
+    if (!once) { prefer_max_smem(k_fstep); once = true; }
     k_fstep<<<fbd_grid(ctx, gs, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, g, part, counter,
                                                                           force_mode);
     ctx->n_launches++;
@@ -276,6 +285,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 
 int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
                     unsigned int* counter) {
+    static bool once = false;
+    if (!once) { prefer_max_smem(k_dstep); once = true; }
     k_dstep<<<fbd_grid(ctx, gs, v.n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, part, counter);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());

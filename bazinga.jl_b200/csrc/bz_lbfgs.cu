@@ -243,38 +243,80 @@ __device__ __forceinline__ void lc_st_remote(void* local_ptr, uint32_t rank, dou
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
 }
 
+__device__ __forceinline__ void lc_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void lc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lc_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void lc_mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = lc_smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// one double into CTA `rank`'s shared memory, completing 8 bytes of tx on that CTA's mbarrier
+__device__ __forceinline__ void lc_st_async(void* local_data, uint64_t* local_bar, uint32_t rank, double v) {
+    uint32_t rdata, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdata) : "r"(lc_smem_u32(local_data)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(lc_smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(rdata),
+                 "d"(v), "r"(rbar)
+                 : "memory");
+}
+
 struct ClusterRed {
     double* wpart;     // [2][8] warp partials (K <= 2)
     double* slots;     // [2 parities][LC_MAXCS][2]
+    uint64_t* bars;    // [2 parities]: all senders' stores of a round complete their tx here
     uint32_t rank, cs;
     int round;
 };
 
-// all-cluster sum of K values per thread; result in every thread of every CTA, identical bits
+// All-cluster sum of K values per thread; result in every thread of every CTA, identical bits.
+// Warp shuffles -> shared-memory block sum -> all-to-all through distributed shared memory:
+// every CTA st.async's its block sums into every CTA's slot row, each store completing on the
+// receiver's mbarrier, so there is no cluster barrier (and no membar) per reduction.  Two slot
+// sets alternate; a CTA can only be one round ahead of the slowest CTA (it needs everybody's
+// value of round r+1 before it can send round r+2), so a set is never overwritten while in use.
 template <int K>
 __device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = bz_warp_sum(v[k]);
+    const int par = cr.round & 1;
+    const uint32_t phase = (uint32_t)((cr.round >> 1) & 1);
+    cr.round++;
+    double* wp = cr.wpart + par * 16;
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) cr.wpart[k * 8 + warp] = v[k];
+        for (int k = 0; k < K; ++k) wp[k * 8 + warp] = v[k];
     }
     __syncthreads();
-    const int par = cr.round & 1;
-    cr.round++;
     double* sl = cr.slots + par * (LC_MAXCS * 2);
+    uint64_t* bar = cr.bars + par;
     if (threadIdx.x < cr.cs) {     // thread t sends this CTA's block sums to CTA t
+        if (threadIdx.x == 0) lc_mbar_expect_tx(bar, cr.cs * K * 8u);
         double bs[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double* w = cr.wpart + k * 8;
+            const double* w = wp + k * 8;
             bs[k] = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) lc_st_remote(&sl[cr.rank * 2 + k], threadIdx.x, bs[k]);
+        for (int k = 0; k < K; ++k) lc_st_async(&sl[cr.rank * 2 + k], bar, threadIdx.x, bs[k]);
     }
-    lc_cluster_sync();             // release/acquire: remote stores are visible; also a CTA barrier
+    lc_mbar_wait_cluster(bar, phase);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double s = 0.0;
@@ -286,15 +328,22 @@ __device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
 template <int EPT>
 __global__ void __launch_bounds__(LC_THREADS)
     k_lstep_cluster(BzState* st, BzVecs v, int force_role) {
-    __shared__ double wpart[2 * 8];
+    __shared__ double wpart[2 * 2 * 8];
     __shared__ double slots[2 * LC_MAXCS * 2];
+    __shared__ uint64_t bars[2];
     int role = force_role;
     if (role < 0) {
         if (__ldcg(&st->next_op) != OP_L) return;     // uniform over the cluster
         role = __ldcg(&st->l_role);
         if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 1);
     }
-    ClusterRed cr{wpart, slots, lc_cluster_rank(), lc_cluster_size(), 0};
+    ClusterRed cr{wpart, slots, bars, lc_cluster_rank(), lc_cluster_size(), 0};
+    if (threadIdx.x == 0) {
+        lc_mbar_init(&bars[0], 1);
+        lc_mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    lc_cluster_sync();   // every CTA's barriers exist before anything is sent to them
     const long long n = v.n;
     const int stride = (int)(cr.cs * LC_THREADS);
     const int j0 = (int)(cr.rank * LC_THREADS + threadIdx.x);
@@ -439,6 +488,13 @@ __global__ void __launch_bounds__(LC_THREADS)
 int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
                     unsigned int* counter, int force_role) {
     const long long per_cta = (long long)LC_THREADS * LC_EPT;
+    static bool once = false;
+    if (!once) {   // same carve-out as the dense passes: no SM reconfiguration inside the cycle
+        cudaFuncSetAttribute(k_lstep_cluster<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_lstep_cluster<LC_EPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_lstep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        once = true;
+    }
     if (v.n <= per_cta * LC_MAXCS) {
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
