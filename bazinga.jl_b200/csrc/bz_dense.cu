@@ -53,6 +53,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// A is streamed exactly once per pass and is 4x larger than L2: load it with an evict-first policy so
+// the megabytes of solver vectors / partial rows stay L2-resident between the kernels of the cycle
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -166,6 +181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     cluster_arrive();   // the peer's barriers exist before anything is sent to them
     cluster_wait();
 
+    const uint64_t l2pol = l2_evict_first_policy();
     // bring local row `row` into ring slot `slot`: one bulk copy + one mbarrier phase (BULK), or a
     // cooperative synchronous fill (ragged / odd shapes)
     auto issue_row = [&](int row, int slot) {
@@ -174,7 +190,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
             if (tid == 0 && W > 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&full[slot], row_bytes);
-                bulk_g2s(ring + (size_t)slot * stride, src, row_bytes, &full[slot]);
+                if (a.evict_first)
+                    bulk_g2s_hint(ring + (size_t)slot * stride, src, row_bytes, &full[slot], l2pol);
+                else
+                    bulk_g2s(ring + (size_t)slot * stride, src, row_bytes, &full[slot]);
                 const int pf = row + a.l2_prefetch_rows;
                 if (a.l2_prefetch_rows > 0 && pf < nrows)
                     l2_prefetch(a.A + (r0 + pf) * a.lda + col0, row_bytes);

@@ -29,6 +29,7 @@ struct BzDenseArgs {
     double* lxpart;        // nclusters partial sums of (t-s)^2/mu
     unsigned int* counter;
     int set_after;         // last CTA sets st->next_op = st->after_g
+    int evict_first;       // stream A with an L2 evict-first policy
     int l2_prefetch_rows;  // >0: cp.async.bulk.prefetch.L2 this many rows ahead of each issue
 };
 

@@ -313,6 +313,7 @@ struct bz_ctx {
     size_t ev_used = 0;
     long long n_launches = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu
 };
 

@@ -102,6 +102,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     }
     BZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     if (const char* e = getenv("BZ_L2_PREFETCH_ROWS")) ctx->l2_prefetch_rows = atoi(e);
+    if (const char* e = getenv("BZ_EVICT_FIRST")) ctx->evict_first = atoi(e);
     *out = ctx;
     return BZ_OK;
 }
@@ -430,6 +431,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.cx = nullptr; a.s = nullptr; a.yupd = nullptr;
         a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
         a.l2_prefetch_rows = ctx->l2_prefetch_rows;
+        a.evict_first = ctx->evict_first;
         BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         p->nfx = std::min<long long>(ctx->num_sms, (p->n + 7) / 8);
@@ -447,6 +449,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.cx = p->cx; a.s = p->s; a.yupd = p->yupd;
         a.P = p->Pc; a.lxpart = p->lxpart; a.counter = p->counters + 1; a.set_after = 1;
         a.l2_prefetch_rows = ctx->l2_prefetch_rows;
+        a.evict_first = ctx->evict_first;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (ctx->profiling) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
         BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
