@@ -131,6 +131,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     uint64_t* xbar = reinterpret_cast<uint64_t*>(xchg + 2);                   // [2]: their arrival barriers
 
     const int tid = threadIdx.x;
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     int target = a.force_target;
     if (target < 0) {
         if (__ldcg(&a.st->next_op) != OP_G) return;   // both CTAs of a cluster take the same branch
@@ -322,13 +324,8 @@ int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) 
     }
     const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
-    if (bulk)
-        k_dense_algrad<true><<<2 * nclusters, DA_THREADS, smem, ctx->stream>>>(args);
-    else
-        k_dense_algrad<false><<<2 * nclusters, DA_THREADS, smem, ctx->stream>>>(args);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
+    if (bulk) return bz_launch_pdl(ctx, k_dense_algrad<true>, dim3(2 * nclusters), dim3(DA_THREADS), smem, 0, args);
+    return bz_launch_pdl(ctx, k_dense_algrad<false>, dim3(2 * nclusters), dim3(DA_THREADS), smem, 0, args);
 }
 
 

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
             int force_mode) {
     __shared__ double scratch[6 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     int mode = force_mode;
     if (mode < 0) {
         if (__ldcg(&st->next_op) != OP_F) return;
@@ -170,11 +172,8 @@ int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
     const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
     static bool once = false;
     if (!once) { prefer_max_smem(k_fstep); once = true; }
-    k_fstep<<<fbd_grid(ctx, gs, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, g, part, counter,
-                                                                          force_mode);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
+    return bz_launch_pdl(ctx, k_fstep, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+                         part, counter, force_mode);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,6 +183,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_dstep(BzState* st, BzVecs v, BzGradSrc gs, double* part, unsigned int* counter) {
     __shared__ double scratch[6 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     if (__ldcg(&st->next_op) != OP_D) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 3);
     const long long n = v.n;
@@ -287,10 +288,8 @@ int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
                     unsigned int* counter) {
     static bool once = false;
     if (!once) { prefer_max_smem(k_dstep); once = true; }
-    k_dstep<<<fbd_grid(ctx, gs, v.n), BZ_VEC_THREADS, 0, ctx->stream>>>(st, v, gs, part, counter);
-    ctx->n_launches++;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
+    return bz_launch_pdl(ctx, k_dstep, dim3(fbd_grid(ctx, gs, v.n)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, part,
+                         counter);
 }
 
 // assemble a gradient + value for the parity entry point bz_auglag_grad

@@ -313,11 +313,50 @@ struct bz_ctx {
     size_t ev_used = 0;
     long long n_launches = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
+    int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu
 };
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);
+
+// Programmatic dependent launch (PDL): the kernels of the PANOC+ cycle are launched with
+// programmatic stream serialization, so the next kernel's CTAs are scheduled while the previous
+// kernel drains; each such kernel starts with bz_pdl_wait() (griddepcontrol.wait: everything the
+// predecessor wrote is visible after it) and immediately allows its own dependents to pre-launch.
+__device__ __forceinline__ void bz_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void bz_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+int bz_launch_pdl(bz_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, int cluster_x,
+                  Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (ctx->pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster_x > 0) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = cluster_x;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    ctx->n_launches++;
+    if (e != cudaSuccess) return bz_fail(ctx, BZ_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e));
+    return BZ_OK;
+}
 #define BZ_CUDA(ctx, call)                                                                   \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \

@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(LC_THREADS)
     __shared__ double wpart[2 * 2 * 8];
     __shared__ double slots[2 * LC_MAXCS * 2];
     __shared__ uint64_t bars[2];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     int role = force_role;
     if (role < 0) {
         if (__ldcg(&st->next_op) != OP_L) return;     // uniform over the cluster
@@ -499,24 +501,9 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
         while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(cs);
-        cfg.blockDim = dim3(LC_THREADS);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = cs;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
         if ((long long)cs * LC_THREADS * 8 >= v.n)
-            BZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstep_cluster<8>, st, v, force_role));
-        else
-            BZ_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstep_cluster<LC_EPT>, st, v, force_role));
-        ctx->n_launches++;
-        return BZ_OK;
+            return bz_launch_pdl(ctx, k_lstep_cluster<8>, dim3(cs), dim3(LC_THREADS), 0, cs, st, v, force_role);
+        return bz_launch_pdl(ctx, k_lstep_cluster<LC_EPT>, dim3(cs), dim3(LC_THREADS), 0, cs, st, v, force_role);
     }
     const int nb = bz_l_grid(ctx, v.n);
     BzVecs vv = v;
