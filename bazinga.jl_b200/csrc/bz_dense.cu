@@ -76,6 +76,9 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_arrive() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() {   // no membar: pairs with fence.mbarrier_init
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -180,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    cluster_arrive();   // the peer's barriers exist before anything is sent to them
+    cluster_arrive_relaxed();   // the peer's barriers exist before anything is sent to them
     cluster_wait();
 
     const uint64_t l2pol = l2_evict_first_policy();
@@ -300,8 +303,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         if (lc + 1 < W) Pq[col0 + lc + 1] = acc[c].y;
     }
     if (rank == 0 && tid == 0) a.lxpart[q] = lx;
-    cluster_arrive();   // neither CTA exits while the other may still address its shared memory
-    cluster_wait();
+    // (no closing cluster barrier: every store into this CTA's shared memory has been waited for
+    // above, and the last store this CTA issued targets a peer that is still waiting for it)
 
     if (bz_last_cta(a.counter, gridDim.x)) {
         if (tid == 0 && a.set_after) {

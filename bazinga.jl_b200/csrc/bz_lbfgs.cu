@@ -234,8 +234,8 @@ __device__ __forceinline__ uint32_t lc_cluster_size() {
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void lc_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+__device__ __forceinline__ void lc_cluster_sync_relaxed() {   // pairs with fence.mbarrier_init, no membar
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void lc_st_remote(void* local_ptr, uint32_t rank, double v) {
     uint32_t remote;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(LC_THREADS)
         lc_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    lc_cluster_sync();   // every CTA's barriers exist before anything is sent to them
+    lc_cluster_sync_relaxed();   // every CTA's barriers exist before anything is sent to them
     const long long n = v.n;
     const int stride = (int)(cr.cs * LC_THREADS);
     const int j0 = (int)(cr.rank * LC_THREADS + threadIdx.x);
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(LC_THREADS)
             const long long j = LC_J(k);
             if (j < n) v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
         }
-        lc_cluster_sync();
+        // (the consumers of this state are later kernels: they see it only after the whole grid is done)
         if (cr.rank == 0 && threadIdx.x == 0) {
             st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
             st->next_op = OP_G;
@@ -464,7 +464,6 @@ __global__ void __launch_bounds__(LC_THREADS)
             v.z_curr[j] = v.z[j];
         }
     }
-    lc_cluster_sync();
     if (cr.rank == 0 && threadIdx.x == 0) {
         const double gamma = st->gamma;
         const double FBE_x =

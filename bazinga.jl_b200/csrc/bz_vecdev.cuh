@@ -113,14 +113,15 @@ __device__ __forceinline__ double bz_sum_group(const double* __restrict__ P, int
     if (p1 > np) p1 = np;
     double s = 0.0;
     const double* q = P + (size_t)p * n + j;
-    for (; p + 8 <= p1; p += 8, q += 8 * (size_t)n) {
-        double v[8];
+    // all loads of a 24-row batch are issued before the (order-fixed) adds: one L2 round trip
+    for (; p < p1; p += 24, q += 24 * (size_t)n) {
+        double v[24];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldcg(q + (size_t)k * n);
+        for (int k = 0; k < 24; ++k) v[k] = (p + k < p1) ? __ldcg(q + (size_t)k * n) : 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += v[k];
+        for (int k = 0; k < 24; ++k)
+            if (p + k < p1) s += v[k];
     }
-    for (; p < p1; ++p, q += n) s += __ldcg(q);
     return s;
 }
 
