@@ -100,6 +100,17 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_from_profile(m, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/); null for other shapes."""
+    p = os.path.join(ROOT, "profiles", "r1_dense_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["traffic_bytes_per_launch"] if d["shape"] == [m, n] else None
+    except Exception:
+        return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -268,10 +279,11 @@ def run_b200(args):
     achieved = (bgrad * dom_launches / (dom_ms * 1e-3)) / 1e9 if dom_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": "k_dense_algrad<true> (fused A-pass: r=Ax-b, w, A'w; A read once)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic_from_profile(m, n),
                 "algorithmic_bytes_per_launch": bgrad, "launches_timed": dom_launches,
                 "avg_launch_us": (1e3 * dom_ms / dom_launches) if dom_launches else None,
-                "kernel_share_of_step": (dom_ms / ms) if ms > 0 else None}
+                "events_bracket_every_nth_launch": 8,
+                "kernel_share_of_step": ((dom_ms / dom_launches) * grads / ms) if (ms > 0 and dom_launches) else None}
 
     # ---- CPU baseline (oracle = restatement of the reference), bounded sample, rank 0 at N=1 only
     cpu = None
@@ -320,7 +332,7 @@ def main():
     ap.add_argument("--rows", type=int, default=M_ROWS)
     ap.add_argument("--cols", type=int, default=N_COLS)
     ap.add_argument("--inner-cap", type=int, default=2000, help="inner iterations per step (0 = full solve)")
-    ap.add_argument("--ref-inner-cap", type=int, default=60, help="inner iterations per CPU-baseline step")
+    ap.add_argument("--ref-inner-cap", type=int, default=600, help="inner iterations per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
