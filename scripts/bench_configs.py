@@ -1,0 +1,88 @@
+"""Secondary measurements for the BASELINE configs that are not bench.py's headline line:
+  C3  65,536 independent either-or / MPVC instances in one launch (solves/s), with the C oracle
+      (OpenMP, all host cores) timed beside it
+  C4  obstacle_l1 on a 4096 x 4096 grid, a fixed budget of PANOC+ inner iterations (it/s, GB/s)
+Prints one JSON line per measurement.  Run on a B200: python scripts/bench_configs.py [c3] [c4]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import bazinga_b200 as bz  # noqa: E402
+
+EPS = 2.220446049250313e-16
+
+
+def grid(lo, hi, k):
+    v = np.linspace(lo, hi, k)
+    return np.array([(i, j) for j in v for i in v])
+
+
+def c3(batch_side=256, reps=3, cpu=True):
+    for name, kind, lo, hi in (("eitheror", 1, -4.0, 8.0), ("mpvca", 3, -5.0, 20.0)):
+        X0 = grid(lo, hi, batch_side)
+        bz.alps_batch(name, X0[:1024])          # warm-up (module load)
+        best, wall = None, None
+        for _ in range(reps):
+            t = time.perf_counter()
+            out = bz.alps_batch(name, X0)
+            w = time.perf_counter() - t
+            if best is None or out["kernel_ms"] < best:
+                best, wall = out["kernel_ms"], w
+        line = {"config": "C3", "workload": f"{len(X0)} independent {name} alps solves (demo options), one launch",
+                "solves_per_s_kernel": len(X0) / (best * 1e-3), "solves_per_s_e2e": len(X0) / wall,
+                "kernel_ms": best, "solved": int((out["status"] == 0).sum()),
+                "inner_iterations_total": int(out["sub_iters"].sum()), "inner_iterations_max": int(out["sub_iters"].max()),
+                "inner_iterations_per_s": float(out["sub_iters"].sum()) / (best * 1e-3)}
+        if cpu:
+            import bazinga_oracle as bo
+            from tiny_oracle_binding import tiny_batch
+            t = time.perf_counter()
+            ref = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000)
+            dt = time.perf_counter() - t
+            line["cpu_baseline"] = {"solves_per_s": len(X0) / dt, "cores": os.cpu_count(), "kind": "port",
+                                    "bit_identical": bool(np.array_equal(out["x"], ref["x"], equal_nan=True)
+                                                          and np.array_equal(out["sub_iters"], ref["sub_iters"]))}
+        print(json.dumps(line), flush=True)
+
+
+def c4(side=4096, inner=200):
+    N = side * side
+    ctx = bz.default_context()
+    p = bz.Problem(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleL1(N), bz.ConstraintObstacle(N, (side, side)),
+                   bz.ZeroSet(), ctx=ctx)
+    from bazinga_b200.solver import _options
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=1_000_000, minimum_gamma=EPS)
+    x0, y0 = 2.0 * np.ones(3 * N), np.zeros(N)
+    for cap in (20, inner):     # first call warms up
+        o = _options(tol=1e-4, tol_prim=None, tol_dual=None, inner_tol=None, maxit=100, theta_penalty=0.8,
+                     kappa_penalty=0.5, kappa_tol=0.1, subsolver_maxit=1_000_000, sub=sub, max_inner_total=cap)
+        ctx.sync()
+        ctx.timer_start()
+        x, y, s, mu, res = p.alps(x0, y0, o)
+        ms = ctx.timer_stop()
+    n = 3 * N
+    bytes_it = 2 * 64 * N + 8 * n * 37
+    line = {"config": "C4", "workload": f"obstacle_l1 on a {side}x{side} grid (N={N}, nx={n}), {res.tot_inner_it} inner iterations",
+            "ms_total_incl_h2d": ms, "inner_iterations": res.tot_inner_it, "n_grad": res.n_grad,
+            "kernel_breakdown_us": {nm: (1e3 * res.kind_ms[k] / res.kind_launches[k] if res.kind_launches[k] else None)
+                                    for k, nm in enumerate(["al_gradient", "lbfgs_step", "fb_step", "decision_step"])},
+            "kernel_ms_sum": sum(res.kind_ms[k] for k in range(4)),
+            "iterations_per_s_kernels": res.tot_inner_it / (1e-3 * sum(res.kind_ms[k] for k in range(4))),
+            "algorithmic_bytes_per_iteration": bytes_it,
+            "achieved_GBs_kernels": bytes_it * res.tot_inner_it / (1e-3 * sum(res.kind_ms[k] for k in range(4))) / 1e9}
+    print(json.dumps(line), flush=True)
+    p.close()
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["c3", "c4"]
+    if "c3" in what:
+        c3()
+    if "c4" in what:
+        c4()
