@@ -166,16 +166,17 @@ __device__ __forceinline__ double f_model(double fx, const double (&g)[2], const
 
 // L-BFGS history kept newest-first and shifted on update, so every index is static (registers);
 // the visiting order (loop1 newest->oldest, loop2 oldest->newest) is that of the upstream ring.
+template <int MM>
 struct Lbfgs {
     int M, currmem;
-    double H, s[TB_MAXMEM][2], y[TB_MAXMEM][2], ys[TB_MAXMEM];
+    double H, s[MM][2], y[MM][2], ys[MM];
     __device__ void reset() { currmem = 0; H = 1.0; }
     __device__ void update(const double (&sv)[2], const double (&yv)[2]) {
         if (M == 0) return;
         const double ysv = dot2(sv, yv);
         if (ysv > 0) {
 #pragma unroll
-            for (int i = TB_MAXMEM - 1; i > 0; --i) {
+            for (int i = MM - 1; i > 0; --i) {
                 s[i][0] = s[i - 1][0]; s[i][1] = s[i - 1][1];
                 y[i][0] = y[i - 1][0]; y[i][1] = y[i - 1][1];
                 ys[i] = ys[i - 1];
@@ -188,10 +189,10 @@ struct Lbfgs {
         }
     }
     __device__ void mul(const double (&v)[2], double (&d)[2]) const {
-        double al[TB_MAXMEM];
+        double al[MM];
         d[0] = v[0]; d[1] = v[1];
 #pragma unroll
-        for (int i = 0; i < TB_MAXMEM; ++i) {
+        for (int i = 0; i < MM; ++i) {
             if (i < currmem) {
                 al[i] = dot2(s[i], d) / ys[i];
                 d[0] -= al[i] * y[i][0];
@@ -200,7 +201,7 @@ struct Lbfgs {
         }
         d[0] = H * d[0]; d[1] = H * d[1];
 #pragma unroll
-        for (int i = TB_MAXMEM - 1; i >= 0; --i) {
+        for (int i = MM - 1; i >= 0; --i) {
             if (i < currmem) {
                 const double beta = dot2(y[i], d) / ys[i];
                 const double coef = al[i] - beta;
@@ -212,7 +213,7 @@ struct Lbfgs {
 };
 
 // PANOCplus (Appendix A.2-A.5); returns k, solution in z
-template <int KIND>
+template <int KIND, int MM>
 __device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts& o, double tol,
                                double (&z)[2]) {
     const double a = o.alpha;
@@ -229,7 +230,7 @@ __device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts
     y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
     double g_z = Prob<KIND>::prox(y, gamma, z);
     res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-    Lbfgs H;
+    Lbfgs<MM> H;
     H.M = o.mem;
     H.reset();
     double f_up = f_model(f_x, grad_x, res, a / gamma);
@@ -286,7 +287,7 @@ __device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts
     }
 }
 
-template <int KIND>
+template <int KIND, int MM>
 __global__ void __launch_bounds__(TB_THREADS)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(TB_THREADS)
 #pragma unroll
         for (int i = 0; i < NY; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20));   // safeguards.jl:2-5
         al.update();
-        const long long sub_it = panocplus<KIND>(al, x, o, inner_tol, z);
+        const long long sub_it = panocplus<KIND, MM>(al, x, o, inner_tol, z);
         x[0] = z[0]; x[1] = z[1];
         objx = al.fx + al.gz;
         tot_inner += sub_it;
@@ -411,12 +412,17 @@ extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double
     BTRY(cudaEventCreate(&e1));
     const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
     cudaEventRecord(e0, ctx->stream);
+    // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
+#define TB_LAUNCH(K, MMV) k_batch_alps<K, MMV><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp)
+#define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
     switch (kind) {
-    case 0: k_batch_alps<0><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
-    case 1: k_batch_alps<1><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
-    case 2: k_batch_alps<2><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
-    default: k_batch_alps<3><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); break;
+    case 0: TB_DISPATCH(0); break;
+    case 1: TB_DISPATCH(1); break;
+    case 2: TB_DISPATCH(2); break;
+    default: TB_DISPATCH(3); break;
     }
+#undef TB_DISPATCH
+#undef TB_LAUNCH
     cudaEventRecord(e1, ctx->stream);
     ctx->n_launches++;
     BTRY(cudaGetLastError());

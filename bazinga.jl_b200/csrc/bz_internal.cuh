@@ -359,6 +359,7 @@ int bz_launch_pdl(bz_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, si
     if (e != cudaSuccess) return bz_fail(ctx, BZ_ERR_CUDA, std::string("cudaLaunchKernelEx: ") + cudaGetErrorString(e));
     return BZ_OK;
 }
+#define BZ_TRY_RC(x) do { int rc__ = (x); if (rc__ != BZ_OK) return rc__; } while (0)
 #define BZ_CUDA(ctx, call)                                                                   \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \

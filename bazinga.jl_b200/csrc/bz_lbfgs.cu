@@ -56,7 +56,7 @@ __device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(BZ_L_THREADS)
+__global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
     k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
     __shared__ double scratch[2 * 32 + 4];
     // the other parity's barrier words are free again: reset them for the launch after this one
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
 
     if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
         const double tau = __ldcg(&st->tau);
-        for (long long j = j0; j < n; j += stride)
+        _Pragma("unroll 4") for (long long j = j0; j < n; j += stride)
             v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
         if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
             st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
     // ---- update!(H, x - x_prev, res - res_prev)
     if (!skip && M > 0) {
         double a[2] = {0.0, 0.0};
-        for (long long j = j0; j < n; j += stride) {
+        _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
             const double s = v.x[j] - v.x_prev[j], yv = v.res[j] - v.res_prev[j];
             a[0] += s * yv;
             a[1] += yv * yv;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
             ys[curridx - 1] = a[0];
             double* sm = v.sM + (size_t)(curridx - 1) * n;
             double* ym = v.yM + (size_t)(curridx - 1) * n;
-            for (long long j = j0; j < n; j += stride) {
+            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
                 sm[j] = v.x[j] - v.x_prev[j];
                 ym[j] = v.res[j] - v.res_prev[j];
             }
@@ -123,13 +123,13 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
         double a[1] = {0.0};
         if (currmem > 0) {
             const double* sm = v.sM + (size_t)(idx - 1) * n;
-            for (long long j = j0; j < n; j += stride) {
+            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
                 const double dj = -v.res[j];
                 v.d[j] = dj;
                 a[0] += sm[j] * dj;
             }
         } else {
-            for (long long j = j0; j < n; j += stride) v.d[j] = H * (-v.res[j]);
+            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) v.d[j] = H * (-v.res[j]);
         }
         for (int t = 0; t < currmem; ++t) {       // loop1!: newest -> oldest
             team_sum<1>(tc, a);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
             a[0] = 0.0;
             if (t < currmem - 1) {
                 const double* sm2 = v.sM + (size_t)(idx2 - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
+                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
                     const double dj = v.d[j] - alpha_i * ym[j];
                     v.d[j] = dj;
                     a[0] += sm2[j] * dj;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
                 int idn = idx2 + 1;
                 if (idn > M) idn = 1;
                 const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
+                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
                     double dj = v.d[j] - alpha_i * ym[j];
                     dj = H * dj;
                     v.d[j] = dj;
@@ -173,18 +173,18 @@ __global__ void __launch_bounds__(BZ_L_THREADS)
                 int idn = idx + 1;
                 if (idn > M) idn = 1;
                 const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                for (long long j = j0; j < n; j += stride) {
+                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
                     const double dj = v.d[j] + coef * sm[j];
                     v.d[j] = dj;
                     a[0] += ymn[j] * dj;
                 }
             } else {
-                for (long long j = j0; j < n; j += stride) v.d[j] = v.d[j] + coef * sm[j];
+                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) v.d[j] = v.d[j] + coef * sm[j];
             }
         }
     }
     // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
-    for (long long j = j0; j < n; j += stride) {
+    _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
         const double xj = v.x[j];
         v.x_prev[j] = xj;
         v.res_prev[j] = v.res[j];

@@ -321,8 +321,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     PTRY(dev_alloc(ctx, &p->fxpart, (size_t)2 * maxgrid));
     PTRY(dev_alloc(ctx, &p->counters, 8));
     PTRY(dev_alloc(ctx, &p->team.bars, 2 * BZ_MAXBAR));
-    p->team.max_ctas = ctx->num_sms;
-    PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * ctx->num_sms * 2));
+    p->team.max_ctas = ctx->num_sms * BZ_L_CTAS_PER_SM;
+    PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * p->team.max_ctas * 2));
     p->team.parity = 0;
     PTRY(dev_alloc(ctx, &p->st, 1));
     BZ_CUDA(ctx, cudaMallocHost((void**)&p->st_host, sizeof(BzState)));
@@ -465,7 +465,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         BZ_TRY(bz_launch_identity_c(ctx, p->st, force_target, src, p->n, p->mu, p->muy, p->D, p->cx,
                                     p->s, p->yupd, p->lxpart, p->counters + 1, 1));
     } else if (d.c_kind == BZ_C_OBSTACLE) {
-        p->nlx = p->nfx = bz_vec_grid(ctx, p->ob.N);
+        p->nlx = p->nfx = bz_obstacle_partials(ctx, p->ob);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         const bool timed = ctx->profiling && (p->dom_counter++ % ctx->prof_stride == 0);
         if (timed) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }

@@ -23,9 +23,10 @@ int bz_vec_grid(const bz_ctx* ctx, long long n) {
     return (int)nb;
 }
 int bz_l_grid(const bz_ctx* ctx, long long n) {
+    // cooperative launch: every CTA must be co-resident; BZ_L_CTAS_PER_SM CTAs of 512 threads fit on an SM
     long long nb = (n + 4 * BZ_L_THREADS - 1) / (4 * BZ_L_THREADS);
     if (nb < 1) nb = 1;
-    if (nb > ctx->num_sms) nb = ctx->num_sms;
+    if (nb > (long long)ctx->num_sms * BZ_L_CTAS_PER_SM) nb = (long long)ctx->num_sms * BZ_L_CTAS_PER_SM;
     return (int)nb;
 }
 
@@ -92,21 +93,30 @@ int bz_launch_identity_c(bz_ctx* ctx, BzState* st, int force_target, const doubl
     return BZ_OK;
 }
 
-// A*v for the obstacle stencil at grid index i (1-D: SymTridiagonal(2,-1); 2-D: 5-point, Dirichlet)
-__device__ __forceinline__ double bz_stencil(const double* __restrict__ v, long long i,
-                                             const BzObstacle& ob) {
-    if (ob.gx == 0) {
-        double out = 2.0 * v[i];
-        if (i > 0) out -= v[i - 1];
-        if (i + 1 < ob.N) out -= v[i + 1];
-        return out;
-    }
-    const long long r = i / ob.gx, c = i % ob.gx;
-    double out = 4.0 * v[i];
+// Obstacle stencil provider (demo/obstacle.jl:92-113; 1-D SymTridiagonal(2,-1), or the 2-D 5-point
+// extension of config C4 with 4 on the diagonal and Dirichlet boundaries).  The grid is walked as
+// (row, column) -- blockIdx.y strides over rows, blockIdx.x * 256 + threadIdx.x is the column -- so
+// no integer division is needed and every access is unit-stride; the vertical neighbours come from
+// rows that the same and neighbouring CTAs touch (L2).  The 1-D operator is the grid (1, N).
+struct StencilGeom {
+    long long GY, GX;     // rows, columns
+    double diag;          // 2 (1-D) or 4 (2-D)
+};
+__device__ __forceinline__ StencilGeom bz_geom(const BzObstacle& ob) {
+    StencilGeom g;
+    if (ob.gx == 0) { g.GY = 1; g.GX = ob.N; g.diag = 2.0; }
+    else { g.GY = ob.gy; g.GX = ob.gx; g.diag = 4.0; }
+    return g;
+}
+// (A v)(r, c): same operation order as the oracle's _stencil_apply (diag*v, then -left, -right, -up, -down)
+__device__ __forceinline__ double bz_stencil_rc(const double* __restrict__ v, long long r, long long c,
+                                                const StencilGeom& g) {
+    const long long i = r * g.GX + c;
+    double out = g.diag * v[i];
     if (c > 0) out -= v[i - 1];
-    if (c + 1 < ob.gx) out -= v[i + 1];
-    if (r > 0) out -= v[i - ob.gx];
-    if (r + 1 < ob.gy) out -= v[i + ob.gx];
+    if (c + 1 < g.GX) out -= v[i + 1];
+    if (r > 0) out -= v[i - g.GX];
+    if (r + 1 < g.GY) out -= v[i + g.GX];
     return out;
 }
 
@@ -117,30 +127,39 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
                  const double* __restrict__ muy, double* cx, double* s, double* yupd, double* lxpart,
                  double* fxpart) {
     __shared__ double scratch[3 * 32];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     int target = force_target;
     if (target < 0) {
         if (__ldcg(&st->next_op) != OP_G) return;
         target = __ldcg(&st->grad_target);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bz_tic(st, 0);
     }
-    const double* x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
+    const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
     const long long N = ob.N;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const StencilGeom g = bz_geom(ob);
     double a[3] = {0.0, 0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const double x2 = x[N + i];
-        const double c = (x[i] + bz_stencil(x + N, i, ob)) - x[2 * N + i];
-        const double t = c + muy[i];
-        const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
-        a[0] += (u * u) / mu[i];
-        cx[i] = c; s[i] = 0.0; yupd[i] = u / mu[i];
-        a[1] += x2 * x2;                     // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
-        a[2] += x2;
+    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
+             c += (long long)gridDim.x * blockDim.x) {
+            const long long i = r * g.GX + c;
+            const double x2 = x[N + i];
+            const double cv = (x[i] + bz_stencil_rc(x + N, r, c, g)) - x[2 * N + i];
+            const double t = cv + muy[i];
+            const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
+            const double mi = mu[i];
+            a[0] += (u * u) / mi;
+            cx[i] = cv; s[i] = 0.0; yupd[i] = u / mi;
+            a[1] += x2 * x2;                     // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
+            a[2] += x2;
+        }
     }
     bz_block_sum<3>(a, scratch);
+    const int nb = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
     if (threadIdx.x == 0) {
-        lxpart[blockIdx.x] = a[0];
-        fxpart[blockIdx.x] = a[1];
-        fxpart[gridDim.x + blockIdx.x] = a[2];
+        lxpart[b] = a[0];
+        fxpart[b] = a[1];
+        fxpart[nb + b] = a[2];
     }
 }
 // pass 2: grad = dfx + jtv with dfx = [0; x2-1; 0], jtv = [w; A w; -w]
@@ -148,38 +167,59 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_obstacle_jt(BzState* st, int force_target, const double* x0, const double* x1p,
                   const double* x2p, BzObstacle ob, const double* __restrict__ yupd, double* Ec,
                   unsigned int* counter, int set_after) {
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
     int target = force_target;
     if (target < 0) {
         if (__ldcg(&st->next_op) != OP_G) return;
         target = __ldcg(&st->grad_target);
     }
-    const double* x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
+    const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
     const long long N = ob.N;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const double w = yupd[i];
-        Ec[i] = 0.0 + w;
-        Ec[N + i] = (x[N + i] - 1.0) + bz_stencil(yupd, i, ob);
-        Ec[2 * N + i] = 0.0 + (-w);
+    const StencilGeom g = bz_geom(ob);
+    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
+             c += (long long)gridDim.x * blockDim.x) {
+            const long long i = r * g.GX + c;
+            const double w = yupd[i];
+            Ec[i] = 0.0 + w;
+            Ec[N + i] = (x[N + i] - 1.0) + bz_stencil_rc(yupd, r, c, g);
+            Ec[2 * N + i] = 0.0 + (-w);
+        }
     }
-    if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0 && set_after) {
+    if (bz_last_cta(counter, gridDim.x * gridDim.y) && threadIdx.x == 0 && set_after) {
         st->next_op = st->after_g;
+        if (force_target < 0) bz_toc(st, 0);
         __threadfence();
     }
+}
+
+// launch geometry of the two passes (also the number of lx / fx partials)
+static dim3 obstacle_grid(const bz_ctx* ctx, const BzObstacle& ob) {
+    const long long GX = ob.gx == 0 ? ob.N : ob.gx, GY = ob.gx == 0 ? 1 : ob.gy;
+    const long long cap = (long long)ctx->num_sms * 8;
+    long long bx = (GX + BZ_VEC_THREADS - 1) / BZ_VEC_THREADS;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    long long by = cap / bx;
+    if (by > GY) by = GY;
+    if (by < 1) by = 1;
+    return dim3((unsigned)bx, (unsigned)by);
+}
+int bz_obstacle_partials(const bz_ctx* ctx, const BzObstacle& ob) {
+    const dim3 g = obstacle_grid(ctx, ob);
+    return (int)(g.x * g.y);
 }
 
 int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
                        const BzObstacle& ob, const double* mu, const double* muy, double* cx,
                        double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
                        unsigned int* counter, int set_after) {
-    const int nb = bz_vec_grid(ctx, ob.N);
-    k_obstacle_c<<<nb, BZ_VEC_THREADS, 0, ctx->stream>>>(st, force_target, src[0], src[1], src[2], ob,
-                                                          mu, muy, cx, s, yupd, lxpart, fxpart);
-    k_obstacle_jt<<<nb, BZ_VEC_THREADS, 0, ctx->stream>>>(st, force_target, src[0], src[1], src[2],
-                                                           ob, yupd, Ec, counter, set_after);
-    ctx->n_launches += 2;
-    BZ_CUDA(ctx, cudaGetLastError());
-    return BZ_OK;
+    const dim3 grid = obstacle_grid(ctx, ob);
+    BZ_TRY_RC(bz_launch_pdl(ctx, k_obstacle_c, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
+                            src[2], ob, mu, muy, cx, s, yupd, lxpart, fxpart));
+    return bz_launch_pdl(ctx, k_obstacle_jt, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
+                         src[2], ob, yupd, Ec, counter, set_after);
 }
 
 // ---------------------------------------------------------------------------------------------

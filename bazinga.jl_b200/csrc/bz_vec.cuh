@@ -5,6 +5,7 @@
 #define BZ_MAXBAR 48          // team barriers per L launch (1 + 2*memory + slack)
 #define BZ_VEC_THREADS 256
 #define BZ_L_THREADS 512
+#define BZ_L_CTAS_PER_SM 3     // co-resident CTAs per SM of the cooperative L kernel (64 regs x 512 thr)
 
 struct BzVecs {
     double *x, *z, *xeps, *x_prev, *x_d, *z_curr, *res, *res_prev, *grad_x, *grad_z, *d;
@@ -45,6 +46,7 @@ int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double*
                        double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
                        unsigned int* counter, int set_after);
 
+int bz_obstacle_partials(const bz_ctx* ctx, const BzObstacle& ob);
 int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, double* out, long long n,
                    const BzGParams& g, double* part, unsigned int* counter);
 int bz_launch_proj(bz_ctx* ctx, const double* in, double* out, long long m, const BzDParams& D);
