@@ -99,8 +99,8 @@ void bz_shard_free(bz_ctx* ctx, BzShard* sh) {
 
 // out[j] = sum_p P[p][j] (fixed order); out[n] = sum_p lxpart[p]
 __global__ void __launch_bounds__(256) k_local_reduce(const double* __restrict__ P, int np,
-                                                      const double* __restrict__ lxpart, long long n,
-                                                      double* __restrict__ out) {
+                                                      const double* __restrict__ lxpart, int nlx,
+                                                      long long n, double* __restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         double s = 0.0;
@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(256) k_local_reduce(const double* __restrict__
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         double s = 0.0;
-        for (int p = 0; p < np; ++p) s += __ldcg(lxpart + p);
+        for (int p = 0; p < nlx; ++p) s += __ldcg(lxpart + p);
         out[n] = s;
     }
 }
 
-int bz_shard_allreduce(bz_ctx* ctx, BzShard* sh, const double* P, int np, const double* lxpart,
+int bz_shard_allreduce(bz_ctx* ctx, BzShard* sh, const double* P, int np, const double* lxpart, int nlx,
                        long long n) {
-    k_local_reduce<<<bz_vec_grid(ctx, n), 256, 0, ctx->stream>>>(P, np, lxpart, n, sh->reduced);
+    k_local_reduce<<<bz_vec_grid(ctx, n), 256, 0, ctx->stream>>>(P, np, lxpart, nlx, n, sh->reduced);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());
     return bz_comm_allreduce(ctx, sh->reduced, n + 8, BZ_COMM_SUM);

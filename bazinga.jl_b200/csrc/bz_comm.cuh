@@ -14,6 +14,6 @@ enum BzCommOp { BZ_COMM_SUM = 0, BZ_COMM_MAX = 2 };
 int bz_shard_alloc(bz_ctx* ctx, BzShard* sh, long long n);
 void bz_shard_free(bz_ctx* ctx, BzShard* sh);
 // local fixed-order reduction of the per-cluster partial rows, then allreduce(sum) over ranks
-int bz_shard_allreduce(bz_ctx* ctx, BzShard* sh, const double* P, int np, const double* lxpart,
+int bz_shard_allreduce(bz_ctx* ctx, BzShard* sh, const double* P, int np, const double* lxpart, int nlx,
                        long long n);
 int bz_comm_allreduce(bz_ctx* ctx, double* dev_buf, long long count, int op);

@@ -418,3 +418,167 @@ int bz_launch_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t s
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Wide path (nx > 16384, e.g. config C5 32768 x 262144 row-sharded): TWO passes over A per
+// AL-gradient, i.e. at most half of the single-pass roofline by construction -- the x slice and the
+// A'w accumulators of the fused kernel no longer fit in one cluster's registers.  Both passes are
+// plain streaming kernels with order-fixed reductions:
+//   k_wide_rows   R = 8 rows per CTA pass, thread t owns columns {1024c + 2t, +1}: x values are
+//                 loaded once per column chunk and reused for the 8 rows (8 independent 16 B loads in
+//                 flight per thread), block sum of the 8 row dots, elementwise stage, lx partial
+//   k_wide_cols   thread owns 2 columns, CTA (colblock, rowchunk) accumulates w[row]*A[row, cols] over
+//                 its row chunk (w staged in shared memory), one partial row per row chunk
+// ---------------------------------------------------------------------------------------------
+#define WR_ROWS 8
+#define WR_THREADS 512
+
+__global__ void __launch_bounds__(WR_THREADS)
+    k_wide_rows(BzDenseArgs a) {
+    __shared__ double scratch[WR_ROWS * 32];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    int target = a.force_target;
+    if (target < 0) {
+        if (__ldcg(&a.st->next_op) != OP_G) return;
+        target = __ldcg(&a.st->grad_target);
+        if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
+    }
+    const double* __restrict__ x = a.src[target];
+    const long long n = a.n, m = a.m;
+    const long long ngroups = (m + WR_ROWS - 1) / WR_ROWS;
+    const bool vec = (n % 2 == 0) && (a.lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    double lx = 0.0;
+    for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const long long row0 = grp * WR_ROWS;
+        const int nr = (int)((m - row0) < WR_ROWS ? (m - row0) : WR_ROWS);
+        double acc[WR_ROWS];
+#pragma unroll
+        for (int r = 0; r < WR_ROWS; ++r) acc[r] = 0.0;
+        if (vec) {
+            for (long long c = 2LL * tid; c < n; c += 2LL * WR_THREADS) {
+                const double2 xv = *reinterpret_cast<const double2*>(x + c);
+                double2 av[WR_ROWS];
+#pragma unroll
+                for (int r = 0; r < WR_ROWS; ++r)
+                    av[r] = (r < nr) ? __ldcs(reinterpret_cast<const double2*>(a.A + (row0 + r) * a.lda + c))
+                                     : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int r = 0; r < WR_ROWS; ++r) acc[r] = fma(av[r].y, xv.y, fma(av[r].x, xv.x, acc[r]));
+            }
+        } else {
+            for (long long c = tid; c < n; c += WR_THREADS) {
+                const double xv = x[c];
+#pragma unroll
+                for (int r = 0; r < WR_ROWS; ++r)
+                    if (r < nr) acc[r] = fma(__ldg(a.A + (row0 + r) * a.lda + c), xv, acc[r]);
+            }
+        }
+        bz_block_sum<WR_ROWS>(acc, scratch);
+        if (tid == 0) {
+            for (int r = 0; r < nr; ++r) {
+                const long long gi = row0 + r;
+                const double cxv = acc[r] - a.b[gi];
+                const double t = cxv + a.muy[gi];
+                const double sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);
+                const double u = t - sv;
+                const double mui = a.mu[gi];
+                lx += (u * u) / mui;
+                if (a.cx) a.cx[gi] = cxv;
+                if (a.s) a.s[gi] = sv;
+                a.yupd[gi] = u / mui;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.lxpart[blockIdx.x] = lx;
+}
+
+#define WC_THREADS 256
+#define WC_COLS (2 * WC_THREADS)
+#define WC_WCHUNK 1024      // rows of w staged in shared memory at a time
+
+__global__ void __launch_bounds__(WC_THREADS)
+    k_wide_cols(BzDenseArgs a, int rows_per_chunk) {
+    __shared__ double wsm[WC_WCHUNK];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
+    const int tid = threadIdx.x;
+    if (a.force_target < 0 && __ldcg(&a.st->next_op) != OP_G) return;
+    const long long n = a.n, m = a.m;
+    const long long c0 = (long long)blockIdx.x * WC_COLS + 2LL * tid;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    long long r1 = r0 + rows_per_chunk;
+    if (r1 > m) r1 = m;
+    const bool vec = (n % 2 == 0) && (a.lda % 2 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    double2 acc = make_double2(0.0, 0.0);
+    for (long long rb = r0; rb < r1; rb += WC_WCHUNK) {
+        const int nr = (int)((r1 - rb) < WC_WCHUNK ? (r1 - rb) : WC_WCHUNK);
+        __syncthreads();
+        for (int k = tid; k < nr; k += WC_THREADS) wsm[k] = a.yupd[rb + k];
+        __syncthreads();
+        if (vec && c0 + 1 < n) {
+            const double* base = a.A + rb * a.lda + c0;
+            int r = 0;
+            for (; r + 8 <= nr; r += 8) {
+                double2 av[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) av[k] = __ldcs(reinterpret_cast<const double2*>(base + (long long)(r + k) * a.lda));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    acc.x = fma(av[k].x, wsm[r + k], acc.x);
+                    acc.y = fma(av[k].y, wsm[r + k], acc.y);
+                }
+            }
+            for (; r < nr; ++r) {
+                const double2 av = __ldcs(reinterpret_cast<const double2*>(base + (long long)r * a.lda));
+                acc.x = fma(av.x, wsm[r], acc.x);
+                acc.y = fma(av.y, wsm[r], acc.y);
+            }
+        } else {
+            for (int r = 0; r < nr; ++r) {
+                const double* row = a.A + (rb + r) * a.lda;
+                if (c0 < n) acc.x = fma(__ldg(row + c0), wsm[r], acc.x);
+                if (c0 + 1 < n) acc.y = fma(__ldg(row + c0 + 1), wsm[r], acc.y);
+            }
+        }
+    }
+    double* Pq = a.P + (size_t)blockIdx.y * n;
+    if (c0 < n) Pq[c0] = acc.x;
+    if (c0 + 1 < n) Pq[c0 + 1] = acc.y;
+    if (bz_last_cta(a.counter, gridDim.x * gridDim.y)) {
+        if (tid == 0 && a.set_after) {
+            a.st->next_op = a.st->after_g;
+            if (a.force_target < 0) bz_toc(a.st, 0);
+            __threadfence();
+        }
+    }
+}
+
+// geometry of the wide path: number of k_wide_rows CTAs (= lx partials) and of row chunks (= partial rows)
+void bz_wide_geometry(const bz_ctx* ctx, long long m, long long n, int* row_ctas, int* row_chunks,
+                      int* rows_per_chunk) {
+    const long long groups = (m + WR_ROWS - 1) / WR_ROWS;
+    long long g1 = (long long)ctx->num_sms * 4;
+    if (g1 > groups) g1 = groups;
+    if (g1 < 1) g1 = 1;
+    *row_ctas = (int)g1;
+    const long long colblocks = (n + WC_COLS - 1) / WC_COLS;
+    long long want = ((long long)ctx->num_sms * 8 + colblocks - 1) / colblocks;   // ~8 CTAs per SM in total
+    if (want > 64) want = 64;
+    if (want < 1) want = 1;
+    long long rpc = (m + want - 1) / want;
+    if (rpc < 1) rpc = 1;
+    *rows_per_chunk = (int)rpc;
+    *row_chunks = (int)((m + rpc - 1) / rpc);
+}
+
+int bz_launch_dense_wide(bz_ctx* ctx, const BzDenseArgs& args) {
+    int row_ctas, row_chunks, rpc;
+    bz_wide_geometry(ctx, args.m, args.n, &row_ctas, &row_chunks, &rpc);
+    BZ_TRY_RC(bz_launch_pdl(ctx, k_wide_rows, dim3(row_ctas), dim3(WR_THREADS), 0, 0, args));
+    const unsigned colblocks = (unsigned)((args.n + WC_COLS - 1) / WC_COLS);
+    return bz_launch_pdl(ctx, k_wide_cols, dim3(colblocks, row_chunks), dim3(WC_THREADS), 0, 0, args, rpc);
+}

@@ -34,6 +34,9 @@ struct BzDenseArgs {
 };
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);
+int bz_launch_dense_wide(bz_ctx* ctx, const BzDenseArgs& args);
+void bz_wide_geometry(const bz_ctx* ctx, long long m, long long n, int* row_ctas, int* row_chunks,
+                      int* rows_per_chunk);
 int bz_launch_quad_grad(bz_ctx* ctx, const double* Q, const double* q, BzState* st, int force_target,
                         const double* const* src, long long n, double* Ef, double* fxpart,
                         int nblocks);

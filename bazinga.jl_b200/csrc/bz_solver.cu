@@ -31,7 +31,7 @@ struct bz_problem {
     // oracle data
     double* cA = nullptr; bool own_cA = false; double* cb = nullptr;
     double* fA = nullptr; double* fb = nullptr; long long fm = 0;
-    double* f_ones = nullptr; double* f_zeros = nullptr;
+    double* f_ones = nullptr; double* f_zeros = nullptr; double* tm1_f = nullptr;
     double* g_u = nullptr;
     // AL m-vectors (local rows)
     double *mu = nullptr, *y = nullptr, *muy = nullptr, *cx = nullptr, *s = nullptr, *yupd = nullptr;
@@ -42,6 +42,8 @@ struct bz_problem {
     // provider partial buffers
     double *Pc = nullptr, *Pf = nullptr, *lxpart = nullptr, *fxpart = nullptr;
     int c_clusters = 0, c_rpc = 0, f_clusters = 0, f_rpc = 0, nlx = 0, nfx = 0, nfx2 = 0;
+    bool c_wide = false, f_wide = false;   // two-pass wide path (nx > 16384)
+    int c_nlx = 0, f_nlx = 0;              // lx partial counts of the dense passes
     double* part = nullptr;
     unsigned int* counters = nullptr;   // [8]
     BzTeam team{};
@@ -105,6 +107,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_L2_PREFETCH_ROWS")) ctx->l2_prefetch_rows = atoi(e);
     if (const char* e = getenv("BZ_EVICT_FIRST")) ctx->evict_first = atoi(e);
     if (const char* e = getenv("BZ_PDL")) ctx->pdl = atoi(e);
+    if (const char* e = getenv("BZ_FORCE_WIDE")) ctx->force_wide = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
     return BZ_OK;
@@ -218,7 +221,7 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     if (p->own_cA) cudaFree(p->cA);
-    double* frees[] = {p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
+    double* frees[] = {p->tm1_f, p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
                        p->s, p->yupd, p->tm1, p->tm2, p->tm3, p->v.x, p->v.z, p->v.xeps, p->v.x_prev,
                        p->v.x_d, p->v.z_curr, p->v.res, p->v.res_prev, p->v.grad_x, p->v.grad_z,
                        p->v.d, p->v.sM, p->v.yM, p->Ec, p->Ef, p->Pc, p->Pf, p->lxpart, p->fxpart,
@@ -258,7 +261,6 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     switch (d->c_kind) {
     case BZ_C_DENSE_AFFINE:
         if (d_pair) return fail(BZ_ERR_UNSUPPORTED, "pair sets with a dense affine c are not in the fused path yet");
-        if (n > DA_MAX_N) return fail(BZ_ERR_UNSUPPORTED, "dense affine c: nx > 16384 needs the column-split path (not built yet)");
         if (!(d->f_kind == BZ_F_ZERO || d->f_kind == BZ_F_LEAST_SQUARES || d->f_kind == BZ_F_QUADRATIC))
             return fail(BZ_ERR_UNSUPPORTED, "f kind not available with a dense affine c");
         break;
@@ -280,8 +282,6 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         return fail(BZ_ERR_UNSUPPORTED,
                     "c kind is only available in the batched tiny-instance path (bz_batch_solve)");
     }
-    if (d->f_kind == BZ_F_LEAST_SQUARES && n > DA_MAX_N)
-        return fail(BZ_ERR_UNSUPPORTED, "LeastSquares f: nx > 16384 not built yet");
     if (d->g_kind == BZ_G_OBSTACLE_L1 && d->c_kind != BZ_C_OBSTACLE)
         return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
     if ((d->g_kind == BZ_G_NORML1_BOX || d->g_kind == BZ_G_NORML0_BOX)) {
@@ -339,8 +339,11 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         cudaMemcpyAsync(p->fb, d->f_b, p->fm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
         PTRY(dev_alloc(ctx, &p->f_ones, p->fm));
         PTRY(dev_alloc(ctx, &p->f_zeros, p->fm));
+        PTRY(dev_alloc(ctx, &p->tm1_f, p->fm));
         PTRY(bz_launch_fill(ctx, p->f_ones, p->fm, 1.0));
-        dense_partition(ctx, p->fm, &p->f_clusters, &p->f_rpc);
+        p->f_wide = n > DA_MAX_N || ctx->force_wide;
+        if (p->f_wide) bz_wide_geometry(ctx, p->fm, n, &p->f_nlx, &p->f_clusters, &p->f_rpc);
+        else { dense_partition(ctx, p->fm, &p->f_clusters, &p->f_rpc); p->f_nlx = p->f_clusters; }
         PTRY(dev_alloc(ctx, &p->Pf, (size_t)p->f_clusters * n));
     } else if (d->f_kind == BZ_F_QUADRATIC) {
         if (!d->f_A || !d->f_b) return fail(BZ_ERR_ARG, "Quadratic needs f_A (Q) and f_b (q)");
@@ -369,7 +372,9 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
                 PTRY(upload_matrix(ctx, d->c_A, d->c_layout, ml, n, p->cA));
             }
         }
-        dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc);
+        p->c_wide = n > DA_MAX_N || ctx->force_wide;
+        if (p->c_wide) bz_wide_geometry(ctx, ml, n, &p->c_nlx, &p->c_clusters, &p->c_rpc);
+        else { dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc); p->c_nlx = p->c_clusters; }
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
     }
@@ -400,7 +405,7 @@ static BzGradSrc grad_src(bz_problem* p) {
     gs.fx_scale = 1.0; gs.fx_scale2 = 0.0;
     if (d.f_kind == BZ_F_LEAST_SQUARES) {
         gs.Pf = p->Pf; gs.npf = p->f_clusters;
-        gs.fxpart = p->fxpart; gs.nfx = p->f_clusters; gs.fx_scale = 0.5;
+        gs.fxpart = p->fxpart; gs.nfx = p->f_nlx; gs.fx_scale = 0.5;
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         gs.Ef = p->Ef;
         gs.fxpart = p->fxpart; gs.nfx = p->nfx; gs.fx_scale = 1.0;
@@ -410,7 +415,7 @@ static BzGradSrc grad_src(bz_problem* p) {
     }
     if (d.c_kind == BZ_C_DENSE_AFFINE) {
         if (p->sharded) { gs.Ec = p->shard.reduced; gs.lxpart = p->shard.reduced + p->n; gs.nlx = 1; }
-        else { gs.Pc = p->Pc; gs.npc = p->c_clusters; gs.lxpart = p->lxpart; gs.nlx = p->c_clusters; }
+        else { gs.Pc = p->Pc; gs.npc = p->c_clusters; gs.lxpart = p->lxpart; gs.nlx = p->c_nlx; }
     } else if (d.c_kind == BZ_C_IDENTITY) {
         gs.Ec = p->yupd; gs.lxpart = p->lxpart; gs.nlx = p->nlx;
     } else {
@@ -435,7 +440,8 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
         a.l2_prefetch_rows = ctx->l2_prefetch_rows;
         a.evict_first = ctx->evict_first;
-        BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
+        if (p->f_wide) { a.yupd = p->tm1_f; BZ_TRY(bz_launch_dense_wide(ctx, a)); }
+        else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         p->nfx = std::min<long long>(ctx->num_sms, (p->n + 7) / 8);
         if (p->nfx < 1) p->nfx = 1;
@@ -456,10 +462,11 @@ static int launch_provider(bz_problem* p, int force_target) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         const bool timed = ctx->profiling && (p->dom_counter++ % ctx->prof_stride == 0);
         if (timed) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
-        BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
+        if (p->c_wide) BZ_TRY(bz_launch_dense_wide(ctx, a));
+        else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
         if (timed) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
         if (p->sharded)
-            BZ_TRY(bz_shard_allreduce(ctx, &p->shard, p->Pc, p->c_clusters, p->lxpart, p->n));
+            BZ_TRY(bz_shard_allreduce(ctx, &p->shard, p->Pc, p->c_clusters, p->lxpart, p->c_nlx, p->n));
     } else if (d.c_kind == BZ_C_IDENTITY) {
         p->nlx = bz_vec_grid(ctx, bz_d_is_pair(p->D.kind) ? p->n / 2 : p->n);
         BZ_TRY(bz_launch_identity_c(ctx, p->st, force_target, src, p->n, p->mu, p->muy, p->D, p->cx,

@@ -460,3 +460,49 @@ def test_iteration_count_parity_aggregate(gpu_ctx):
     # the oracle's own aggregate moves by +-1.5 % when the order of its sums is permuted
     assert abs(tot_g - tot_o) <= 0.03 * tot_o
     assert abs(out_g - out_o) <= 0.10 * out_o
+
+
+# ------------------------------------------------------------------------------- wide (two-pass) dense path
+@pytest.mark.parametrize("m,n", [(5, 40000), (37, 16390), (100, 20001), (9, 262144), (64, 256), (3, 5)])
+def test_wide_dense_gradient_parity(m, n, monkeypatch):
+    """nx > 16384 uses the two-pass wide kernels (k_wide_rows / k_wide_cols); BZ_FORCE_WIDE routes small
+    shapes through them too.  Same tolerances as the fused kernel."""
+    monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+    ctx = bz.Context(0)
+    A, b, p = _bp_problem(ctx, m, n, D=bz.ClosedSet(bz.IndBox(-0.5, 0.7)), seed=m + n)
+    rng = np.random.default_rng(m * 7 + n)
+    mu, y, x = rng.uniform(0.05, 3.0, m), rng.standard_normal(m), rng.standard_normal(n)
+    p.auglag_update(mu, y)
+    g = p.gradient(x)
+    al = bo.AugLagFun(bo.FZero(), bo.CDenseAffine(A, b), bo.BoxSet(-0.5, 0.7), mu.copy(), y.copy(), x)
+    dl = np.empty(n)
+    lx = al.gradient(dl, x)
+    nA = np.linalg.norm(A, 2) if m * n < 5_000_000 else np.linalg.norm(A) 
+    cscale = nA * np.linalg.norm(x) + np.linalg.norm(b)
+    assert np.max(np.abs(g["cx"] - al.cx)) <= KTOL * cscale
+    assert np.max(np.abs(g["yupd"] - al.yupd)) <= KTOL * cscale / mu.min()
+    assert np.max(np.abs(g["dlx"] - dl)) <= KTOL * (nA * np.linalg.norm(al.yupd) + 1e-300)
+    assert abs(g["lx"] - lx) <= KTOL * max(abs(lx), np.sum(al.yupd**2 * mu))
+    p.close()
+    ctx.close()
+
+
+def test_wide_path_whole_solve(monkeypatch):
+    monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+    ctx = bz.Context(0)
+    A, _, b = bo.make_basis_pursuit(20, 100)
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
+    out = bz.alps(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100), np.zeros(20),
+                  subsolver=sub, subsolver_maxit=100_000, ctx=ctx)
+    r = bo.solve(bo.problem_basis_pursuit(A, b), np.zeros(100))
+    assert out[5] == r.status == "first_order"
+    assert abs(np.sum(np.abs(out[0])) - np.sum(np.abs(r.x))) <= 1e-5 * np.sum(np.abs(r.x))
+    assert np.max(np.abs(A @ out[0] - b)) <= 1e-5
+    # LeastSquares f through the wide passes as well (reference's LASSO test)
+    A2 = np.array([[1, -2, 3, -4, 5], [2, -1, 0, -1, 3], [-1, 0, 4, -3, 2], [-1, -1, -1, 1, 3]], float)
+    b2 = np.array([1.0, 2.0, 3.0, 4.0])
+    lam = 0.1 * np.max(np.abs(A2.T @ b2))
+    o2 = bz.alps(bz.LeastSquares(A2, b2), bz.NormL1(lam), bz.IdentityFunction(), bz.FreeSet(), np.zeros(5), np.zeros(5), ctx=ctx)
+    x_star = np.array([-3.877278911564627e-01, 0, 0, 2.174149659863943e-02, 6.168435374149660e-01])
+    assert np.max(np.abs(o2[0] - x_star)) <= 1e-4 and o2[2] < 10 and o2[3] < 50
+    ctx.close()
