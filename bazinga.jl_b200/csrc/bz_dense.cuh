@@ -31,10 +31,19 @@ struct BzDenseArgs {
     int set_after;         // last CTA sets st->next_op = st->after_g
     int evict_first;       // stream A with an L2 evict-first policy
     int l2_prefetch_rows;  // >0: cp.async.bulk.prefetch.L2 this many rows ahead of each issue
+    // grid-wide single-pass kernel (bz_grid.cu) only
+    unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters
+    unsigned long long* gseq;  // sequence base of the exchange tags, advanced by m per launch
+    int xflags;                // tuning: 2 = exchange warps spin on test_wait, 4 = compute warps spin on test_wait
 };
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);
 int bz_launch_dense_wide(bz_ctx* ctx, const BzDenseArgs& args);
+// grid-wide single-pass kernel for wide A (bz_grid.cu)
+#define BZ_GRID_EXCHANGE_WORDS (256 * 160 * 2 + 256 * 16 * 32)   // entries + 16 arrival-counter shards per position, 256 B apart
+bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, int* G,
+                      int* W, int* nlx);
+int bz_launch_grid_algrad(bz_ctx* ctx, const BzDenseArgs& args);
 void bz_wide_geometry(const bz_ctx* ctx, long long m, long long n, int* row_ctas, int* row_chunks,
                       int* rows_per_chunk);
 int bz_launch_quad_grad(bz_ctx* ctx, const double* Q, const double* q, BzState* st, int force_target,

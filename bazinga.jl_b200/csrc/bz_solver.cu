@@ -42,7 +42,10 @@ struct bz_problem {
     // provider partial buffers
     double *Pc = nullptr, *Pf = nullptr, *lxpart = nullptr, *fxpart = nullptr;
     int c_clusters = 0, c_rpc = 0, f_clusters = 0, f_rpc = 0, nlx = 0, nfx = 0, nfx2 = 0;
-    bool c_wide = false, f_wide = false;   // two-pass wide path (nx > 16384)
+    bool c_wide = false, f_wide = false;   // wide path (nx > 16384)
+    bool c_grid = false, f_grid = false;   // ... served by the grid-wide single-pass kernel (bz_grid.cu)
+    unsigned long long* gridD = nullptr;   // its exchange ring and tag sequence base
+    unsigned long long* gseq = nullptr;
     int c_nlx = 0, f_nlx = 0;              // lx partial counts of the dense passes
     double* part = nullptr;
     unsigned int* counters = nullptr;   // [8]
@@ -108,6 +111,11 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_EVICT_FIRST")) ctx->evict_first = atoi(e);
     if (const char* e = getenv("BZ_PDL")) ctx->pdl = atoi(e);
     if (const char* e = getenv("BZ_FORCE_WIDE")) ctx->force_wide = atoi(e);
+    if (const char* e = getenv("BZ_WIDE_TWO_PASS")) ctx->wide_two_pass = atoi(e);
+    if (const char* e = getenv("BZ_GRID_INFLIGHT")) ctx->grid_inflight = atoi(e);
+    if (const char* e = getenv("BZ_GRID_XFLAGS")) ctx->grid_xflags = atoi(e);
+    if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
+    if (const char* e = getenv("BZ_GRID_PREFETCH")) ctx->grid_prefetch = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
     return BZ_OK;
@@ -228,6 +236,8 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
                        p->part, p->team.slots};
     for (double* f : frees) if (f) cudaFree(f);
     if (p->counters) cudaFree(p->counters);
+    if (p->gridD) cudaFree(p->gridD);
+    if (p->gseq) cudaFree(p->gseq);
     if (p->team.bars) cudaFree(p->team.bars);
     if (p->st) cudaFree(p->st);
     if (p->st_host) cudaFreeHost(p->st_host);
@@ -342,7 +352,9 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         PTRY(dev_alloc(ctx, &p->tm1_f, p->fm));
         PTRY(bz_launch_fill(ctx, p->f_ones, p->fm, 1.0));
         p->f_wide = n > DA_MAX_N || ctx->force_wide;
-        if (p->f_wide) bz_wide_geometry(ctx, p->fm, n, &p->f_nlx, &p->f_clusters, &p->f_rpc);
+        int gG, gW;
+        if (p->f_wide && bz_grid_geometry(ctx, p->fA, p->fm, n, n, &gG, &gW, &p->f_nlx)) { p->f_grid = true; p->f_clusters = 1; }
+        else if (p->f_wide) bz_wide_geometry(ctx, p->fm, n, &p->f_nlx, &p->f_clusters, &p->f_rpc);
         else { dense_partition(ctx, p->fm, &p->f_clusters, &p->f_rpc); p->f_nlx = p->f_clusters; }
         PTRY(dev_alloc(ctx, &p->Pf, (size_t)p->f_clusters * n));
     } else if (d->f_kind == BZ_F_QUADRATIC) {
@@ -373,10 +385,16 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
             }
         }
         p->c_wide = n > DA_MAX_N || ctx->force_wide;
-        if (p->c_wide) bz_wide_geometry(ctx, ml, n, &p->c_nlx, &p->c_clusters, &p->c_rpc);
+        int gG, gW;
+        if (p->c_wide && bz_grid_geometry(ctx, p->cA, ml, n, n, &gG, &gW, &p->c_nlx)) { p->c_grid = true; p->c_clusters = 1; }
+        else if (p->c_wide) bz_wide_geometry(ctx, ml, n, &p->c_nlx, &p->c_clusters, &p->c_rpc);
         else { dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc); p->c_nlx = p->c_clusters; }
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
+    }
+    if (p->c_grid || p->f_grid) {
+        PTRY(dev_alloc(ctx, &p->gridD, (size_t)BZ_GRID_EXCHANGE_WORDS));
+        PTRY(dev_alloc(ctx, &p->gseq, 1));
     }
 #undef PTRY
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -440,7 +458,9 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
         a.l2_prefetch_rows = ctx->l2_prefetch_rows;
         a.evict_first = ctx->evict_first;
-        if (p->f_wide) { a.yupd = p->tm1_f; BZ_TRY(bz_launch_dense_wide(ctx, a)); }
+        a.D = p->gridD; a.gseq = p->gseq;
+        if (p->f_grid) BZ_TRY(bz_launch_grid_algrad(ctx, a));
+        else if (p->f_wide) { a.yupd = p->tm1_f; BZ_TRY(bz_launch_dense_wide(ctx, a)); }
         else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         p->nfx = std::min<long long>(ctx->num_sms, (p->n + 7) / 8);
@@ -462,7 +482,9 @@ static int launch_provider(bz_problem* p, int force_target) {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         const bool timed = ctx->profiling && (p->dom_counter++ % ctx->prof_stride == 0);
         if (timed) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
-        if (p->c_wide) BZ_TRY(bz_launch_dense_wide(ctx, a));
+        a.D = p->gridD; a.gseq = p->gseq;
+        if (p->c_grid) BZ_TRY(bz_launch_grid_algrad(ctx, a));
+        else if (p->c_wide) BZ_TRY(bz_launch_dense_wide(ctx, a));
         else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
         if (timed) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
         if (p->sharded)

@@ -462,12 +462,16 @@ def test_iteration_count_parity_aggregate(gpu_ctx):
     assert abs(out_g - out_o) <= 0.10 * out_o
 
 
-# ------------------------------------------------------------------------------- wide (two-pass) dense path
-@pytest.mark.parametrize("m,n", [(5, 40000), (37, 16390), (100, 20001), (9, 262144), (64, 256), (3, 5)])
-def test_wide_dense_gradient_parity(m, n, monkeypatch):
-    """nx > 16384 uses the two-pass wide kernels (k_wide_rows / k_wide_cols); BZ_FORCE_WIDE routes small
-    shapes through them too.  Same tolerances as the fused kernel."""
+# ------------------------------------------------------------------------------- wide dense paths (nx > 16384)
+@pytest.mark.parametrize("two_pass", [0, 1])
+@pytest.mark.parametrize("m,n", [(5, 40000), (37, 16390), (100, 20001), (9, 262144), (64, 256), (3, 5), (1, 300000),
+                                 (700, 30000), (40, 400000), (33, 2)])
+def test_wide_dense_gradient_parity(m, n, two_pass, monkeypatch):
+    """nx > 16384 uses the grid-wide single-pass kernel (k_grid_algrad: even n, slice width <= 4096) or the
+    two-pass kernels (k_wide_rows / k_wide_cols: everything else, or BZ_WIDE_TWO_PASS=1); BZ_FORCE_WIDE routes
+    small shapes through them too.  Same tolerances as the fused cluster kernel."""
     monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+    monkeypatch.setenv("BZ_WIDE_TWO_PASS", str(two_pass))
     ctx = bz.Context(0)
     A, b, p = _bp_problem(ctx, m, n, D=bz.ClosedSet(bz.IndBox(-0.5, 0.7)), seed=m + n)
     rng = np.random.default_rng(m * 7 + n)
@@ -487,8 +491,10 @@ def test_wide_dense_gradient_parity(m, n, monkeypatch):
     ctx.close()
 
 
-def test_wide_path_whole_solve(monkeypatch):
+@pytest.mark.parametrize("two_pass", [0, 1])
+def test_wide_path_whole_solve(two_pass, monkeypatch):
     monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+    monkeypatch.setenv("BZ_WIDE_TWO_PASS", str(two_pass))
     ctx = bz.Context(0)
     A, _, b = bo.make_basis_pursuit(20, 100)
     sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
