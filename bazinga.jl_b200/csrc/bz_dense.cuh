@@ -34,7 +34,6 @@ struct BzDenseArgs {
     // grid-wide single-pass kernel (bz_grid.cu) only
     unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters
     unsigned long long* gseq;  // sequence base of the exchange tags, advanced by m per launch
-    int xflags;                // tuning: 2 = exchange warps spin on test_wait, 4 = compute warps spin on test_wait
 };
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);

@@ -322,9 +322,6 @@ struct bz_ctx {
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu
     int wide_two_pass = 0;      // nx > 16384: use the two-pass kernels instead of the grid-wide single pass (env BZ_WIDE_TWO_PASS)
     int grid_variant = 0;       // tuning knob of bz_grid.cu: warp-role split (env BZ_GRID_VARIANT)
-    int grid_prefetch = 0;      // tuning knob of bz_grid.cu: L2 prefetch distance in rows (env BZ_GRID_PREFETCH)
-    int grid_xflags = 0;        // tuning knob of bz_grid.cu (env BZ_GRID_XFLAGS)
-    int grid_inflight = 0;      // tuning knob of bz_grid.cu: ring slots left to loads in flight (env BZ_GRID_INFLIGHT)
 };
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);

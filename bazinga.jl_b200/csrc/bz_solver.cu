@@ -112,10 +112,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_PDL")) ctx->pdl = atoi(e);
     if (const char* e = getenv("BZ_FORCE_WIDE")) ctx->force_wide = atoi(e);
     if (const char* e = getenv("BZ_WIDE_TWO_PASS")) ctx->wide_two_pass = atoi(e);
-    if (const char* e = getenv("BZ_GRID_INFLIGHT")) ctx->grid_inflight = atoi(e);
-    if (const char* e = getenv("BZ_GRID_XFLAGS")) ctx->grid_xflags = atoi(e);
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
-    if (const char* e = getenv("BZ_GRID_PREFETCH")) ctx->grid_prefetch = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
     return BZ_OK;
