@@ -38,10 +38,10 @@ struct BzDenseArgs {
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);
 int bz_launch_dense_wide(bz_ctx* ctx, const BzDenseArgs& args);
-// grid-wide single-pass kernel for wide A (bz_grid.cu)
+// grid-wide single-pass kernel (bz_grid.cu): teams of CTAs split the columns of a row block
 #define BZ_GRID_EXCHANGE_WORDS (256 * 160 * 2 + 256 * 16 * 32)   // entries + 16 arrival-counter shards per position, 256 B apart
-bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, int* G,
-                      int* W, int* nlx);
+struct BzGridGeom { int GS, T, W, rpt; };   // team size, teams (= partial rows), slice width, rows per team
+bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, BzGridGeom* g);
 int bz_launch_grid_algrad(bz_ctx* ctx, const BzDenseArgs& args);
 void bz_wide_geometry(const bz_ctx* ctx, long long m, long long n, int* row_ctas, int* row_chunks,
                       int* rows_per_chunk);

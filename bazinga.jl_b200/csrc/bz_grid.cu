@@ -39,9 +39,9 @@
 #define GR_MAXSLOTS 24
 #define GR_PRING 32         // ring of per-row warp-partial sets / published w values (>= GR_MAXSLOTS)
 #define GR_DRING 256        // rows of the global exchange ring
-#define GR_RING_DOUBLES 28640   // 223.75 KB of row slices (16 slots of the C5 slice width 1772)
+#define GR_RING_DOUBLES 28624   // 223.6 KB of row slices (16 slots of the C5 slice width 1772)
 #define GR_SHARDS 16        // arrival-counter shards per ring position (same-address L2 atomics serialise at ~27 cycles each)
-#define GR_SMEM_BYTES (GR_RING_DOUBLES * 8 + 2 * GR_MAXSLOTS * 8 + 2 * GR_PRING * 8 + GR_PRING * 8 * 8 + GR_PRING * 8)
+#define GR_SMEM_BYTES (GR_RING_DOUBLES * 8 + 2 * GR_MAXSLOTS * 8 + 2 * GR_PRING * 8 + GR_PRING * 8 * 8 + GR_PRING * 8 + 16 * 8)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -60,7 +60,7 @@ __device__ __forceinline__ void ld_relaxed_v2(const unsigned long long* p, unsig
 // XW exchange warps, one producer warp; RB rows per loop trip of the dot / update warps
 template <int CH, int NCH, int XW, int RB>
 __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
-    k_grid_algrad(BzDenseArgs a, int W, int nslots) {
+    k_grid_algrad(BzDenseArgs a, int W, int nslots, int GS, int use_hint) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + GR_RING_DOUBLES);   // [GR_MAXSLOTS] TMA landed
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
     uint64_t* wbar = pbar + GR_PRING;                                        // [GR_PRING] w published
     double* wsum = reinterpret_cast<double*>(wbar + GR_PRING);               // [GR_PRING][8]
     double* wring = wsum + GR_PRING * 8;                                     // [GR_PRING]
+    double* lxs = wring + GR_PRING;                                          // [16] lx of the exchange warps
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bz_pdl_wait();
@@ -82,13 +83,18 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
     const double* __restrict__ xsrc = a.src[target];
     const unsigned long long seq0 = __ldcg(a.gseq);
 
-    const int G = gridDim.x, cta = blockIdx.x;
+    // team geometry: GS CTAs share the rows [r0, r0 + m) and split their columns; G = GS, cta = rank in team
+    const int G = GS, team = blockIdx.x / GS, cta = blockIdx.x % GS;
     const long long n = a.n;
-    const int m = (int)a.m;
+    const long long r0 = (long long)team * a.rows_per_cluster;
+    const long long mrem = a.m - r0;
+    const int m = (int)(mrem < 0 ? 0 : (mrem < a.rows_per_cluster ? mrem : a.rows_per_cluster));
     const long long col0 = (long long)cta * W;
     const int Wl = (int)((n - col0) < W ? (n - col0) : W);    // local slice width (even, > 0)
     const int stride = W;                                      // slot stride in doubles (even)
     const uint32_t row_bytes = (uint32_t)Wl * 8u;
+    unsigned long long* const Dteam = a.D + (size_t)team * ((size_t)GR_DRING * GS * 2);   // this team's exchange ring
+    unsigned long long* const Dcnt = a.D + (size_t)GR_DRING * 160 * 2;                   // arrival counters (one team only)
 
     if (tid == 0) {
         for (int s = 0; s < GR_MAXSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CH); }
@@ -227,25 +233,25 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
                 }
             }
         }
-        // each column is owned by exactly one CTA: P is the finished A'w (one "partial" row)
+        // within a team each column is owned by exactly one CTA: P[team] is the team's partial A'w
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             const int lc = c * (64 * CH) + lc0;
-            if (lc < Wl) *reinterpret_cast<double2*>(a.P + col0 + lc) = acc[c];
+            if (lc < Wl) *reinterpret_cast<double2*>(a.P + (size_t)team * n + col0 + lc) = acc[c];
         }
     } else if (warp < 2 * CH + XW) {
         // ------------------------------------------------------------------ exchange warps
         const int e = warp - 2 * CH;
         double lx = 0.0;
         for (int j = e; j < m; j += XW) {
-            const double b_j = __ldg(a.b + j), mu_j = __ldg(a.mu + j), muy_j = __ldg(a.muy + j);
+            const double b_j = __ldg(a.b + r0 + j), mu_j = __ldg(a.mu + r0 + j), muy_j = __ldg(a.muy + r0 + j);
             const int pr = j % GR_PRING;
             mbar_wait(&pbar[pr], (uint32_t)((j / GR_PRING) & 1));
             // ring position, tag and arrival counts are all derived from the global row sequence number
             const unsigned long long sq = seq0 + (unsigned long long)j;
             const unsigned long long tag = ((sq + 1ULL) & 0xffffffffULL) << 32;
             const unsigned int pos = (unsigned int)(sq % GR_DRING);
-            const unsigned long long* Drow = a.D + (size_t)pos * (size_t)G * 2;
+            unsigned long long* Drow = Dteam + (size_t)pos * (size_t)G * 2;
             {   // this CTA's slice dot: fixed tree over the CH warp partials, posted by lane 0
                 double v = (lane < CH) ? wsum[pr * 8 + lane] : 0.0;
                 if (CH > 4) v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -253,16 +259,18 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 if (lane == 0) {
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-                    st_relaxed_v2(a.D + ((size_t)pos * (size_t)G + cta) * 2, tag | (bits & 0xffffffffULL), tag | (bits >> 32));
-                    unsigned long long* mycnt = a.D + (size_t)GR_DRING * 160 * 2 + ((size_t)pos * GR_SHARDS + (cta % GR_SHARDS)) * 32;
-                    asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(mycnt) : "memory");
+                    st_relaxed_v2(Drow + 2 * cta, tag | (bits & 0xffffffffULL), tag | (bits >> 32));
+                    if (use_hint) {
+                        unsigned long long* mycnt = Dcnt + ((size_t)pos * GR_SHARDS + (cta % GR_SHARDS)) * 32;
+                        asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(mycnt) : "memory");
+                    }
                 }
             }
             // The arrival counters are only a HINT that keeps 148 x XW warps from hammering L2 with gather
             // rounds: correctness rests on the self-validating tags below.  CTA c counts on shard c % 16
             // (same-address L2 atomics from 148 CTAs serialise at ~27 cycles each: 4000 cycles unsharded).
-            if (lane < GR_SHARDS && lane < G) {
-                const unsigned long long* cnt = a.D + (size_t)GR_DRING * 160 * 2 + ((size_t)pos * GR_SHARDS + lane) * 32;
+            if (use_hint && lane < GR_SHARDS && lane < G) {
+                const unsigned long long* cnt = Dcnt + ((size_t)pos * GR_SHARDS + lane) * 32;
                 const unsigned long long want = (sq / GR_DRING + 1ULL) * (unsigned long long)((G - lane + GR_SHARDS - 1) / GR_SHARDS);
                 unsigned long long have;
                 do {
@@ -305,20 +313,17 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
                 wring[pr] = w;
                 mbar_arrive(&wbar[pr]);
                 if (cta == 0) {
-                    if (a.cx) a.cx[j] = cxv;
-                    if (a.s) a.s[j] = sv;
-                    if (a.yupd) a.yupd[j] = w;
+                    if (a.cx) a.cx[r0 + j] = cxv;
+                    if (a.s) a.s[r0 + j] = sv;
+                    if (a.yupd) a.yupd[r0 + j] = w;
                 }
             }
         }
-        if (cta == 0 && lane == 0) {
-            a.lxpart[e] = lx;
-            if (e == 0) for (int q = XW; q < 16; ++q) a.lxpart[q] = 0.0;   // the consumers add 16 partials
-        }
+        if (lane == 0) lxs[e] = lx;
     } else if (lane == 0) {
         // ------------------------------------------------------------------ producer
         const uint64_t l2pol = l2_evict_first_policy();
-        const double* src = a.A + col0;
+        const double* src = a.A + r0 * a.lda + col0;
         for (int r = 0; r < m; ++r) {
             const int slot = r % nslots;
             if (r >= nslots) mbar_wait(&empty[slot], (uint32_t)(((r / nslots) - 1) & 1));
@@ -331,9 +336,15 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
         }
     }
 
+    __syncthreads();
+    if (cta == 0 && tid == 0) {   // the team's lx partial: exchange warps in fixed order
+        double lx = 0.0;
+        for (int e = 0; e < XW; ++e) lx += (e < m) ? lxs[e] : 0.0;
+        a.lxpart[team] = lx;
+    }
     if (bz_last_cta(a.counter, gridDim.x)) {
         if (tid == 0) {
-            *a.gseq = seq0 + (unsigned long long)m;   // next launch: fresh tags
+            *a.gseq = seq0 + (unsigned long long)a.rows_per_cluster;   // next launch: fresh tags
             if (a.set_after) {
                 a.st->next_op = a.st->after_g;
                 if (a.force_target < 0) bz_toc(a.st, 0);
@@ -343,49 +354,77 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
     }
 }
 
-// geometry of the grid-wide pass; returns false when the shape cannot take it (then the two-pass
-// kernels of bz_dense.cu run instead)
-bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, int* G,
-                      int* W, int* nlx) {
+// Geometry of the pass.  The SMs are divided into T teams of GS CTAs; team t owns the rows
+// [t*rpt, (t+1)*rpt) and its CTAs split the columns into slices of W.  Wanted: every SM busy, and slices of
+// 1024..4096 columns (below ~1024 a row takes less HBM time than one exchange can sustain; above 4096 the x slice
+// and the accumulators no longer fit in registers).  C5 (n = 262144): one team of 148, W = 1772; n = 65536: 4 teams
+// of 37; n = 32768: 9 teams of 16.  Returns false when the shape cannot take it (odd n, tiny problems, ...): the cluster
+// kernel / the two-pass kernels of bz_dense.cu run instead.
+bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, BzGridGeom* g) {
     if (ctx->wide_two_pass) return false;
-    // one exchange per row sustains ~6 rows/us: below ~64k columns a row takes less HBM time than that and the
-    // two-pass kernels (half the roofline by construction) are no slower
-    if (n < 65536 && !ctx->force_wide) return false;
     if (n % 2 || lda % 2 || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
-    if (m > 0x7fffff00LL) return false;
+    if (m < 1 || m > 0x7fffff00LL) return false;
     const int sms = ctx->num_sms < 160 ? ctx->num_sms : 160;
-    long long w = (n + sms - 1) / sms;
-    w = (w + 1) & ~1LL;
-    if (w < 2) w = 2;
-    if (w > 4096) return false;
-    *W = (int)w;
-    *G = (int)((n + w - 1) / w);
-    *nlx = 16;   // lx partials: one per exchange warp (<= 15), the rest stay zero
+    const bool forced = ctx->force_wide != 0;
+    // n <= 16384 stays with the 2-CTA cluster kernel of bz_dense.cu: measured on C2 (4096 x 16384) it needs 90 us per
+    // pass, this kernel 103 us (37 teams of 4) / 106 us (18 teams of 8) -- a team's rows are few (111) and each pays the
+    // exchange latency the cluster kernel's DSMEM hand-over does not have
+    if (!forced && n <= DA_MAX_N) return false;
+    long long gs_min = (n + 4095) / 4096;
+    if (gs_min > sms) return false;
+    int best_gs = 0, best_w = 0, best_t = 0;
+    double best_u = -1.0;
+    for (long long gs0 = gs_min; gs0 <= sms; ++gs0) {
+        long long w = (n + gs0 - 1) / gs0;
+        w = (w + 1) & ~1LL;
+        if (w < 2) w = 2;
+        if (w > 4096) continue;
+        if (w < 1024 && !forced && gs0 > gs_min) break;         // slices only get narrower from here
+        const long long gs = (n + w - 1) / w;                    // CTAs that really get columns
+        long long t = sms / gs;
+        const long long tmax = (m + 7) / 8;                      // at least ~8 rows per team
+        if (t > tmax) t = tmax;
+        if (t < 1) t = 1;
+        if (ctx->grid_team > 0 && gs != ctx->grid_team) continue;
+        const double u = (double)(gs * t) / sms;
+        if (u > best_u + 1e-9 || (u > best_u - 1e-9 && gs > best_gs)) { best_u = u; best_gs = (int)gs; best_w = (int)w; best_t = (int)t; }
+    }
+    if (best_gs == 0) return false;
+    if (!forced && best_w < 512) return false;   // rows too short for one exchange per row
+    g->GS = best_gs; g->W = best_w; g->T = best_t;
+    g->rpt = (int)((m + best_t - 1) / best_t);
+    g->T = (int)((m + g->rpt - 1) / g->rpt);
     return true;
 }
 
 template <int CH, int NCH, int XW, int RB>
-static int launch_variant(bz_ctx* ctx, const BzDenseArgs& a, int G, int W, int nslots) {
+static int launch_variant(bz_ctx* ctx, const BzDenseArgs& a, const BzGridGeom& g, int nslots) {
     static_assert(CH >= 2 && CH <= 8 && (CH & (CH - 1)) == 0, "wsum holds 8 warp partials per row");
-    if (W > NCH * 64 * CH) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "grid-wide dense pass: slice wider than the variant");
+    static_assert(XW <= 16, "lxs holds 16 partials");
+    if (g.W > NCH * 64 * CH) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "grid-wide dense pass: slice wider than the variant");
     static bool attr_set = false;
     if (!attr_set) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_grid_algrad<CH, NCH, XW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
         attr_set = true;
     }
-    return bz_launch_pdl(ctx, k_grid_algrad<CH, NCH, XW, RB>, dim3(G), dim3((2 * CH + XW + 1) * 32), GR_SMEM_BYTES, 0, a, W, nslots);
+    // the sharded arrival counters exist once: they serve the single-team geometry (148 CTAs per exchange); small
+    // teams validate the few entries directly
+    const int use_hint = (g.T == 1 && g.GS > 32) ? 1 : 0;
+    return bz_launch_pdl(ctx, k_grid_algrad<CH, NCH, XW, RB>, dim3(g.GS * g.T), dim3((2 * CH + XW + 1) * 32), GR_SMEM_BYTES, 0, a,
+                         g.W, nslots, g.GS, use_hint);
 }
 
 int bz_launch_grid_algrad(bz_ctx* ctx, const BzDenseArgs& args) {
-    int G, W, nlx;
-    if (!bz_grid_geometry(ctx, args.A, args.m, args.n, args.lda, &G, &W, &nlx))
+    BzGridGeom g;
+    if (!bz_grid_geometry(ctx, args.A, args.m, args.n, args.lda, &g))
         return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "grid-wide dense pass: unsupported shape");
-    int nslots = GR_RING_DOUBLES / W;          // >= 7 (W <= 4096)
+    int nslots = GR_RING_DOUBLES / g.W;          // >= 6 (W <= 4096)
     if (nslots > GR_MAXSLOTS) nslots = GR_MAXSLOTS;
-    const BzDenseArgs& a2 = args;
-    if (W > 2048) return launch_variant<8, 8, 7, 2>(ctx, a2, G, W, nslots);
+    BzDenseArgs a2 = args;
+    a2.rows_per_cluster = g.rpt;
+    if (g.W > 2048) return launch_variant<8, 8, 7, 2>(ctx, a2, g, nslots);
     // measured on 8192 x 262144 (us per pass): <4,8,15,2> 2818, <4,8,11,2> 2858, <4,8,15,4> 2962, <4,8,15,1> 3150,
     // <8,4,15,2> 3157, <2,16,15,2> 4352; BZ_GRID_VARIANT=1 keeps the 8+8-warp split reachable for the tests
-    if (ctx->grid_variant == 1) return launch_variant<8, 4, 15, 2>(ctx, a2, G, W, nslots);
-    return launch_variant<4, 8, 15, 2>(ctx, a2, G, W, nslots);
+    if (ctx->grid_variant == 1) return launch_variant<8, 4, 15, 2>(ctx, a2, g, nslots);
+    return launch_variant<4, 8, 15, 2>(ctx, a2, g, nslots);
 }

@@ -321,6 +321,7 @@ struct bz_ctx {
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu
     int wide_two_pass = 0;      // nx > 16384: use the two-pass kernels instead of the grid-wide single pass (env BZ_WIDE_TWO_PASS)
+    int grid_team = 0;          // tuning knob of bz_grid.cu: CTAs per team (env BZ_GRID_TEAM)
     int grid_variant = 0;       // tuning knob of bz_grid.cu: warp-role split (env BZ_GRID_VARIANT)
 };
 

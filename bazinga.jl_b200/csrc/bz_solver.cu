@@ -113,6 +113,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_FORCE_WIDE")) ctx->force_wide = atoi(e);
     if (const char* e = getenv("BZ_WIDE_TWO_PASS")) ctx->wide_two_pass = atoi(e);
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
+    if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
     return BZ_OK;
@@ -349,8 +350,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         PTRY(dev_alloc(ctx, &p->tm1_f, p->fm));
         PTRY(bz_launch_fill(ctx, p->f_ones, p->fm, 1.0));
         p->f_wide = n > DA_MAX_N || ctx->force_wide;
-        int gG, gW;
-        if (p->f_wide && bz_grid_geometry(ctx, p->fA, p->fm, n, n, &gG, &gW, &p->f_nlx)) { p->f_grid = true; p->f_clusters = 1; }
+        BzGridGeom gg;
+        if (bz_grid_geometry(ctx, p->fA, p->fm, n, n, &gg)) { p->f_grid = true; p->f_clusters = p->f_nlx = gg.T; }
         else if (p->f_wide) bz_wide_geometry(ctx, p->fm, n, &p->f_nlx, &p->f_clusters, &p->f_rpc);
         else { dense_partition(ctx, p->fm, &p->f_clusters, &p->f_rpc); p->f_nlx = p->f_clusters; }
         PTRY(dev_alloc(ctx, &p->Pf, (size_t)p->f_clusters * n));
@@ -382,8 +383,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
             }
         }
         p->c_wide = n > DA_MAX_N || ctx->force_wide;
-        int gG, gW;
-        if (p->c_wide && bz_grid_geometry(ctx, p->cA, ml, n, n, &gG, &gW, &p->c_nlx)) { p->c_grid = true; p->c_clusters = 1; }
+        BzGridGeom gg;
+        if (bz_grid_geometry(ctx, p->cA, ml, n, n, &gg)) { p->c_grid = true; p->c_clusters = p->c_nlx = gg.T; }
         else if (p->c_wide) bz_wide_geometry(ctx, ml, n, &p->c_nlx, &p->c_clusters, &p->c_rpc);
         else { dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc); p->c_nlx = p->c_clusters; }
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
