@@ -33,13 +33,13 @@ struct BzDenseArgs {
     int l2_prefetch_rows;  // >0: cp.async.bulk.prefetch.L2 this many rows ahead of each issue
     // grid-wide single-pass kernel (bz_grid.cu) only
     unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters
-    unsigned long long* gseq;  // sequence base of the exchange tags, advanced by m per launch
+    unsigned long long* gseq;  // [teams] sequence base of the exchange tags, advanced by the team's row count per launch
 };
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters);
 int bz_launch_dense_wide(bz_ctx* ctx, const BzDenseArgs& args);
 // grid-wide single-pass kernel (bz_grid.cu): teams of CTAs split the columns of a row block
-#define BZ_GRID_EXCHANGE_WORDS (256 * 160 * 2 + 256 * 16 * 32)   // entries + 16 arrival-counter shards per position, 256 B apart
+#define BZ_GRID_EXCHANGE_WORDS (256 * 160 * 2 + 160 * 256 * 32)   // entries + arrival counters (256 B apart): teams x shards <= 160
 struct BzGridGeom { int GS, T, W, rpt; };   // team size, teams (= partial rows), slice width, rows per team
 bool bz_grid_geometry(const bz_ctx* ctx, const double* A, long long m, long long n, long long lda, BzGridGeom* g);
 int bz_launch_grid_algrad(bz_ctx* ctx, const BzDenseArgs& args);

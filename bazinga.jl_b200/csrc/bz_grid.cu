@@ -60,7 +60,7 @@ __device__ __forceinline__ void ld_relaxed_v2(const unsigned long long* p, unsig
 // XW exchange warps, one producer warp; RB rows per loop trip of the dot / update warps
 template <int CH, int NCH, int XW, int RB>
 __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
-    k_grid_algrad(BzDenseArgs a, int W, int nslots, int GS, int use_hint) {
+    k_grid_algrad(BzDenseArgs a, int W, int nslots, int GS, int nshards) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + GR_RING_DOUBLES);   // [GR_MAXSLOTS] TMA landed
@@ -81,10 +81,12 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
         if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
     }
     const double* __restrict__ xsrc = a.src[target];
-    const unsigned long long seq0 = __ldcg(a.gseq);
 
     // team geometry: GS CTAs share the rows [r0, r0 + m) and split their columns; G = GS, cta = rank in team
     const int G = GS, team = blockIdx.x / GS, cta = blockIdx.x % GS;
+    // the team's row sequence base: every team consumes consecutive sequence numbers (its own row count per launch),
+    // so ring positions, tags and arrival counts stay in step even when the last team has fewer rows
+    const unsigned long long seq0 = __ldcg(a.gseq + team);
     const long long n = a.n;
     const long long r0 = (long long)team * a.rows_per_cluster;
     const long long mrem = a.m - r0;
@@ -94,7 +96,8 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
     const int stride = W;                                      // slot stride in doubles (even)
     const uint32_t row_bytes = (uint32_t)Wl * 8u;
     unsigned long long* const Dteam = a.D + (size_t)team * ((size_t)GR_DRING * GS * 2);   // this team's exchange ring
-    unsigned long long* const Dcnt = a.D + (size_t)GR_DRING * 160 * 2;                   // arrival counters (one team only)
+    // this team's arrival counters: GR_DRING positions x nshards counters, 256 B apart
+    unsigned long long* const Dcnt = a.D + (size_t)GR_DRING * 160 * 2 + (size_t)team * ((size_t)GR_DRING * nshards * 32);
 
     if (tid == 0) {
         for (int s = 0; s < GR_MAXSLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CH); }
@@ -260,18 +263,18 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
                 if (lane == 0) {
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
                     st_relaxed_v2(Drow + 2 * cta, tag | (bits & 0xffffffffULL), tag | (bits >> 32));
-                    if (use_hint) {
-                        unsigned long long* mycnt = Dcnt + ((size_t)pos * GR_SHARDS + (cta % GR_SHARDS)) * 32;
+                    if (nshards > 0) {
+                        unsigned long long* mycnt = Dcnt + ((size_t)pos * nshards + (cta % nshards)) * 32;
                         asm volatile("red.relaxed.gpu.global.add.u64 [%0], 1;" ::"l"(mycnt) : "memory");
                     }
                 }
             }
             // The arrival counters are only a HINT that keeps 148 x XW warps from hammering L2 with gather
-            // rounds: correctness rests on the self-validating tags below.  CTA c counts on shard c % 16
+            // rounds: correctness rests on the self-validating tags below.  CTA c counts on shard c % nshards
             // (same-address L2 atomics from 148 CTAs serialise at ~27 cycles each: 4000 cycles unsharded).
-            if (use_hint && lane < GR_SHARDS && lane < G) {
-                const unsigned long long* cnt = Dcnt + ((size_t)pos * GR_SHARDS + lane) * 32;
-                const unsigned long long want = (sq / GR_DRING + 1ULL) * (unsigned long long)((G - lane + GR_SHARDS - 1) / GR_SHARDS);
+            if (lane < nshards) {
+                const unsigned long long* cnt = Dcnt + ((size_t)pos * nshards + lane) * 32;
+                const unsigned long long want = (sq / GR_DRING + 1ULL) * (unsigned long long)((G - lane + nshards - 1) / nshards);
                 unsigned long long have;
                 do {
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(have) : "l"(cnt) : "memory");
@@ -343,8 +346,12 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
         a.lxpart[team] = lx;
     }
     if (bz_last_cta(a.counter, gridDim.x)) {
+        const int T = gridDim.x / GS;
+        for (int t = tid; t < T; t += blockDim.x) {   // next launch: fresh tags for every team
+            const long long rem = a.m - (long long)t * a.rows_per_cluster;
+            a.gseq[t] += (unsigned long long)(rem < a.rows_per_cluster ? rem : a.rows_per_cluster);
+        }
         if (tid == 0) {
-            *a.gseq = seq0 + (unsigned long long)a.rows_per_cluster;   // next launch: fresh tags
             if (a.set_after) {
                 a.st->next_op = a.st->after_g;
                 if (a.force_target < 0) bz_toc(a.st, 0);
@@ -407,11 +414,12 @@ static int launch_variant(bz_ctx* ctx, const BzDenseArgs& a, const BzGridGeom& g
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_grid_algrad<CH, NCH, XW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
         attr_set = true;
     }
-    // the sharded arrival counters exist once: they serve the single-team geometry (148 CTAs per exchange); small
-    // teams validate the few entries directly
-    const int use_hint = (g.T == 1 && g.GS > 32) ? 1 : 0;
+    // arrival-counter shards per ring position: ~8 CTAs per counter, at most 16 (GR_SHARDS); teams of <= 8 CTAs
+    // validate their few entries directly (measured on 37 teams of 4: 103 us per pass without the hint, 490 us with it)
+    int nshards = g.GS <= 8 ? 0 : g.GS / 8;
+    if (nshards > GR_SHARDS) nshards = GR_SHARDS;
     return bz_launch_pdl(ctx, k_grid_algrad<CH, NCH, XW, RB>, dim3(g.GS * g.T), dim3((2 * CH + XW + 1) * 32), GR_SMEM_BYTES, 0, a,
-                         g.W, nslots, g.GS, use_hint);
+                         g.W, nslots, g.GS, nshards);
 }
 
 int bz_launch_grid_algrad(bz_ctx* ctx, const BzDenseArgs& args) {

@@ -392,7 +392,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     }
     if (p->c_grid || p->f_grid) {
         PTRY(dev_alloc(ctx, &p->gridD, (size_t)BZ_GRID_EXCHANGE_WORDS));
-        PTRY(dev_alloc(ctx, &p->gseq, 1));
+        PTRY(dev_alloc(ctx, &p->gseq, 160));   // one row-sequence base per team
     }
 #undef PTRY
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

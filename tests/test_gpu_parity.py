@@ -491,6 +491,33 @@ def test_wide_dense_gradient_parity(m, n, two_pass, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("team", [8, 2, 1])
+def test_team_kernel_ragged_teams_many_launches(team, monkeypatch):
+    """k_grid_algrad keeps per-team row sequence numbers across launches (exchange ring positions, tags, arrival
+    counts).  Ragged teams (the last one has fewer rows) and > 256 rows per team through the ring, many launches."""
+    monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+    monkeypatch.setenv("BZ_GRID_TEAM", str(team))
+    ctx = bz.Context(0)
+    m, n = 50, 4096
+    A, b, p = _bp_problem(ctx, m, n, seed=77)
+    rng = np.random.default_rng(5)
+    mu, y = rng.uniform(0.05, 3.0, m), rng.standard_normal(m)
+    p.auglag_update(mu, y)
+    nA = np.linalg.norm(A, 2)
+    for it in range(90):
+        x = rng.standard_normal(n)
+        g = p.gradient(x)
+        if it % 15 == 14 or it < 2:
+            al = bo.AugLagFun(bo.FZero(), bo.CDenseAffine(A, b), bo.ZeroSet(), mu.copy(), y.copy(), x)
+            dl = np.empty(n)
+            lx = al.gradient(dl, x)
+            assert np.max(np.abs(g["cx"] - al.cx)) <= KTOL * (nA * np.linalg.norm(x) + np.linalg.norm(b))
+            assert np.max(np.abs(g["dlx"] - dl)) <= KTOL * nA * np.linalg.norm(al.yupd)
+            assert abs(g["lx"] - lx) <= KTOL * abs(lx)
+    p.close()
+    ctx.close()
+
+
 @pytest.mark.parametrize("two_pass", [0, 1])
 def test_wide_path_whole_solve(two_pass, monkeypatch):
     monkeypatch.setenv("BZ_FORCE_WIDE", "1")
