@@ -35,15 +35,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     uint64_t* xbar = reinterpret_cast<uint64_t*>(xchg + 2);                   // [2]: their arrival barriers
 
     const int tid = threadIdx.x;
-    bz_pdl_wait();
     bz_pdl_launch_dependents();
-    int target = a.force_target;
-    if (target < 0) {
-        if (__ldcg(&a.st->next_op) != OP_G) return;   // both CTAs of a cluster take the same branch
-        target = __ldcg(&a.st->grad_target);
-        if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
-    }
-    const double* __restrict__ xsrc = a.src[target];
+    // Everything up to bz_pdl_wait() below overlaps the tail of the predecessor kernel (programmatic
+    // dependent launch): barrier setup and -- because no kernel of the cycle ever writes A -- the
+    // bulk copies that fill the ring.  Only x and the state machine have to wait.
 
     const uint32_t rank = cluster_ctarank();
     const int q = blockIdx.x >> 1;
@@ -64,17 +59,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     int nslots = DA_RING_DOUBLES / stride;
     if (nslots > DA_MAXSLOTS) nslots = DA_MAXSLOTS;
     const uint32_t row_bytes = (uint32_t)W * 8u;
-
-    // x slice and accumulators in registers; lane validity is per (chunk, element)
-    const int lc0 = 2 * tid;
-    double2 xr[DA_MAXCH], acc[DA_MAXCH];
-#pragma unroll
-    for (int c = 0; c < DA_MAXCH; ++c) {
-        const int lc = c * DA_CHUNK + lc0;
-        xr[c].x = (lc < W) ? xsrc[col0 + lc] : 0.0;
-        xr[c].y = (lc + 1 < W) ? xsrc[col0 + lc + 1] : 0.0;
-        acc[c] = make_double2(0.0, 0.0);
-    }
 
     if (tid == 0) {
         if (BULK)
@@ -113,7 +97,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     };
 
     const int npre = nrows < nslots ? nrows : nslots;
-    for (int r = 0; r < npre; ++r) issue_row(r, r);
+    if (BULK)
+        for (int r = 0; r < npre; ++r) issue_row(r, r);
+
+    bz_pdl_wait();
+    int target = a.force_target;
+    if (target < 0) {
+        if (__ldcg(&a.st->next_op) != OP_G) {          // both CTAs of a cluster take the same branch
+            if (BULK && W > 0)                           // the copies in flight must land before the CTA may exit
+                for (int r = 0; r < npre; ++r) mbar_wait(&full[r], 0u);
+            return;
+        }
+        target = __ldcg(&a.st->grad_target);
+        if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
+    }
+    const double* __restrict__ xsrc = a.src[target];
+    if (!BULK)
+        for (int r = 0; r < npre; ++r) issue_row(r, r);
+
+    // x slice and accumulators in registers; lane validity is per (chunk, element)
+    const int lc0 = 2 * tid;
+    double2 xr[DA_MAXCH], acc[DA_MAXCH];
+#pragma unroll
+    for (int c = 0; c < DA_MAXCH; ++c) {
+        const int lc = c * DA_CHUNK + lc0;
+        xr[c].x = (lc < W) ? xsrc[col0 + lc] : 0.0;
+        xr[c].y = (lc + 1 < W) ? xsrc[col0 + lc + 1] : 0.0;
+        acc[c] = make_double2(0.0, 0.0);
+    }
 
     double lx = 0.0;
     double own_prev = 0.0;           // this CTA's slice dot of the previous row

@@ -401,12 +401,15 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
 }
 
 extern "C" int bz_problem_upload_dense(bz_problem* p, const double* c_A, const double* c_b) {
-    if (!p || !c_A || !c_b) return BZ_ERR_ARG;
+    if (!p || !c_b) return BZ_ERR_ARG;
     bz_ctx* ctx = p->ctx;
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (p->desc.c_kind != BZ_C_DENSE_AFFINE || !p->own_cA)
-        return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_upload_dense: problem does not own a dense A");
-    BZ_TRY(upload_matrix(ctx, c_A, p->desc.c_layout, p->ml, p->n, p->cA));
+    if (p->desc.c_kind != BZ_C_DENSE_AFFINE)
+        return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_upload_dense: problem has no dense affine c");
+    if (c_A) {   // c_A == NULL: keep the matrix (adopted or generated on the device), replace b only
+        if (!p->own_cA) return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_upload_dense: problem does not own its dense A");
+        BZ_TRY(upload_matrix(ctx, c_A, p->desc.c_layout, p->ml, p->n, p->cA));
+    }
     BZ_CUDA(ctx, cudaMemcpyAsync(p->cb, c_b, p->ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     return BZ_OK;
 }

@@ -241,7 +241,12 @@ class Problem:
         return x, y, s, mu, res
 
     def upload_dense(self, A, b):
-        A, b = np.asarray(A, dtype=np.float64), _f64(b)
+        """Replace the dense constraint data; ``A=None`` keeps the device-resident matrix and replaces b only."""
+        b = _f64(b)
+        if A is None:
+            K.check(self.lib.bz_problem_upload_dense(self.handle, None, _ptr(b)), self.ctx.handle)
+            return
+        A = np.asarray(A, dtype=np.float64)
         K.check(self.lib.bz_problem_upload_dense(self.handle, _ptr(A), _ptr(b)), self.ctx.handle)
 
     def panocplus(self, mu, y, x0, sub: PANOCplus):

@@ -167,7 +167,8 @@ void bz_default_options(bz_options* opt);
  * all solver state.  Replaces constructing the Julia oracle structs + AugLagFun (auglagfun.jl:32-54). */
 int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* desc, bz_problem** out);
 int bz_problem_destroy(bz_problem* p);
-/* Re-upload the dense constraint data of an existing problem (host -> device), for end-to-end timing. */
+/* Re-upload the dense constraint data of an existing problem (host -> device), for end-to-end timing.
+ * c_A == NULL keeps the matrix (e.g. one generated on the device from a seed) and replaces b only. */
 int bz_problem_upload_dense(bz_problem* p, const double* c_A, const double* c_b);
 
 /* alps(f,g,c,D,x0,y0; ...) -> (x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol,
