@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbazinga_b200.so")
 
-BZ_ABI_VERSION = 1
+BZ_ABI_VERSION = 2
 
 # enums (include/bazinga_b200.h)
 F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1 = range(7)
@@ -37,6 +37,7 @@ class ProblemDesc(C.Structure):
         ("grid_y", C.c_int64), ("grid_x", C.c_int64),
         ("d_lo", C.c_double), ("d_hi", C.c_double), ("d_pair_stride", C.c_int64),
         ("row_begin", C.c_int64), ("ny_local", C.c_int64),
+        ("slab_nranks", C.c_int32), ("slab_rank", C.c_int32), ("nx_global", C.c_int64),
     ]
 
 
@@ -79,6 +80,8 @@ SYMBOLS = {
     "bz_problem_create": (C.c_int, [_vp, C.POINTER(ProblemDesc), C.POINTER(_vp)]),
     "bz_problem_destroy": (C.c_int, [_vp]),
     "bz_problem_upload_dense": (C.c_int, [_vp, _vp, _vp]),
+    "bz_problem_xr_handle": (C.c_int, [_vp, _vp]),
+    "bz_problem_xr_attach": (C.c_int, [_vp, _vp]),
     "bz_alps_solve": (C.c_int, [_vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp, C.POINTER(Result)]),
     "bz_panocplus_solve": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Options), C.c_double, _vp,
                                      C.POINTER(C.c_int64), _dp, _dp]),

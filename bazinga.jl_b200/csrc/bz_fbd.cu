@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     double sums[6];
     bz_final_sums<6>(ptrs, counts, sums, scratch);
     if (threadIdx.x != 0) return;
+    bz_xr_allreduce(st, sums, 6, 0u);         // slab mode: sums over ranks
     const double s0 = sums[0], s1 = sums[1], s2 = sums[2];
     double fx = 0.0, lx = 0.0;
     if (need_value) lx = bz_value_from_sums(gs, st->musqy, sums[3], sums[4], sums[5], fx);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
         st->mode = MODE_INIT1;
         st->next_op = OP_G;
     } else if (mode == MODE_INIT1) {
-        const double Lest = sqrt(s0) / sqrt((double)n);
+        const double Lest = sqrt(s0) / sqrt((double)(st->n_global > 0 ? st->n_global : n));
         st->Lest = Lest;
         st->gamma = st->alpha / Lest;     // L = 0 -> gamma = Inf, IEEE semantics as upstream
         st->n_grad += 1;
@@ -220,13 +221,18 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     }
     if (!bz_last_cta(counter, nb)) return;
 
-    const double stop1 = bz_final_nanmax(part, nb, scratch);
-    const double stop2 = bz_final_nanmax(part + nb, nb, scratch);
+    double stop1 = bz_final_nanmax(part, nb, scratch);
+    double stop2 = bz_final_nanmax(part + nb, nb, scratch);
     const double* const ptrs[3] = {gs.lxpart, gs.fxpart, gs.fxpart2};
     const int counts[3] = {gs.nlx, gs.nfx, gs.nfx2};
     double sums[3];
     bz_final_sums<3>(ptrs, counts, sums, scratch);
     if (threadIdx.x != 0) return;
+    if (st->xr.nranks > 1) {                  // slab mode: max / sums over ranks
+        double v5[5] = {stop1, stop2, sums[0], sums[1], sums[2]};
+        bz_xr_allreduce(st, v5, 5, 3u);
+        stop1 = v5[0]; stop2 = v5[1]; sums[0] = v5[2]; sums[1] = v5[3]; sums[2] = v5[4];
+    }
     double fx;
     const double f_z = bz_value_from_sums(gs, st->musqy, sums[0], sums[1], sums[2], fx);
 
@@ -311,8 +317,13 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     }
     if (!bz_last_cta(counter, gridDim.x)) return;
     double fx;
-    const double lx = bz_assemble_value(gs, st, scratch, fx);
+    double lx = bz_assemble_value(gs, st, scratch, fx);
     if (threadIdx.x == 0) {
+        if (st->xr.nranks > 1) {              // slab mode: lx = sum_r (0.5*slx_r + fx_r) - musqy (musqy is global already)
+            double v2[2] = {lx + st->musqy, fx};
+            bz_xr_allreduce(st, v2, 2, 0u);
+            lx = v2[0] - st->musqy; fx = v2[1];
+        }
         st->al_fx = fx; st->al_lx = lx;
         st->out[0] = lx; st->out[1] = fx;
         __threadfence();

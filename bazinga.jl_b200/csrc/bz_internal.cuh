@@ -25,6 +25,27 @@ enum BzLRole : int { LROLE_NEWITER = 0, LROLE_INTERP = 1 };
 enum BzTarget : int { TGT_X = 0, TGT_Z = 1, TGT_XEPS = 2 };
 enum BzInnerStatus : int { IST_RUNNING = 0, IST_CONVERGED = 1, IST_MAXIT = 2 };
 
+// ---------------------------------------------------------------------------------------------
+// Cross-rank exchange over peer memory (slab-decomposed obstacle grid): one process per
+// GPU, every rank maps every other rank's "slab" (cudaIpc) -- a mailbox ring plus the n-vectors whose
+// boundary rows the neighbours read.  A scalar all-reduce is an all-gather of tagged words: rank r
+// stores its K values into slot (seq % XR_RING, r) of EVERY rank's mailbox (NVLink P2P stores), each
+// value as two 64-bit words {tag:32 | half of the double}; every aligned 8-byte word is single-copy
+// atomic and validates itself, so relaxed system-scope accesses suffice.  All ranks then add the
+// gathered values in rank order: bitwise identical results everywhere, which keeps the blind state
+// machines of the ranks in lock-step.
+// ---------------------------------------------------------------------------------------------
+#define XR_MAXR 8
+#define XR_K 8
+#define XR_RING 64
+#define XR_MAIL_WORDS (XR_RING * XR_MAXR * XR_K * 2)
+struct BzXr {
+    int nranks, rank;                    // nranks <= 1: disabled
+    unsigned long long* mail[XR_MAXR];   // mailbox of every rank (peer-mapped; mail[rank] is local)
+    double* slab[XR_MAXR];               // base of every rank's exported vectors (same layout on every rank)
+    unsigned long long* seq;             // local: number of exchanges completed (identical on all ranks)
+};
+
 struct BzState {
     // ---- control words
     int next_op;
@@ -40,6 +61,7 @@ struct BzState {
     int mem;            // L-BFGS memory M
     int currmem, curridx;  // curridx is 1-based like upstream, 0 = empty
     int err_flag;       // nonpositive mu etc.
+    long long n_global; // slab mode: global nx (0: the local n is the global one)
     long long iter;     // k of the IterativeAlgorithm driver (initial state counts as 1)
     long long maxit;
     long long n_grad, n_prox;
@@ -65,6 +87,7 @@ struct BzState {
     // launch that really runs and at its last-CTA epilogue (diagnostic breakdown; the roofline number
     // of the dominant kernel uses CUDA events, see bz_solver.cu)
     unsigned long long t0[4], tsum[4], tcnt[4];
+    BzXr xr;
 };
 
 __device__ __forceinline__ unsigned long long bz_globaltimer() {
@@ -298,6 +321,59 @@ __device__ inline double bz_sum_parts(const double* part, int n) {
     return s;
 }
 
+
+// ---- cross-rank exchange (see BzXr).  err_flag = 3: a peer did not answer within ~4 s.
+__device__ __forceinline__ void bz_xr_post(const BzXr& xr, unsigned long long s, const double* v, int K) {
+    __threadfence_system();   // what this GPU wrote before the post is visible to a peer that sees the post
+    const unsigned long long tag = ((s + 1ULL) & 0xffffffffULL) << 32;
+    const size_t off = (((size_t)(s % XR_RING) * XR_MAXR + xr.rank) * XR_K) * 2;
+    for (int p = 0; p < xr.nranks; ++p) {
+        unsigned long long* base = xr.mail[p] + off;
+        for (int k = 0; k < K; ++k) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[k]);
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(base + 2 * k),
+                         "l"(tag | (bits & 0xffffffffULL)), "l"(tag | (bits >> 32)) : "memory");
+        }
+    }
+}
+// gather the K values of every rank for exchange s from the local mailbox: out[r * XR_K + k]
+__device__ inline void bz_xr_gather(BzState* st, unsigned long long s, int K, double* out) {
+    const BzXr& xr = st->xr;
+    const unsigned long long tag = ((s + 1ULL) & 0xffffffffULL) << 32;
+    const unsigned long long* base = xr.mail[xr.rank] + ((size_t)(s % XR_RING) * XR_MAXR * XR_K) * 2;
+    const long long t0 = clock64();
+    for (int r = 0; r < xr.nranks; ++r)
+        for (int k = 0; k < K; ++k) {
+            const unsigned long long* q = base + ((size_t)r * XR_K + k) * 2;
+            unsigned long long w0, w1;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(q) : "memory");
+                if ((((w0 ^ tag) | (w1 ^ tag)) >> 32) == 0) break;
+                if (clock64() - t0 > 8000000000LL) { st->err_flag = 3; w0 = w1 = 0; break; }
+            }
+            out[r * XR_K + k] = __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
+        }
+}
+// All-reduce of K <= XR_K scalars by ONE thread per GPU (the thread that holds the local totals).
+// ismax bit k set: NaN-propagating max (Julia's), else sum; both in rank order.
+__device__ inline void bz_xr_allreduce(BzState* st, double* v, int K, unsigned int ismax) {
+    if (st->xr.nranks <= 1) return;
+    const unsigned long long s = *st->xr.seq;
+    bz_xr_post(st->xr, s, v, K);
+    double g[XR_MAXR * XR_K];
+    bz_xr_gather(st, s, K, g);
+    for (int k = 0; k < K; ++k) {
+        double acc = g[k];
+        for (int r = 1; r < st->xr.nranks; ++r) {
+            const double w = g[r * XR_K + k];
+            if ((ismax >> k) & 1u) acc = (acc != acc || w != w) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(acc, w);
+            else acc += w;
+        }
+        v[k] = acc;
+    }
+    *st->xr.seq = s + 1ULL;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side objects
 // ---------------------------------------------------------------------------------------------
@@ -317,6 +393,7 @@ struct bz_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
+    int slab_mode = 0;          // a slab-decomposed problem lives on this context (cross-rank exchanges in the kernels)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu

@@ -23,37 +23,62 @@ struct TeamCtx {
     BzTeam tm;
     int idx;
     double* scratch;   // >= 2*32 + 2 doubles of shared memory
+    BzState* st;
+    unsigned long long seq0;   // slab mode: cross-rank exchange sequence number at kernel start
+    int xidx;                  // ... and the number of exchanges this launch has done
 };
 
 template <int K>
 __device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
     bz_block_sum<K>(v, tc.scratch);
     const int nb = gridDim.x;
-    if (nb == 1) return;
-    const int j = tc.idx++;
-    unsigned int* bar = tc.tm.bars + tc.tm.parity * BZ_MAXBAR + j;
-    double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 2;
-    if (threadIdx.x == 0) {
+    if (nb > 1) {
+        const int j = tc.idx++;
+        unsigned int* bar = tc.tm.bars + tc.tm.parity * BZ_MAXBAR + j;
+        double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 2;
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) sl[blockIdx.x * 2 + k] = v[k];
-        __threadfence();
-        atomicAdd(bar, 1u);
-        while (ld_acquire_u32(bar) < (unsigned int)nb) { }
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double s = 0.0;
-            for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 2 + k);
-            s = bz_warp_sum(s);
-            if (threadIdx.x == 0) tc.scratch[64 + k] = s;
+            for (int k = 0; k < K; ++k) sl[blockIdx.x * 2 + k] = v[k];
+            __threadfence();
+            atomicAdd(bar, 1u);
+            while (ld_acquire_u32(bar) < (unsigned int)nb) { }
         }
-    }
-    __syncthreads();
+        __syncthreads();
+        if (threadIdx.x < 32) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
-    __syncthreads();
+            for (int k = 0; k < K; ++k) {
+                double s = 0.0;
+                for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 2 + k);
+                s = bz_warp_sum(s);
+                if (threadIdx.x == 0) tc.scratch[64 + k] = s;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
+        __syncthreads();
+    }
+    if (tc.st->xr.nranks > 1) {
+        // slab mode: the local totals of all ranks, added in rank order by every CTA (identical bits
+        // everywhere).  CTA 0 posts; the local grid barrier of the next team_sum keeps any CTA from
+        // running more than one exchange ahead of the slowest one.
+        const unsigned long long s = tc.seq0 + (unsigned long long)(tc.xidx++);
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) bz_xr_post(tc.st->xr, s, v, K);
+            double g[XR_MAXR * XR_K];
+            bz_xr_gather(tc.st, s, K, g);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double acc = g[k];
+                for (int r = 1; r < tc.st->xr.nranks; ++r) acc += g[r * XR_K + k];
+                tc.scratch[64 + k] = acc;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
@@ -85,7 +110,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
         return;
     }
 
-    TeamCtx tc{tm, 0, scratch};
+    TeamCtx tc{tm, 0, scratch, st, st->xr.nranks > 1 ? *st->xr.seq : 0ULL, 0};
     const int M = __ldcg(&st->mem);
     int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
     double H = __ldcg(&st->H);
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
         st->skip_update = 0;
         st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
         st->next_op = OP_G;
+        if (st->xr.nranks > 1) *st->xr.seq = tc.seq0 + (unsigned long long)tc.xidx;
         if (force_role < 0) bz_toc(st, 1);
         __threadfence();
     }
@@ -496,7 +522,7 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
         cudaFuncSetAttribute(k_lstep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         once = true;
     }
-    if (v.n <= per_cta * LC_MAXCS) {
+    if (v.n <= per_cta * LC_MAXCS && !ctx->slab_mode) {   // (slab mode: only the cooperative kernel exchanges across ranks)
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
         while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;

@@ -59,6 +59,13 @@ struct bz_problem {
     BzObstacle ob{};
     bool sharded = false;
     BzShard shard{};
+    // slab-decomposed obstacle grid (cross-rank exchange over peer memory)
+    bool slab = false;
+    unsigned long long* slab_base = nullptr;   // [mailbox | seq | x | z | xeps | yupd]
+    size_t slab_bytes = 0;
+    BzXr xr_host{};
+    void* peer_ptr[XR_MAXR] = {};
+    long long n_global = 0;
     // dominant-kernel timing
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dom_events;
     long long dom_counter = 0;
@@ -227,6 +234,13 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     if (p->own_cA) cudaFree(p->cA);
+    if (p->slab_base) {   // x, z, xeps, yupd live inside the exported slab
+        p->v.x = p->v.z = p->v.xeps = nullptr;
+        p->yupd = nullptr;
+        for (int r = 0; r < XR_MAXR; ++r)
+            if (p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
+        cudaFree(p->slab_base);
+    }
     double* frees[] = {p->tm1_f, p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
                        p->s, p->yupd, p->tm1, p->tm2, p->tm3, p->v.x, p->v.z, p->v.xeps, p->v.x_prev,
                        p->v.x_d, p->v.z_curr, p->v.res, p->v.res_prev, p->v.grad_x, p->v.grad_z,
@@ -290,6 +304,17 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         return fail(BZ_ERR_UNSUPPORTED,
                     "c kind is only available in the batched tiny-instance path (bz_batch_solve)");
     }
+    if (d->slab_nranks > 1) {
+        if (d->c_kind != BZ_C_OBSTACLE || d->grid_x <= 0 || d->grid_y <= 0)
+            return fail(BZ_ERR_UNSUPPORTED, "slab decomposition is built for the 2-D obstacle grid only");
+        if (d->slab_nranks > XR_MAXR || d->slab_rank < 0 || d->slab_rank >= d->slab_nranks)
+            return fail(BZ_ERR_ARG, "slab: bad rank / more than 8 ranks");
+        if (d->nx_global != 3 * d->ny * (long long)d->slab_nranks)
+            return fail(BZ_ERR_ARG, "slab: nx_global must be 3 * ny_local * slab_nranks (equal slabs)");
+        p->slab = true;
+        p->n_global = d->nx_global;
+        ctx->slab_mode = 1;
+    }
     if (d->g_kind == BZ_G_OBSTACLE_L1 && d->c_kind != BZ_C_OBSTACLE)
         return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
     if ((d->g_kind == BZ_G_NORML1_BOX || d->g_kind == BZ_G_NORML0_BOX)) {
@@ -315,14 +340,23 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         p->g.u = p->g_u;
     }
     // ---- vectors
+    if (p->slab) {
+        // one exportable allocation: mailbox ring, sequence word, and the vectors whose boundary rows the
+        // neighbouring ranks read through the peer mapping (same layout on every rank)
+        const size_t head = (size_t)XR_MAIL_WORDS + 8;
+        p->slab_bytes = (head + 3 * (size_t)n + (size_t)ml) * sizeof(double);
+        PTRY(dev_alloc(ctx, &p->slab_base, p->slab_bytes / sizeof(double)));
+        double* vecs = reinterpret_cast<double*>(p->slab_base + head);
+        p->v.x = vecs; p->v.z = vecs + n; p->v.xeps = vecs + 2 * n; p->yupd = vecs + 3 * n;
+    }
     double** nvecs[] = {&p->v.x, &p->v.z, &p->v.xeps, &p->v.x_prev, &p->v.x_d, &p->v.z_curr, &p->v.res,
                         &p->v.res_prev, &p->v.grad_x, &p->v.grad_z, &p->v.d, &p->Ec, &p->Ef};
-    for (double** q : nvecs) PTRY(dev_alloc(ctx, q, n));
+    for (double** q : nvecs) if (!*q) PTRY(dev_alloc(ctx, q, n));
     PTRY(dev_alloc(ctx, &p->v.sM, (size_t)BZ_MAXMEM * n));
     PTRY(dev_alloc(ctx, &p->v.yM, (size_t)BZ_MAXMEM * n));
     p->v.n = n;
     double** mvecs[] = {&p->mu, &p->y, &p->muy, &p->cx, &p->s, &p->yupd, &p->tm1, &p->tm2, &p->tm3};
-    for (double** q : mvecs) PTRY(dev_alloc(ctx, q, ml));
+    for (double** q : mvecs) if (!*q) PTRY(dev_alloc(ctx, q, ml));
     const int maxgrid = ctx->num_sms * 8;
     PTRY(dev_alloc(ctx, &p->part, (size_t)4 * maxgrid));
     PTRY(dev_alloc(ctx, &p->lxpart, (size_t)maxgrid));
@@ -411,6 +445,54 @@ extern "C" int bz_problem_upload_dense(bz_problem* p, const double* c_A, const d
         BZ_TRY(upload_matrix(ctx, c_A, p->desc.c_layout, p->ml, p->n, p->cA));
     }
     BZ_CUDA(ctx, cudaMemcpyAsync(p->cb, c_b, p->ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return BZ_OK;
+}
+
+static int fetch_state(bz_problem* p);
+static int push_state(bz_problem* p);
+
+extern "C" int bz_problem_xr_handle(bz_problem* p, void* handle64) {
+    if (!p || !handle64) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->slab) return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_xr_handle: not a slab-decomposed problem");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hnd;
+    BZ_CUDA(ctx, cudaIpcGetMemHandle(&hnd, p->slab_base));
+    memcpy(handle64, &hnd, 64);
+    return BZ_OK;
+}
+
+extern "C" int bz_problem_xr_attach(bz_problem* p, const void* handles64) {
+    if (!p || !handles64) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->slab) return bz_fail(ctx, BZ_ERR_ARG, "bz_problem_xr_attach: not a slab-decomposed problem");
+    const int R = p->desc.slab_nranks, me = p->desc.slab_rank;
+    const size_t head = (size_t)XR_MAIL_WORDS + 8;
+    BzXr xr{};
+    xr.nranks = R; xr.rank = me;
+    for (int r = 0; r < R; ++r) {
+        unsigned long long* base = p->slab_base;
+        if (r != me) {
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, (const char*)handles64 + 64 * (size_t)r, 64);
+            void* ptr = nullptr;
+            BZ_CUDA(ctx, cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+            p->peer_ptr[r] = ptr;
+            base = reinterpret_cast<unsigned long long*>(ptr);
+        }
+        xr.mail[r] = base;
+        xr.slab[r] = reinterpret_cast<double*>(base);
+    }
+    xr.seq = p->slab_base + XR_MAIL_WORDS;
+    (void)head;
+    p->xr_host = xr;
+    BZ_TRY(fetch_state(p));
+    p->st_host->xr = xr;
+    p->st_host->n_global = p->n_global;
+    BZ_TRY(push_state(p));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BZ_OK;
 }
 
@@ -620,6 +702,8 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     BZ_TRY(h2d(p, p->y, y0 + (p->sharded ? p->desc.row_begin : 0), ml));
     BzState* h = p->st_host;
     memset(h, 0, sizeof(BzState));
+    h->xr = p->xr_host;            // slab mode: peer mapping (zero otherwise)
+    h->n_global = p->n_global;
     h->next_op = OP_DONE;
     h->H = 1.0;
     h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
@@ -663,6 +747,7 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
             BZ_TRY(bz_launch_outer_logic(ctx, p->st));
         }
         BZ_TRY(fetch_state(p));                               // the one sync per outer iteration
+        if (h->err_flag == 3) return bz_fail(ctx, BZ_ERR_COMM, "slab mode: a peer rank did not answer a cross-rank exchange");
         if (h->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
         objx = h->objx;
         tot_inner = h->tot_inner_it;

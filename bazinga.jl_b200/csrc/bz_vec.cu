@@ -108,16 +108,43 @@ __device__ __forceinline__ StencilGeom bz_geom(const BzObstacle& ob) {
     else { g.GY = ob.gy; g.GX = ob.gx; g.diag = 4.0; }
     return g;
 }
-// (A v)(r, c): same operation order as the oracle's _stencil_apply (diag*v, then -left, -right, -up, -down)
+// (A v)(r, c): same operation order as the oracle's _stencil_apply (diag*v, then -left, -right, -up, -down).
+// `up` / `dn`: the neighbouring ranks' boundary rows in slab mode (null: Dirichlet zero beyond the grid)
 __device__ __forceinline__ double bz_stencil_rc(const double* __restrict__ v, long long r, long long c,
-                                                const StencilGeom& g) {
+                                                const StencilGeom& g, const double* up = nullptr,
+                                                const double* dn = nullptr) {
     const long long i = r * g.GX + c;
     double out = g.diag * v[i];
     if (c > 0) out -= v[i - 1];
     if (c + 1 < g.GX) out -= v[i + 1];
     if (r > 0) out -= v[i - g.GX];
+    else if (up) out -= up[c];
     if (r + 1 < g.GY) out -= v[i + g.GX];
+    else if (dn) out -= dn[c];
     return out;
+}
+
+// Slab mode (the grid rows are split over the ranks): every stencil pass starts with a
+// cross-rank barrier -- after it the previous kernel of EVERY rank is complete, so the neighbours' boundary
+// rows may be read through the peer mapping.  Exchange number s; CTA (0,0) posts, every CTA waits.
+__device__ inline void bz_xr_barrier_all(BzState* st, unsigned long long s) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) { double z[1] = {0.0}; bz_xr_post(st->xr, s, z, 1); }
+        double g[XR_MAXR * XR_K];
+        bz_xr_gather(st, s, 1, g);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+// boundary rows of the neighbours' copy of local vector `v` (a vector inside the exported slab), block offset
+// `off` (0 or N), grid GY x GX: up = last row of rank-1, dn = first row of rank+1
+__device__ __forceinline__ void bz_xr_halo(const BzXr& xr, const double* v, long long off, const StencilGeom& g,
+                                           const double*& up, const double*& dn) {
+    up = dn = nullptr;
+    if (xr.nranks <= 1) return;
+    const long long rel = v - xr.slab[xr.rank];
+    if (xr.rank > 0) up = xr.slab[xr.rank - 1] + rel + off + (g.GY - 1) * g.GX;
+    if (xr.rank + 1 < xr.nranks) dn = xr.slab[xr.rank + 1] + rel + off;
 }
 
 // pass 1: cx = x1 + A x2 - x3; yupd = (cx + mu*y - 0)/mu; partials of lx and of f(x)
@@ -138,13 +165,16 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
     const long long N = ob.N;
     const StencilGeom g = bz_geom(ob);
+    const double *up, *dn;
+    if (st->xr.nranks > 1) bz_xr_barrier_all(st, *st->xr.seq);
+    bz_xr_halo(st->xr, x, N, g, up, dn);
     double a[3] = {0.0, 0.0, 0.0};
     for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
             const long long i = r * g.GX + c;
             const double x2 = x[N + i];
-            const double cv = (x[i] + bz_stencil_rc(x + N, r, c, g)) - x[2 * N + i];
+            const double cv = (x[i] + bz_stencil_rc(x + N, r, c, g, up, dn)) - x[2 * N + i];
             const double t = cv + muy[i];
             const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
             const double mi = mu[i];
@@ -177,19 +207,26 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
     const long long N = ob.N;
     const StencilGeom g = bz_geom(ob);
+    const double *up, *dn;
+    const unsigned long long xseq = st->xr.nranks > 1 ? *st->xr.seq : 0ULL;
+    if (st->xr.nranks > 1) bz_xr_barrier_all(st, xseq + 1ULL);   // every rank's yupd (pass 1) is complete
+    bz_xr_halo(st->xr, yupd, 0, g, up, dn);
     for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
             const long long i = r * g.GX + c;
             const double w = yupd[i];
             Ec[i] = 0.0 + w;
-            Ec[N + i] = (x[N + i] - 1.0) + bz_stencil_rc(yupd, r, c, g);
+            Ec[N + i] = (x[N + i] - 1.0) + bz_stencil_rc(yupd, r, c, g, up, dn);
             Ec[2 * N + i] = 0.0 + (-w);
         }
     }
-    if (bz_last_cta(counter, gridDim.x * gridDim.y) && threadIdx.x == 0 && set_after) {
-        st->next_op = st->after_g;
-        if (force_target < 0) bz_toc(st, 0);
+    if (bz_last_cta(counter, gridDim.x * gridDim.y) && threadIdx.x == 0) {
+        if (st->xr.nranks > 1) *st->xr.seq = xseq + 2ULL;   // the two barriers of this gradient
+        if (set_after) {
+            st->next_op = st->after_g;
+            if (force_target < 0) bz_toc(st, 0);
+        }
         __threadfence();
     }
 }
@@ -249,7 +286,9 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (!bz_last_cta(counter, gridDim.x)) return;
     const double s = bz_final_sum(part, gridDim.x, scratch);
     if (threadIdx.x == 0) {
-        st->g_z = bz_g_value_scale(g) * s;
+        double v1[1] = {s};
+        bz_xr_allreduce(st, v1, 1, 0u);       // slab mode: sum over ranks
+        st->g_z = bz_g_value_scale(g) * v1[0];
         st->out[0] = st->g_z;
         __threadfence();
     }
@@ -309,8 +348,10 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const double s = bz_final_sum(part, gridDim.x, scratch);
     const double b = bz_final_sum(part + gridDim.x, gridDim.x, scratch);
     if (threadIdx.x == 0) {
-        st->musqy = 0.5 * s;
-        if (b > 0.0) st->err_flag = 1;
+        double v2[2] = {s, b};
+        bz_xr_allreduce(st, v2, 2, 0u);       // slab mode: sums over ranks
+        st->musqy = 0.5 * v2[0];
+        if (v2[1] > 0.0) st->err_flag = 1;
         if (count_outer) st->tot_it += 1;
         __threadfence();
     }
@@ -387,8 +428,9 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     bz_block_max<1>(f, scratch);
     if (threadIdx.x == 0) part[blockIdx.x] = f[0] > 0.0 ? NANQ : a[0];
     if (!bz_last_cta(counter, gridDim.x)) return;
-    const double nrp = bz_final_nanmax(part, gridDim.x, scratch);
+    double nrp = bz_final_nanmax(part, gridDim.x, scratch);
     if (threadIdx.x != 0) return;
+    { double v1[1] = {nrp}; bz_xr_allreduce(st, v1, 1, 1u); nrp = v1[0]; }   // slab mode: max over ranks
     st->out[0] = nrp;
     if (outer_logic) bz_outer_logic(st, nrp);
     __threadfence();

@@ -164,12 +164,17 @@ class ConstraintBasisPursuit:
 
 
 class ConstraintObstacle:
-    """demo/obstacle.jl:92-113; ``grid=(gy, gx)`` selects the 2-D 5-point extension (config C4)."""
+    """demo/obstacle.jl:92-113; ``grid=(gy, gx)`` selects the 2-D 5-point extension (config C4).
+    ``slab=(rank, nranks)``: this object describes ONE rank's slab of a grid split by rows over ranks
+    (N and grid are local: gy local grid rows; every rank the same) -- SURVEY.md §8e."""
     c_kind = K.C_OBSTACLE
 
-    def __init__(self, N, grid=None):
+    def __init__(self, N, grid=None, slab=None):
         self.N = int(N)
         self.grid = grid
+        self.slab = slab
+        if slab is not None and (grid is None or int(grid[0]) * int(grid[1]) != self.N):
+            raise ValueError("slab decomposition needs the local 2-D grid: grid=(gy_local, gx), N = gy_local*gx")
 
 
 # ------------------------------------------------------------------ closed sets D

@@ -192,6 +192,9 @@ class Problem:
             ny = c.N if ny is None else ny
             if c.grid is not None:
                 d.grid_y, d.grid_x = int(c.grid[0]), int(c.grid[1])
+            if c.slab is not None:
+                d.slab_rank, d.slab_nranks = int(c.slab[0]), int(c.slab[1])
+                d.nx_global = 3 * c.N * int(c.slab[1])
         # ---- f
         if isinstance(f, O.LeastSquares):
             d.f_A, d.f_b, d.f_m = _ptr(f.A), _ptr(f.b), f.A.shape[0]
@@ -239,6 +242,17 @@ class Problem:
         K.check(self.lib.bz_alps_solve(self.handle, _ptr(x0), _ptr(y0), C.byref(options), _ptr(x), _ptr(y),
                                        _ptr(s), _ptr(mu), C.byref(res)), self.ctx.handle)
         return x, y, s, mu, res
+
+    # ---- slab-decomposed obstacle grid (one process per GPU): export / attach the peer-mapped slabs
+    def xr_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        K.check(self.lib.bz_problem_xr_handle(self.handle, buf), self.ctx.handle)
+        return buf.raw
+
+    def xr_attach(self, handles):
+        """``handles``: the 64-byte handles of all ranks in rank order (e.g. from dist.all_gather_object)."""
+        blob = b"".join(handles)
+        K.check(self.lib.bz_problem_xr_attach(self.handle, C.c_char_p(blob)), self.ctx.handle)
 
     def upload_dense(self, A, b):
         """Replace the dense constraint data; ``A=None`` keeps the device-resident matrix and replaces b only."""

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define BZ_ABI_VERSION 1
+#define BZ_ABI_VERSION 2
 #define BZ_LBFGS_MAX_MEMORY 16
 
 typedef struct bz_ctx bz_ctx;
@@ -114,6 +114,14 @@ typedef struct {
     /* Row sharding of a DENSE_AFFINE instance over ranks.  ny is the GLOBAL row
      * count; this rank owns rows [row_begin, row_begin + ny_local).  ny_local = 0 means unsharded. */
     int64_t row_begin, ny_local;
+    /* Slab decomposition of the 2-D OBSTACLE grid over ranks: slab_nranks > 1 means
+     * nx, ny, grid_y describe THIS rank's slab (grid_y local grid rows of grid_x columns, equal on all
+     * ranks; rank r owns global rows [r*grid_y, (r+1)*grid_y)), nx_global = 3 * grid_x * grid_y *
+     * slab_nranks.  After bz_problem_create every rank exports its slab (bz_problem_xr_handle), the
+     * handles are all-gathered by the host and attached (bz_problem_xr_attach); from then on the
+     * kernels exchange boundary rows and reduction scalars over peer memory (NVLink), no host sync. */
+    int32_t slab_nranks, slab_rank;
+    int64_t nx_global;
 } bz_problem_desc;
 
 /* Options of `alps` (alps.jl:14-25) plus the PANOCplus closure options the demos bake in
@@ -170,6 +178,10 @@ int bz_problem_destroy(bz_problem* p);
 /* Re-upload the dense constraint data of an existing problem (host -> device), for end-to-end timing.
  * c_A == NULL keeps the matrix (e.g. one generated on the device from a seed) and replaces b only. */
 int bz_problem_upload_dense(bz_problem* p, const double* c_A, const double* c_b);
+/* Slab mode: export this rank's slab (64 bytes, a cudaIpcMemHandle_t) / attach the slabs of all ranks
+ * (slab_nranks x 64 bytes in rank order; this rank's own entry is ignored). */
+int bz_problem_xr_handle(bz_problem* p, void* handle64);
+int bz_problem_xr_attach(bz_problem* p, const void* handles64);
 
 /* alps(f,g,c,D,x0,y0; ...) -> (x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol,
  * norm_res_prim, s, mu), src/algorithms/alps.jl:7-117.  x0,y0 are read-only. */
