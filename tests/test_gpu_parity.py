@@ -3,6 +3,8 @@
 same seeded inputs.  Tolerances (BASELINE.json north_star): per-kernel outputs 1e-12 relative in
 fp64 (normwise for results of dense products); final objective / constraint violation
 / multipliers 1e-6 relative; iteration counts within +-2 % where the trajectory is not chaotic."""
+import os
+
 import numpy as np
 import pytest
 
@@ -539,3 +541,37 @@ def test_wide_path_whole_solve(two_pass, monkeypatch):
     x_star = np.array([-3.877278911564627e-01, 0, 0, 2.174149659863943e-02, 6.168435374149660e-01])
     assert np.max(np.abs(o2[0] - x_star)) <= 1e-4 and o2[2] < 10 and o2[3] < 50
     ctx.close()
+
+
+# ------------------------------------------------------------------------------- slab-decomposed obstacle grid
+def test_slab_decomposed_obstacle_two_ranks():
+    """SURVEY.md §8e, third mode: the obstacle grid split by rows over two ranks (one process each), boundary rows
+    and every reduction scalar exchanged over peer-mapped memory from inside the kernels.  On a one-GPU box both
+    ranks share cuda:0 (time-sliced processes); with two GPUs each rank gets its own.  One AL-gradient must equal
+    the un-decomposed kernels' bit for bit, the scalars must be identical on all ranks, and a short solve must
+    follow the un-decomposed one."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    import torch
+    sk = socket.socket()
+    sk.bind(("127.0.0.1", 0))
+    port = sk.getsockname()[1]
+    sk.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "scripts", "bench_obstacle_slab.py"),
+           "--side", "32", "--inner", "10", "--check"]
+    if torch.cuda.device_count() < 2:
+        cmd.append("--same-device")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{"config"')]
+    assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
+    d = json.loads(lines[-1])
+    g, sc = d["gradient_check"], d["solve_check"]
+    assert g["dlx_bit_identical"] and g["cx_bit_identical"] and g["yupd_bit_identical"]
+    assert g["lx_rel_err"] <= 1e-14 and g["fx_rel_err"] <= 1e-14 and g["lx_identical_on_all_ranks"]
+    assert sc["same_counts_on_all_ranks"] and sc["same_objective_on_all_ranks"]
+    assert d["inner_iterations"] == sc["inner_iterations_single_gpu"] == 10
+    assert sc["max_abs_dx"] <= 1e-10 * sc["max_abs_x"]

@@ -105,3 +105,82 @@ def test_row_sharded_gradient_equals_unsharded_gloo_world2():
         assert abs(nrp - np.max(np.abs(al.cx))) <= 1e-14
     # identical bits on every rank -> replicated x-space control flow stays in lock-step
     assert np.array_equal(ret[0][0], ret[1][0])
+
+
+def _slab_worker(rank, world, port, gy, gx, ret):
+    """Per-rank work of the slab-decomposed obstacle AL-gradient: local grid rows, the neighbours'
+    boundary rows of x2 and of yupd exchanged point to point, scalars summed in rank order."""
+    import torch.distributed as dist
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N = gy * gx
+    rng = np.random.default_rng(11)
+    x, mu, y = rng.standard_normal(3 * N), rng.uniform(0.1, 2.0, N), rng.standard_normal(N)
+    gl = gy // world
+    r0 = rank * gl
+    rows = slice(r0 * gx, (r0 + gl) * gx)
+    x1, x2, x3 = (x[b * N:(b + 1) * N][rows].reshape(gl, gx) for b in range(3))
+
+    def halo(v):   # last row of rank-1 / first row of rank+1; zeros beyond the grid (Dirichlet)
+        up, dn = np.zeros(gx), np.zeros(gx)
+        reqs = []
+        if rank > 0:
+            reqs.append(dist.isend(torch.from_numpy(v[0].copy()), rank - 1))
+        if rank + 1 < world:
+            reqs.append(dist.isend(torch.from_numpy(v[-1].copy()), rank + 1))
+        if rank > 0:
+            t = torch.empty(gx, dtype=torch.float64); dist.recv(t, rank - 1); up = t.numpy()
+        if rank + 1 < world:
+            t = torch.empty(gx, dtype=torch.float64); dist.recv(t, rank + 1); dn = t.numpy()
+        for r in reqs:
+            r.wait()
+        return up, dn
+
+    def stencil(v):   # 5-point, 4 on the diagonal, same operation order as the oracle / the kernel
+        up, dn = halo(v)
+        ext = np.vstack([up, v, dn])
+        out = 4.0 * v
+        out[:, 1:] -= v[:, :-1]
+        out[:, :-1] -= v[:, 1:]
+        out -= ext[:-2]
+        out -= ext[2:]
+        return out
+
+    cx = (x1 + stencil(x2)) - x3
+    t = cx + (mu * y)[rows].reshape(gl, gx)
+    w = t / mu[rows].reshape(gl, gx)                       # D = {0}
+    grad = np.concatenate([w.ravel(), ((x2 - 1.0) + stencil(w)).ravel(), (-w).ravel()])
+    part = torch.tensor([np.sum(t * t / mu[rows].reshape(gl, gx)), np.sum(x2 * x2), np.sum(x2)])
+    allp = [torch.empty(3, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(allp, part)                            # the mailbox all-gather; every rank adds in rank order
+    tot = allp[0].clone()
+    for q in allp[1:]:
+        tot += q
+    ret[rank] = (grad, cx.ravel(), tot.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_decomposed_obstacle_gradient_equals_global_gloo_world2():
+    import torch.multiprocessing as mp
+    gy, gx, world = 8, 6, 2
+    N = gy * gx
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_slab_worker, args=(world, port, gy, gx, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(11)
+    x, mu, y = rng.standard_normal(3 * N), rng.uniform(0.1, 2.0, N), rng.standard_normal(N)
+    al = bo.AugLagFun(bo.FObstacleL1(N), bo.CObstacle(N, (gy, gx)), bo.ZeroSet(), mu.copy(), y.copy(), x)
+    dl = np.empty(3 * N)
+    lx = al.gradient(dl, x)
+    Nl = N // world
+    got = np.concatenate([np.concatenate([ret[r][0][b * Nl:(b + 1) * Nl] for r in range(world)]) for b in range(3)])
+    assert np.array_equal(got, dl)                                           # elementwise + halo: exact
+    assert np.array_equal(np.concatenate([ret[r][1] for r in range(world)]), al.cx)
+    tot = ret[0][2]
+    assert np.array_equal(ret[0][2], ret[1][2])                              # rank-order sums: identical bits
+    fx = 0.5 * tot[1] - tot[2]
+    assert abs((0.5 * tot[0] + fx - al.musqy) - lx) <= 1e-13 * abs(lx)
