@@ -26,6 +26,7 @@ struct ProblemDesc
     grid_y::Int64; grid_x::Int64
     d_lo::Float64; d_hi::Float64; d_pair_stride::Int64
     row_begin::Int64; ny_local::Int64
+    slab_nranks::Int32; slab_rank::Int32; nx_global::Int64
 end
 
 mutable struct Options
@@ -123,7 +124,8 @@ function alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::Abstrac
                        haskey(fp, :A) ? size(fp.A, 1) : 0, Int32(1) #= column-major =#, (0.0, 0.0, 0.0, 0.0),
                        glam, glo, ghi, ptr(gu),
                        ptr(get(cp, :A, nothing)), ptr(get(cp, :b, nothing)), Int32(1) #= column-major =#,
-                       Int32(0), Int32(0), UInt64(0), 0, 0, dlo, dhi, 1, 0, 0)
+                       Int32(0), Int32(0), UInt64(0), 0, 0, dlo, dhi, 1, 0, 0,
+                       Int32(0), Int32(0), 0)   # no slab decomposition
     prob = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         check(ccall((:bz_problem_create, lib), Cint, (Ptr{Cvoid}, Ref{ProblemDesc}, Ref{Ptr{Cvoid}}),
