@@ -99,6 +99,8 @@ SYMBOLS = {
     "bz_randn_fill": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _vp]),
     "bz_batch_solve": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
                                  _vp, _vp, _vp, _dp]),
+    "bz_batch_solve_als": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
+                                     _vp, _vp, _vp, _dp]),
     "bz_comm_unique_id": (C.c_int, [_vp]),
     "bz_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "bz_comm_destroy": (C.c_int, [_vp]),

@@ -121,9 +121,12 @@ template <> struct Prob<3> {   // demo/mpvca.jl:77-150 (c = (4,2))
     }
 };
 
-// ---- per-thread augmented-Lagrangian state (auglagfun.jl:11-26) -----------------------------------
-template <int KIND> struct Al {
+// ---- per-thread augmented-Lagrangian state (auglagfun.jl:11-26; SLACK: auglagfunslack.jl:15-29) -----
+// SLACK = 0: AugLagFun + NonsmoothCostFun on x (alps).  SLACK = 1: AugLagFunSlack + NonsmoothCostFunSlack on the
+// stacked variable [x; s] (als); NV is the length of the PANOC+ variable.
+template <int KIND, int SLACK> struct Al {
     static constexpr int NY = Prob<KIND>::NY;
+    static constexpr int NV = SLACK ? 2 + NY : 2;
     double mu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;
 
     __device__ void update() {   // AugLagUpdate!
@@ -132,8 +135,29 @@ template <int KIND> struct Al {
         for (int i = 0; i < NY; ++i) { muy[i] = mu[i] * y[i]; acc += muy[i] * y[i]; }
         musqy = 0.5 * acc;
     }
-    __device__ double gradient(const double (&x)[2], double (&dlx)[2]) {   // gradient!(dlx, al, x)
+    __device__ double gradient(const double (&xv)[NV], double (&dlx)[NV]) {   // gradient!(dlx, al, x)
         double dfx[2], jtv[2], acc = 0.0;
+        const double x[2] = {xv[0], xv[1]};
+        if constexpr (SLACK != 0) {   // auglagfunslack.jl:77-97
+            fx = Prob<KIND>::f_grad(x, dfx);
+            Prob<KIND>::c_eval(x, cx);
+#pragma unroll
+            for (int i = 0; i < NY; ++i) {
+                const double t = (cx[i] + muy[i]) - xv[2 + i];
+                acc += (t * t) / mu[i];
+            }
+            double Fxs = 0.5 * acc;
+            Fxs += fx;
+            Fxs -= musqy;
+#pragma unroll
+            for (int i = 0; i < NY; ++i) yupd[i] = y[i] + (cx[i] - xv[2 + i]) / mu[i];
+            Prob<KIND>::c_jt(x, yupd, jtv);
+            dlx[0] = dfx[0] + jtv[0];
+            dlx[1] = dfx[1] + jtv[1];
+#pragma unroll
+            for (int i = 0; i < NY; ++i) dlx[2 + i] = -yupd[i];
+            return Fxs;
+        } else {
         Prob<KIND>::c_eval(x, cx);
 #pragma unroll
         for (int i = 0; i < NY; ++i) yupd[i] = cx[i] + muy[i];
@@ -152,122 +176,167 @@ template <int KIND> struct Al {
         dlx[0] = dfx[0] + jtv[0];
         dlx[1] = dfx[1] + jtv[1];
         return lx;
+        }
+    }
+    // prox!(z, gFun, x, gamma): prox of g on x, and for SLACK the projection onto D of the slack part
+    __device__ double prox(const double (&xv)[NV], double gamma, double (&z)[NV]) {
+        const double x[2] = {xv[0], xv[1]};
+        double zx[2];
+        const double g = Prob<KIND>::prox(x, gamma, zx);
+        z[0] = zx[0]; z[1] = zx[1];
+        if constexpr (SLACK != 0) {   // auglagfunslack.jl:147-164
+            double sv[NY], zs[NY];
+#pragma unroll
+            for (int i = 0; i < NY; ++i) sv[i] = xv[2 + i];
+            Prob<KIND>::proj(sv, zs);
+#pragma unroll
+            for (int i = 0; i < NY; ++i) z[2 + i] = zs[i];
+        }
+        return g;
     }
 };
 
-__device__ __forceinline__ double dot2(const double (&a)[2], const double (&b)[2]) {
-    return a[0] * b[0] + a[1] * b[1];
+// left-to-right dot product (NV = 2: a0*b0 + a1*b1, the order of oracle/tiny_oracle.c dotn)
+template <int NV>
+__device__ __forceinline__ double dotn(const double (&a)[NV], const double (&b)[NV]) {
+    double acc = a[0] * b[0];
+#pragma unroll
+    for (int j = 1; j < NV; ++j) acc += a[j] * b[j];
+    return acc;
 }
-__device__ __forceinline__ double f_model(double fx, const double (&g)[2], const double (&res)[2],
-                                          double L) {
-    const double nr = sqrt(dot2(res, res));
-    return fx - dot2(g, res) + (L / 2) * (nr * nr);
+template <int NV>
+__device__ __forceinline__ double f_model(double fx, const double (&g)[NV], const double (&res)[NV], double L) {
+    const double nr = sqrt(dotn<NV>(res, res));
+    return fx - dotn<NV>(g, res) + (L / 2) * (nr * nr);
 }
 
 // L-BFGS history kept newest-first and shifted on update, so every index is static (registers);
 // the visiting order (loop1 newest->oldest, loop2 oldest->newest) is that of the upstream ring.
-template <int MM>
+template <int MM, int NV>
 struct Lbfgs {
     int M, currmem;
-    double H, s[MM][2], y[MM][2], ys[MM];
+    double H, s[MM][NV], y[MM][NV], ys[MM];
     __device__ void reset() { currmem = 0; H = 1.0; }
-    __device__ void update(const double (&sv)[2], const double (&yv)[2]) {
+    __device__ void update(const double (&sv)[NV], const double (&yv)[NV]) {
         if (M == 0) return;
-        const double ysv = dot2(sv, yv);
+        const double ysv = dotn<NV>(sv, yv);
         if (ysv > 0) {
 #pragma unroll
             for (int i = MM - 1; i > 0; --i) {
-                s[i][0] = s[i - 1][0]; s[i][1] = s[i - 1][1];
-                y[i][0] = y[i - 1][0]; y[i][1] = y[i - 1][1];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) { s[i][j] = s[i - 1][j]; y[i][j] = y[i - 1][j]; }
                 ys[i] = ys[i - 1];
             }
-            s[0][0] = sv[0]; s[0][1] = sv[1];
-            y[0][0] = yv[0]; y[0][1] = yv[1];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { s[0][j] = sv[j]; y[0][j] = yv[j]; }
             ys[0] = ysv;
             currmem = currmem + 1 > M ? M : currmem + 1;
-            H = ysv / dot2(yv, yv);
+            H = ysv / dotn<NV>(yv, yv);
         }
     }
-    __device__ void mul(const double (&v)[2], double (&d)[2]) const {
+    __device__ void mul(const double (&v)[NV], double (&d)[NV]) const {
         double al[MM];
-        d[0] = v[0]; d[1] = v[1];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) d[j] = v[j];
 #pragma unroll
         for (int i = 0; i < MM; ++i) {
             if (i < currmem) {
-                al[i] = dot2(s[i], d) / ys[i];
-                d[0] -= al[i] * y[i][0];
-                d[1] -= al[i] * y[i][1];
+                al[i] = dotn<NV>(s[i], d) / ys[i];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) d[j] -= al[i] * y[i][j];
             }
         }
-        d[0] = H * d[0]; d[1] = H * d[1];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) d[j] = H * d[j];
 #pragma unroll
         for (int i = MM - 1; i >= 0; --i) {
             if (i < currmem) {
-                const double beta = dot2(y[i], d) / ys[i];
+                const double beta = dotn<NV>(y[i], d) / ys[i];
                 const double coef = al[i] - beta;
-                d[0] += coef * s[i][0];
-                d[1] += coef * s[i][1];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) d[j] += coef * s[i][j];
             }
         }
     }
 };
 
-// PANOCplus (Appendix A.2-A.5); returns k, solution in z
-template <int KIND, int MM>
-__device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts& o, double tol,
-                               double (&z)[2]) {
+// PANOCplus (Appendix A.2-A.5) on a variable of NV entries; returns k, solution in z
+template <int KIND, int MM, int SLACK>
+__device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, SLACK>::NV], const TbOpts& o, double tol,
+                               double (&z)[Al<KIND, SLACK>::NV]) {
+    constexpr int NV = Al<KIND, SLACK>::NV;
     const double a = o.alpha;
-    double x[2] = {x0[0], x0[1]}, grad_x[2], grad_z[2], tmpg[2], y[2], res[2];
-    double x_prev[2], res_prev[2], x_d[2], z_curr[2], d[2];
+    double x[NV], grad_x[NV], grad_z[NV], tmpg[NV], y[NV], res[NV];
+    double x_prev[NV], res_prev[NV], x_d[NV], z_curr[NV], d[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = x0[j];
     double f_x = al.gradient(x, grad_x);
     {
-        const double xe[2] = {x[0] + 1.0, x[1] + 1.0};
+        double xe[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) xe[j] = x[j] + 1.0;
         al.gradient(xe, tmpg);
     }
-    const double df[2] = {tmpg[0] - grad_x[0], tmpg[1] - grad_x[1]};
-    const double Lest = sqrt(dot2(df, df)) / sqrt(2.0);
+    double df[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) df[j] = tmpg[j] - grad_x[j];
+    const double Lest = sqrt(dotn<NV>(df, df)) / sqrt((double)NV);
     double gamma = a / Lest;
-    y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
-    double g_z = Prob<KIND>::prox(y, gamma, z);
-    res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-    Lbfgs<MM> H;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
+    double g_z = al.prox(y, gamma, z);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
+    Lbfgs<MM, NV> H;
     H.M = o.mem;
     H.reset();
-    double f_up = f_model(f_x, grad_x, res, a / gamma);
+    double f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
     double f_z = al.gradient(z, grad_z);
     while (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
         gamma /= 2;
-        y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
-        g_z = Prob<KIND>::prox(y, gamma, z);
-        res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-        f_up = f_model(f_x, grad_x, res, a / gamma);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
+        g_z = al.prox(y, gamma, z);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
+        f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
         f_z = al.gradient(z, grad_z);
     }
     double tau = 1.0;
     long long k = 1;
     for (;;) {
-        const double v0 = (res[0] / gamma - grad_x[0]) + grad_z[0];
-        const double v1 = (res[1] / gamma - grad_x[1]) + grad_z[1];
-        const double stopnorm = jmax(fabs(v0), fabs(v1));
+        double stopnorm = 0.0;
+        bool isnan_ = false;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const double v = (res[j] / gamma - grad_x[j]) + grad_z[j];
+            if (v != v) isnan_ = true; else stopnorm = fmax(stopnorm, fabs(v));
+        }
+        if (isnan_) stopnorm = __longlong_as_double(0x7ff8000000000000LL);
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
-        x_prev[0] = x[0]; x_prev[1] = x[1];
-        res_prev[0] = res[0]; res_prev[1] = res[1];
-        const double FBE_x = f_model(f_x, grad_x, res, a / gamma) + g_z;
-        const double nres[2] = {-res[0], -res[1]};
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
+        const double FBE_x = f_model<NV>(f_x, grad_x, res, a / gamma) + g_z;
+        double nres[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) nres[j] = -res[j];
         H.mul(nres, d);
-        x_d[0] = x[0] + d[0]; x_d[1] = x[1] + d[1];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) x_d[j] = x[j] + d[j];
         f_x = al.gradient(x_d, grad_x);
-        x[0] = x_d[0]; x[1] = x_d[1];
-        z_curr[0] = z[0]; z_curr[1] = z[1];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { x[j] = x_d[j]; z_curr[j] = z[j]; }
         tau = 1.0;
         const double sigma = o.beta * (0.5 / gamma) * (1 - a);
-        const double nr = sqrt(dot2(res, res));
+        const double nr = sqrt(dotn<NV>(res, res));
         const double thresh = FBE_x - sigma * (nr * nr) + 10 * BZ_EPS * (1 + fabs(FBE_x));
         for (int kb = 1; kb <= o.max_backtracks; ++kb) {
-            y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
-            g_z = Prob<KIND>::prox(y, gamma, z);
-            res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-            f_up = f_model(f_x, grad_x, res, a / gamma);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
+            g_z = al.prox(y, gamma, z);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
+            f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
             f_z = al.gradient(z, grad_z);
             if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
                 gamma *= 0.5;
@@ -276,29 +345,32 @@ __device__ long long panocplus(Al<KIND>& al, const double (&x0)[2], const TbOpts
             }
             if (f_up + g_z <= thresh || kb >= o.max_backtracks) break;
             tau = (kb >= o.max_backtracks - 1) ? 0.0 : tau / 2;
-            x[0] = tau * x_d[0] + (1 - tau) * z_curr[0];
-            x[1] = tau * x_d[1] + (1 - tau) * z_curr[1];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) x[j] = tau * x_d[j] + (1 - tau) * z_curr[j];
             f_x = al.gradient(x, grad_x);
         }
-        const double sv[2] = {x[0] - x_prev[0], x[1] - x_prev[1]};
-        const double yv[2] = {res[0] - res_prev[0], res[1] - res_prev[1]};
+        double sv[NV], yv[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { sv[j] = x[j] - x_prev[j]; yv[j] = res[j] - res_prev[j]; }
         H.update(sv, yv);
         k += 1;
     }
 }
 
-template <int KIND, int MM>
+// one thread = one complete solve: SLACK = 0 `alps` (alps.jl:7-117), SLACK = 1 `als` (als.jl:7-120)
+template <int KIND, int MM, int SLACK>
 __global__ void __launch_bounds__(TB_THREADS)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
                  double* __restrict__ nrps) {
     constexpr int NY = Prob<KIND>::NY;
+    constexpr int NV = Al<KIND, SLACK>::NV;
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= batch) return;
-    Al<KIND> al;
-    double x[2], z[2], cx[NY], s[NY];
-    {   // alps.jl:37-45
+    Al<KIND, SLACK> al;
+    double x[2], cx[NY], s[NY];
+    {   // alps.jl:37-45 / als.jl:38-44
         const double x0[2] = {x0s[inst * 2], x0s[inst * 2 + 1]};
         al.gz = Prob<KIND>::prox(x0, BZ_EPS, x);
     }
@@ -324,18 +396,33 @@ __global__ void __launch_bounds__(TB_THREADS)
 #pragma unroll
         for (int i = 0; i < NY; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20));   // safeguards.jl:2-5
         al.update();
-        const long long sub_it = panocplus<KIND, MM>(al, x, o, inner_tol, z);
+        double v0[NV], z[NV];
+        v0[0] = x[0]; v0[1] = x[1];
+        if constexpr (SLACK != 0) {
+#pragma unroll
+            for (int i = 0; i < NY; ++i) v0[2 + i] = s[i];       // xSlack = [x; s], als.jl:69-70
+        }
+        const long long sub_it = panocplus<KIND, MM, SLACK>(al, v0, o, inner_tol, z);
         x[0] = z[0]; x[1] = z[1];
-        objx = al.fx + al.gz;
         tot_inner += sub_it;
         const bool sub_solved = sub_it < o.subsolver_maxit;
-        Prob<KIND>::c_eval(x, cx);
-        double t[NY];
+        if constexpr (SLACK != 0) {
 #pragma unroll
-        for (int i = 0; i < NY; ++i) t[i] = cx[i] + al.muy[i];
-        Prob<KIND>::proj(t, s);
+            for (int i = 0; i < NY; ++i) s[i] = z[2 + i];
+            objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;           // f(x) + gSlack.gz, als.jl:78
+            Prob<KIND>::c_eval(x, cx);
 #pragma unroll
-        for (int i = 0; i < NY; ++i) al.y[i] = (t[i] - s[i]) / al.mu[i];
+            for (int i = 0; i < NY; ++i) al.y[i] = al.y[i] + (cx[i] - s[i]) / al.mu[i];   // als.jl:83
+        } else {
+            objx = al.fx + al.gz;
+            Prob<KIND>::c_eval(x, cx);
+            double t[NY];
+#pragma unroll
+            for (int i = 0; i < NY; ++i) t[i] = cx[i] + al.muy[i];
+            Prob<KIND>::proj(t, s);
+#pragma unroll
+            for (int i = 0; i < NY; ++i) al.y[i] = (t[i] - s[i]) / al.mu[i];
+        }
         nrp_old = nrp;
         nrp = 0.0;
 #pragma unroll
@@ -364,10 +451,10 @@ __global__ void __launch_bounds__(TB_THREADS)
 
 }  // namespace
 
-extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
-                              const bz_options* opt, double* x, double* y, int32_t* tot_it,
-                              int64_t* tot_inner_it, int32_t* status, double* norm_res_prim,
-                              double* kernel_ms) {
+static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const double* x0, const double* y0,
+                       const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                       int64_t* tot_inner_it, int32_t* status, double* norm_res_prim,
+                       double* kernel_ms) {
     if (!ctx || !x0 || !y0 || !opt || !x || !y || !tot_it || !tot_inner_it || !status || !norm_res_prim)
         return bz_fail(ctx, BZ_ERR_ARG, "bz_batch_solve: NULL argument");
     if (kind < 0 || kind > 3) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_batch_solve: unknown problem kind");
@@ -413,7 +500,8 @@ extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double
     const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
     cudaEventRecord(e0, ctx->stream);
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
-#define TB_LAUNCH(K, MMV) k_batch_alps<K, MMV><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp)
+#define TB_LAUNCH(K, MMV) do { if (slack) k_batch_alps<K, MMV, 1><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); \
+                                else k_batch_alps<K, MMV, 0><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); } while (0)
 #define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
     switch (kind) {
     case 0: TB_DISPATCH(0); break;
@@ -441,4 +529,18 @@ extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double
     cleanup();
 #undef BTRY
     return BZ_OK;
+}
+
+extern "C" int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
+                              const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                              int64_t* tot_inner_it, int32_t* status, double* norm_res_prim,
+                              double* kernel_ms) {
+    return batch_solve(ctx, 0, kind, batch, x0, y0, opt, x, y, tot_it, tot_inner_it, status, norm_res_prim, kernel_ms);
+}
+
+extern "C" int bz_batch_solve_als(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
+                                  const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                                  int64_t* tot_inner_it, int32_t* status, double* norm_res_prim,
+                                  double* kernel_ms) {
+    return batch_solve(ctx, 1, kind, batch, x0, y0, opt, x, y, tot_it, tot_inner_it, status, norm_res_prim, kernel_ms);
 }

@@ -397,12 +397,20 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
 BATCH_KINDS = {"rosenbrock": 0, "eitheror": 1, "xor": 2, "mpvca": 3}
 
 
+def als_batch(kind, X0, Y0=None, **kw):
+    """``als`` (src/algorithms/als.jl:7-120) over a batch of starting points; see alps_batch."""
+    return alps_batch(kind, X0, Y0, solver="als", **kw)
+
+
 def alps_batch(kind, X0, Y0=None, *, tol=1e-8, inner_tol=1.0, maxit=100, theta_penalty=0.8,
-               kappa_penalty=0.5, kappa_tol=0.1, subsolver=None, subsolver_maxit=1000, ctx=None):
+               kappa_penalty=0.5, kappa_tol=0.1, subsolver=None, subsolver_maxit=1000, ctx=None, solver="alps"):
     """The demos' ``for i = 1:ntests`` loop over starting points (demo/eitheror.jl:238-271,
     demo/mpvca.jl:241-281, demo/rosenbrock.jl:154-177) as one launch: one alps solve per row of X0.
     Returns dict(x, y, iters, sub_iters, status, norm_res_prim, kernel_ms) -- the columns the demos
-    write to CSV (id, xfinal, iters, sub_iters, is_solved)."""
+    write to CSV (id, xfinal, iters, sub_iters, is_solved).  ``solver="als"`` runs ``Bazinga.als``
+    (src/algorithms/als.jl) instead, as the demos do beside alps (demo/mpvca.jl:404-418)."""
+    if solver not in ("alps", "als"):
+        raise ValueError("solver must be 'alps' or 'als'")
     ctx = ctx or default_context()
     lib = ctx.lib
     k = BATCH_KINDS[kind] if isinstance(kind, str) else int(kind)
@@ -418,6 +426,7 @@ def alps_batch(kind, X0, Y0=None, *, tol=1e-8, inner_tol=1.0, maxit=100, theta_p
     it, st = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     inn, nrp = np.empty(B, dtype=np.int64), np.empty(B)
     ms = C.c_double()
-    K.check(lib.bz_batch_solve(ctx.handle, k, B, _ptr(X0), _ptr(Y0), C.byref(o), _ptr(x), _ptr(y), _ptr(it),
-                               _ptr(inn), _ptr(st), _ptr(nrp), C.byref(ms)), ctx.handle)
+    fn = lib.bz_batch_solve_als if solver == "als" else lib.bz_batch_solve
+    K.check(fn(ctx.handle, k, B, _ptr(X0), _ptr(Y0), C.byref(o), _ptr(x), _ptr(y), _ptr(it),
+               _ptr(inn), _ptr(st), _ptr(nrp), C.byref(ms)), ctx.handle)
     return dict(x=x, y=y, iters=it, sub_iters=inn, status=st, norm_res_prim=nrp, kernel_ms=ms.value)

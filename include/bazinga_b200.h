@@ -233,6 +233,11 @@ int bz_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, i
 int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
                    const bz_options* opt, double* x, double* y, int32_t* tot_it,
                    int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
+/* The same batch through `als` (src/algorithms/als.jl:7-120): PANOCplus on the stacked variable [x; s] with
+ * AugLagFunSlack / NonsmoothCostFunSlack (src/utilities/auglagfunslack.jl); same arguments and outputs. */
+int bz_batch_solve_als(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
+                   const bz_options* opt, double* x, double* y, int32_t* tot_it,
+                   int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
 
 /* ---- row-sharded multi-GPU: one process per GPU --------------------------------------- */
 int bz_comm_unique_id(void* id128); /* 128-byte NCCL unique id, generate on rank 0 and broadcast */

@@ -892,6 +892,163 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
 
 
 # ----------------------------------------------------------------------------------------------
+# ALS: the augmented-Lagrangian method on the stacked variable [x; s] with explicit slacks
+# ----------------------------------------------------------------------------------------------
+class AugLagFunSlack:
+    """src/utilities/auglagfunslack.jl:15-126: al_f(x, s) = f(x) + 1/(2 mu) ||c(x) + mu y - s||^2 - (mu/2)||y||^2."""
+
+    def __init__(self, f, c, mu, y, x):
+        if np.any(mu <= 0):
+            raise ValueError("parameters `mu` must be positive")          # auglagfunslack.jl:33-35
+        self.f, self.c = f, c
+        self.nx, self.ny = x.shape[0], y.shape[0]
+        self.mu, self.y = mu, y
+        self.muy = mu * y
+        self.musqy = 0.5 * float(np.sum(self.muy * y))
+        self.cx = np.empty_like(y)
+        self.yupd = np.empty_like(y)
+        self.dfx = np.empty_like(x)
+        self.jtv = np.empty_like(x)
+        self.fx = 0.0
+        self.n_grad = 0
+
+    def update(self, mu, y):  # AugLagUpdate! auglagfunslack.jl:114-126
+        if np.any(mu <= 0):
+            raise ValueError("parameters `mu` must be positive")
+        if y.shape[0] != self.ny:
+            raise ValueError("wrong length of passed argument y")
+        self.mu[:] = mu
+        self.y[:] = y
+        self.muy[:] = self.mu * self.y
+        self.musqy = 0.5 * float(np.sum(self.muy * self.y))
+
+    def value(self, xs):  # auglagfunslack.jl:58-72
+        if xs.shape[0] != self.nx + self.ny:
+            raise ValueError("wrong length of passed argument xs")
+        x, s = xs[: self.nx], xs[self.nx :]
+        self.fx = self.f.value(x)
+        self.c.eval(self.cx, x)
+        self.yupd[:] = self.cx + self.muy - s
+        Fxs = 0.5 * float(np.sum(self.yupd**2 / self.mu))
+        Fxs += self.fx
+        Fxs -= self.musqy
+        self.yupd[:] = self.y + (self.cx - s) / self.mu
+        return Fxs
+
+    def gradient(self, dFxs, xs):  # auglagfunslack.jl:77-97
+        if xs.shape[0] != self.nx + self.ny or dFxs.shape[0] != self.nx + self.ny:
+            raise ValueError("wrong length of passed argument xs")
+        self.n_grad += 1
+        x, s = xs[: self.nx], xs[self.nx :]
+        self.fx = self.f.gradient(self.dfx, x)
+        self.c.eval(self.cx, x)
+        Fxs = 0.5 * float(np.sum((self.cx + self.muy - s) ** 2 / self.mu))
+        Fxs += self.fx
+        Fxs -= self.musqy
+        self.yupd[:] = self.y + (self.cx - s) / self.mu
+        self.c.jtprod(self.jtv, x, self.yupd)
+        dFxs[: self.nx] = self.dfx + self.jtv
+        dFxs[self.nx :] = -self.yupd
+        return Fxs
+
+
+class NonsmoothCostFunSlack:
+    """src/utilities/auglagfunslack.jl:130-164: prox of g on x, projection onto D on s."""
+
+    def __init__(self, g, D, nx, ny):
+        self.g, self.D, self.nx, self.ny = g, D, nx, ny
+        self.gamma, self.gz = 0.0, 0.0
+        self.n_prox = 0
+
+    def prox(self, z, xs, gamma):
+        if xs.shape[0] != self.nx + self.ny or z.shape[0] != self.nx + self.ny:
+            raise ValueError("wrong length of passed argument xs")
+        self.n_prox += 1
+        self.gamma = gamma
+        zx = np.empty(self.nx)
+        gz = self.g.prox(zx, xs[: self.nx].copy(), gamma)
+        z[: self.nx] = zx
+        self.gz = gz
+        zs = np.empty(self.ny)
+        self.D.proj(zs, xs[self.nx :].copy())
+        z[self.nx :] = zs
+        return gz
+
+
+def als(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_tol=None,
+        maxit=100, theta_penalty=0.8, kappa_penalty=0.5, kappa_tol=0.1,
+        subsolver=None, subsolver_maxit=1_000_000_000):
+    """src/algorithms/als.jl:7-120 (same keywords and return tuple as alps)."""
+    start = time.time()
+    tol_prim = tol if tol_prim is None else tol_prim
+    tol_dual = tol if tol_dual is None else tol_dual
+    inner_tol = float(np.cbrt(tol_dual)) if inner_tol is None else inner_tol
+    sub = subsolver if subsolver is not None else PanocOptions()
+    x0 = np.asarray(x0, dtype=np.float64)
+    y0 = np.asarray(y0, dtype=np.float64)
+    nx, ny = x0.shape[0], y0.shape[0]
+    x = np.empty_like(x0)
+    s = np.empty_like(y0)
+    xSlack = np.zeros(nx + ny)
+    y = np.empty_like(y0)
+    cx = np.empty_like(y0)
+    mu = np.empty_like(y0)
+    gFun = NonsmoothCostFun(g)
+    gFun.prox(x, x0, EPS)
+    objx = f.value(x) + gFun.gz
+    c.eval(cx, x)
+    D.proj(s, cx)
+    default_penalty_parameter(mu, cx, s, objx)
+    y[:] = y0
+    norm_res_prim = None
+    norm_res_prim_old = None
+    fSlack = AugLagFunSlack(f, c, mu, y, x)
+    gSlack = NonsmoothCostFunSlack(g, D, nx, ny)
+    tot_it = 0
+    tot_inner_it = 0
+    solved = False
+    tired = tot_it >= maxit
+    broken = math.isnan(objx)
+    sub_its = []
+    can_stop = solved or tired or broken
+    while not can_stop:
+        tot_it += 1
+        default_dual_safeguard(y, cx)
+        opt = PanocOptions(alpha=sub.alpha, beta=sub.beta, minimum_gamma=sub.minimum_gamma,
+                           max_backtracks=sub.max_backtracks, memory=sub.memory,
+                           maxit=sub.maxit, tol=inner_tol, trace=sub.trace)
+        fSlack.update(mu, y)
+        xSlack[:nx] = x
+        xSlack[nx:] = s
+        sub_sol, sub_it = panocplus(fSlack, gSlack, xSlack, opt)
+        xSlack[:] = sub_sol
+        x[:] = xSlack[:nx]
+        s[:] = xSlack[nx:]
+        objx = f.value(x) + gSlack.gz
+        tot_inner_it += sub_it
+        sub_its.append(sub_it)
+        sub_solved = sub_it < subsolver_maxit
+        c.eval(cx, x)
+        y[:] = y + (cx - s) / mu
+        norm_res_prim_old = norm_res_prim
+        norm_res_prim = float(np.max(np.abs(cx - s))) if cx.size else 0.0
+        solved = (inner_tol <= tol_dual and sub_solved) and (norm_res_prim <= tol_prim)
+        tired = tot_it >= maxit
+        broken = math.isnan(objx)
+        can_stop = solved or tired or broken
+        if not can_stop:
+            if norm_res_prim_old is None:
+                pass
+            elif norm_res_prim > max(theta_penalty * norm_res_prim_old, tol_prim):
+                mu *= kappa_penalty
+            inner_tol = max(kappa_tol * inner_tol, tol_dual)
+    elapsed = time.time() - start
+    status = "first_order" if solved else "max_iter" if tired else "exception" if broken else "unknown"
+    return AlpsResult(x, y, tot_it, tot_inner_it, elapsed, status, inner_tol, norm_res_prim, s, mu,
+                      objective=objx, n_grad=fSlack.n_grad, n_prox=gSlack.n_prox, sub_its=sub_its)
+
+
+# ----------------------------------------------------------------------------------------------
 # Counter-based synthetic data (shared bit-for-bit with the CUDA generator, csrc/bz_rng.cuh)
 # ----------------------------------------------------------------------------------------------
 _PHILOX_M0 = np.uint64(0xD2511F53)

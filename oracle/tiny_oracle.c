@@ -14,6 +14,9 @@
  *   2 xor         demo/eitheror.jl:128-132   nx=2 ny=4  D = 2 XOR pairs
  *   3 mpvca       demo/mpvca.jl:77-150       nx=2 ny=4  g = max(0,x), D = 2 VC pairs
  *
+ * tiny_als / tiny_als_batch: the same problems through `Bazinga.als` (src/algorithms/als.jl:7-120) -- PANOCplus
+ * on the stacked variable [x; s] with AugLagFunSlack / NonsmoothCostFunSlack (src/utilities/auglagfunslack.jl).
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this file's shared object.
  */
@@ -23,6 +26,7 @@
 
 #define TNX 2
 #define TNY 4
+#define TNV (TNX + TNY)   /* largest PANOCplus variable: [x; s] of als */
 #define TMEM 16
 #define T_EPS 2.220446049250313e-16
 
@@ -38,6 +42,7 @@ typedef struct {
 
 typedef struct {
     int kind, ny;
+    int slack, nv;   /* slack = 1: AugLagFunSlack / NonsmoothCostFunSlack on [x; s] (nv = TNX + ny), else nv = TNX */
     double mu[TNY], y[TNY], muy[TNY], musqy;
     double cx[TNY], s[TNY], yupd[TNY], fx;
     double gz;
@@ -141,6 +146,23 @@ static void al_update(tiny_al* al) {
 static double al_gradient(tiny_al* al, const double* x, double* dlx) {
     double dfx[TNX], jtv[TNX], acc = 0.0;
     al->n_grad++;
+    if (al->slack) { /* gradient!(dFxs, F::AugLagFunSlack, xs), auglagfunslack.jl:77-97 */
+        const double* sl = x + TNX;
+        al->fx = f_grad(al->kind, x, dfx);
+        c_eval(al->kind, x, al->cx);
+        for (int i = 0; i < al->ny; ++i) {
+            double t = (al->cx[i] + al->muy[i]) - sl[i];
+            acc += (t * t) / al->mu[i];
+        }
+        double Fxs = 0.5 * acc;
+        Fxs += al->fx;
+        Fxs -= al->musqy;
+        for (int i = 0; i < al->ny; ++i) al->yupd[i] = al->y[i] + (al->cx[i] - sl[i]) / al->mu[i];
+        c_jtprod(al->kind, x, al->yupd, jtv);
+        for (int j = 0; j < TNX; ++j) dlx[j] = dfx[j] + jtv[j];
+        for (int i = 0; i < al->ny; ++i) dlx[TNX + i] = -al->yupd[i];
+        return Fxs;
+    }
     c_eval(al->kind, x, al->cx);
     for (int i = 0; i < al->ny; ++i) al->yupd[i] = al->cx[i] + al->muy[i];
     projD(al->kind, al->yupd, al->s);
@@ -158,111 +180,121 @@ static double al_gradient(tiny_al* al, const double* x, double* dlx) {
 static double al_prox(tiny_al* al, const double* x, double gamma, double* z) {
     al->n_prox++;
     al->gz = g_prox(al->kind, x, gamma, z);
+    if (al->slack) projD(al->kind, x + TNX, z + TNX);   /* NonsmoothCostFunSlack, auglagfunslack.jl:147-164 */
     return al->gz;
 }
 
 /* ---- LBFGS + PANOCplus ------------------------------------------------------- */
 typedef struct {
-    int M, currmem, curridx;
-    double H, s[TMEM][TNX], y[TMEM][TNX], ys[TMEM], alphas[TMEM];
+    int M, currmem, curridx, nv;
+    double H, s[TMEM][TNV], y[TMEM][TNV], ys[TMEM], alphas[TMEM];
 } tiny_lbfgs;
 
-static double dot2(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1]; }
+/* left-to-right dot product (for nv = 2: a[0]*b[0] + a[1]*b[1]) */
+static double dotn(const double* a, const double* b, int n) {
+    double acc = a[0] * b[0];
+    for (int j = 1; j < n; ++j) acc += a[j] * b[j];
+    return acc;
+}
 
 static void lbfgs_update(tiny_lbfgs* L, const double* s, const double* yv) {
     if (L->M == 0) return;
-    double ys = dot2(s, yv);
+    const int n = L->nv;
+    double ys = dotn(s, yv, n);
     if (ys > 0) {
         L->curridx += 1;
         if (L->curridx > L->M) L->curridx = 1;
         L->currmem = L->currmem + 1 > L->M ? L->M : L->currmem + 1;
         int i = L->curridx - 1;
         L->ys[i] = ys;
-        L->s[i][0] = s[0]; L->s[i][1] = s[1];
-        L->y[i][0] = yv[0]; L->y[i][1] = yv[1];
-        L->H = ys / dot2(yv, yv);
+        for (int j = 0; j < n; ++j) { L->s[i][j] = s[j]; L->y[i][j] = yv[j]; }
+        L->H = ys / dotn(yv, yv, n);
     }
 }
 static void lbfgs_mul(tiny_lbfgs* L, const double* v, double* d) {
-    d[0] = v[0]; d[1] = v[1];
+    const int n = L->nv;
+    for (int j = 0; j < n; ++j) d[j] = v[j];
     int idx = L->curridx;
     for (int t = 0; t < L->currmem; ++t) {
         int i = idx - 1;
-        L->alphas[i] = dot2(L->s[i], d) / L->ys[i];
-        d[0] -= L->alphas[i] * L->y[i][0];
-        d[1] -= L->alphas[i] * L->y[i][1];
+        L->alphas[i] = dotn(L->s[i], d, n) / L->ys[i];
+        for (int j = 0; j < n; ++j) d[j] -= L->alphas[i] * L->y[i][j];
         idx -= 1;
         if (idx == 0) idx = L->M;
     }
-    d[0] = L->H * d[0]; d[1] = L->H * d[1];
+    for (int j = 0; j < n; ++j) d[j] = L->H * d[j];
     for (int t = 0; t < L->currmem; ++t) {
         idx += 1;
         if (idx > L->M) idx = 1;
         int i = idx - 1;
-        double beta = dot2(L->y[i], d) / L->ys[i];
+        double beta = dotn(L->y[i], d, n) / L->ys[i];
         double coef = L->alphas[i] - beta;
-        d[0] += coef * L->s[i][0];
-        d[1] += coef * L->s[i][1];
+        for (int j = 0; j < n; ++j) d[j] += coef * L->s[i][j];
     }
 }
-static double f_model(double fx, const double* grad, const double* res, double L) {
-    double nr = sqrt(dot2(res, res));
-    return fx - dot2(grad, res) + (L / 2) * (nr * nr);
+static double f_model(double fx, const double* grad, const double* res, double L, int n) {
+    double nr = sqrt(dotn(res, res, n));
+    return fx - dotn(grad, res, n) + (L / 2) * (nr * nr);
 }
 
-/* returns k; solution in z */
+/* returns k; solution in z.  The variable has al->nv entries: x (alps) or [x; s] (als). */
 static long long panocplus(tiny_al* al, const double* x0, const tiny_opts* o, double tol,
                            long long maxit, double* z) {
     const double a = o->alpha;
-    double x[TNX] = {x0[0], x0[1]}, grad_x[TNX], grad_z[TNX], tmpg[TNX], xe[TNX];
-    double y[TNX], res[TNX], x_prev[TNX], res_prev[TNX], x_d[TNX], z_curr[TNX], d[TNX], nres[TNX];
+    const int n = al->nv;
+    double x[TNV], grad_x[TNV], grad_z[TNV], tmpg[TNV], xe[TNV], df[TNV];
+    double y[TNV], res[TNV], x_prev[TNV], res_prev[TNV], x_d[TNV], z_curr[TNV], d[TNV], nres[TNV];
+    double sv[TNV], yv[TNV];
+    for (int j = 0; j < n; ++j) x[j] = x0[j];
     double f_x = al_gradient(al, x, grad_x);
-    xe[0] = x[0] + 1.0; xe[1] = x[1] + 1.0;
+    for (int j = 0; j < n; ++j) xe[j] = x[j] + 1.0;
     al_gradient(al, xe, tmpg);
-    double df[TNX] = {tmpg[0] - grad_x[0], tmpg[1] - grad_x[1]};
-    double Lest = sqrt(dot2(df, df)) / sqrt((double)TNX);
+    for (int j = 0; j < n; ++j) df[j] = tmpg[j] - grad_x[j];
+    double Lest = sqrt(dotn(df, df, n)) / sqrt((double)n);
     double gamma = a / Lest;
-    y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+    for (int j = 0; j < n; ++j) y[j] = x[j] - gamma * grad_x[j];
     double g_z = al_prox(al, y, gamma, z);
-    res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
+    for (int j = 0; j < n; ++j) res[j] = x[j] - z[j];
     tiny_lbfgs H;
     memset(&H, 0, sizeof H);
-    H.M = o->lbfgs_memory; H.H = 1.0;
-    double f_up = f_model(f_x, grad_x, res, a / gamma);
+    H.M = o->lbfgs_memory; H.H = 1.0; H.nv = n;
+    double f_up = f_model(f_x, grad_x, res, a / gamma, n);
     double f_z = al_gradient(al, z, grad_z);
     while (f_z > f_up + 10 * T_EPS * (1 + fabs(f_z)) && gamma >= o->minimum_gamma) {
         gamma /= 2;
-        y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+        for (int j = 0; j < n; ++j) y[j] = x[j] - gamma * grad_x[j];
         g_z = al_prox(al, y, gamma, z);
-        res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-        f_up = f_model(f_x, grad_x, res, a / gamma);
+        for (int j = 0; j < n; ++j) res[j] = x[j] - z[j];
+        f_up = f_model(f_x, grad_x, res, a / gamma, n);
         f_z = al_gradient(al, z, grad_z);
     }
     double tau = 1.0;
     long long k = 1;
     for (;;) {
-        double v0 = (res[0] / gamma - grad_x[0]) + grad_z[0], v1 = (res[1] / gamma - grad_x[1]) + grad_z[1];
-        double stopnorm;
-        if (v0 != v0 || v1 != v1) stopnorm = NAN; else stopnorm = fmax(fabs(v0), fabs(v1));
+        double stopnorm = 0.0;
+        int isnan_ = 0;
+        for (int j = 0; j < n; ++j) {
+            double v = (res[j] / gamma - grad_x[j]) + grad_z[j];
+            if (v != v) isnan_ = 1; else stopnorm = fmax(stopnorm, fabs(v));
+        }
+        if (isnan_) stopnorm = NAN;
         if (k >= maxit || stopnorm <= tol) return k;
-        x_prev[0] = x[0]; x_prev[1] = x[1];
-        res_prev[0] = res[0]; res_prev[1] = res[1];
-        double FBE_x = f_model(f_x, grad_x, res, a / gamma) + g_z;
-        nres[0] = -res[0]; nres[1] = -res[1];
+        for (int j = 0; j < n; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
+        double FBE_x = f_model(f_x, grad_x, res, a / gamma, n) + g_z;
+        for (int j = 0; j < n; ++j) nres[j] = -res[j];
         lbfgs_mul(&H, nres, d);
-        x_d[0] = x[0] + d[0]; x_d[1] = x[1] + d[1];
+        for (int j = 0; j < n; ++j) x_d[j] = x[j] + d[j];
         f_x = al_gradient(al, x_d, grad_x);
-        x[0] = x_d[0]; x[1] = x_d[1];
-        z_curr[0] = z[0]; z_curr[1] = z[1];
+        for (int j = 0; j < n; ++j) { x[j] = x_d[j]; z_curr[j] = z[j]; }
         tau = 1.0;
         double sigma = o->beta * (0.5 / gamma) * (1 - a);
-        double nr = sqrt(dot2(res, res));
+        double nr = sqrt(dotn(res, res, n));
         double thresh = FBE_x - sigma * (nr * nr) + 10 * T_EPS * (1 + fabs(FBE_x));
         for (int kb = 1; kb <= o->max_backtracks; ++kb) {
-            y[0] = x[0] - gamma * grad_x[0]; y[1] = x[1] - gamma * grad_x[1];
+            for (int j = 0; j < n; ++j) y[j] = x[j] - gamma * grad_x[j];
             g_z = al_prox(al, y, gamma, z);
-            res[0] = x[0] - z[0]; res[1] = x[1] - z[1];
-            f_up = f_model(f_x, grad_x, res, a / gamma);
+            for (int j = 0; j < n; ++j) res[j] = x[j] - z[j];
+            f_up = f_model(f_x, grad_x, res, a / gamma, n);
             f_z = al_gradient(al, z, grad_z);
             if (f_z > f_up + 10 * T_EPS * (1 + fabs(f_z)) && gamma >= o->minimum_gamma) {
                 gamma *= 0.5;
@@ -271,12 +303,10 @@ static long long panocplus(tiny_al* al, const double* x0, const tiny_opts* o, do
             }
             if (f_up + g_z <= thresh || kb >= o->max_backtracks) break;
             tau = (kb >= o->max_backtracks - 1) ? 0.0 : tau / 2;
-            x[0] = tau * x_d[0] + (1 - tau) * z_curr[0];
-            x[1] = tau * x_d[1] + (1 - tau) * z_curr[1];
+            for (int j = 0; j < n; ++j) x[j] = tau * x_d[j] + (1 - tau) * z_curr[j];
             f_x = al_gradient(al, x, grad_x);
         }
-        double sv[TNX] = {x[0] - x_prev[0], x[1] - x_prev[1]};
-        double yv[TNX] = {res[0] - res_prev[0], res[1] - res_prev[1]};
+        for (int j = 0; j < n; ++j) { sv[j] = x[j] - x_prev[j]; yv[j] = res[j] - res_prev[j]; }
         lbfgs_update(&H, sv, yv);
         k += 1;
     }
@@ -294,7 +324,7 @@ int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, 
     double inner_tol = o->inner_tol >= 0 ? o->inner_tol : cbrt(tol_dual);
     tiny_al al;
     memset(&al, 0, sizeof al);
-    al.kind = kind; al.ny = ny;
+    al.kind = kind; al.ny = ny; al.slack = 0; al.nv = TNX;
     double x[TNX], cx[TNY], s[TNY], z[TNX];
     al_prox(&al, x0, T_EPS, x);
     double objx = f_value(kind, x) + al.gz;
@@ -359,6 +389,84 @@ int tiny_alps_batch(int kind, long long batch, const double* x0, const double* y
     for (long long i = 0; i < batch; ++i)
         tiny_alps(kind, x0 + i * TNX, y0 + i * ny, o, x + i * TNX, y + i * ny, tot_it + i,
                   tot_inner + i, status + i, nrp + i, 0);
+    return 0;
+}
+
+/* one als solve (src/algorithms/als.jl:7-120): PANOCplus on [x; s]; same outputs and status codes as tiny_alps */
+int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, double* x_out,
+             double* y_out, int* tot_it_out, long long* tot_inner_out, int* status_out,
+             double* nrp_out, long long* ngrad_out) {
+    const int ny = kind == 0 ? 2 : 4;
+    double tol_prim = o->tol_prim >= 0 ? o->tol_prim : o->tol;
+    double tol_dual = o->tol_dual >= 0 ? o->tol_dual : o->tol;
+    double inner_tol = o->inner_tol >= 0 ? o->inner_tol : cbrt(tol_dual);
+    tiny_al al;
+    memset(&al, 0, sizeof al);
+    al.kind = kind; al.ny = ny; al.slack = 0; al.nv = TNX;
+    double x[TNX], cx[TNY], s[TNY], xs[TNV], zs[TNV];
+    al_prox(&al, x0, T_EPS, x);                       /* als.jl:38-39 (plain NonsmoothCostFun) */
+    double objx = f_value(kind, x) + al.gz;
+    c_eval(kind, x, cx);
+    projD(kind, cx, s);
+    for (int i = 0; i < ny; ++i) { /* safeguards.jl:13-18 */
+        double df = cx[i] - s[i];
+        double m = jl_max(1.0, 0.5 * (df * df)) / jl_max(1.0, objx);
+        m *= 0.1;
+        al.mu[i] = jl_max(1e-8, (m != m) ? NAN : fmin(m, 1e8));
+        al.y[i] = y0[i];
+    }
+    al.slack = 1; al.nv = TNX + ny;                   /* fSlack / gSlack from here on (als.jl:46-47) */
+    int tot_it = 0, solved = 0, tired = tot_it >= o->maxit, broken = objx != objx, have_old = 0;
+    long long tot_inner = 0;
+    double nrp = NAN, nrp_old = NAN;
+    while (!(solved || tired || broken)) {
+        tot_it++;
+        for (int i = 0; i < ny; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20)); /* safeguards.jl:2-5 */
+        al_update(&al);
+        for (int j = 0; j < TNX; ++j) xs[j] = x[j];
+        for (int i = 0; i < ny; ++i) xs[TNX + i] = s[i];
+        long long sub_it = panocplus(&al, xs, o, inner_tol, o->sub_maxit, zs);
+        for (int j = 0; j < TNX; ++j) x[j] = zs[j];
+        for (int i = 0; i < ny; ++i) s[i] = zs[TNX + i];
+        objx = f_value(kind, x) + al.gz;              /* als.jl:78 */
+        tot_inner += sub_it;
+        int sub_solved = sub_it < o->subsolver_maxit;
+        c_eval(kind, x, cx);
+        for (int i = 0; i < ny; ++i) al.y[i] = al.y[i] + (cx[i] - s[i]) / al.mu[i];   /* als.jl:83 */
+        nrp_old = nrp;
+        nrp = 0.0;
+        for (int i = 0; i < ny; ++i) {
+            double v = fabs(cx[i] - s[i]);
+            nrp = (v != v || nrp != nrp) ? NAN : fmax(nrp, v);
+        }
+        solved = (inner_tol <= tol_dual && sub_solved) && (nrp <= tol_prim);
+        tired = tot_it >= o->maxit;
+        broken = objx != objx;
+        if (!(solved || tired || broken)) {
+            if (have_old && nrp > jl_max(o->theta_penalty * nrp_old, tol_prim))
+                for (int i = 0; i < ny; ++i) al.mu[i] *= o->kappa_penalty;
+            inner_tol = jl_max(o->kappa_tol * inner_tol, tol_dual);
+        }
+        have_old = 1;
+    }
+    x_out[0] = x[0]; x_out[1] = x[1];
+    for (int i = 0; i < ny; ++i) y_out[i] = al.y[i];
+    *tot_it_out = tot_it;
+    *tot_inner_out = tot_inner;
+    *status_out = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+    *nrp_out = nrp;
+    if (ngrad_out) *ngrad_out = al.n_grad;
+    return 0;
+}
+
+int tiny_als_batch(int kind, long long batch, const double* x0, const double* y0,
+                   const tiny_opts* o, double* x, double* y, int* tot_it, long long* tot_inner,
+                   int* status, double* nrp) {
+    const int ny = kind == 0 ? 2 : 4;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long i = 0; i < batch; ++i)
+        tiny_als(kind, x0 + i * TNX, y0 + i * ny, o, x + i * TNX, y + i * ny, tot_it + i,
+                 tot_inner + i, status + i, nrp + i, 0);
     return 0;
 }
 

@@ -418,6 +418,30 @@ def test_batched_demo_grids_bit_exact(gpu_ctx, kind, name, grid, mg, sm):
     assert np.array_equal(out["norm_res_prim"], ref["norm_res_prim"], equal_nan=True)
 
 
+@pytest.mark.parametrize("kind,name,grid", [(1, "eitheror", (-4.0, 8.0, 0.5)), (2, "xor", (-4.0, 8.0, 1.0)),
+                                            (3, "mpvca", (-5.0, 20.0, 1.0)), (0, "rosenbrock", (-5.0, 5.0, 2.5))])
+def test_batched_als_bit_exact(gpu_ctx, kind, name, grid):
+    """`als` (src/algorithms/als.jl; PANOCplus on the stacked [x; s] with AugLagFunSlack / NonsmoothCostFunSlack)
+    over a grid of starting points, as the demos run it beside alps: bit-identical to the C oracle, and the same
+    solutions as the numpy restatement of als.jl on a sample."""
+    X0 = _grid(*grid)
+    out = bz.als_batch(name, X0, ctx=gpu_ctx)
+    ref = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000, solver="als")
+    assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["sub_iters"], ref["sub_iters"])
+    assert np.array_equal(out["status"], ref["status"])
+    assert np.array_equal(out["x"], ref["x"], equal_nan=True) and np.array_equal(out["y"], ref["y"], equal_nan=True)
+    assert np.array_equal(out["norm_res_prim"], ref["norm_res_prim"], equal_nan=True)
+    pr = {"eitheror": bo.problem_eitheror(), "xor": bo.problem_eitheror("xor"), "mpvca": bo.problem_mpvca(),
+          "rosenbrock": bo.problem_rosenbrock()}[name]
+    kw = dict(pr["kw"])
+    kw["subsolver"] = bo.PanocOptions(minimum_gamma=bo.EPS, maxit=1000)
+    kw["subsolver_maxit"] = 1000
+    for i in range(0, len(X0), max(1, len(X0) // 12)):
+        o = bo.als(pr["f"], pr["g"], pr["c"], pr["D"], X0[i].copy(), np.zeros(pr["ny"]), **kw)
+        if o.status == "first_order":   # nonconvex: the same SET of stationary points (which one moves with summation order)
+            assert np.min(np.max(np.abs(out["x"] - o.x), axis=1)) <= 1e-5 * (1 + np.max(np.abs(o.x)))
+
+
 def test_batched_rosenbrock_c1(gpu_ctx):
     # config C1: demo/rosenbrock.jl (w=10, lambda=1, minimum_gamma=1e-32, maxit=1e9); a coarse grid keeps the
     # 2e5-iteration tail instances out of the test

@@ -167,3 +167,35 @@ def test_golden_fixtures_frozen():
     lx = al.gradient(dl, np.array(gold["grad"]["x"]))
     assert abs(lx - gold["grad"]["lx"]) <= 1e-12 * abs(lx)
     assert np.max(np.abs(dl - np.array(gold["grad"]["dlx"]))) <= 1e-11 * np.max(np.abs(dl))
+
+
+def test_als_c_oracle_matches_numpy_restatement():
+    """`als` (src/algorithms/als.jl:7-120 with src/utilities/auglagfunslack.jl) has no test in the reference; the two
+    independent restatements (numpy, following the Julia source statement by statement; plain C, the batched
+    kernel's bit-exact oracle) must agree on the demo problems.  These problems are nonconvex with a handful of
+    stationary points, and which one a start ends in -- like the iteration counts -- moves with the summation order
+    of the 6-element dot products (numpy's dot vs the C loop): most starts must agree point for point, all must end
+    in the same solution set, and als must end in the solution set of alps."""
+    from tiny_oracle_binding import tiny_batch
+    v = np.arange(-4.0, 8.0 + 1e-9, 2.0)
+    X0 = np.array([(i, j) for j in v for i in v])
+    for kind, pr in ((1, bo.problem_eitheror()), (3, bo.problem_mpvca())):
+        kw = dict(pr["kw"])
+        ra = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000, solver="als")
+        rp = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000, solver="alps")
+        assert (ra["status"] == 0).all()
+        xs_np, tot_np, same = [], 0, 0
+        for i, x0 in enumerate(X0):
+            o = bo.als(pr["f"], pr["g"], pr["c"], pr["D"], x0.copy(), np.zeros(pr["ny"]), **kw)
+            assert o.status == "first_order"
+            xs_np.append(o.x.copy())
+            tot_np += o.tot_it
+            same += np.max(np.abs(o.x - ra["x"][i])) <= 1e-6
+        xs_np = np.array(xs_np)
+        assert same >= 0.8 * len(X0)
+        assert abs(tot_np - int(ra["iters"].sum())) <= 0.2 * tot_np
+        for x in xs_np:
+            assert np.min(np.max(np.abs(ra["x"] - x), axis=1)) <= 1e-5
+        for x in ra["x"]:
+            assert np.min(np.max(np.abs(xs_np - x), axis=1)) <= 1e-5
+            assert np.min(np.max(np.abs(rp["x"] - x), axis=1)) <= 1e-5

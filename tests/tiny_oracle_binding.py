@@ -26,7 +26,9 @@ class TinyOpts(C.Structure):
                 ("lbfgs_memory", C.c_int), ("sub_maxit", C.c_longlong)]
 
 
-def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inner_tol=1.0, maxit=100, memory=5):
+def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inner_tol=1.0, maxit=100, memory=5,
+               solver="alps"):
+    """solver = "alps" (src/algorithms/alps.jl) or "als" (src/algorithms/als.jl)"""
     lib = C.CDLL(build_tiny_oracle())
     X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, 2)
     B = X0.shape[0]
@@ -37,7 +39,8 @@ def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inn
     it, st = np.zeros(B, np.int32), np.zeros(B, np.int32)
     inn, nrp = np.zeros(B, np.int64), np.zeros(B)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
-    lib.tiny_alps_batch(C.c_int(kind), C.c_longlong(B), P(X0), P(Y0), C.byref(o), P(x), P(y), P(it), P(inn), P(st), P(nrp))
+    fn = lib.tiny_als_batch if solver == "als" else lib.tiny_alps_batch
+    fn(C.c_int(kind), C.c_longlong(B), P(X0), P(Y0), C.byref(o), P(x), P(y), P(it), P(inn), P(st), P(nrp))
     return dict(x=x, y=y, iters=it, sub_iters=inn, status=st, norm_res_prim=nrp)
 
 
