@@ -10,7 +10,7 @@ from ._capi import BazingaError, LIB_PATH, STATUS_SYMBOLS, load_library  # noqa:
 from .oracles import (  # noqa: F401
     ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, FreeSet, IdentityFunction, IndBox, IndFree,
     IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NormL0, NormL0Box, NormL1, NormL1Box,
-    NormL1Nonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
+    NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
 )
 from .solver import (  # noqa: F401
     BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, alps_batch, als_batch, comm_unique_id,

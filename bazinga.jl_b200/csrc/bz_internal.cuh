@@ -225,6 +225,36 @@ __device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma
         return z;
     }
     case BZ_G_NONNEG: return fmax(0.0, x);   // demo/mpvca.jl:90-93
+    case BZ_G_NORMLP_BOX:       // normLpBox.jl:46-97: Newton on the scalar subproblem, then the global-minimum tests
+    case BZ_G_NORMLP_NONNEG: {  // normLpNonneg.jl:43-85 (no upper bound, perturbation 1 instead of 0.1)
+        const bool box = g.kind == BZ_G_NORMLP_BOX;
+        const double p = g.lo, alpha = g.lambda * gamma;
+        const double u = box ? g.u[j] : 0.0;
+        if (x <= 0.0 || (box && u == 0.0)) return 0.0;
+        const double zbar = pow(1 / (alpha * p * (1 - p)), 1 / (p - 2));
+        const double psi_zbar = zbar + alpha * p * pow(zbar, p - 1);
+        if (psi_zbar >= x) return 0.0;
+        double z = zbar + (box ? 0.1 : 1.0);   // perturbation to the right
+        for (int it = 0; it < 1000; ) {
+            const double dphi = z - x + alpha * p * pow(z, p - 1);
+            if (fabs(dphi) <= 1e-12) break;
+            ++it;
+            const double ddphi = 1 + alpha * p * (p - 1) * pow(z, p - 2);
+            z -= dphi / ddphi;
+        }
+        const double phi_0 = 0.5 * (x * x);
+        const double dz = z - x;
+        const double phi_z = 0.5 * (dz * dz) + alpha * pow(z, p);
+        if (phi_0 <= phi_z) return 0.0;
+        if (box && z > u) {
+            const double du = u - x;
+            const double phi_u = 0.5 * (du * du) + alpha * pow(u, p);
+            if (!(phi_u < phi_0)) return 0.0;
+            z = u;
+        }
+        acc += pow(z, p);
+        return z;
+    }
     default: return x;  // BZ_G_ZERO
     }
 }
@@ -232,7 +262,7 @@ __device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma
 __host__ __device__ inline double bz_g_value_scale(const BzGParams& g) {
     switch (g.kind) {
     case BZ_G_NORM_L1: case BZ_G_NORM_L0: case BZ_G_NORML1_BOX: case BZ_G_NORML1_NONNEG:
-    case BZ_G_NORML0_BOX: case BZ_G_ROSENBROCK: return g.lambda;
+    case BZ_G_NORML0_BOX: case BZ_G_ROSENBROCK: case BZ_G_NORMLP_BOX: case BZ_G_NORMLP_NONNEG: return g.lambda;
     case BZ_G_OBSTACLE_L1: return 1.0;
     default: return 0.0;
     }

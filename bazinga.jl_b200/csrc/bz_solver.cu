@@ -325,6 +325,16 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     }
     if (d->g_kind == BZ_G_NORML1_NONNEG && d->g_lambda < 0)
         return fail(BZ_ERR_ARG, "λ must be nonnegative");
+    if (d->g_kind == BZ_G_NORMLP_BOX || d->g_kind == BZ_G_NORMLP_NONNEG) {   // normLpBox.jl:16-29, normLpNonneg.jl:15-24
+        if (d->g_lo <= 0) return fail(BZ_ERR_ARG, "p must be positive");
+        if (d->g_lo >= 1) return fail(BZ_ERR_ARG, "p must be smaller than one");
+        if (d->g_lambda < 0) return fail(BZ_ERR_ARG, "alpha must be nonnegative");
+        if (d->g_kind == BZ_G_NORMLP_BOX) {
+            if (!d->g_u) return fail(BZ_ERR_ARG, "g_u is required for the *_BOX prox kinds");
+            for (long long j = 0; j < n; ++j)
+                if (d->g_u[j] < 0) return fail(BZ_ERR_ARG, "vector u must have nonnegative entries");
+        }
+    }
 
     int rc = BZ_OK;
 #define PTRY(x) do { rc = (x); if (rc != BZ_OK) { bz_problem_destroy(p); return rc; } } while (0)

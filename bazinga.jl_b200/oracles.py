@@ -121,6 +121,36 @@ class NormL0Box:
         self.lam, self.u = float(lam), u
 
 
+def _check_lp(p, alpha):
+    if p <= 0:
+        raise ValueError("p must be positive")                  # normLpBox.jl:17-18
+    if p >= 1:
+        raise ValueError("p must be smaller than one")          # :19-20
+    if alpha < 0:
+        raise ValueError("alpha must be nonnegative")           # :22-23
+
+
+class NormLpPowerBox:
+    """src/proxoperators/normLpBox.jl:11-97: alpha * sum_i x_i^p, 0 < p < 1, on the box [0, u]."""
+    g_kind = K.G_NORMLP_BOX
+
+    def __init__(self, p, alpha=1.0, *, u):
+        u = _f64(u)
+        _check_lp(p, alpha)
+        if np.any(u < 0):
+            raise ValueError("vector u must have nonnegative entries")
+        self.lam, self.lo, self.hi, self.u = float(alpha), float(p), 0.0, u
+
+
+class NormLpPowerNonneg:
+    """src/proxoperators/normLpNonneg.jl:12-90: alpha * sum_i x_i^p, 0 < p < 1, on x >= 0."""
+    g_kind = K.G_NORMLP_NONNEG
+
+    def __init__(self, p, alpha=1.0):
+        _check_lp(p, alpha)
+        self.lam, self.lo, self.hi = float(alpha), float(p), 0.0
+
+
 class NonsmoothCostObstacleL1:
     """demo/obstacle.jl:64-81."""
     g_kind = K.G_OBSTACLE_L1

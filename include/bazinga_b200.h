@@ -58,7 +58,9 @@ typedef enum { /* nonsmooth cost g: prox!(z,g,x,gamma)->g(z) */
     BZ_G_NORML0_BOX = 6,    /* src/proxoperators/normL0Box.jl:33-58 (u vector) */
     BZ_G_ROSENBROCK = 7,    /* demo/rosenbrock.jl:52-64 */
     BZ_G_NONNEG = 8,        /* demo/mpvca.jl:89-93 */
-    BZ_G_OBSTACLE_L1 = 9    /* demo/obstacle.jl:64-81 */
+    BZ_G_OBSTACLE_L1 = 9,   /* demo/obstacle.jl:64-81 */
+    BZ_G_NORMLP_BOX = 10,   /* src/proxoperators/normLpBox.jl:37-97: alpha*sum x^p on [0,u], g_lambda = alpha, g_lo = p */
+    BZ_G_NORMLP_NONNEG = 11 /* src/proxoperators/normLpNonneg.jl:36-90: alpha*sum x^p on x >= 0, g_lambda = alpha, g_lo = p */
 } bz_g_kind;
 
 typedef enum { /* constraint function c: eval!(cx,c,x), jtprod!(jtv,c,x,v) */

@@ -292,6 +292,74 @@ class GNormL0Box:
         return self.lam * float(np.count_nonzero(keep))
 
 
+def _lp_subproblem(x, p, a, gamma, u=None, perturb=0.1):
+    """src/proxoperators/normLpBox.jl:46-97 (u given, perturbation 0.1) / normLpNonneg.jl:43-85 (u None,
+    perturbation 1): min a z^p + (z-x)^2/(2 gamma) over 0 <= z (<= u); Newton from the right of the inflection."""
+    alpha = a * gamma
+    if x <= 0 or (u is not None and u == 0):
+        return 0.0
+    zbar = (1 / (alpha * p * (1 - p))) ** (1 / (p - 2))
+    psi_zbar = zbar + alpha * p * zbar ** (p - 1)
+    if psi_zbar >= x:
+        return 0.0
+    z = zbar + perturb
+    it = 0
+    while it < 1000:
+        dphi = z - x + alpha * p * z ** (p - 1)
+        if abs(dphi) <= 1e-12:
+            break
+        it += 1
+        ddphi = 1 + alpha * p * (p - 1) * z ** (p - 2)
+        z -= dphi / ddphi
+    phi_0 = 0.5 * x**2
+    phi_z = 0.5 * (z - x) ** 2 + alpha * z**p
+    if phi_0 <= phi_z:
+        return 0.0
+    if u is not None and z > u:
+        phi_u = 0.5 * (u - x) ** 2 + alpha * u**p
+        return u if phi_u < phi_0 else 0.0
+    return z
+
+
+class GNormLpBox:
+    """src/proxoperators/normLpBox.jl:11-44."""
+
+    def __init__(self, p, alpha, u):
+        if p <= 0:
+            raise ValueError("p must be positive")
+        if p >= 1:
+            raise ValueError("p must be smaller than one")
+        if alpha < 0:
+            raise ValueError("alpha must be nonnegative")
+        u = np.asarray(u, dtype=np.float64)
+        if np.any(u < 0):
+            raise ValueError("vector u must have nonnegative entries")
+        self.p, self.alpha, self.u = float(p), float(alpha), u
+
+    def prox(self, z, x, gamma):
+        for i in range(x.shape[0]):
+            z[i] = _lp_subproblem(float(x[i]), self.p, self.alpha, gamma, float(self.u[i]), 0.1)
+        return self.alpha * float(np.sum(z**self.p))
+
+
+class GNormLpNonneg:
+    """src/proxoperators/normLpNonneg.jl:12-41."""
+
+    def __init__(self, p, alpha=1.0):
+        if p <= 0:
+            raise ValueError("p must be positive")
+        if p >= 1:
+            raise ValueError("p must be smaller than one")
+        if alpha < 0:
+            raise ValueError("alpha must be nonnegative")
+        self.p, self.alpha = float(p), float(alpha)
+
+    def prox(self, z, x, gamma):
+        for i in range(x.shape[0]):
+            z[i] = _lp_subproblem(float(x[i]), self.p, self.alpha, gamma, None, 1.0)
+        return self.alpha * float(np.sum(z**self.p))
+
+
 class GRosenbrock:
     """demo/rosenbrock.jl:55-64: soft threshold on x[1] only."""
 

@@ -139,6 +139,33 @@ def test_prox_thresholds_and_ties(gpu_ctx):
         p.close()
 
 
+@pytest.mark.parametrize("p,alpha", [(0.5, 1.0), (0.1, 0.3), (0.9, 2.5)])
+def test_lp_quasi_norm_prox(gpu_ctx, p, alpha):
+    """src/proxoperators/normLpBox.jl:37-97 and normLpNonneg.jl:36-90: per-element Newton iteration with x^p; pow is
+    not bit-reproducible across libms, so 1e-10 instead of bit-exactness.  Covers every branch: x <= 0, u == 0,
+    below the threshold psi(zbar), Newton result rejected against z = 0, clipped to u, clip rejected."""
+    rng = np.random.default_rng(int(100 * p))
+    n = 4001
+    x = np.concatenate([rng.uniform(-2.0, 6.0, n - 6), [0.0, -1.0, 1e-9, 50.0, 3.0, 3.0]])
+    u = np.concatenate([rng.uniform(0.0, 4.0, n - 6), [1.0, 1.0, 1.0, 2.0, 0.0, 1e-3]])
+    u[::17] = 0.0
+    for gamma in (0.05, 1.0, 7.0):
+        for gg, og in ((bz.NormLpPowerBox(p, alpha, u=u), bo.GNormLpBox(p, alpha, u)),
+                       (bz.NormLpPowerNonneg(p, alpha), bo.GNormLpNonneg(p, alpha))):
+            prob = bz.Problem(bz.Zero(), gg, bz.IdentityFunction(), bz.FreeSet(), nx=n, ny=n, ctx=gpu_ctx)
+            z, gz = prob.prox(x, gamma)
+            zo = np.empty(n)
+            gzo = og.prox(zo, x, gamma)
+            # a start exactly at the jump of the prox (phi_0 == phi_z up to rounding) may land on either side
+            jump = np.abs(0.5 * x**2 - (0.5 * (np.maximum(z, zo) - x) ** 2 + alpha * gamma * np.maximum(z, zo) ** p)) <= 1e-9
+            ok = (np.abs(z - zo) <= 1e-10 * (1 + np.abs(zo))) | jump
+            assert ok.all(), (np.flatnonzero(~ok)[:5], z[~ok][:5], zo[~ok][:5])
+            assert (z >= 0).all() and (gamma > 0.05 or np.count_nonzero(z) > n // 10)
+            if not jump.any():
+                assert abs(gz - gzo) <= 1e-10 * (1 + abs(gzo))
+            prob.close()
+
+
 def test_obstacle_prox_bit_exact(gpu_ctx):
     N = 257
     rng = np.random.default_rng(2)

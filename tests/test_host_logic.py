@@ -20,6 +20,12 @@ def test_constructor_guards_match_reference_messages():
         bz.NormL1Nonneg(-0.5)                     # normL1Nonneg.jl:14-19
     with pytest.raises(bz.BazingaError):
         bz.IndicatorSet(bz.NormL1(1.0))           # not in the catalogue -> error, never a CPU fallback
+    with pytest.raises(ValueError, match="smaller than one"):
+        bz.NormLpPowerNonneg(1.0)                 # normLpNonneg.jl:17-20
+    with pytest.raises(ValueError, match="positive"):
+        bz.NormLpPowerBox(0.0, u=np.ones(2))      # normLpBox.jl:17-18
+    with pytest.raises(ValueError, match="nonnegative"):
+        bz.NormLpPowerBox(0.5, -1.0, u=np.ones(2))
 
 
 def test_subsolver_slot_call_protocol():
