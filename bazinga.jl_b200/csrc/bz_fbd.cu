@@ -29,7 +29,8 @@ static int fbd_grid(const bz_ctx* ctx, const BzGradSrc& gs, long long items) {
 // ---------------------------------------------------------------------------------------------
 // F
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
+template <bool HEAVY>
+__global__ void __launch_bounds__(BZ_VEC_THREADS, HEAVY ? 1 : 4)
     k_fstep(BzState* st, BzVecs v, BzGradSrc gs, BzGParams g, double* part, unsigned int* counter,
             int force_mode) {
     __shared__ double scratch[6 * 32];
@@ -48,22 +49,28 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const int fresh = (mode >= MODE_INITFB) ? __ldcg(&st->grad_x_fresh) : 0;
     double a[3] = {0.0, 0.0, 0.0};
 
-    // elementwise work for entry j given the assembled gradient value (or the stored grad_x)
+    // elementwise work for entry j given the assembled gradient value (or the stored grad_x).  The vectors never
+    // alias: every load is issued before the first store so that the loads of an entry overlap.
+    const double* __restrict__ vx = v.x;
+    double* __restrict__ vgx = v.grad_x;
+    double* __restrict__ vz = v.z;
+    double* __restrict__ vres = v.res;
     auto elem = [&](long long j, double gr) {
         if (mode == MODE_INIT0) {
-            v.grad_x[j] = gr;
-            v.xeps[j] = v.x[j] + 1.0;            // lower_bound_smoothness_constant: x .+ 1
+            const double xj = vx[j];
+            vgx[j] = gr;
+            v.xeps[j] = xj + 1.0;                // lower_bound_smoothness_constant: x .+ 1
         } else if (mode == MODE_INIT1) {
-            const double df = gr - v.grad_x[j];
+            const double df = gr - vgx[j];
             a[0] += df * df;
         } else {
-            if (fresh) v.grad_x[j] = gr;
-            const double xj = v.x[j];
+            const double xj = vx[j];
+            if (fresh) vgx[j] = gr;
             const double y = xj - gamma * gr;
-            const double z = bz_prox_elem(g, y, gamma, j, a[2]);
+            const double z = bz_prox_elem<HEAVY>(g, y, gamma, j, a[2]);
             const double r = xj - z;
-            v.z[j] = z;
-            v.res[j] = r;
+            vz[j] = z;
+            vres[j] = r;
             a[0] += gr * r;
             a[1] += r * r;
         }
@@ -75,14 +82,15 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
         // complementarity zeroing between blocks 2 and 3 (tie zeroes the block-2 entry)
         const long long N = g.N;
         const long long stride = (long long)gridDim.x * blockDim.x;
+        const double* __restrict__ Ec = gs.Ec;
+        const bool plain = fresh && gs.Ec && !gs.Pf && !gs.Pc && !gs.Ef;   // the stencil provider: grad = Ec
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
             double gr[3], xv[3], zv[3];
 #pragma unroll
-            for (int b = 0; b < 3; ++b) {
+            for (int b = 0; b < 3; ++b) {        // all six loads first (no store in between: they overlap)
                 const long long j = i + b * N;
-                gr[b] = fresh ? bz_assemble_grad(gs, j, n) : v.grad_x[j];
-                if (fresh) v.grad_x[j] = gr[b];
-                xv[b] = v.x[j];
+                gr[b] = plain ? __ldcg(Ec + j) : (fresh ? bz_assemble_grad(gs, j, n) : vgx[j]);
+                xv[b] = vx[j];
             }
             zv[0] = fmax(0.0, (xv[0] - gamma * gr[0]) - gamma);
             zv[1] = fmax(0.0, xv[1] - gamma * gr[1]);
@@ -93,8 +101,9 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
             for (int b = 0; b < 3; ++b) {
                 const long long j = i + b * N;
                 const double r = xv[b] - zv[b];
-                v.z[j] = zv[b];
-                v.res[j] = r;
+                if (fresh) vgx[j] = gr[b];
+                vz[j] = zv[b];
+                vres[j] = r;
                 a[0] += gr[b] * r;
                 a[1] += r * r;
             }
@@ -172,8 +181,11 @@ int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
                     const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
     const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
     static bool once = false;
-    if (!once) { prefer_max_smem(k_fstep); once = true; }
-    return bz_launch_pdl(ctx, k_fstep, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+    if (!once) { prefer_max_smem(k_fstep<false>); prefer_max_smem(k_fstep<true>); once = true; }
+    if (bz_g_is_heavy(g.kind))
+        return bz_launch_pdl(ctx, k_fstep<true>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+                             part, counter, force_mode);
+    return bz_launch_pdl(ctx, k_fstep<false>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
                          part, counter, force_mode);
 }
 
@@ -192,9 +204,12 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const double gamma = __ldcg(&st->gamma);
     const double gamma_h = gamma * 0.5;
     double m1 = 0.0, m2 = 0.0;
+    const double* __restrict__ vres = v.res;
+    const double* __restrict__ vgx = v.grad_x;
+    double* __restrict__ vgz = v.grad_z;
     auto elem = [&](long long j, double gz) {
-        v.grad_z[j] = gz;
-        const double r = v.res[j], gx = v.grad_x[j];
+        const double r = vres[j], gx = vgx[j];          // loads before the store: they overlap
+        vgz[j] = gz;
         m1 = bz_nanmax(m1, (r / gamma - gx) + gz);      // norm(res/gamma - grad_x + grad_z, Inf)
         m2 = bz_nanmax(m2, (r / gamma_h - gx) + gz);    // same with the halved gamma (edge case below)
     };
@@ -206,8 +221,17 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
         }
     } else {
         const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-            elem(j, bz_assemble_grad(gs, j, n));
+        long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; j + stride < n; j += 2 * stride) {       // two entries per trip: six loads in flight
+            const double g0 = bz_assemble_grad(gs, j, n), g1 = bz_assemble_grad(gs, j + stride, n);
+            const double r0 = vres[j], x0 = vgx[j], r1 = vres[j + stride], x1 = vgx[j + stride];
+            vgz[j] = g0; vgz[j + stride] = g1;
+            m1 = bz_nanmax(m1, (r0 / gamma - x0) + g0);
+            m2 = bz_nanmax(m2, (r0 / gamma_h - x0) + g0);
+            m1 = bz_nanmax(m1, (r1 / gamma - x1) + g1);
+            m2 = bz_nanmax(m2, (r1 / gamma_h - x1) + g1);
+        }
+        if (j < n) elem(j, bz_assemble_grad(gs, j, n));
     }
     // NaN-propagating block max: the NaN flag travels in a second lane
     double a[2] = {m1 != m1 ? 0.0 : m1, m2 != m2 ? 0.0 : m2};

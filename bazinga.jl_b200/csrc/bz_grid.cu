@@ -410,10 +410,16 @@ static int launch_variant(bz_ctx* ctx, const BzDenseArgs& a, const BzGridGeom& g
     static_assert(XW <= 16, "lxs holds 16 partials");
     if (g.W > NCH * 64 * CH) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "grid-wide dense pass: slice wider than the variant");
     static bool attr_set = false;
+    static int resident_per_sm = 0;
     if (!attr_set) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_grid_algrad<CH, NCH, XW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
+        BZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_per_sm, k_grid_algrad<CH, NCH, XW, RB>,
+                                                                   (2 * CH + XW + 1) * 32, GR_SMEM_BYTES));
         attr_set = true;
     }
+    // the CTAs of a team wait for each other: the whole grid has to be resident at once
+    if ((long long)g.GS * g.T > (long long)resident_per_sm * ctx->num_sms)
+        return bz_fail(ctx, BZ_ERR_CUDA, "grid-wide dense pass: the grid cannot be co-resident on this device");
     // arrival-counter shards per ring position: ~8 CTAs per counter, at most 16 (GR_SHARDS); teams of <= 8 CTAs
     // validate their few entries directly (measured on 37 teams of 4: 103 us per pass without the hint, 490 us with it)
     int nshards = g.GS <= 8 ? 0 : g.GS / 8;

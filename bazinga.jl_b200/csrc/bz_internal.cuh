@@ -171,8 +171,15 @@ __host__ __device__ inline bool bz_d_is_pair(int kind) { return kind >= BZ_D_EIT
 
 // Elementwise prox of the g kinds that do not couple entries.  Returns z and adds this entry's
 // contribution to the value accumulator `acc` (sum |z|, sum z, or a nonzero count).
+// HEAVY = false leaves out the Lp quasi-norm kinds (a Newton loop around pow(): ~110 registers, which would halve
+// the occupancy of every kernel this is inlined into); the launchers pick the instantiation from g.kind.
+__host__ __device__ inline bool bz_g_is_heavy(int kind) { return kind == BZ_G_NORMLP_BOX || kind == BZ_G_NORMLP_NONNEG; }
+template <bool HEAVY = true>
 __device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma, long long j,
                                       double& acc) {
+    if constexpr (!HEAVY) {
+        if (g.kind == BZ_G_NORMLP_BOX || g.kind == BZ_G_NORMLP_NONNEG) return x;   // never launched with these kinds
+    }
     switch (g.kind) {
     case BZ_G_NORM_L1: {  // sign(x)*max(|x|-gamma*lambda,0)
         double gl = gamma * g.lambda;
@@ -227,6 +234,7 @@ __device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma
     case BZ_G_NONNEG: return fmax(0.0, x);   // demo/mpvca.jl:90-93
     case BZ_G_NORMLP_BOX:       // normLpBox.jl:46-97: Newton on the scalar subproblem, then the global-minimum tests
     case BZ_G_NORMLP_NONNEG: {  // normLpNonneg.jl:43-85 (no upper bound, perturbation 1 instead of 0.1)
+        if constexpr (!HEAVY) return x;
         const bool box = g.kind == BZ_G_NORMLP_BOX;
         const double p = g.lo, alpha = g.lambda * gamma;
         const double u = box ? g.u[j] : 0.0;

@@ -148,11 +148,11 @@ __device__ __forceinline__ void bz_xr_halo(const BzXr& xr, const double* v, long
 }
 
 // pass 1: cx = x1 + A x2 - x3; yupd = (cx + mu*y - 0)/mu; partials of lx and of f(x)
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
+__global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
     k_obstacle_c(BzState* st, int force_target, const double* x0, const double* x1p,
                  const double* x2p, BzObstacle ob, const double* __restrict__ mu,
-                 const double* __restrict__ muy, double* cx, double* s, double* yupd, double* lxpart,
-                 double* fxpart) {
+                 const double* __restrict__ muy, double* __restrict__ cx, double* __restrict__ s,
+                 double* __restrict__ yupd, double* lxpart, double* fxpart) {
     __shared__ double scratch[3 * 32];
     bz_pdl_wait();
     bz_pdl_launch_dependents();
@@ -169,19 +169,39 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (st->xr.nranks > 1) bz_xr_barrier_all(st, *st->xr.seq);
     bz_xr_halo(st->xr, x, N, g, up, dn);
     double a[3] = {0.0, 0.0, 0.0};
-    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+    // two grid rows per trip, every load of both rows before the first store (the outputs are __restrict__):
+    // twice the bytes in flight per thread -- these passes are DRAM-latency-bound, not issue-bound
+    for (long long r = blockIdx.y; r < g.GY; r += 2LL * gridDim.y) {
+        const long long r2 = r + gridDim.y;
+        const bool two = r2 < g.GY;
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
-            const long long i = r * g.GX + c;
-            const double x2 = x[N + i];
-            const double cv = (x[i] + bz_stencil_rc(x + N, r, c, g, up, dn)) - x[2 * N + i];
-            const double t = cv + muy[i];
-            const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
-            const double mi = mu[i];
-            a[0] += (u * u) / mi;
-            cx[i] = cv; s[i] = 0.0; yupd[i] = u / mi;
-            a[1] += x2 * x2;                     // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
-            a[2] += x2;
+            const long long i = r * g.GX + c, i2 = r2 * g.GX + c;
+            const double x2a = x[N + i];
+            const double cva = (x[i] + bz_stencil_rc(x + N, r, c, g, up, dn)) - x[2 * N + i];
+            const double mua = mu[i], muya = muy[i];
+            double x2b = 0.0, cvb = 0.0, mub = 1.0, muyb = 0.0;
+            if (two) {
+                x2b = x[N + i2];
+                cvb = (x[i2] + bz_stencil_rc(x + N, r2, c, g, up, dn)) - x[2 * N + i2];
+                mub = mu[i2]; muyb = muy[i2];
+            }
+            {
+                const double t = cva + muya;
+                const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
+                a[0] += (u * u) / mua;
+                cx[i] = cva; s[i] = 0.0; yupd[i] = u / mua;
+                a[1] += x2a * x2a;                   // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
+                a[2] += x2a;
+            }
+            if (two) {
+                const double t = cvb + muyb;
+                const double u = t - 0.0;
+                a[0] += (u * u) / mub;
+                cx[i2] = cvb; s[i2] = 0.0; yupd[i2] = u / mub;
+                a[1] += x2b * x2b;
+                a[2] += x2b;
+            }
         }
     }
     bz_block_sum<3>(a, scratch);
@@ -193,9 +213,9 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     }
 }
 // pass 2: grad = dfx + jtv with dfx = [0; x2-1; 0], jtv = [w; A w; -w]
-__global__ void __launch_bounds__(BZ_VEC_THREADS)
+__global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
     k_obstacle_jt(BzState* st, int force_target, const double* x0, const double* x1p,
-                  const double* x2p, BzObstacle ob, const double* __restrict__ yupd, double* Ec,
+                  const double* x2p, BzObstacle ob, const double* __restrict__ yupd, double* __restrict__ Ec,
                   unsigned int* counter, int set_after) {
     bz_pdl_wait();
     bz_pdl_launch_dependents();
@@ -211,14 +231,27 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const unsigned long long xseq = st->xr.nranks > 1 ? *st->xr.seq : 0ULL;
     if (st->xr.nranks > 1) bz_xr_barrier_all(st, xseq + 1ULL);   // every rank's yupd (pass 1) is complete
     bz_xr_halo(st->xr, yupd, 0, g, up, dn);
-    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+    for (long long r = blockIdx.y; r < g.GY; r += 2LL * gridDim.y) {   // two rows per trip, loads before stores
+        const long long r2 = r + gridDim.y;
+        const bool two = r2 < g.GY;
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
-            const long long i = r * g.GX + c;
-            const double w = yupd[i];
-            Ec[i] = 0.0 + w;
-            Ec[N + i] = (x[N + i] - 1.0) + bz_stencil_rc(yupd, r, c, g, up, dn);
-            Ec[2 * N + i] = 0.0 + (-w);
+            const long long i = r * g.GX + c, i2 = r2 * g.GX + c;
+            const double wa = yupd[i];
+            const double ea = (x[N + i] - 1.0) + bz_stencil_rc(yupd, r, c, g, up, dn);
+            double wb = 0.0, eb = 0.0;
+            if (two) {
+                wb = yupd[i2];
+                eb = (x[N + i2] - 1.0) + bz_stencil_rc(yupd, r2, c, g, up, dn);
+            }
+            Ec[i] = 0.0 + wa;
+            Ec[N + i] = ea;
+            Ec[2 * N + i] = 0.0 + (-wa);
+            if (two) {
+                Ec[i2] = 0.0 + wb;
+                Ec[N + i2] = eb;
+                Ec[2 * N + i2] = 0.0 + (-wb);
+            }
         }
     }
     if (bz_last_cta(counter, gridDim.x * gridDim.y) && threadIdx.x == 0) {
@@ -262,6 +295,7 @@ int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double*
 // ---------------------------------------------------------------------------------------------
 // standalone prox / proj, and the ALPS outer-step kernels
 // ---------------------------------------------------------------------------------------------
+template <bool HEAVY>
 __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_prox(BzState* st, const double* in, double gamma, double* out, long long n, BzGParams g,
            double* part, unsigned int* counter) {
@@ -279,7 +313,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
             a[0] += z0;
         }
     } else {
-        for (long long j = j0; j < n; j += stride) out[j] = bz_prox_elem(g, in[j], gamma, j, a[0]);
+        for (long long j = j0; j < n; j += stride) out[j] = bz_prox_elem<HEAVY>(g, in[j], gamma, j, a[0]);
     }
     bz_block_sum<1>(a, scratch);
     if (threadIdx.x == 0) part[blockIdx.x] = a[0];
@@ -296,8 +330,10 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, double* out, long long n,
                    const BzGParams& g, double* part, unsigned int* counter) {
     const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : n;
-    k_prox<<<bz_vec_grid(ctx, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, in, gamma, out, n, g, part,
-                                                                        counter);
+    if (bz_g_is_heavy(g.kind))
+        k_prox<true><<<bz_vec_grid(ctx, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, in, gamma, out, n, g, part, counter);
+    else
+        k_prox<false><<<bz_vec_grid(ctx, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, in, gamma, out, n, g, part, counter);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;
