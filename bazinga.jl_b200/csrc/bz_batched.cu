@@ -29,10 +29,12 @@ __device__ __forceinline__ double jmax(double a, double b) {
     return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, b);
 }
 
-// ---- problem definitions: KIND 0 rosenbrock, 1 either-or, 2 xor, 3 mpvca ------------------------
+// ---- problem definitions: KIND 0 rosenbrock, 1 either-or, 2 xor, 3 mpvca, and the demos' slack variants
+// 4 eitheror_fullslack, 5 xor_fullslack, 6 mpvca_slack, 7 mpvca_fullslack (x carries explicit slacks, D = {0})
 template <int KIND> struct Prob;
 
 template <> struct Prob<0> {   // demo/rosenbrock.jl:39-80 (w = 10, lambda = 1)
+    static constexpr int NX = 2;
     static constexpr int NY = 2;
     __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
         const double w = 10.0;
@@ -62,6 +64,7 @@ template <> struct Prob<0> {   // demo/rosenbrock.jl:39-80 (w = 10, lambda = 1)
 };
 
 template <int DK> struct ProbOr {   // demo/eitheror.jl:58-132 (c = (8,-3))
+    static constexpr int NX = 2;
     static constexpr int NY = 4;
     __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
         const double d0 = x[0] - 8.0, d1 = x[1] - (-3.0);
@@ -94,6 +97,7 @@ template <> struct Prob<1> : ProbOr<BZ_D_EITHEROR> {};
 template <> struct Prob<2> : ProbOr<BZ_D_XOR> {};
 
 template <> struct Prob<3> {   // demo/mpvca.jl:77-150 (c = (4,2))
+    static constexpr int NX = 2;
     static constexpr int NY = 4;
     __device__ static double f_grad(const double (&x)[2], double (&dfx)[2]) {
         dfx[0] = 4.0;
@@ -121,12 +125,101 @@ template <> struct Prob<3> {   // demo/mpvca.jl:77-150 (c = (4,2))
     }
 };
 
+// demo/eitheror.jl:76-90,106-119: x = [x1, x2, s1..s4]; g projects (s1,s2), (s3,s4) onto EITHEROR / XOR; D = ZeroSet
+template <int DK> struct ProbOrFullSlack {
+    static constexpr int NX = 6;
+    static constexpr int NY = 4;
+    __device__ static double f_grad(const double (&x)[NX], double (&dfx)[NX]) {
+        const double d0 = x[0] - 8.0, d1 = x[1] - (-3.0);
+        dfx[0] = 2 * d0;
+        dfx[1] = 2 * d1;
+        dfx[2] = 0.0; dfx[3] = 0.0; dfx[4] = 0.0; dfx[5] = 0.0;
+        const double nr = sqrt(d0 * d0 + d1 * d1);
+        return nr * nr;
+    }
+    __device__ static void c_eval(const double (&x)[NX], double (&cx)[NY]) {
+        cx[0] = 2 * x[1] - x[0] - 4 - x[2];
+        cx[1] = 2 - x[0] - x[3];
+        cx[2] = 4 * x[1] - x[0] * x[0] - x[4];
+        cx[3] = 10 - (x[0] - 3) * (x[0] - 3) - (x[1] - 1) * (x[1] - 1) - x[5];
+    }
+    __device__ static void c_jt(const double (&x)[NX], const double (&v)[NY], double (&jtv)[NX]) {
+        jtv[0] = -v[0] - v[1] - 2 * x[0] * v[2] + 2 * (3 - x[0]) * v[3];
+        jtv[1] = 2 * v[0] + 4 * v[2] + 2 * (1 - x[1]) * v[3];
+        jtv[2] = -v[0]; jtv[3] = -v[1]; jtv[4] = -v[2]; jtv[5] = -v[3];
+    }
+    __device__ static void proj(const double (&)[NY], double (&z)[NY]) { z[0] = 0.0; z[1] = 0.0; z[2] = 0.0; z[3] = 0.0; }
+    __device__ static double prox(const double (&x)[NX], double, double (&z)[NX]) {
+        z[0] = x[0];
+        z[1] = x[1];
+        bz_proj_pair(DK, x[2], x[3], z[2], z[3]);
+        bz_proj_pair(DK, x[4], x[5], z[4], z[5]);
+        return 0.0;
+    }
+};
+template <> struct Prob<4> : ProbOrFullSlack<BZ_D_EITHEROR> {};
+template <> struct Prob<5> : ProbOrFullSlack<BZ_D_XOR> {};
+
+template <> struct Prob<6> {   // demo/mpvca.jl:95-100,120-128 mpvca_slack: x = [x1, x2, s1, s2]
+    static constexpr int NX = 4;
+    static constexpr int NY = 2;
+    __device__ static double f_grad(const double (&x)[NX], double (&dfx)[NX]) {
+        dfx[0] = 4.0; dfx[1] = 2.0; dfx[2] = 0.0; dfx[3] = 0.0;
+        return 4.0 * x[0] + 2.0 * x[1];
+    }
+    __device__ static void c_eval(const double (&x)[NX], double (&cx)[NY]) {
+        cx[0] = x[0] + x[1] - 5.0 * sqrt(2.0) - x[2];
+        cx[1] = x[0] + x[1] - 5.0 - x[3];
+    }
+    __device__ static void c_jt(const double (&)[NX], const double (&v)[NY], double (&jtv)[NX]) {
+        jtv[0] = v[0] + v[1];
+        jtv[1] = v[0] + v[1];
+        jtv[2] = -v[0];
+        jtv[3] = -v[1];
+    }
+    __device__ static void proj(const double (&)[NY], double (&z)[NY]) { z[0] = 0.0; z[1] = 0.0; }
+    __device__ static double prox(const double (&x)[NX], double, double (&z)[NX]) {
+        bz_proj_pair(BZ_D_VC, x[0], x[2], z[0], z[2]);   // pairs (x1, s1), (x2, s2)
+        bz_proj_pair(BZ_D_VC, x[1], x[3], z[1], z[3]);
+        return 0.0;
+    }
+};
+
+template <> struct Prob<7> {   // demo/mpvca.jl:102-108,130-143 mpvca_fullslack: x = [x1, x2, s1..s4]
+    static constexpr int NX = 6;
+    static constexpr int NY = 4;
+    __device__ static double f_grad(const double (&x)[NX], double (&dfx)[NX]) {
+        dfx[0] = 4.0; dfx[1] = 2.0; dfx[2] = 0.0; dfx[3] = 0.0; dfx[4] = 0.0; dfx[5] = 0.0;
+        return 4.0 * x[0] + 2.0 * x[1];
+    }
+    __device__ static void c_eval(const double (&x)[NX], double (&cx)[NY]) {
+        cx[0] = x[0] - x[2];
+        cx[1] = x[0] + x[1] - 5.0 * sqrt(2.0) - x[3];
+        cx[2] = x[1] - x[4];
+        cx[3] = x[0] + x[1] - 5.0 - x[5];
+    }
+    __device__ static void c_jt(const double (&)[NX], const double (&v)[NY], double (&jtv)[NX]) {
+        jtv[0] = v[0] + v[1] + v[3];
+        jtv[1] = v[1] + v[2] + v[3];
+        jtv[2] = -v[0]; jtv[3] = -v[1]; jtv[4] = -v[2]; jtv[5] = -v[3];
+    }
+    __device__ static void proj(const double (&)[NY], double (&z)[NY]) { z[0] = 0.0; z[1] = 0.0; z[2] = 0.0; z[3] = 0.0; }
+    __device__ static double prox(const double (&x)[NX], double, double (&z)[NX]) {
+        z[0] = fmax(0.0, x[0]);
+        z[1] = fmax(0.0, x[1]);
+        bz_proj_pair(BZ_D_VC, x[2], x[3], z[2], z[3]);
+        bz_proj_pair(BZ_D_VC, x[4], x[5], z[4], z[5]);
+        return 0.0;
+    }
+};
+
 // ---- per-thread augmented-Lagrangian state (auglagfun.jl:11-26; SLACK: auglagfunslack.jl:15-29) -----
 // SLACK = 0: AugLagFun + NonsmoothCostFun on x (alps).  SLACK = 1: AugLagFunSlack + NonsmoothCostFunSlack on the
 // stacked variable [x; s] (als); NV is the length of the PANOC+ variable.
 template <int KIND, int SLACK> struct Al {
+    static constexpr int NX = Prob<KIND>::NX;
     static constexpr int NY = Prob<KIND>::NY;
-    static constexpr int NV = SLACK ? 2 + NY : 2;
+    static constexpr int NV = SLACK ? NX + NY : NX;
     double mu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;
 
     __device__ void update() {   // AugLagUpdate!
@@ -136,26 +229,27 @@ template <int KIND, int SLACK> struct Al {
         musqy = 0.5 * acc;
     }
     __device__ double gradient(const double (&xv)[NV], double (&dlx)[NV]) {   // gradient!(dlx, al, x)
-        double dfx[2], jtv[2], acc = 0.0;
-        const double x[2] = {xv[0], xv[1]};
+        double dfx[NX], jtv[NX], x[NX], acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = xv[j];
         if constexpr (SLACK != 0) {   // auglagfunslack.jl:77-97
             fx = Prob<KIND>::f_grad(x, dfx);
             Prob<KIND>::c_eval(x, cx);
 #pragma unroll
             for (int i = 0; i < NY; ++i) {
-                const double t = (cx[i] + muy[i]) - xv[2 + i];
+                const double t = (cx[i] + muy[i]) - xv[NX + i];
                 acc += (t * t) / mu[i];
             }
             double Fxs = 0.5 * acc;
             Fxs += fx;
             Fxs -= musqy;
 #pragma unroll
-            for (int i = 0; i < NY; ++i) yupd[i] = y[i] + (cx[i] - xv[2 + i]) / mu[i];
+            for (int i = 0; i < NY; ++i) yupd[i] = y[i] + (cx[i] - xv[NX + i]) / mu[i];
             Prob<KIND>::c_jt(x, yupd, jtv);
-            dlx[0] = dfx[0] + jtv[0];
-            dlx[1] = dfx[1] + jtv[1];
 #pragma unroll
-            for (int i = 0; i < NY; ++i) dlx[2 + i] = -yupd[i];
+            for (int j = 0; j < NX; ++j) dlx[j] = dfx[j] + jtv[j];
+#pragma unroll
+            for (int i = 0; i < NY; ++i) dlx[NX + i] = -yupd[i];
             return Fxs;
         } else {
         Prob<KIND>::c_eval(x, cx);
@@ -173,24 +267,26 @@ template <int KIND, int SLACK> struct Al {
         lx += fx;
         lx -= musqy;
         Prob<KIND>::c_jt(x, yupd, jtv);
-        dlx[0] = dfx[0] + jtv[0];
-        dlx[1] = dfx[1] + jtv[1];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) dlx[j] = dfx[j] + jtv[j];
         return lx;
         }
     }
     // prox!(z, gFun, x, gamma): prox of g on x, and for SLACK the projection onto D of the slack part
     __device__ double prox(const double (&xv)[NV], double gamma, double (&z)[NV]) {
-        const double x[2] = {xv[0], xv[1]};
-        double zx[2];
+        double x[NX], zx[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = xv[j];
         const double g = Prob<KIND>::prox(x, gamma, zx);
-        z[0] = zx[0]; z[1] = zx[1];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) z[j] = zx[j];
         if constexpr (SLACK != 0) {   // auglagfunslack.jl:147-164
             double sv[NY], zs[NY];
 #pragma unroll
-            for (int i = 0; i < NY; ++i) sv[i] = xv[2 + i];
+            for (int i = 0; i < NY; ++i) sv[i] = xv[NX + i];
             Prob<KIND>::proj(sv, zs);
 #pragma unroll
-            for (int i = 0; i < NY; ++i) z[2 + i] = zs[i];
+            for (int i = 0; i < NY; ++i) z[NX + i] = zs[i];
         }
         return g;
     }
@@ -364,17 +460,20 @@ __global__ void __launch_bounds__(TB_THREADS)
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
                  double* __restrict__ nrps) {
+    constexpr int NX = Prob<KIND>::NX;
     constexpr int NY = Prob<KIND>::NY;
     constexpr int NV = Al<KIND, SLACK>::NV;
     const long long inst = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= batch) return;
     Al<KIND, SLACK> al;
-    double x[2], cx[NY], s[NY];
+    double x[NX], cx[NY], s[NY];
     {   // alps.jl:37-45 / als.jl:38-44
-        const double x0[2] = {x0s[inst * 2], x0s[inst * 2 + 1]};
+        double x0[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x0[j] = x0s[inst * NX + j];
         al.gz = Prob<KIND>::prox(x0, BZ_EPS, x);
     }
-    double dtmp[2];
+    double dtmp[NX];
     double objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;
     Prob<KIND>::c_eval(x, cx);
     Prob<KIND>::proj(cx, s);
@@ -397,18 +496,20 @@ __global__ void __launch_bounds__(TB_THREADS)
         for (int i = 0; i < NY; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20));   // safeguards.jl:2-5
         al.update();
         double v0[NV], z[NV];
-        v0[0] = x[0]; v0[1] = x[1];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) v0[j] = x[j];
         if constexpr (SLACK != 0) {
 #pragma unroll
-            for (int i = 0; i < NY; ++i) v0[2 + i] = s[i];       // xSlack = [x; s], als.jl:69-70
+            for (int i = 0; i < NY; ++i) v0[NX + i] = s[i];       // xSlack = [x; s], als.jl:69-70
         }
         const long long sub_it = panocplus<KIND, MM, SLACK>(al, v0, o, inner_tol, z);
-        x[0] = z[0]; x[1] = z[1];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = z[j];
         tot_inner += sub_it;
         const bool sub_solved = sub_it < o.subsolver_maxit;
         if constexpr (SLACK != 0) {
 #pragma unroll
-            for (int i = 0; i < NY; ++i) s[i] = z[2 + i];
+            for (int i = 0; i < NY; ++i) s[i] = z[NX + i];
             objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;           // f(x) + gSlack.gz, als.jl:78
             Prob<KIND>::c_eval(x, cx);
 #pragma unroll
@@ -439,8 +540,8 @@ __global__ void __launch_bounds__(TB_THREADS)
         }
         have_old = true;
     }
-    xs[inst * 2] = x[0];
-    xs[inst * 2 + 1] = x[1];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) xs[inst * NX + j] = x[j];
 #pragma unroll
     for (int i = 0; i < NY; ++i) ys[inst * NY + i] = al.y[i];
     tot_its[inst] = tot_it;
@@ -457,14 +558,15 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
                        double* kernel_ms) {
     if (!ctx || !x0 || !y0 || !opt || !x || !y || !tot_it || !tot_inner_it || !status || !norm_res_prim)
         return bz_fail(ctx, BZ_ERR_ARG, "bz_batch_solve: NULL argument");
-    if (kind < 0 || kind > 3) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_batch_solve: unknown problem kind");
+    if (kind < 0 || kind > 7) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_batch_solve: unknown problem kind");
     if (batch < 0) return bz_fail(ctx, BZ_ERR_ARG, "batch must be nonnegative");
     if (opt->lbfgs_memory < 0 || opt->lbfgs_memory > TB_MAXMEM)
         return bz_fail(ctx, BZ_ERR_ARG, "batched path supports lbfgs_memory in [0, 8]");
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
     if (kernel_ms) *kernel_ms = 0.0;
     if (batch == 0) return BZ_OK;
-    const int ny = kind == 0 ? 2 : 4;
+    const int nx = kind <= 3 ? 2 : (kind == 6 ? 4 : 6);
+    const int ny = (kind == 0 || kind == 6) ? 2 : 4;
     TbOpts o;
     o.tol_prim = opt->tol_prim >= 0 ? opt->tol_prim : opt->tol;
     o.tol_dual = opt->tol_dual >= 0 ? opt->tol_dual : opt->tol;
@@ -484,15 +586,15 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     };
 #define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
         return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
-    BTRY(cudaMalloc((void**)&dx0, batch * 2 * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dx0, batch * nx * sizeof(double)));
     BTRY(cudaMalloc((void**)&dy0, batch * ny * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dx, batch * 2 * sizeof(double)));
+    BTRY(cudaMalloc((void**)&dx, batch * nx * sizeof(double)));
     BTRY(cudaMalloc((void**)&dy, batch * ny * sizeof(double)));
     BTRY(cudaMalloc((void**)&dnrp, batch * sizeof(double)));
     BTRY(cudaMalloc((void**)&dit, batch * sizeof(int)));
     BTRY(cudaMalloc((void**)&dst, batch * sizeof(int)));
     BTRY(cudaMalloc((void**)&din, batch * sizeof(long long)));
-    BTRY(cudaMemcpyAsync(dx0, x0, batch * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BTRY(cudaMemcpyAsync(dx0, x0, batch * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     BTRY(cudaMemcpyAsync(dy0, y0, batch * ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     cudaEvent_t e0, e1;
     BTRY(cudaEventCreate(&e0));
@@ -507,14 +609,18 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     case 0: TB_DISPATCH(0); break;
     case 1: TB_DISPATCH(1); break;
     case 2: TB_DISPATCH(2); break;
-    default: TB_DISPATCH(3); break;
+    case 3: TB_DISPATCH(3); break;
+    case 4: TB_DISPATCH(4); break;
+    case 5: TB_DISPATCH(5); break;
+    case 6: TB_DISPATCH(6); break;
+    default: TB_DISPATCH(7); break;
     }
 #undef TB_DISPATCH
 #undef TB_LAUNCH
     cudaEventRecord(e1, ctx->stream);
     ctx->n_launches++;
     BTRY(cudaGetLastError());
-    BTRY(cudaMemcpyAsync(x, dx, batch * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BTRY(cudaMemcpyAsync(x, dx, batch * nx * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaMemcpyAsync(y, dy, batch * ny * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaMemcpyAsync(norm_res_prim, dnrp, batch * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaMemcpyAsync(tot_it, dit, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

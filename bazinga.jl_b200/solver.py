@@ -394,7 +394,9 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
     return (out, res) if return_result else out
 
 
-BATCH_KINDS = {"rosenbrock": 0, "eitheror": 1, "xor": 2, "mpvca": 3}
+BATCH_KINDS = {"rosenbrock": 0, "eitheror": 1, "xor": 2, "mpvca": 3, "eitheror_fullslack": 4, "xor_fullslack": 5,
+               "mpvca_slack": 6, "mpvca_fullslack": 7}
+BATCH_DIMS = {0: (2, 2), 1: (2, 4), 2: (2, 4), 3: (2, 4), 4: (6, 4), 5: (6, 4), 6: (4, 2), 7: (6, 4)}   # kind -> (nx, ny)
 
 
 def als_batch(kind, X0, Y0=None, **kw):
@@ -414,15 +416,15 @@ def alps_batch(kind, X0, Y0=None, *, tol=1e-8, inner_tol=1.0, maxit=100, theta_p
     ctx = ctx or default_context()
     lib = ctx.lib
     k = BATCH_KINDS[kind] if isinstance(kind, str) else int(kind)
-    ny = 2 if k == 0 else 4
-    X0 = _f64(X0).reshape(-1, 2)
+    nx, ny = BATCH_DIMS[k]
+    X0 = _f64(X0).reshape(-1, nx)
     B = X0.shape[0]
     Y0 = np.zeros((B, ny)) if Y0 is None else _f64(Y0).reshape(B, ny)
     sub = subsolver or PANOCplus(minimum_gamma=float(np.finfo(np.float64).eps), maxit=1000)
     o = _options(tol=tol, tol_prim=None, tol_dual=None, inner_tol=inner_tol, maxit=maxit,
                  theta_penalty=theta_penalty, kappa_penalty=kappa_penalty, kappa_tol=kappa_tol,
                  subsolver_maxit=subsolver_maxit, sub=sub)
-    x, y = np.empty((B, 2)), np.empty((B, ny))
+    x, y = np.empty((B, nx)), np.empty((B, ny))
     it, st = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
     inn, nrp = np.empty(B, dtype=np.int64), np.empty(B)
     ms = C.c_double()

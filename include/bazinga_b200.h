@@ -229,8 +229,9 @@ int bz_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, i
                   double* out);
 
 /* ---- batched tiny instances (the demos' `for i = 1:ntests` loop) --------------------
- * kind: 0 rosenbrock (demo/rosenbrock.jl), 1 either-or, 2 xor (demo/eitheror.jl), 3 mpvca
- * (demo/mpvca.jl).  x0 is batch x nx (instance-major), y0 batch x ny.  One full alps solve per
+ * kind: 0 rosenbrock (demo/rosenbrock.jl; nx 2, ny 2), 1 either-or, 2 xor (demo/eitheror.jl; 2, 4), 3 mpvca
+ * (demo/mpvca.jl; 2, 4), and the demos' slack variants 4 eitheror_fullslack, 5 xor_fullslack (6, 4),
+ * 6 mpvca_slack (4, 2), 7 mpvca_fullslack (6, 4).  x0 is batch x nx (instance-major), y0 batch x ny.  One full alps solve per
  * instance, on the device, no collectives. */
 int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
                    const bz_options* opt, double* x, double* y, int32_t* tot_it,

@@ -1205,6 +1205,95 @@ def problem_mpvca():
                         subsolver=PanocOptions(minimum_gamma=EPS, maxit=1000)))
 
 
+class CEitherOrFullSlack(CEitherOr):
+    """demo/eitheror.jl:106-119 ConstraintORfullslack: x = [x1, x2, s1..s4], c(x) = c_OR(x1, x2) - s."""
+
+    def eval(self, cx, x):
+        CEitherOr.eval(self, cx, x)
+        cx -= x[2:6]
+
+    def jtprod(self, jtv, x, v):
+        CEitherOr.jtprod(self, jtv, x, v)
+        jtv[2:6] = -v[0:4]
+
+
+class CMpvcaSlack:
+    """demo/mpvca.jl:120-128 ConstraintMPVCAslack: x = [x1, x2, s1, s2]."""
+
+    def eval(self, cx, x):
+        cx[0] = x[0] + x[1] - 5.0 * math.sqrt(2.0) - x[2]
+        cx[1] = x[0] + x[1] - 5.0 - x[3]
+
+    def jtprod(self, jtv, x, v):
+        jtv[0] = v[0] + v[1]
+        jtv[1] = v[0] + v[1]
+        jtv[2] = -v[0]
+        jtv[3] = -v[1]
+
+
+class CMpvcaFullSlack(CMpvca):
+    """demo/mpvca.jl:130-143 ConstraintMPVCAfullslack: x = [x1, x2, s1..s4]."""
+
+    def eval(self, cx, x):
+        cx[0] = x[0] - x[2]
+        cx[1] = x[0] + x[1] - 5.0 * math.sqrt(2.0) - x[3]
+        cx[2] = x[1] - x[4]
+        cx[3] = x[0] + x[1] - 5.0 - x[5]
+
+    def jtprod(self, jtv, x, v):
+        CMpvca.jtprod(self, jtv, x, v)
+        jtv[2:6] = -v[0:4]
+
+
+class GPairSlack:
+    """The nonsmooth terms of the demos' slack variants: the identity or max(0, .) on (x1, x2) and a 2-element
+    projection on pairs of slacks -- demo/eitheror.jl:76-90 (EITHEROR / XOR on (3,4), (5,6)), demo/mpvca.jl:95-100
+    (VC on (1,3), (2,4)) and :102-108 (max(0,.) on 1:2, VC on (3,4), (5,6)); all return 0."""
+
+    def __init__(self, kind, pairs, nonneg_head=False):
+        self.kind, self.pairs, self.nonneg_head = kind, pairs, nonneg_head
+
+    def prox(self, z, x, gamma):
+        z[:] = x
+        if self.nonneg_head:
+            z[0:2] = np.maximum(0.0, x[0:2])
+        fn = {"eitheror": project_onto_EITHEROR_set, "xor": project_onto_XOR_set, "vc": project_onto_VC_set}[self.kind]
+        for i, j in self.pairs:
+            z[i], z[j] = fn(float(x[i]), float(x[j]))
+        return 0.0
+
+
+def problem_eitheror_fullslack(kind="eitheror"):
+    """demo/eitheror.jl:147-165 ('eitheror_fullslack' / 'xor_fullslack'): nx = 6, ny = 4, D = ZeroSet."""
+    return dict(f=FSqDist2([8.0, -3.0]), g=GPairSlack(kind, [(2, 3), (4, 5)]), c=CEitherOrFullSlack(), D=ZeroSet(), nx=6, ny=4,
+                kw=dict(tol=1e-8, inner_tol=1.0, subsolver_maxit=1000,
+                        subsolver=PanocOptions(minimum_gamma=EPS, maxit=1000)))
+
+
+def problem_mpvca_slack(full=False):
+    """demo/mpvca.jl:165-176 ('mpvca_slack': nx = 4, ny = 2; 'mpvca_fullslack': nx = 6, ny = 4), D = ZeroSet."""
+    if full:
+        g, c, nx, ny = GPairSlack("vc", [(2, 3), (4, 5)], nonneg_head=True), CMpvcaFullSlack(), 6, 4
+    else:
+        g, c, nx, ny = GPairSlack("vc", [(0, 2), (1, 3)]), CMpvcaSlack(), 4, 2
+    return dict(f=FLinear2([4.0, 2.0]), g=g, c=c, D=ZeroSet(), nx=nx, ny=ny,
+                kw=dict(tol=1e-8, inner_tol=1.0, subsolver_maxit=1000,
+                        subsolver=PanocOptions(minimum_gamma=EPS, maxit=1000)))
+
+
+def slack_start(name, X):
+    """The demos' starting points for the slack variants: [x; c(x)] (demo/eitheror.jl:241-250, demo/mpvca.jl:244-259)."""
+    X = np.asarray(X, dtype=np.float64).reshape(-1, 2)
+    x1, x2 = X[:, 0], X[:, 1]
+    if name in ("eitheror_fullslack", "xor_fullslack"):
+        return np.stack([x1, x2, 2 * x2 - x1 - 4, 2 - x1, 4 * x2 - x1**2, 10 - (x1 - 3) ** 2 - (x2 - 1) ** 2], axis=1)
+    if name == "mpvca_slack":
+        return np.stack([x1, x2, x1 + x2 - 5 * math.sqrt(2), x1 + x2 - 5], axis=1)
+    if name == "mpvca_fullslack":
+        return np.stack([x1, x2, x1, x1 + x2 - 5 * math.sqrt(2), x2, x1 + x2 - 5], axis=1)
+    return X
+
+
 def problem_basis_pursuit(A, b, g="l1"):
     """demo/basispursuit.jl:62-89."""
     return dict(f=FZero(), g=GNormL1(1.0) if g == "l1" else GNormL0(1.0), c=CDenseAffine(A, b),

@@ -13,6 +13,10 @@
  *   1 either-or   demo/eitheror.jl:58-126    nx=2 ny=4  D = 2 EITHEROR pairs
  *   2 xor         demo/eitheror.jl:128-132   nx=2 ny=4  D = 2 XOR pairs
  *   3 mpvca       demo/mpvca.jl:77-150       nx=2 ny=4  g = max(0,x), D = 2 VC pairs
+ *   4 eitheror_fullslack  demo/eitheror.jl:76-82,106-119   nx=6 ny=4  x = [x1,x2,s1..s4], g projects (s1,s2),(s3,s4) onto EITHEROR, D = {0}
+ *   5 xor_fullslack       demo/eitheror.jl:84-90,106-119   nx=6 ny=4  the same with XOR
+ *   6 mpvca_slack         demo/mpvca.jl:95-100,120-128     nx=4 ny=2  x = [x1,x2,s1,s2], g projects (x1,s1),(x2,s2) onto VC, D = {0}
+ *   7 mpvca_fullslack     demo/mpvca.jl:102-108,130-143    nx=6 ny=4  g = max(0,.) on x1,x2 and VC on (s1,s2),(s3,s4), D = {0}
  *
  * tiny_als / tiny_als_batch: the same problems through `Bazinga.als` (src/algorithms/als.jl:7-120) -- PANOCplus
  * on the stacked variable [x; s] with AugLagFunSlack / NonsmoothCostFunSlack (src/utilities/auglagfunslack.jl).
@@ -24,7 +28,7 @@
 #include <stdint.h>
 #include <string.h>
 
-#define TNX 2
+#define TNX 6            /* largest nx (the *_fullslack variants) */
 #define TNY 4
 #define TNV (TNX + TNY)   /* largest PANOCplus variable: [x; s] of als */
 #define TMEM 16
@@ -41,8 +45,8 @@ typedef struct {
 } tiny_opts;
 
 typedef struct {
-    int kind, ny;
-    int slack, nv;   /* slack = 1: AugLagFunSlack / NonsmoothCostFunSlack on [x; s] (nv = TNX + ny), else nv = TNX */
+    int kind, nx, ny;
+    int slack, nv;   /* slack = 1: AugLagFunSlack / NonsmoothCostFunSlack on [x; s] (nv = nx + ny), else nv = nx */
     double mu[TNY], y[TNY], muy[TNY], musqy;
     double cx[TNY], s[TNY], yupd[TNY], fx;
     double gz;
@@ -72,29 +76,38 @@ static void proj_vc(const double* x, double* z) { /* vanishingConstraints.jl:27-
         else z[1] = x[1];
     }
 }
+static void kind_dims(int kind, int* nx, int* ny) {
+    *nx = (kind <= 3) ? 2 : (kind == 6 ? 4 : 6);
+    *ny = (kind == 0 || kind == 6) ? 2 : 4;
+}
 static void projD(int kind, const double* v, double* z) {
     switch (kind) {
     case 0: proj_eitheror(v, z); break;                               /* demo/rosenbrock.jl:77-80 */
     case 1: proj_eitheror(v, z); proj_eitheror(v + 2, z + 2); break;  /* demo/eitheror.jl:122-126 */
     case 2: proj_xor(v, z); proj_xor(v + 2, z + 2); break;            /* demo/eitheror.jl:128-132 */
-    default: proj_vc(v, z); proj_vc(v + 2, z + 2); break;             /* demo/mpvca.jl:146-150 */
+    case 3: proj_vc(v, z); proj_vc(v + 2, z + 2); break;              /* demo/mpvca.jl:146-150 */
+    case 6: z[0] = 0.0; z[1] = 0.0; break;                            /* Bazinga.ZeroSet, zeroSet.jl:17-20 */
+    default: z[0] = z[1] = z[2] = z[3] = 0.0; break;                  /* 4, 5, 7: ZeroSet */
     }
 }
 
 /* ---- oracles --------------------------------------------------------------------------------- */
 static double f_grad(int kind, const double* x, double* dfx) {
+    int nx, ny;
+    kind_dims(kind, &nx, &ny);
+    for (int j = 2; j < nx; ++j) dfx[j] = 0.0;   /* dfx .= 0 (eitheror.jl:65, mpvca.jl:84) */
     if (kind == 0) { /* demo/rosenbrock.jl:45-50, w = 10 */
         const double w = 10.0;
         double tmp = x[1] + 1 - (x[0] + 1) * (x[0] + 1);
         dfx[0] = -4 * w * tmp * (x[0] + 1);
         dfx[1] = 2 * w * tmp;
         return w * (tmp * tmp);
-    } else if (kind == 1 || kind == 2) { /* demo/eitheror.jl:64-68, c = (8,-3): norm(.)^2 */
+    } else if (kind == 1 || kind == 2 || kind == 4 || kind == 5) { /* demo/eitheror.jl:64-68, c = (8,-3): norm(x[1:2]-c)^2 */
         double d0 = x[0] - 8.0, d1 = x[1] - (-3.0);
         dfx[0] = 2 * d0; dfx[1] = 2 * d1;
         double nr = sqrt(d0 * d0 + d1 * d1);
         return nr * nr;
-    } else { /* demo/mpvca.jl:83-87, c = (4,2) */
+    } else { /* demo/mpvca.jl:83-87, c = (4,2): dot(c, x[1:2]) */
         dfx[0] = 4.0; dfx[1] = 2.0;
         return 4.0 * x[0] + 2.0 * x[1];
     }
@@ -108,21 +121,38 @@ static void c_eval(int kind, const double* x, double* cx) {
         cx[1] = 2 - x[0];
         cx[2] = 4 * x[1] - x[0] * x[0];
         cx[3] = 10 - (x[0] - 3) * (x[0] - 3) - (x[1] - 1) * (x[1] - 1);
-    } else {                                                             /* mpvca.jl:111-114 */
+    } else if (kind == 4 || kind == 5) {                                 /* eitheror.jl:107-113 ConstraintORfullslack */
+        cx[0] = 2 * x[1] - x[0] - 4 - x[2];
+        cx[1] = 2 - x[0] - x[3];
+        cx[2] = 4 * x[1] - x[0] * x[0] - x[4];
+        cx[3] = 10 - (x[0] - 3) * (x[0] - 3) - (x[1] - 1) * (x[1] - 1) - x[5];
+    } else if (kind == 3) {                                              /* mpvca.jl:111-114 */
         cx[0] = x[0];
         cx[1] = x[0] + x[1] - 5.0 * sqrt(2.0);
         cx[2] = x[1];
         cx[3] = x[0] + x[1] - 5.0;
+    } else if (kind == 6) {                                              /* mpvca.jl:121-124 ConstraintMPVCAslack */
+        cx[0] = x[0] + x[1] - 5.0 * sqrt(2.0) - x[2];
+        cx[1] = x[0] + x[1] - 5.0 - x[3];
+    } else {                                                             /* mpvca.jl:131-139 ConstraintMPVCAfullslack */
+        cx[0] = x[0] - x[2];
+        cx[1] = x[0] + x[1] - 5.0 * sqrt(2.0) - x[3];
+        cx[2] = x[1] - x[4];
+        cx[3] = x[0] + x[1] - 5.0 - x[5];
     }
 }
 static void c_jtprod(int kind, const double* x, const double* v, double* jtv) {
     if (kind == 0) { jtv[0] = -v[0] - v[1]; jtv[1] = v[1] - v[0]; }     /* rosenbrock.jl:71-74 */
-    else if (kind == 1 || kind == 2) {                                   /* eitheror.jl:100-104 */
+    else if (kind == 1 || kind == 2 || kind == 4 || kind == 5) {         /* eitheror.jl:100-104, 114-119 */
         jtv[0] = -v[0] - v[1] - 2 * x[0] * v[2] + 2 * (3 - x[0]) * v[3];
         jtv[1] = 2 * v[0] + 4 * v[2] + 2 * (1 - x[1]) * v[3];
-    } else {                                                             /* mpvca.jl:115-118 */
+        if (kind >= 4) { jtv[2] = -v[0]; jtv[3] = -v[1]; jtv[4] = -v[2]; jtv[5] = -v[3]; }
+    } else if (kind == 6) {                                              /* mpvca.jl:125-128 */
+        jtv[0] = v[0] + v[1]; jtv[1] = v[0] + v[1]; jtv[2] = -v[0]; jtv[3] = -v[1];
+    } else {                                                             /* mpvca.jl:115-118, 140-143 */
         jtv[0] = v[0] + v[1] + v[3];
         jtv[1] = v[1] + v[2] + v[3];
+        if (kind == 7) { jtv[2] = -v[0]; jtv[3] = -v[1]; jtv[4] = -v[2]; jtv[5] = -v[3]; }
     }
 }
 static double g_prox(int kind, const double* x, double gamma, double* z) {
@@ -134,7 +164,22 @@ static double g_prox(int kind, const double* x, double gamma, double* z) {
         z[1] = x[1];
         return lambda * fabs(z[0]);
     } else if (kind == 1 || kind == 2) { z[0] = x[0]; z[1] = x[1]; return 0.0; } /* eitheror.jl:71-74 */
-    else { z[0] = fmax(0.0, x[0]); z[1] = fmax(0.0, x[1]); return 0.0; }         /* mpvca.jl:90-93 */
+    else if (kind == 4 || kind == 5) {                                             /* eitheror.jl:76-90 */
+        z[0] = x[0]; z[1] = x[1];
+        if (kind == 4) { proj_eitheror(x + 2, z + 2); proj_eitheror(x + 4, z + 4); }
+        else { proj_xor(x + 2, z + 2); proj_xor(x + 4, z + 4); }
+        return 0.0;
+    } else if (kind == 3) { z[0] = fmax(0.0, x[0]); z[1] = fmax(0.0, x[1]); return 0.0; }   /* mpvca.jl:90-93 */
+    else if (kind == 6) {                                                          /* mpvca.jl:95-100: pairs (x1,s1), (x2,s2) */
+        double a[2] = {x[0], x[2]}, b[2] = {x[1], x[3]}, za[2], zb[2];
+        proj_vc(a, za); proj_vc(b, zb);
+        z[0] = za[0]; z[2] = za[1]; z[1] = zb[0]; z[3] = zb[1];
+        return 0.0;
+    } else {                                                                       /* mpvca.jl:102-108 */
+        z[0] = fmax(0.0, x[0]); z[1] = fmax(0.0, x[1]);
+        proj_vc(x + 2, z + 2); proj_vc(x + 4, z + 4);
+        return 0.0;
+    }
 }
 
 /* ---- AugLagFun (auglagfun.jl:73-101) ------------------------------------------------------------- */
@@ -147,7 +192,7 @@ static double al_gradient(tiny_al* al, const double* x, double* dlx) {
     double dfx[TNX], jtv[TNX], acc = 0.0;
     al->n_grad++;
     if (al->slack) { /* gradient!(dFxs, F::AugLagFunSlack, xs), auglagfunslack.jl:77-97 */
-        const double* sl = x + TNX;
+        const double* sl = x + al->nx;
         al->fx = f_grad(al->kind, x, dfx);
         c_eval(al->kind, x, al->cx);
         for (int i = 0; i < al->ny; ++i) {
@@ -159,8 +204,8 @@ static double al_gradient(tiny_al* al, const double* x, double* dlx) {
         Fxs -= al->musqy;
         for (int i = 0; i < al->ny; ++i) al->yupd[i] = al->y[i] + (al->cx[i] - sl[i]) / al->mu[i];
         c_jtprod(al->kind, x, al->yupd, jtv);
-        for (int j = 0; j < TNX; ++j) dlx[j] = dfx[j] + jtv[j];
-        for (int i = 0; i < al->ny; ++i) dlx[TNX + i] = -al->yupd[i];
+        for (int j = 0; j < al->nx; ++j) dlx[j] = dfx[j] + jtv[j];
+        for (int i = 0; i < al->ny; ++i) dlx[al->nx + i] = -al->yupd[i];
         return Fxs;
     }
     c_eval(al->kind, x, al->cx);
@@ -174,13 +219,13 @@ static double al_gradient(tiny_al* al, const double* x, double* dlx) {
     lx += al->fx;
     lx -= al->musqy;
     c_jtprod(al->kind, x, al->yupd, jtv);
-    for (int j = 0; j < TNX; ++j) dlx[j] = dfx[j] + jtv[j];
+    for (int j = 0; j < al->nx; ++j) dlx[j] = dfx[j] + jtv[j];
     return lx;
 }
 static double al_prox(tiny_al* al, const double* x, double gamma, double* z) {
     al->n_prox++;
     al->gz = g_prox(al->kind, x, gamma, z);
-    if (al->slack) projD(al->kind, x + TNX, z + TNX);   /* NonsmoothCostFunSlack, auglagfunslack.jl:147-164 */
+    if (al->slack) projD(al->kind, x + al->nx, z + al->nx);   /* NonsmoothCostFunSlack, auglagfunslack.jl:147-164 */
     return al->gz;
 }
 
@@ -318,13 +363,14 @@ static double jl_max(double a, double b) { return (a != a || b != b) ? NAN : fma
 int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, double* x_out,
               double* y_out, int* tot_it_out, long long* tot_inner_out, int* status_out,
               double* nrp_out, long long* ngrad_out) {
-    const int ny = kind == 0 ? 2 : 4;
+    int nx, ny;
+    kind_dims(kind, &nx, &ny);
     double tol_prim = o->tol_prim >= 0 ? o->tol_prim : o->tol;
     double tol_dual = o->tol_dual >= 0 ? o->tol_dual : o->tol;
     double inner_tol = o->inner_tol >= 0 ? o->inner_tol : cbrt(tol_dual);
     tiny_al al;
     memset(&al, 0, sizeof al);
-    al.kind = kind; al.ny = ny; al.slack = 0; al.nv = TNX;
+    al.kind = kind; al.nx = nx; al.ny = ny; al.slack = 0; al.nv = nx;
     double x[TNX], cx[TNY], s[TNY], z[TNX];
     al_prox(&al, x0, T_EPS, x);
     double objx = f_value(kind, x) + al.gz;
@@ -345,7 +391,7 @@ int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, 
         for (int i = 0; i < ny; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20)); /* safeguards.jl:2-5 */
         al_update(&al);
         long long sub_it = panocplus(&al, x, o, inner_tol, o->sub_maxit, z);
-        x[0] = z[0]; x[1] = z[1];
+        for (int j = 0; j < nx; ++j) x[j] = z[j];
         objx = al.fx + al.gz;
         tot_inner += sub_it;
         int sub_solved = sub_it < o->subsolver_maxit;
@@ -370,7 +416,7 @@ int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, 
         }
         have_old = 1;
     }
-    x_out[0] = x[0]; x_out[1] = x[1];
+    for (int j = 0; j < nx; ++j) x_out[j] = x[j];
     for (int i = 0; i < ny; ++i) y_out[i] = al.y[i];
     *tot_it_out = tot_it;
     *tot_inner_out = tot_inner;
@@ -384,10 +430,11 @@ int tiny_alps(int kind, const double* x0, const double* y0, const tiny_opts* o, 
 int tiny_alps_batch(int kind, long long batch, const double* x0, const double* y0,
                     const tiny_opts* o, double* x, double* y, int* tot_it, long long* tot_inner,
                     int* status, double* nrp) {
-    const int ny = kind == 0 ? 2 : 4;
+    int nx, ny;
+    kind_dims(kind, &nx, &ny);
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long i = 0; i < batch; ++i)
-        tiny_alps(kind, x0 + i * TNX, y0 + i * ny, o, x + i * TNX, y + i * ny, tot_it + i,
+        tiny_alps(kind, x0 + i * nx, y0 + i * ny, o, x + i * nx, y + i * ny, tot_it + i,
                   tot_inner + i, status + i, nrp + i, 0);
     return 0;
 }
@@ -396,13 +443,14 @@ int tiny_alps_batch(int kind, long long batch, const double* x0, const double* y
 int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, double* x_out,
              double* y_out, int* tot_it_out, long long* tot_inner_out, int* status_out,
              double* nrp_out, long long* ngrad_out) {
-    const int ny = kind == 0 ? 2 : 4;
+    int nx, ny;
+    kind_dims(kind, &nx, &ny);
     double tol_prim = o->tol_prim >= 0 ? o->tol_prim : o->tol;
     double tol_dual = o->tol_dual >= 0 ? o->tol_dual : o->tol;
     double inner_tol = o->inner_tol >= 0 ? o->inner_tol : cbrt(tol_dual);
     tiny_al al;
     memset(&al, 0, sizeof al);
-    al.kind = kind; al.ny = ny; al.slack = 0; al.nv = TNX;
+    al.kind = kind; al.nx = nx; al.ny = ny; al.slack = 0; al.nv = nx;
     double x[TNX], cx[TNY], s[TNY], xs[TNV], zs[TNV];
     al_prox(&al, x0, T_EPS, x);                       /* als.jl:38-39 (plain NonsmoothCostFun) */
     double objx = f_value(kind, x) + al.gz;
@@ -415,7 +463,7 @@ int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, d
         al.mu[i] = jl_max(1e-8, (m != m) ? NAN : fmin(m, 1e8));
         al.y[i] = y0[i];
     }
-    al.slack = 1; al.nv = TNX + ny;                   /* fSlack / gSlack from here on (als.jl:46-47) */
+    al.slack = 1; al.nv = nx + ny;                   /* fSlack / gSlack from here on (als.jl:46-47) */
     int tot_it = 0, solved = 0, tired = tot_it >= o->maxit, broken = objx != objx, have_old = 0;
     long long tot_inner = 0;
     double nrp = NAN, nrp_old = NAN;
@@ -423,11 +471,11 @@ int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, d
         tot_it++;
         for (int i = 0; i < ny; ++i) al.y[i] = fmax(-1e20, fmin(al.y[i], 1e20)); /* safeguards.jl:2-5 */
         al_update(&al);
-        for (int j = 0; j < TNX; ++j) xs[j] = x[j];
-        for (int i = 0; i < ny; ++i) xs[TNX + i] = s[i];
+        for (int j = 0; j < nx; ++j) xs[j] = x[j];
+        for (int i = 0; i < ny; ++i) xs[nx + i] = s[i];
         long long sub_it = panocplus(&al, xs, o, inner_tol, o->sub_maxit, zs);
-        for (int j = 0; j < TNX; ++j) x[j] = zs[j];
-        for (int i = 0; i < ny; ++i) s[i] = zs[TNX + i];
+        for (int j = 0; j < nx; ++j) x[j] = zs[j];
+        for (int i = 0; i < ny; ++i) s[i] = zs[nx + i];
         objx = f_value(kind, x) + al.gz;              /* als.jl:78 */
         tot_inner += sub_it;
         int sub_solved = sub_it < o->subsolver_maxit;
@@ -449,7 +497,7 @@ int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, d
         }
         have_old = 1;
     }
-    x_out[0] = x[0]; x_out[1] = x[1];
+    for (int j = 0; j < nx; ++j) x_out[j] = x[j];
     for (int i = 0; i < ny; ++i) y_out[i] = al.y[i];
     *tot_it_out = tot_it;
     *tot_inner_out = tot_inner;
@@ -462,10 +510,11 @@ int tiny_als(int kind, const double* x0, const double* y0, const tiny_opts* o, d
 int tiny_als_batch(int kind, long long batch, const double* x0, const double* y0,
                    const tiny_opts* o, double* x, double* y, int* tot_it, long long* tot_inner,
                    int* status, double* nrp) {
-    const int ny = kind == 0 ? 2 : 4;
+    int nx, ny;
+    kind_dims(kind, &nx, &ny);
 #pragma omp parallel for schedule(dynamic, 64)
     for (long long i = 0; i < batch; ++i)
-        tiny_als(kind, x0 + i * TNX, y0 + i * ny, o, x + i * TNX, y + i * ny, tot_it + i,
+        tiny_als(kind, x0 + i * nx, y0 + i * ny, o, x + i * nx, y + i * ny, tot_it + i,
                  tot_inner + i, status + i, nrp + i, 0);
     return 0;
 }

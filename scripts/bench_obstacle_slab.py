@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--inner", type=int, default=100)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--same-device", action="store_true")
+    ap.add_argument("--cpu-baseline", type=int, default=0, metavar="K",
+                    help="rank 0 also times K inner iterations of the CPU restatement (numpy) of the same problem")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -109,6 +111,15 @@ def main():
                                    "max_abs_dx": float(np.max(np.abs(xg - x1))), "max_abs_x": float(np.max(np.abs(x1))),
                                    "same_counts_on_all_ranks": len({q[1] for q in xs}) == 1,
                                    "same_objective_on_all_ranks": len({q[2] for q in xs}) == 1}
+    if args.cpu_baseline > 0 and rank == 0:
+        # the reference's CPU path cannot run here (no Julia): its numpy restatement on the same grid, a bounded sample
+        import time
+        import bazinga_oracle as bo
+        t0 = time.perf_counter()
+        r = bo.solve(bo.problem_obstacle(N, (S, S)), 2.0 * np.ones(3 * N), tol=1e-4, max_inner_total=args.cpu_baseline)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": r.tot_inner_it / dt, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"first {r.tot_inner_it} PANOC+ inner iterations ({r.n_grad} AL-gradients), numpy restatement"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     p.close()

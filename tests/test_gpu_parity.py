@@ -469,6 +469,26 @@ def test_batched_als_bit_exact(gpu_ctx, kind, name, grid):
             assert np.min(np.max(np.abs(out["x"] - o.x), axis=1)) <= 1e-5 * (1 + np.max(np.abs(o.x)))
 
 
+@pytest.mark.parametrize("solver", ["alps", "als"])
+@pytest.mark.parametrize("kind,name", [(4, "eitheror_fullslack"), (5, "xor_fullslack"), (6, "mpvca_slack"), (7, "mpvca_fullslack")])
+def test_batched_slack_variants_bit_exact(gpu_ctx, kind, name, solver):
+    """The demos' slack formulations (demo/eitheror.jl:76-119,147-165; demo/mpvca.jl:95-143,165-176): x carries explicit
+    slacks, g projects them, D = ZeroSet; started from [x; c(x)] like the demos (eitheror.jl:241-250, mpvca.jl:244-259)
+    and solved by alps and by als.  Bit-identical to the C oracle -- including mpvca_slack under als, where the gradient
+    of the slack AL function is invariant under x .+ 1, the Lipschitz estimate is 0, gamma = Inf, the slacks turn NaN and
+    every solve ends in :max_iter, in the oracle as on the GPU (the reference's arithmetic does the same)."""
+    lo, hi, step = (-4.0, 8.0, 1.0) if kind <= 5 else (-5.0, 20.0, 2.5)
+    X0 = bo.slack_start(name, _grid(lo, hi, step))
+    out = bz.alps_batch(name, X0, ctx=gpu_ctx, solver=solver)
+    ref = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000, solver=solver)
+    assert out["x"].shape == ref["x"].shape == (len(X0), X0.shape[1])
+    assert np.array_equal(out["iters"], ref["iters"]) and np.array_equal(out["sub_iters"], ref["sub_iters"])
+    assert np.array_equal(out["status"], ref["status"])
+    assert np.array_equal(out["x"], ref["x"], equal_nan=True) and np.array_equal(out["y"], ref["y"], equal_nan=True)
+    if not (kind == 6 and solver == "als"):
+        assert (out["status"] == 0).sum() >= 0.9 * len(X0)
+
+
 def test_batched_rosenbrock_c1(gpu_ctx):
     # config C1: demo/rosenbrock.jl (w=10, lambda=1, minimum_gamma=1e-32, maxit=1e9); a coarse grid keeps the
     # 2e5-iteration tail instances out of the test

@@ -199,3 +199,22 @@ def test_als_c_oracle_matches_numpy_restatement():
         for x in ra["x"]:
             assert np.min(np.max(np.abs(xs_np - x), axis=1)) <= 1e-5
             assert np.min(np.max(np.abs(rp["x"] - x), axis=1)) <= 1e-5
+
+
+def test_slack_variant_oracles_agree():
+    """The demos' slack formulations (kinds 4..7 of the batched path: demo/eitheror.jl:76-119, demo/mpvca.jl:95-143): the
+    plain-C oracle and the numpy restatement (separately written problem classes) end in the same points."""
+    from tiny_oracle_binding import tiny_batch
+    G = np.array([(1.0, 2.0), (-3.0, 5.0)])
+    for kind, name, pr in ((4, "eitheror_fullslack", bo.problem_eitheror_fullslack()), (5, "xor_fullslack", bo.problem_eitheror_fullslack("xor")),
+                           (6, "mpvca_slack", bo.problem_mpvca_slack()), (7, "mpvca_fullslack", bo.problem_mpvca_slack(True))):
+        X0 = bo.slack_start(name, G)
+        assert X0.shape == (2, pr["nx"])
+        r = tiny_batch(kind, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000)
+        assert (r["status"] == 0).all()
+        for i, x0 in enumerate(X0):
+            o = bo.alps(pr["f"], pr["g"], pr["c"], pr["D"], x0.copy(), np.zeros(pr["ny"]), **pr["kw"])
+            assert o.status == "first_order" and np.max(np.abs(o.x - r["x"][i])) <= 1e-6
+            cx = np.empty(pr["ny"])
+            pr["c"].eval(cx, r["x"][i])
+            assert np.max(np.abs(cx)) <= 1e-7            # D = {0}: the slacks equal the constraint values

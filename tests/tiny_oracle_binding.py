@@ -30,12 +30,13 @@ def tiny_batch(kind, X0, *, min_gamma, sub_maxit, subsolver_maxit, tol=1e-8, inn
                solver="alps"):
     """solver = "alps" (src/algorithms/alps.jl) or "als" (src/algorithms/als.jl)"""
     lib = C.CDLL(build_tiny_oracle())
-    X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, 2)
+    nx = 2 if kind <= 3 else (4 if kind == 6 else 6)      # kinds 4..7: the demos' slack variants
+    X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, nx)
     B = X0.shape[0]
-    ny = 2 if kind == 0 else 4
+    ny = 2 if kind in (0, 6) else 4
     o = TinyOpts(tol, -1.0, -1.0, inner_tol, maxit, 0.8, 0.5, 0.1, subsolver_maxit, 0.95, 0.5, min_gamma, 20, memory, sub_maxit)
     Y0 = np.zeros((B, ny))
-    x, y = np.zeros((B, 2)), np.zeros((B, ny))
+    x, y = np.zeros((B, nx)), np.zeros((B, ny))
     it, st = np.zeros(B, np.int32), np.zeros(B, np.int32)
     inn, nrp = np.zeros(B, np.int64), np.zeros(B)
     P = lambda a: a.ctypes.data_as(C.c_void_p)
