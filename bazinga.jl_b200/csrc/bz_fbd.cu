@@ -29,8 +29,10 @@ static int fbd_grid(const bz_ctx* ctx, const BzGradSrc& gs, long long items) {
 // ---------------------------------------------------------------------------------------------
 // F
 // ---------------------------------------------------------------------------------------------
-template <bool HEAVY>
-__global__ void __launch_bounds__(BZ_VEC_THREADS, HEAVY ? 1 : 4)
+// MINB = 4 caps the kernel at 64 registers: twice the resident threads for long vectors (C4: 651 -> 366 us); the
+// latency-bound short-vector case (C2) is 1 us faster with the registers the compiler wants
+template <bool HEAVY, int MINB>
+__global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
     k_fstep(BzState* st, BzVecs v, BzGradSrc gs, BzGParams g, double* part, unsigned int* counter,
             int force_mode) {
     __shared__ double scratch[6 * 32];
@@ -181,11 +183,14 @@ int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
                     const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
     const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
     static bool once = false;
-    if (!once) { prefer_max_smem(k_fstep<false>); prefer_max_smem(k_fstep<true>); once = true; }
+    if (!once) { prefer_max_smem(k_fstep<false, 1>); prefer_max_smem(k_fstep<false, 4>); prefer_max_smem(k_fstep<true, 1>); once = true; }
     if (bz_g_is_heavy(g.kind))
-        return bz_launch_pdl(ctx, k_fstep<true>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+        return bz_launch_pdl(ctx, k_fstep<true, 1>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
                              part, counter, force_mode);
-    return bz_launch_pdl(ctx, k_fstep<false>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+    if (items > (1LL << 20))
+        return bz_launch_pdl(ctx, k_fstep<false, 4>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
+                             part, counter, force_mode);
+    return bz_launch_pdl(ctx, k_fstep<false, 1>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
                          part, counter, force_mode);
 }
 
