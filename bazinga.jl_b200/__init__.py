@@ -13,6 +13,6 @@ from .oracles import (  # noqa: F401
     NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
 )
 from .solver import (  # noqa: F401
-    BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, alps_batch, als_batch, comm_unique_id,
+    BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, als, alps_batch, als_batch, comm_unique_id,
     default_context, default_subsolver, row_shard,
 )

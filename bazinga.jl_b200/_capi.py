@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbazinga_b200.so")
 
-BZ_ABI_VERSION = 2
+BZ_ABI_VERSION = 3
 
 # enums (include/bazinga_b200.h)
 F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1 = range(7)
@@ -38,6 +38,7 @@ class ProblemDesc(C.Structure):
         ("d_lo", C.c_double), ("d_hi", C.c_double), ("d_pair_stride", C.c_int64),
         ("row_begin", C.c_int64), ("ny_local", C.c_int64),
         ("slab_nranks", C.c_int32), ("slab_rank", C.c_int32), ("nx_global", C.c_int64),
+        ("slack_formulation", C.c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ SYMBOLS = {
     "bz_problem_xr_handle": (C.c_int, [_vp, _vp]),
     "bz_problem_xr_attach": (C.c_int, [_vp, _vp]),
     "bz_alps_solve": (C.c_int, [_vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp, C.POINTER(Result)]),
+    "bz_als_solve": (C.c_int, [_vp, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp, _vp, C.POINTER(Result)]),
     "bz_panocplus_solve": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Options), C.c_double, _vp,
                                      C.POINTER(C.c_int64), _dp, _dp]),
     "bz_auglag_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _dp]),

@@ -24,7 +24,8 @@
 // fused AL-gradient pass
 // ---------------------------------------------------------------------------------------------
 
-template <bool BULK>
+// SLACK: the als formulation (AugLagFunSlack) -- a separate instantiation, so that the alps kernel keeps its registers
+template <bool BULK, bool SLACK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     k_dense_algrad(BzDenseArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -112,6 +113,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
     }
     const double* __restrict__ xsrc = a.src[target];
+    const double* __restrict__ sslack = xsrc + a.n;   // als: the slack part of the stacked input
     if (!BULK)
         for (int r = 0; r < npre; ++r) issue_row(r, r);
 
@@ -136,11 +138,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
                           double muyi) {
         const double p0 = rank ? peer : own, p1 = rank ? own : peer;
         const double cxv = (p0 + p1) - bi;                           // cx = A*x - b
-        const double t = cxv + muyi;                                 // auglagfun.jl:75
-        const double sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);    // :76
-        const double u = t - sv;                                     // :77
-        lx += (u * u) / mui;                                         // :78 (0.5 applied later)
-        const double w = u / mui;                                    // :79
+        double sv, w;
+        if constexpr (SLACK) {                                       // auglagfunslack.jl:88-92
+            sv = __ldg(sslack + r0 + rowp);
+            const double tt = (cxv + muyi) - sv;
+            lx += (tt * tt) / mui;
+            w = __ldg(a.y + r0 + rowp) + (cxv - sv) / mui;
+        } else {
+            const double t = cxv + muyi;                             // auglagfun.jl:75
+            sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);             // :76
+            const double u = t - sv;                                 // :77
+            lx += (u * u) / mui;                                     // :78 (0.5 applied later)
+            w = u / mui;                                             // :79
+        }
         if (rank == 0 && tid == 0) {
             const long long gi = r0 + rowp;
             if (a.cx) a.cx[gi] = cxv;
@@ -231,16 +241,20 @@ int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) 
     static bool attr_set = false;
     const size_t smem = (size_t)DA_RING_DOUBLES * 8 + DA_MAXSLOTS * 8 + 32 * 8 + 4 * 8 + 2 * 8;
     if (!attr_set) {
-        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
-    if (bulk) return bz_launch_pdl(ctx, k_dense_algrad<true>, dim3(2 * nclusters), dim3(DA_THREADS), smem, 0, args);
-    return bz_launch_pdl(ctx, k_dense_algrad<false>, dim3(2 * nclusters), dim3(DA_THREADS), smem, 0, args);
+    const dim3 grid(2 * nclusters), block(DA_THREADS);
+    if (args.slack)
+        return bulk ? bz_launch_pdl(ctx, k_dense_algrad<true, true>, grid, block, smem, 0, args)
+                    : bz_launch_pdl(ctx, k_dense_algrad<false, true>, grid, block, smem, 0, args);
+    return bulk ? bz_launch_pdl(ctx, k_dense_algrad<true, false>, grid, block, smem, 0, args)
+                : bz_launch_pdl(ctx, k_dense_algrad<false, false>, grid, block, smem, 0, args);
 }
 
 
@@ -393,14 +407,23 @@ __global__ void __launch_bounds__(WR_THREADS)
             for (int r = 0; r < nr; ++r) {
                 const long long gi = row0 + r;
                 const double cxv = acc[r] - a.b[gi];
-                const double t = cxv + a.muy[gi];
-                const double sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);
-                const double u = t - sv;
                 const double mui = a.mu[gi];
-                lx += (u * u) / mui;
+                double sv, w;
+                if (a.slack) {                                   // auglagfunslack.jl:88-92
+                    sv = x[n + gi];
+                    const double tt = (cxv + a.muy[gi]) - sv;
+                    lx += (tt * tt) / mui;
+                    w = a.y[gi] + (cxv - sv) / mui;
+                } else {
+                    const double t = cxv + a.muy[gi];
+                    sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);
+                    const double u = t - sv;
+                    lx += (u * u) / mui;
+                    w = u / mui;
+                }
                 if (a.cx) a.cx[gi] = cxv;
                 if (a.s) a.s[gi] = sv;
-                a.yupd[gi] = u / mui;
+                a.yupd[gi] = w;
             }
         }
         __syncthreads();

@@ -31,6 +31,10 @@ struct BzDenseArgs {
     int set_after;         // last CTA sets st->next_op = st->after_g
     int evict_first;       // stream A with an L2 evict-first policy
     int l2_prefetch_rows;  // >0: cp.async.bulk.prefetch.L2 this many rows ahead of each issue
+    // als (AugLagFunSlack, auglagfunslack.jl:77-97): the input vector is [x; s] (n + m entries) and the slack s replaces
+    // proj_D:  lx += (cx + mu*y - s)^2/mu,  yupd = y + (cx - s)/mu
+    int slack;
+    const double* y;       // m multipliers (slack mode only)
     // grid-wide single-pass kernel (bz_grid.cu) only
     unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters
     unsigned long long* gseq;  // [teams] sequence base of the exchange tags, advanced by the team's row count per launch

@@ -307,11 +307,19 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
             __syncwarp();
             const double tot = bz_warp_sum(sum);
             const double cxv = tot - b_j;                                // cx = A*x - b
-            const double t = cxv + muy_j;                                // auglagfun.jl:75
-            const double sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);    // :76
-            const double u = t - sv;                                     // :77
-            lx += (u * u) / mu_j;                                        // :78 (0.5 applied later)
-            const double w = u / mu_j;                                   // :79
+            double sv, w;
+            if (a.slack) {                                               // als, auglagfunslack.jl:88-92
+                sv = __ldg(xsrc + n + r0 + j);
+                const double tt = (cxv + muy_j) - sv;
+                lx += (tt * tt) / mu_j;
+                w = __ldg(a.y + r0 + j) + (cxv - sv) / mu_j;
+            } else {
+                const double t = cxv + muy_j;                            // auglagfun.jl:75
+                sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);             // :76
+                const double u = t - sv;                                 // :77
+                lx += (u * u) / mu_j;                                    // :78 (0.5 applied later)
+                w = u / mu_j;                                            // :79
+            }
             if (lane == 0) {
                 wring[pr] = w;
                 mbar_arrive(&wbar[pr]);

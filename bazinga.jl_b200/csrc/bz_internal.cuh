@@ -113,6 +113,9 @@ struct BzGradSrc {
     double fx_scale;
     const double* fxpart2; int nfx2;
     double fx_scale2;
+    // als (AugLagFunSlack, auglagfunslack.jl:93-95): the gradient has nx + ny entries, entries >= nx are -tail[j - nx]
+    // (tail = yupd); nx is also the row stride of the partial arrays.  nx = 0: plain AugLagFun.
+    long long nx; const double* tail;
 };
 
 // g / D parameter blocks passed by value to kernels
@@ -121,6 +124,8 @@ struct BzGParams {
     double lambda, lo, hi;
     const double* u;
     long long N;   // obstacle block size
+    // als (NonsmoothCostFunSlack, auglagfunslack.jl:147-164): entries >= snx of the stacked variable are projected onto D
+    long long snx; int sdk; double slo, shi;   // snx = 0: plain NonsmoothCostFun
 };
 struct BzDParams {
     int kind;

@@ -28,6 +28,8 @@ struct bz_problem {
     bz_ctx* ctx = nullptr;
     bz_problem_desc desc{};
     long long n = 0, m = 0, ml = 0;   // nx, global ny, local rows
+    long long nv = 0;                 // length of the PANOC+ variable: nx, or nx + ny for als (desc.slack_formulation)
+    bool slack = false, slack_active = false;
     // oracle data
     double* cA = nullptr; bool own_cA = false; double* cb = nullptr;
     double* fA = nullptr; double* fb = nullptr; long long fm = 0;
@@ -304,6 +306,13 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         return fail(BZ_ERR_UNSUPPORTED,
                     "c kind is only available in the batched tiny-instance path (bz_batch_solve)");
     }
+    p->nv = p->n;
+    if (d->slack_formulation) {   // als: PANOC+ on [x; s]
+        if (!(d->c_kind == BZ_C_DENSE_AFFINE || d->c_kind == BZ_C_IDENTITY) || d_pair || d->ny_local > 0 || d->slab_nranks > 1)
+            return fail(BZ_ERR_UNSUPPORTED, "als (slack formulation) is built for dense-affine / identity c with an elementwise D on one GPU");
+        p->slack = true;
+        p->nv = p->n + p->m;
+    }
     if (d->slab_nranks > 1) {
         if (d->c_kind != BZ_C_OBSTACLE || d->grid_x <= 0 || d->grid_y <= 0)
             return fail(BZ_ERR_UNSUPPORTED, "slab decomposition is built for the 2-D obstacle grid only");
@@ -361,10 +370,10 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     }
     double** nvecs[] = {&p->v.x, &p->v.z, &p->v.xeps, &p->v.x_prev, &p->v.x_d, &p->v.z_curr, &p->v.res,
                         &p->v.res_prev, &p->v.grad_x, &p->v.grad_z, &p->v.d, &p->Ec, &p->Ef};
-    for (double** q : nvecs) if (!*q) PTRY(dev_alloc(ctx, q, n));
-    PTRY(dev_alloc(ctx, &p->v.sM, (size_t)BZ_MAXMEM * n));
-    PTRY(dev_alloc(ctx, &p->v.yM, (size_t)BZ_MAXMEM * n));
-    p->v.n = n;
+    for (double** q : nvecs) if (!*q) PTRY(dev_alloc(ctx, q, p->nv));
+    PTRY(dev_alloc(ctx, &p->v.sM, (size_t)BZ_MAXMEM * p->nv));
+    PTRY(dev_alloc(ctx, &p->v.yM, (size_t)BZ_MAXMEM * p->nv));
+    p->v.n = p->nv;
     double** mvecs[] = {&p->mu, &p->y, &p->muy, &p->cx, &p->s, &p->yupd, &p->tm1, &p->tm2, &p->tm3};
     for (double** q : mvecs) if (!*q) PTRY(dev_alloc(ctx, q, ml));
     const int maxgrid = ctx->num_sms * 8;
@@ -532,6 +541,7 @@ static BzGradSrc grad_src(bz_problem* p) {
     } else {
         gs.Ec = p->Ec; gs.lxpart = p->lxpart; gs.nlx = p->nlx;
     }
+    if (p->slack_active) { gs.nx = p->n; gs.tail = p->yupd; }   // als: gradient = [dfx + jtv; -yupd]
     return gs;
 }
 
@@ -576,6 +586,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         const bool timed = ctx->profiling && (p->dom_counter++ % ctx->prof_stride == 0);
         if (timed) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
         a.D = p->gridD; a.gseq = p->gseq;
+        a.slack = p->slack_active ? 1 : 0; a.y = p->y;
         if (p->c_grid) BZ_TRY(bz_launch_grid_algrad(ctx, a));
         else if (p->c_wide) BZ_TRY(bz_launch_dense_wide(ctx, a));
         else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
@@ -585,7 +596,7 @@ static int launch_provider(bz_problem* p, int force_target) {
     } else if (d.c_kind == BZ_C_IDENTITY) {
         p->nlx = bz_vec_grid(ctx, bz_d_is_pair(p->D.kind) ? p->n / 2 : p->n);
         BZ_TRY(bz_launch_identity_c(ctx, p->st, force_target, src, p->n, p->mu, p->muy, p->D, p->cx,
-                                    p->s, p->yupd, p->lxpart, p->counters + 1, 1));
+                                    p->s, p->yupd, p->lxpart, p->counters + 1, 1, p->slack_active ? 1 : 0, p->y));
     } else if (d.c_kind == BZ_C_OBSTACLE) {
         p->nlx = p->nfx = bz_obstacle_partials(ctx, p->ob);
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -598,6 +609,13 @@ static int launch_provider(bz_problem* p, int force_target) {
     return BZ_OK;
 }
 
+// g parameters as the F step sees them: in als mode the entries >= nx of the stacked variable are projected onto D
+static BzGParams g_params(const bz_problem* p) {
+    BzGParams g = p->g;
+    if (p->slack_active) { g.snx = p->n; g.sdk = p->D.kind; g.slo = p->D.lo; g.shi = p->D.hi; }
+    return g;
+}
+
 // one pass of the fixed cycle [L, G, F, G, D]
 static int launch_cycle(bz_problem* p) {
     bz_ctx* ctx = p->ctx;
@@ -607,7 +625,7 @@ static int launch_cycle(bz_problem* p) {
     p->team.parity ^= 1;
     BZ_TRY(launch_provider(p, -1));
     gs = grad_src(p);
-    BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs, p->g, p->part, p->counters + 3, -1));
+    BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs, g_params(p), p->part, p->counters + 3, -1));
     BZ_TRY(launch_provider(p, -1));
     BZ_TRY(bz_launch_dstep(ctx, p->st, p->v, gs, p->part, p->counters + 4));
     return BZ_OK;
@@ -697,6 +715,7 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_alps_solve: NULL argument");
     bz_ctx* ctx = p->ctx;
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (p->slack) return bz_fail(ctx, BZ_ERR_ARG, "bz_alps_solve: the problem was created with slack_formulation (use bz_als_solve)");
     const auto t0 = std::chrono::steady_clock::now();
     const long long launches0 = ctx->n_launches;
     p->dom_events.clear();
@@ -796,6 +815,113 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// als (src/algorithms/als.jl:7-120): the same outer loop on the stacked variable [x; s]
+// ---------------------------------------------------------------------------------------------
+extern "C" int bz_als_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
+                             double* x, double* y, double* s, double* mu, bz_result* res) {
+    if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_als_solve: NULL argument");
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->slack) return bz_fail(ctx, BZ_ERR_ARG, "bz_als_solve: create the problem with slack_formulation = 1");
+    p->slack_active = false;   // als.jl:38-44: the initial prox / c(x) / proj_D / mu use the plain oracles
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long launches0 = ctx->n_launches;
+    p->dom_events.clear();
+    ctx->ev_used = 0;
+    const double tol = o->tol;
+    const double tol_prim = o->tol_prim >= 0 ? o->tol_prim : tol;
+    const double tol_dual = o->tol_dual >= 0 ? o->tol_dual : tol;
+    double inner_tol = o->inner_tol >= 0 ? o->inner_tol : std::cbrt(tol_dual);
+    const long long n = p->n, ml = p->ml;
+
+    // ---- initialise (alps.jl:31-46)
+    BZ_TRY(h2d(p, p->v.z_curr, x0, n));
+    BZ_TRY(h2d(p, p->y, y0 + (p->sharded ? p->desc.row_begin : 0), ml));
+    BzState* h = p->st_host;
+    memset(h, 0, sizeof(BzState));
+    h->xr = p->xr_host;            // slab mode: peer mapping (zero otherwise)
+    h->n_global = p->n_global;
+    h->next_op = OP_DONE;
+    h->H = 1.0;
+    h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
+    h->theta_penalty = o->theta_penalty; h->kappa_penalty = o->kappa_penalty; h->kappa_tol = o->kappa_tol;
+    h->outer_maxit = o->maxit; h->subsolver_maxit = o->subsolver_maxit;
+    h->n_prox = 1;   // the prox!(x, gFun, x0, eps(T)) of alps.jl:38
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_prox(ctx, p->st, p->v.z_curr, BZ_EPS, p->v.x, n, p->g, p->part, p->counters + 5));
+    BZ_TRY(bz_launch_fill(ctx, p->mu, ml, 1.0));
+    BZ_TRY(bz_launch_fill(ctx, p->muy, ml, 0.0));
+    BZ_TRY(launch_provider(p, TGT_X));       // cx = c(x), f(x)
+    {
+        BzGradSrc gs = grad_src(p);
+        BZ_TRY(bz_launch_assemble(ctx, p->st, gs, n, p->v.grad_x, p->part, p->counters + 6));
+    }
+    BZ_TRY(fetch_state(p));
+    double objx = h->al_fx + h->g_z;         // objx = f(x) + gFun.gz
+    h->objx = objx;
+    BZ_TRY(push_state(p));
+    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->cx, p->s, p->mu, ml, p->D, 1, nullptr));   // also s = proj_D(cx), als.jl:42
+    p->slack_active = true;    // fSlack / gSlack from here on (als.jl:46-47)
+
+    int tot_it = 0;
+    long long tot_inner = 0;
+    bool solved = false, tired = tot_it >= o->maxit, broken = std::isnan(objx);
+    double norm_res_prim = NAN;
+    long long n_grad = 0, n_prox = 0;
+    bool can_stop = solved || tired || broken;
+    while (!can_stop) {
+        tot_it++;
+        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, 1, 1, p->part, p->counters + 5));
+        if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));
+        long long maxit_inner = o->sub_maxit;
+        if (o->max_inner_total > 0)
+            maxit_inner = std::max<long long>(1, std::min<long long>(maxit_inner, o->max_inner_total - tot_inner));
+        BZ_TRY(d2d(p, p->v.x + n, p->s, ml));                // xSlack = [x; s], als.jl:69-70
+        BZ_TRY(panoc_run(p, o, inner_tol, maxit_inner));
+        BZ_TRY(d2d(p, p->v.x, p->v.z, n + ml));             // xSlack .= sub_sol; x, s = its two parts
+        BZ_TRY(d2d(p, p->s, p->v.z + n, ml));
+        // y .+= (cx .- s) ./ mu with cx = c(x) as left by the last gradient at the returned point (als.jl:81-87)
+        BZ_TRY(bz_launch_multiplier_als(ctx, p->st, p->cx, p->mu, p->y, p->s, ml, p->part, p->counters + 5));
+        BZ_TRY(fetch_state(p));                               // the one sync per outer iteration
+        if (h->err_flag == 3) return bz_fail(ctx, BZ_ERR_COMM, "slab mode: a peer rank did not answer a cross-rank exchange");
+        if (h->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
+        objx = h->objx;
+        tot_inner = h->tot_inner_it;
+        norm_res_prim = h->norm_res_prim;
+        solved = h->solved; tired = h->tired; broken = h->broken;
+        n_grad = h->n_grad; n_prox = h->n_prox;
+        can_stop = solved || tired || broken;
+        if (o->max_inner_total > 0 && tot_inner >= o->max_inner_total) can_stop = true;
+        if (!can_stop && h->scale_mu) BZ_TRY(bz_launch_scale(ctx, p->mu, ml, o->kappa_penalty));
+        inner_tol = h->inner_tol;
+    }
+    BZ_TRY(d2h(p, x, p->v.x, n));
+    BZ_TRY(d2h(p, y, p->y, ml));
+    BZ_TRY(d2h(p, s, p->s, ml));
+    BZ_TRY(d2h(p, mu, p->mu, ml));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    res->tot_it = tot_it;
+    res->tot_inner_it = tot_inner;
+    res->status = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+    res->inner_tol = inner_tol;
+    res->norm_res_prim = norm_res_prim;
+    res->objective = objx;
+    res->n_grad = n_grad;
+    res->n_prox = n_prox;
+    res->n_launches = ctx->n_launches - launches0;
+    res->dominant_kernel_ms = 0.0;
+    res->dominant_kernel_launches = 0;
+    if (ctx->profiling) collect_dominant(p, res);
+    for (int k = 0; k < 4; ++k) {
+        res->kind_ms[k] = 1e-6 * (double)h->tsum[k];
+        res->kind_launches[k] = (int64_t)h->tcnt[k];
+    }
+    res->elapsed_time =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return BZ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // subsolver slot and parity entry points
 // ---------------------------------------------------------------------------------------------
 static int set_mu_y(bz_problem* p, const double* mu, const double* y) {
@@ -822,14 +948,15 @@ extern "C" int bz_auglag_grad(bz_problem* p, const double* x, double* dlx, doubl
     if (!p || !x) return BZ_ERR_ARG;
     bz_ctx* ctx = p->ctx;
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    BZ_TRY(h2d(p, p->v.xeps, x, p->n));
+    if (p->slack) p->slack_active = true;       // gradient!(dFxs, F::AugLagFunSlack, xs): nx + ny entries in and out
+    BZ_TRY(h2d(p, p->v.xeps, x, p->nv));
     BZ_TRY(launch_provider(p, TGT_XEPS));
     BzGradSrc gs = grad_src(p);
-    BZ_TRY(bz_launch_assemble(ctx, p->st, gs, p->n, p->v.d, p->part, p->counters + 6));
+    BZ_TRY(bz_launch_assemble(ctx, p->st, gs, p->nv, p->v.d, p->part, p->counters + 6));
     BZ_TRY(fetch_state(p));
     if (lx) *lx = p->st_host->out[0];
     if (fx) *fx = p->st_host->out[1];
-    BZ_TRY(d2h(p, dlx, p->v.d, p->n));
+    BZ_TRY(d2h(p, dlx, p->v.d, p->nv));
     BZ_TRY(d2h(p, cx, p->cx, p->ml));
     BZ_TRY(d2h(p, s, p->s, p->ml));
     BZ_TRY(d2h(p, yupd, p->yupd, p->ml));

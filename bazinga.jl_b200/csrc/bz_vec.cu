@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_identity_c(BzState* st, int force_target, const double* x0, const double* x1, const double* x2,
                  long long n, const double* __restrict__ mu, const double* __restrict__ muy,
                  BzDParams D, double* cx, double* s, double* yupd, double* lxpart,
-                 unsigned int* counter, int set_after) {
+                 unsigned int* counter, int set_after, int slack, const double* __restrict__ yv) {
     __shared__ double scratch[32];
     int target = force_target;
     if (target < 0) {
@@ -66,6 +66,13 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     } else {
         for (long long j = j0; j < n; j += stride) {
             const double c = x[j];
+            if (slack) {                                 // als, auglagfunslack.jl:88-92: input [x; s]
+                const double sv = x[n + j];
+                const double tt = (c + muy[j]) - sv;
+                a[0] += (tt * tt) / mu[j];
+                cx[j] = c; s[j] = sv; yupd[j] = yv[j] + (c - sv) / mu[j];
+                continue;
+            }
             const double t = c + muy[j];
             const double sv = bz_proj_elem(D.kind, D.lo, D.hi, t);
             const double u = t - sv;
@@ -84,10 +91,10 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 int bz_launch_identity_c(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
                          long long n, const double* mu, const double* muy, const BzDParams& D,
                          double* cx, double* s, double* yupd, double* lxpart, unsigned int* counter,
-                         int set_after) {
+                         int set_after, int slack, const double* y) {
     k_identity_c<<<bz_vec_grid(ctx, n), BZ_VEC_THREADS, 0, ctx->stream>>>(
         st, force_target, src[0], src[1], src[2], n, mu, muy, D, cx, s, yupd, lxpart, counter,
-        set_after);
+        set_after, slack, y);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;
@@ -471,6 +478,37 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (outer_logic) bz_outer_logic(st, nrp);
     __threadfence();
 }
+// als.jl:83-87: y .= y .+ (cx .- s) ./ mu with the slack s of the sub-solution; norm(cx .- s, Inf); outer logic
+__global__ void __launch_bounds__(BZ_VEC_THREADS)
+    k_multiplier_als(BzState* st, const double* __restrict__ cx, const double* __restrict__ mu, double* y,
+                     const double* __restrict__ s, long long m, double* part, unsigned int* counter) {
+    __shared__ double scratch[2 * 32];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double mx = 0.0;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {
+        const double d = cx[j] - s[j];
+        y[j] = y[j] + d / mu[j];
+        mx = bz_nanmax(mx, d);
+    }
+    double a[1] = {mx != mx ? 0.0 : mx}, f[1] = {mx != mx ? 1.0 : 0.0};
+    bz_block_max<1>(a, scratch);
+    bz_block_max<1>(f, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = f[0] > 0.0 ? NANQ : a[0];
+    if (!bz_last_cta(counter, gridDim.x)) return;
+    const double nrp = bz_final_nanmax(part, gridDim.x, scratch);
+    if (threadIdx.x != 0) return;
+    st->out[0] = nrp;
+    bz_outer_logic(st, nrp);
+    __threadfence();
+}
+int bz_launch_multiplier_als(bz_ctx* ctx, BzState* st, const double* cx, const double* mu, double* y, const double* s,
+                             long long m, double* part, unsigned int* counter) {
+    k_multiplier_als<<<bz_vec_grid(ctx, m), BZ_VEC_THREADS, 0, ctx->stream>>>(st, cx, mu, y, s, m, part, counter);
+    ctx->n_launches++;
+    BZ_CUDA(ctx, cudaGetLastError());
+    return BZ_OK;
+}
+
 int bz_launch_multiplier(bz_ctx* ctx, BzState* st, const double* cx, const double* muy,
                          const double* mu, double* y, double* s, long long m, const BzDParams& D,
                          int outer_logic, double* part, unsigned int* counter) {

@@ -40,7 +40,7 @@ int bz_launch_assemble(bz_ctx* ctx, BzState* st, const BzGradSrc& gs, long long 
 int bz_launch_identity_c(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
                          long long n, const double* mu, const double* muy, const BzDParams& D,
                          double* cx, double* s, double* yupd, double* lxpart, unsigned int* counter,
-                         int set_after);
+                         int set_after, int slack = 0, const double* y = nullptr);
 int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
                        const BzObstacle& ob, const double* mu, const double* muy, double* cx,
                        double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
@@ -55,6 +55,8 @@ int bz_launch_al_update(bz_ctx* ctx, BzState* st, double* mu, double* y, double*
 int bz_launch_multiplier(bz_ctx* ctx, BzState* st, const double* cx, const double* muy,
                          const double* mu, double* y, double* s, long long m, const BzDParams& D,
                          int outer_logic, double* part, unsigned int* counter);
+int bz_launch_multiplier_als(bz_ctx* ctx, BzState* st, const double* cx, const double* mu, double* y, const double* s,
+                             long long m, double* part, unsigned int* counter);
 int bz_launch_init_mu(bz_ctx* ctx, BzState* st, const double* cx, double* s, double* mu, long long m,
                       const BzDParams& D, int compute_s, const double* objx_ptr);
 int bz_launch_outer_logic(bz_ctx* ctx, BzState* st);

@@ -16,6 +16,10 @@ __device__ __forceinline__ double jl_max(double a, double b) {   // Julia max pr
 // gradient / value assembly from the provider outputs (auglagfun.jl:78-84)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bz_assemble_grad(const BzGradSrc& gs, long long j, long long n) {
+    if (gs.nx > 0) {                      // als: [dfx + jtv; -yupd]
+        if (j >= gs.nx) return -__ldcg(gs.tail + (j - gs.nx));
+        n = gs.nx;                        // row stride of the partial arrays
+    }
     double dfx = 0.0, jtv = 0.0;
     if (gs.Pf) {
         double s = 0.0;
@@ -130,16 +134,18 @@ __device__ __forceinline__ bool bz_gs_blocked(const BzGradSrc& gs) { return gs.P
 __device__ inline double bz_assemble_blocked(const BzGradSrc& gs, long long jb, long long n, double* sm) {
     const int col = threadIdx.x & (BZ_ASM_COLS - 1), grp = threadIdx.x / BZ_ASM_COLS;
     const long long j = jb + col;
+    const long long nhead = gs.nx > 0 ? gs.nx : n;     // als: entries >= nx are -yupd (no partial rows there)
     double sf = 0.0, sc = 0.0;
-    if (j < n) {
-        if (gs.Pf) sf = bz_sum_group(gs.Pf, gs.npf, grp, j, n);
-        if (gs.Pc) sc = bz_sum_group(gs.Pc, gs.npc, grp, j, n);
+    if (j < nhead) {
+        if (gs.Pf) sf = bz_sum_group(gs.Pf, gs.npf, grp, j, nhead);
+        if (gs.Pc) sc = bz_sum_group(gs.Pc, gs.npc, grp, j, nhead);
     }
     sm[grp * BZ_ASM_COLS + col] = sf;
     sm[BZ_VEC_THREADS + grp * BZ_ASM_COLS + col] = sc;
     __syncthreads();
     double out = 0.0;
-    if (grp == 0 && j < n) {
+    if (grp == 0 && j >= nhead && j < n) out = -__ldcg(gs.tail + (j - nhead));
+    if (grp == 0 && j < nhead) {
         double dfx = 0.0, jtv = 0.0;
         if (gs.Pf) dfx = (sm[col] + sm[BZ_ASM_COLS + col]) + (sm[2 * BZ_ASM_COLS + col] + sm[3 * BZ_ASM_COLS + col]);
         else if (gs.Ef) dfx = __ldcg(gs.Ef + j);

@@ -27,6 +27,7 @@ struct ProblemDesc
     d_lo::Float64; d_hi::Float64; d_pair_stride::Int64
     row_begin::Int64; ny_local::Int64
     slab_nranks::Int32; slab_rank::Int32; nx_global::Int64
+    slack_formulation::Int32
 end
 
 mutable struct Options
@@ -125,7 +126,8 @@ function alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::Abstrac
                        glam, glo, ghi, ptr(gu),
                        ptr(get(cp, :A, nothing)), ptr(get(cp, :b, nothing)), Int32(1) #= column-major =#,
                        Int32(0), Int32(0), UInt64(0), 0, 0, dlo, dhi, 1, 0, 0,
-                       Int32(0), Int32(0), 0)   # no slab decomposition
+                       Int32(0), Int32(0), 0,   # no slab decomposition
+                       Int32(0))                # alps (Int32(1): als, bz_als_solve)
     prob = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         check(ccall((:bz_problem_create, lib), Cint, (Ptr{Cvoid}, Ref{ProblemDesc}, Ref{Ptr{Cvoid}}),

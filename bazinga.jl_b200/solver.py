@@ -161,7 +161,7 @@ class Problem:
     """The four oracles on the device (bz_problem): the GPU counterpart of the Julia oracle structs
     plus ``AugLagFun`` / ``NonsmoothCostFun`` (src/utilities/auglagfun.jl, nonsmoothcostfun.jl)."""
 
-    def __init__(self, f, g, c, D, nx=None, ny=None, ctx: Context | None = None):
+    def __init__(self, f, g, c, D, nx=None, ny=None, ctx: Context | None = None, slack=False):
         self.handle = C.c_void_p()
         for name, obj, attr in (("f", f, "f_kind"), ("g", g, "g_kind"), ("c", c, "c_kind"), ("D", D, "d_kind")):
             if not hasattr(obj, attr):
@@ -224,6 +224,8 @@ class Problem:
         # ---- D
         d.d_lo, d.d_hi = getattr(D, "lo", 0.0), getattr(D, "hi", 0.0)
         d.d_pair_stride = getattr(D, "stride", 1)
+        d.slack_formulation = 1 if slack else 0     # als: PANOC+ on [x; s] (src/algorithms/als.jl)
+        self.slack = bool(slack)
         self.nx, self.ny = int(nx), int(ny)
         self.ny_local = int(d.ny_local) if d.ny_local > 0 else self.ny
         self.row_begin = int(d.row_begin)
@@ -241,6 +243,18 @@ class Problem:
         res = K.Result()
         K.check(self.lib.bz_alps_solve(self.handle, _ptr(x0), _ptr(y0), C.byref(options), _ptr(x), _ptr(y),
                                        _ptr(s), _ptr(mu), C.byref(res)), self.ctx.handle)
+        return x, y, s, mu, res
+
+    def als(self, x0, y0, options: K.Options):
+        """``als`` (src/algorithms/als.jl:7-120) on a problem created with ``slack=True``."""
+        x0, y0 = _f64(x0), _f64(y0)
+        if x0.shape[0] != self.nx or y0.shape[0] != self.ny:
+            raise ValueError("x0 / y0 have the wrong length")
+        x = np.empty(self.nx)
+        y, s, mu = np.empty(self.ny_local), np.empty(self.ny_local), np.empty(self.ny_local)
+        res = K.Result()
+        K.check(self.lib.bz_als_solve(self.handle, _ptr(x0), _ptr(y0), C.byref(options), _ptr(x), _ptr(y),
+                                      _ptr(s), _ptr(mu), C.byref(res)), self.ctx.handle)
         return x, y, s, mu, res
 
     # ---- slab-decomposed obstacle grid (one process per GPU): export / attach the peer-mapped slabs
@@ -283,7 +297,10 @@ class Problem:
     def gradient(self, x):
         """lx = gradient!(dlx, alFun, x) -> dict(dlx, lx, fx, cx, s, yupd) (auglagfun.jl:73-86)."""
         x = _f64(x)
-        dlx = np.empty(self.nx)
+        nv = self.nx + self.ny if getattr(self, "slack", False) else self.nx    # slack: gradient! of AugLagFunSlack on [x; s]
+        if x.shape[0] != nv:
+            raise ValueError("x has the wrong length")
+        dlx = np.empty(nv)
         cx, s, yupd = (np.empty(self.ny_local) for _ in range(3))
         lx, fx = C.c_double(), C.c_double()
         K.check(self.lib.bz_auglag_grad(self.handle, _ptr(x), _ptr(dlx), C.byref(lx), C.byref(fx), _ptr(cx),
@@ -388,6 +405,43 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
             p.close()
     if verbose:
         print(f"[bazinga_b200] alps: it={res.tot_it} inner={res.tot_inner_it} status={K.STATUS_SYMBOLS[res.status]} "
+              f"res_prim={res.norm_res_prim:.3e} inner_tol={res.inner_tol:.3e}")
+    out = (x, y, res.tot_it, res.tot_inner_it, res.elapsed_time, K.STATUS_SYMBOLS[res.status], res.inner_tol,
+           res.norm_res_prim, s, mu)
+    return (out, res) if return_result else out
+
+
+def als(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_tol=None, maxit=100,
+         theta_penalty=0.8, kappa_penalty=0.5, kappa_tol=0.1, verbose=False, dual_safeguard=None,
+         subsolver=default_subsolver, subsolver_maxit=1_000_000_000, ctx=None, problem=None,
+         return_result=False, max_inner_total=0):
+    """Drop-in for ``Bazinga.als`` (src/algorithms/als.jl:7-26): the augmented-Lagrangian method with explicit slack
+    variables (PANOCplus on [x; s] with AugLagFunSlack / NonsmoothCostFunSlack).  Returns the reference's 10-tuple
+    ``(x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol, norm_res_prim, s, mu)`` with
+    ``status`` in {"first_order", "max_iter", "exception", "unknown"} (the Julia Symbols).
+    x0 and y0 are never modified (test/problems/test_nonconvex_qp.jl:36)."""
+    if dual_safeguard is not None:
+        raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "custom dual_safeguard functions cannot cross the C ABI; "
+                                                   "the default (clamp to ±1e20) runs on the device")
+    sub = subsolver(tol=1.0, verbose=verbose)   # alps.jl:64: constructor call with two kwargs only
+    if not isinstance(sub, PANOCplus):
+        raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "subsolver must be (a closure over) PANOCplus")
+    x0 = np.asarray(x0, dtype=np.float64)
+    y0 = np.asarray(y0, dtype=np.float64)
+    own = problem is None
+    p = problem or Problem(f, g, c, D, nx=x0.shape[0], ny=None if isinstance(c, O.ConstraintBasisPursuit) else y0.shape[0], ctx=ctx,
+                           slack=True)
+    try:
+        o = _options(tol=tol, tol_prim=tol_prim, tol_dual=tol_dual, inner_tol=inner_tol, maxit=maxit,
+                     theta_penalty=theta_penalty, kappa_penalty=kappa_penalty, kappa_tol=kappa_tol,
+                     subsolver_maxit=subsolver_maxit, sub=sub, max_inner_total=max_inner_total,
+                     verbose=verbose)
+        x, y, s, mu, res = p.als(x0, y0, o)
+    finally:
+        if own:
+            p.close()
+    if verbose:
+        print(f"[bazinga_b200] als: it={res.tot_it} inner={res.tot_inner_it} status={K.STATUS_SYMBOLS[res.status]} "
               f"res_prim={res.norm_res_prim:.3e} inner_tol={res.inner_tol:.3e}")
     out = (x, y, res.tot_it, res.tot_inner_it, res.elapsed_time, K.STATUS_SYMBOLS[res.status], res.inner_tol,
            res.norm_res_prim, s, mu)

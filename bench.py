@@ -277,7 +277,7 @@ def run_b200(args):
     peak, peak_src = measured_peak_hbm()
     bgrad = algorithmic_bytes_per_grad(m, n)
     achieved = (bgrad * dom_launches / (dom_ms * 1e-3)) / 1e9 if dom_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_dense_algrad<true> (fused A-pass: r=Ax-b, w, A'w; A read once)",
+    roofline = {"bound": "hbm", "kernel": "k_dense_algrad<true, false> (fused A-pass: r=Ax-b, w, A'w; A read once)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic_from_profile(m, n),
                 "algorithmic_bytes_per_launch": bgrad, "launches_timed": dom_launches,

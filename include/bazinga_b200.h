@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define BZ_ABI_VERSION 2
+#define BZ_ABI_VERSION 3
 #define BZ_LBFGS_MAX_MEMORY 16
 
 typedef struct bz_ctx bz_ctx;
@@ -124,6 +124,11 @@ typedef struct {
      * kernels exchange boundary rows and reduction scalars over peer memory (NVLink), no host sync. */
     int32_t slab_nranks, slab_rank;
     int64_t nx_global;
+    /* != 0: the problem will be solved by bz_als_solve (src/algorithms/als.jl): PANOCplus runs on the stacked
+     * variable [x; s] (nx + ny entries) with AugLagFunSlack / NonsmoothCostFunSlack
+     * (src/utilities/auglagfunslack.jl).  Dense-affine and identity c, elementwise D (ZeroSet, FreeSet, box).
+     * bz_auglag_grad then takes / returns nx + ny entries (gradient! of AugLagFunSlack). */
+    int32_t slack_formulation;
 } bz_problem_desc;
 
 /* Options of `alps` (alps.jl:14-25) plus the PANOCplus closure options the demos bake in
@@ -189,6 +194,10 @@ int bz_problem_xr_attach(bz_problem* p, const void* handles64);
  * norm_res_prim, s, mu), src/algorithms/alps.jl:7-117.  x0,y0 are read-only. */
 int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* opt,
                   double* x, double* y, double* s, double* mu, bz_result* res);
+
+/* als(f,g,c,D,x0,y0; ...) -> the same 10-tuple, src/algorithms/als.jl:7-120 (desc.slack_formulation must be set). */
+int bz_als_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* opt,
+                 double* x, double* y, double* s, double* mu, bz_result* res);
 
 /* The `subsolver` plugin slot, alps.jl:64,66: PANOCplus on (alFun, gFun) from x0 with fixed mu, y.
  * Leaves the AugLagFun / NonsmoothCostFun side-effect state (fx, gz, cx, s, yupd) at the returned

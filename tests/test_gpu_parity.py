@@ -359,6 +359,76 @@ def test_basis_pursuit_demo_size(gpu_ctx):
             assert abs(out[3] - r.tot_inner_it) <= 0.1 * r.tot_inner_it
 
 
+@pytest.mark.parametrize("cname", ["dense", "identity", "dense_grid", "dense_two_pass"])
+def test_als_slack_gradient_parity(gpu_ctx, cname, monkeypatch):
+    """gradient!(dFxs, F::AugLagFunSlack, xs) (src/utilities/auglagfunslack.jl:77-97) on the stacked variable [x; s]:
+    dense-affine c through the fused cluster kernel, identity c through the vector kernel."""
+    rng = np.random.default_rng(8)
+    if cname in ("dense_grid", "dense_two_pass"):      # the wide kernels (k_grid_algrad / k_wide_rows + k_wide_cols)
+        monkeypatch.setenv("BZ_FORCE_WIDE", "1")
+        monkeypatch.setenv("BZ_WIDE_TWO_PASS", "1" if cname == "dense_two_pass" else "0")
+        gpu_ctx = bz.Context(0)
+    if cname.startswith("dense"):
+        m, n = 37, 210
+        A, _, b = bo.make_basis_pursuit(m, n, seed=4)
+        c, oc, f, of = bz.ConstraintBasisPursuit(A, b), bo.CDenseAffine(A, b), bz.Zero(), bo.FZero()
+        scale = np.linalg.norm(A, 2)
+    else:
+        m = n = 500
+        A2, b2 = rng.standard_normal((9, n)), rng.standard_normal(9)
+        c, oc, f, of = bz.IdentityFunction(), bo.CIdentity(), bz.LeastSquares(A2, b2), bo.FLeastSquares(A2, b2)
+        scale = np.linalg.norm(A2, 2) ** 2 + 1.0
+    p = bz.Problem(f, bz.NormL1(0.3), c, bz.ClosedSet(bz.IndBox(-0.5, 0.7)), nx=n, ny=m, ctx=gpu_ctx, slack=True)
+    mu, y, xs = rng.uniform(0.05, 3.0, m), rng.standard_normal(m), rng.standard_normal(n + m)
+    p.auglag_update(mu, y)
+    g = p.gradient(xs)
+    F = bo.AugLagFunSlack(of, oc, mu.copy(), y.copy(), xs[:n].copy())
+    d = np.empty(n + m)
+    Fxs = F.gradient(d, xs)
+    assert g["dlx"].shape == (n + m,)
+    assert np.max(np.abs(g["yupd"] - F.yupd)) <= KTOL * (scale * np.linalg.norm(xs) + 10) / mu.min()
+    assert np.array_equal(g["dlx"][n:], -g["yupd"])
+    assert np.max(np.abs(g["dlx"][:n] - d[:n])) <= KTOL * (scale * (np.linalg.norm(F.yupd) + np.linalg.norm(xs)) + 1)
+    assert abs(g["lx"] - Fxs) <= KTOL * max(abs(Fxs), float(np.sum(F.yupd**2 * mu)))
+    p.close()
+
+
+def test_als_whole_solves_match_oracle(gpu_ctx):
+    """als (src/algorithms/als.jl:7-120) on the device: basis pursuit (dense c, D = {0}) and the reference's LASSO test
+    data with a box D (identity c), against the numpy restatement bo.als."""
+    A, _, b = bo.make_basis_pursuit(20, 100)
+    sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
+    out = bz.als(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100), np.zeros(20),
+                 tol=1e-5, subsolver=sub, subsolver_maxit=100_000, ctx=gpu_ctx)
+    pr = bo.problem_basis_pursuit(A, b)
+    r = bo.als(pr["f"], pr["g"], pr["c"], pr["D"], np.zeros(100), np.zeros(20), tol=1e-5, **{k: v for k, v in pr["kw"].items() if k != "tol"})
+    assert out[5] == r.status == "first_order"
+    assert np.max(np.abs(A @ out[0] - b)) <= 1e-4 and np.max(np.abs(out[8])) <= 1e-12        # s in D = {0}
+    assert abs(np.sum(np.abs(out[0])) - np.sum(np.abs(r.x))) <= 1e-4 * np.sum(np.abs(r.x))
+    assert abs(out[3] - r.tot_inner_it) <= 0.25 * r.tot_inner_it + 10
+    # the same point as alps finds (convex problem)
+    o2 = bz.alps(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100), np.zeros(20),
+                 tol=1e-5, subsolver=sub, subsolver_maxit=100_000, ctx=gpu_ctx)
+    assert np.max(np.abs(out[0] - o2[0])) <= 1e-3
+    # identity c with a box: min 0.5||A2 x - b2||^2 + lam |x|_1  s.t. x in [-0.3, 0.3]
+    A2 = np.array([[1, -2, 3, -4, 5], [2, -1, 0, -1, 3], [-1, 0, 4, -3, 2], [-1, -1, -1, 1, 3]], float)
+    b2 = np.array([1.0, 2.0, 3.0, 4.0])
+    lam = 0.1 * np.max(np.abs(A2.T @ b2))
+    o3 = bz.als(bz.LeastSquares(A2, b2), bz.NormL1(lam), bz.IdentityFunction(), bz.ClosedSet(bz.IndBox(-0.3, 0.3)), np.zeros(5), np.zeros(5), ctx=gpu_ctx)
+    r3 = bo.als(bo.FLeastSquares(A2, b2), bo.GNormL1(lam), bo.CIdentity(), bo.BoxSet(-0.3, 0.3), np.zeros(5), np.zeros(5))
+    assert o3[5] == r3.status == "first_order" and o3[2] == r3.tot_it
+    assert np.max(np.abs(o3[0] - r3.x)) <= 1e-7 and np.max(np.abs(o3[1] - r3.y)) <= 1e-6 * (1 + np.max(np.abs(r3.y)))
+    assert np.all(np.abs(o3[0]) <= 0.3 + 1e-6)
+    with pytest.raises(bz.BazingaError):      # a problem built for alps cannot be run through als and vice versa
+        p = bz.Problem(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), ctx=gpu_ctx)
+        try:
+            from bazinga_b200.solver import _options
+            p.als(np.zeros(100), np.zeros(20), _options(tol=1e-6, tol_prim=None, tol_dual=None, inner_tol=None, maxit=100, theta_penalty=0.8,
+                                                        kappa_penalty=0.5, kappa_tol=0.1, subsolver_maxit=10, sub=sub))
+        finally:
+            p.close()
+
+
 def test_subsolver_slot_postconditions(gpu_ctx):
     # alps.jl:66-68 reads alFun.fx / gFun.gz after the subsolver returns: they must refer to the
     # returned point (SURVEY Appendix A.7)
