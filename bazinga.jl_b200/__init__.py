@@ -8,8 +8,8 @@ Host code here is a thin mirror of the reference's operator/plugin interface ove
 """
 from ._capi import BazingaError, LIB_PATH, STATUS_SYMBOLS, load_library  # noqa: F401
 from .oracles import (  # noqa: F401
-    ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, FreeSet, IdentityFunction, IndBox, IndFree,
-    IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NormL0, NormL0Box, NormL1, NormL1Box,
+    ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, ConstraintObstacleRed, FreeSet, IdentityFunction, IndBox, IndFree,
+    IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NonsmoothCostObstacleRedL1, NormL0, NormL0Box, NormL1, NormL1Box,
     NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
 )
 from .solver import (  # noqa: F401

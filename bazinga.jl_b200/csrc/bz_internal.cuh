@@ -237,6 +237,12 @@ __device__ inline double bz_prox_elem(const BzGParams& g, double x, double gamma
         return z;
     }
     case BZ_G_NONNEG: return fmax(0.0, x);   // demo/mpvca.jl:90-93
+    case BZ_G_OBSTACLE_RED_L1: {             // demo/obstacle.jl:86-91: max(0, x1 - gamma) on block 1, identity on block 2
+        if (j >= g.N) return x;
+        const double z = fmax(0.0, x - gamma);
+        acc += z;
+        return z;
+    }
     case BZ_G_NORMLP_BOX:       // normLpBox.jl:46-97: Newton on the scalar subproblem, then the global-minimum tests
     case BZ_G_NORMLP_NONNEG: {  // normLpNonneg.jl:43-85 (no upper bound, perturbation 1 instead of 0.1)
         if constexpr (!HEAVY) return x;
@@ -276,7 +282,7 @@ __host__ __device__ inline double bz_g_value_scale(const BzGParams& g) {
     switch (g.kind) {
     case BZ_G_NORM_L1: case BZ_G_NORM_L0: case BZ_G_NORML1_BOX: case BZ_G_NORML1_NONNEG:
     case BZ_G_NORML0_BOX: case BZ_G_ROSENBROCK: case BZ_G_NORMLP_BOX: case BZ_G_NORMLP_NONNEG: return g.lambda;
-    case BZ_G_OBSTACLE_L1: return 1.0;
+    case BZ_G_OBSTACLE_L1: case BZ_G_OBSTACLE_RED_L1: return 1.0;
     default: return 0.0;
     }
 }

@@ -302,6 +302,14 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         if (d->grid_y * d->grid_x != 0 && d->grid_y * d->grid_x != d->ny)
             return fail(BZ_ERR_ARG, "obstacle: grid_y*grid_x must equal ny");
         break;
+    case BZ_C_OBSTACLE_RED:
+        if (d->f_kind != BZ_F_OBSTACLE_L1 || d->g_kind != BZ_G_OBSTACLE_RED_L1 || d->d_kind != BZ_D_CC)
+            return fail(BZ_ERR_UNSUPPORTED, "reduced obstacle c is built for the obstacle_l1red variant only (D = CC pairs)");
+        if (d->nx != d->ny || d->nx % 2) return fail(BZ_ERR_ARG, "obstacle_l1red: nx = ny = 2N");
+        if (d->d_pair_stride * 2 != d->ny) return fail(BZ_ERR_ARG, "obstacle_l1red: the CC pairs are (i, i+N)");
+        if (d->grid_y * d->grid_x != 0 && d->grid_y * d->grid_x * 2 != d->ny)
+            return fail(BZ_ERR_ARG, "obstacle_l1red: grid_y*grid_x must equal N");
+        break;
     default:
         return fail(BZ_ERR_UNSUPPORTED,
                     "c kind is only available in the batched tiny-instance path (bz_batch_solve)");
@@ -326,6 +334,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     }
     if (d->g_kind == BZ_G_OBSTACLE_L1 && d->c_kind != BZ_C_OBSTACLE)
         return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
+    if (d->g_kind == BZ_G_OBSTACLE_RED_L1 && d->c_kind != BZ_C_OBSTACLE_RED)
+        return fail(BZ_ERR_UNSUPPORTED, "reduced obstacle g needs the reduced obstacle c");
     if ((d->g_kind == BZ_G_NORML1_BOX || d->g_kind == BZ_G_NORML0_BOX)) {
         if (!d->g_u) return fail(BZ_ERR_ARG, "g_u is required for the *_BOX prox kinds");
         if (d->g_lambda < 0) return fail(BZ_ERR_ARG, "parameter λ must be nonnegative");
@@ -352,7 +362,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     p->g.u = nullptr; p->g.N = d->ny;
     p->D.kind = d->d_kind; p->D.lo = d->d_lo; p->D.hi = d->d_hi;
     p->D.stride = d->d_pair_stride > 0 ? d->d_pair_stride : 1;
-    p->ob.N = d->ny; p->ob.gy = d->grid_y; p->ob.gx = d->grid_x;
+    p->ob.N = d->c_kind == BZ_C_OBSTACLE_RED ? d->ny / 2 : d->ny; p->ob.gy = d->grid_y; p->ob.gx = d->grid_x;
+    if (d->c_kind == BZ_C_OBSTACLE_RED) p->g.N = d->ny / 2;
     if (d->g_u) {
         PTRY(dev_alloc(ctx, &p->g_u, n));
         cudaMemcpyAsync(p->g_u, d->g_u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
@@ -605,6 +616,10 @@ static int launch_provider(bz_problem* p, int force_target) {
         BZ_TRY(bz_launch_obstacle(ctx, p->st, force_target, src, p->ob, p->mu, p->muy, p->cx, p->s,
                                   p->yupd, p->Ec, p->lxpart, p->fxpart, p->counters + 1, 1));
         if (timed) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
+    } else if (d.c_kind == BZ_C_OBSTACLE_RED) {
+        p->nlx = p->nfx = bz_obstacle_partials(ctx, p->ob);
+        BZ_TRY(bz_launch_obstacle_red(ctx, p->st, force_target, src, p->ob, p->mu, p->muy, p->cx, p->s,
+                                      p->yupd, p->Ec, p->lxpart, p->fxpart, p->counters + 1, 1));
     }
     return BZ_OK;
 }

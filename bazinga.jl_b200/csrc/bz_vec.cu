@@ -271,6 +271,91 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Reduced obstacle variant (demo/obstacle.jl:128-168, obstacle_l1red): x = [x1; x2] (2N),
+//   c(x) = [x1 + A x2; x2],  D = complementarity pairs (i, i+N) (project_onto_CC_set!),
+//   jtv = [v1; A v1 + v2],  dfx = [0; x2 - 1]
+// pass 1: cx, t = cx + mu*y, s = proj_CC pairwise, yupd = (t - s)/mu, partials of lx and f
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
+    k_obstacle_red_c(BzState* st, int force_target, const double* x0, const double* x1p,
+                     const double* x2p, BzObstacle ob, const double* __restrict__ mu,
+                     const double* __restrict__ muy, double* __restrict__ cx, double* __restrict__ s,
+                     double* __restrict__ yupd, double* lxpart, double* fxpart) {
+    __shared__ double scratch[3 * 32];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
+    int target = force_target;
+    if (target < 0) {
+        if (__ldcg(&st->next_op) != OP_G) return;
+        target = __ldcg(&st->grad_target);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) bz_tic(st, 0);
+    }
+    const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
+    const long long N = ob.N;
+    const StencilGeom g = bz_geom(ob);
+    double a[3] = {0.0, 0.0, 0.0};
+    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
+             c += (long long)gridDim.x * blockDim.x) {
+            const long long i = r * g.GX + c;
+            const double x2 = x[N + i];
+            const double c1 = x[i] + bz_stencil_rc(x + N, r, c, g);   // cx[1:N] = x1 + A x2
+            const double c2 = x2;                                      // cx[N+1:2N] = x2
+            const double m1 = mu[i], m2 = mu[N + i];
+            const double t1 = c1 + muy[i], t2 = c2 + muy[N + i];
+            double s1, s2;
+            bz_proj_pair(BZ_D_CC, t1, t2, s1, s2);                     // SetObstacleRed, obstacle.jl:150-156
+            const double u1 = t1 - s1, u2 = t2 - s2;
+            a[0] += (u1 * u1) / m1;
+            a[0] += (u2 * u2) / m2;
+            cx[i] = c1; cx[N + i] = c2;
+            s[i] = s1; s[N + i] = s2;
+            yupd[i] = u1 / m1; yupd[N + i] = u2 / m2;
+            a[1] += x2 * x2;                     // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
+            a[2] += x2;
+        }
+    }
+    bz_block_sum<3>(a, scratch);
+    const int nb = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        lxpart[b] = a[0];
+        fxpart[b] = a[1];
+        fxpart[nb + b] = a[2];
+    }
+}
+// pass 2: grad = dfx + jtv = [w1; (x2 - 1) + (A w1 + w2)]
+__global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
+    k_obstacle_red_jt(BzState* st, int force_target, const double* x0, const double* x1p,
+                      const double* x2p, BzObstacle ob, const double* __restrict__ yupd, double* __restrict__ Ec,
+                      unsigned int* counter, int set_after) {
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
+    int target = force_target;
+    if (target < 0) {
+        if (__ldcg(&st->next_op) != OP_G) return;
+        target = __ldcg(&st->grad_target);
+    }
+    const double* __restrict__ x = target == 0 ? x0 : (target == 1 ? x1p : x2p);
+    const long long N = ob.N;
+    const StencilGeom g = bz_geom(ob);
+    for (long long r = blockIdx.y; r < g.GY; r += gridDim.y) {
+        for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
+             c += (long long)gridDim.x * blockDim.x) {
+            const long long i = r * g.GX + c;
+            const double w1 = yupd[i];
+            const double e2 = (x[N + i] - 1.0) + (bz_stencil_rc(yupd, r, c, g) + yupd[N + i]);
+            Ec[i] = 0.0 + w1;
+            Ec[N + i] = e2;
+        }
+    }
+    if (bz_last_cta(counter, gridDim.x * gridDim.y) && threadIdx.x == 0 && set_after) {
+        st->next_op = st->after_g;
+        if (force_target < 0) bz_toc(st, 0);
+        __threadfence();
+    }
+}
+
 // launch geometry of the two passes (also the number of lx / fx partials)
 static dim3 obstacle_grid(const bz_ctx* ctx, const BzObstacle& ob) {
     const long long GX = ob.gx == 0 ? ob.N : ob.gx, GY = ob.gx == 0 ? 1 : ob.gy;
@@ -296,6 +381,17 @@ int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double*
     BZ_TRY_RC(bz_launch_pdl(ctx, k_obstacle_c, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
                             src[2], ob, mu, muy, cx, s, yupd, lxpart, fxpart));
     return bz_launch_pdl(ctx, k_obstacle_jt, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
+                         src[2], ob, yupd, Ec, counter, set_after);
+}
+
+int bz_launch_obstacle_red(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
+                           const BzObstacle& ob, const double* mu, const double* muy, double* cx,
+                           double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
+                           unsigned int* counter, int set_after) {
+    const dim3 grid = obstacle_grid(ctx, ob);
+    BZ_TRY_RC(bz_launch_pdl(ctx, k_obstacle_red_c, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
+                            src[2], ob, mu, muy, cx, s, yupd, lxpart, fxpart));
+    return bz_launch_pdl(ctx, k_obstacle_red_jt, grid, dim3(BZ_VEC_THREADS), 0, 0, st, force_target, src[0], src[1],
                          src[2], ob, yupd, Ec, counter, set_after);
 }
 

@@ -46,6 +46,10 @@ int bz_launch_obstacle(bz_ctx* ctx, BzState* st, int force_target, const double*
                        double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
                        unsigned int* counter, int set_after);
 
+int bz_launch_obstacle_red(bz_ctx* ctx, BzState* st, int force_target, const double* const* src,
+                           const BzObstacle& ob, const double* mu, const double* muy, double* cx,
+                           double* s, double* yupd, double* Ec, double* lxpart, double* fxpart,
+                           unsigned int* counter, int set_after);
 int bz_obstacle_partials(const bz_ctx* ctx, const BzObstacle& ob);
 int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, double* out, long long n,
                    const BzGParams& g, double* part, unsigned int* counter);

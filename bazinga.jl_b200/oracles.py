@@ -159,6 +159,14 @@ class NonsmoothCostObstacleL1:
         self.N = int(N)
 
 
+class NonsmoothCostObstacleRedL1:
+    """demo/obstacle.jl:83-91: soft threshold + max(0, .) on block 1, identity on block 2 (nx = 2N)."""
+    g_kind = K.G_OBSTACLE_RED_L1
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
 # ------------------------------------------------------------------ constraint functions c
 class IdentityFunction:
     """test/definitions/identityFunction.jl:3-13."""
@@ -205,6 +213,16 @@ class ConstraintObstacle:
         self.slab = slab
         if slab is not None and (grid is None or int(grid[0]) * int(grid[1]) != self.N):
             raise ValueError("slab decomposition needs the local 2-D grid: grid=(gy_local, gx), N = gy_local*gx")
+
+
+class ConstraintObstacleRed:
+    """demo/obstacle.jl:128-146: c(x) = [x1 + A x2; x2] (nx = ny = 2N); used with D = SetObstacleRed = CC pairs (i, i+N)."""
+    c_kind = K.C_OBSTACLE_RED
+
+    def __init__(self, N, grid=None):
+        self.N = int(N)
+        self.grid = grid
+        self.slab = None
 
 
 # ------------------------------------------------------------------ closed sets D

@@ -187,9 +187,10 @@ class Problem:
             if c.ny_global is not None and c.ny_global != ny_local:
                 d.row_begin, d.ny_local = c.row_begin, ny_local
             self._keep += [c.A, c.b]
-        elif isinstance(c, O.ConstraintObstacle):
-            nx = 3 * c.N if nx is None else nx
-            ny = c.N if ny is None else ny
+        elif isinstance(c, (O.ConstraintObstacle, O.ConstraintObstacleRed)):
+            red = isinstance(c, O.ConstraintObstacleRed)
+            nx = (2 if red else 3) * c.N if nx is None else nx
+            ny = (2 if red else 1) * c.N if ny is None else ny
             if c.grid is not None:
                 d.grid_y, d.grid_x = int(c.grid[0]), int(c.grid[1])
             if c.slab is not None:

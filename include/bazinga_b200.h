@@ -60,7 +60,8 @@ typedef enum { /* nonsmooth cost g: prox!(z,g,x,gamma)->g(z) */
     BZ_G_NONNEG = 8,        /* demo/mpvca.jl:89-93 */
     BZ_G_OBSTACLE_L1 = 9,   /* demo/obstacle.jl:64-81 */
     BZ_G_NORMLP_BOX = 10,   /* src/proxoperators/normLpBox.jl:37-97: alpha*sum x^p on [0,u], g_lambda = alpha, g_lo = p */
-    BZ_G_NORMLP_NONNEG = 11 /* src/proxoperators/normLpNonneg.jl:36-90: alpha*sum x^p on x >= 0, g_lambda = alpha, g_lo = p */
+    BZ_G_NORMLP_NONNEG = 11, /* src/proxoperators/normLpNonneg.jl:36-90: alpha*sum x^p on x >= 0, g_lambda = alpha, g_lo = p */
+    BZ_G_OBSTACLE_RED_L1 = 12 /* demo/obstacle.jl:83-91 NonsmoothCostObstacleRedL1 (nx = 2N) */
 } bz_g_kind;
 
 typedef enum { /* constraint function c: eval!(cx,c,x), jtprod!(jtv,c,x,v) */
@@ -69,7 +70,8 @@ typedef enum { /* constraint function c: eval!(cx,c,x), jtprod!(jtv,c,x,v) */
     BZ_C_ROSENBROCK = 2,    /* demo/rosenbrock.jl:66-74 */
     BZ_C_EITHEROR = 3,      /* demo/eitheror.jl:92-104 ConstraintOR */
     BZ_C_MPVCA = 4,         /* demo/mpvca.jl:110-118 ConstraintMPVCA */
-    BZ_C_OBSTACLE = 5       /* demo/obstacle.jl:92-113 ConstraintObstacle (1-D, or 2-D grid) */
+    BZ_C_OBSTACLE = 5,      /* demo/obstacle.jl:92-113 ConstraintObstacle (1-D, or 2-D grid) */
+    BZ_C_OBSTACLE_RED = 6   /* demo/obstacle.jl:128-146 ConstraintObstacleRed: nx = ny = 2N, D = CC pairs (i, i+N) */
 } bz_c_kind;
 
 typedef enum { /* closed set D: proj!(z,D,v) */

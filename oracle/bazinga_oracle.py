@@ -621,6 +621,44 @@ class CObstacle:
 # ----------------------------------------------------------------------------------------------
 # AugLagFun / NonsmoothCostFun (src/utilities)
 # ----------------------------------------------------------------------------------------------
+class CObstacleRed:
+    """demo/obstacle.jl:128-146 ConstraintObstacleRed: cx = [x1 + A x2; x2]."""
+
+    def __init__(self, N, grid=None):
+        self.N, self.grid = N, grid
+
+    def eval(self, cx, x):
+        N = self.N
+        cx[:N] = x[:N] + _stencil_apply(x[N : 2 * N], self.grid)
+        cx[N : 2 * N] = x[N : 2 * N]
+
+    def jtprod(self, jtv, x, v):
+        N = self.N
+        jtv[:N] = v[:N]
+        jtv[N : 2 * N] = _stencil_apply(v[:N], self.grid) + v[N : 2 * N]
+
+
+class GObstacleRedL1:
+    """demo/obstacle.jl:83-91 NonsmoothCostObstacleRedL1."""
+
+    def __init__(self, N):
+        self.N = N
+
+    def prox(self, y, x, gamma):
+        N = self.N
+        y[:N] = np.maximum(0.0, x[:N] - gamma)
+        y[N : 2 * N] = x[N : 2 * N]
+        return float(np.sum(y[:N]))
+
+
+def problem_obstacle_red(N, grid=None):
+    """demo/obstacle.jl:233-239 (obstacle_l1red): nx = ny = 2N, D = SetObstacleRed (CC pairs (i, i+N))."""
+    return dict(f=FObstacleL1(N), g=GObstacleRedL1(N), c=CObstacleRed(N, grid), D=PairSet("cc", stride=N),
+                nx=2 * N, ny=2 * N,
+                kw=dict(subsolver_maxit=1_000_000,
+                        subsolver=PanocOptions(minimum_gamma=EPS, maxit=1_000_000)))
+
+
 class AugLagFun:
     """src/utilities/auglagfun.jl:11-101."""
 

@@ -477,6 +477,42 @@ def test_obstacle_1d(gpu_ctx):
     assert np.all(x >= 0) and np.all(np.minimum(x[N:2 * N], x[2 * N:]) == 0)      # complementarity holds exactly
 
 
+@pytest.mark.parametrize("grid", [None, (12, 20)])
+def test_obstacle_reduced_variant(gpu_ctx, grid):
+    """demo/obstacle.jl:121-168,233-239 (obstacle_l1red): x = [x1; x2], c(x) = [x1 + A x2; x2], D = complementarity pairs
+    (i, i+N), g = NonsmoothCostObstacleRedL1.  AL-gradient: elementwise outputs bit for bit; whole solve at the demo's
+    size against the oracle."""
+    N = 48 if grid is None else grid[0] * grid[1]
+    p = bz.Problem(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleRedL1(N), bz.ConstraintObstacleRed(N, grid),
+                   bz.PairSet("cc", stride=N), ctx=gpu_ctx)
+    rng = np.random.default_rng(2)
+    x, mu, y = rng.standard_normal(2 * N), rng.uniform(0.1, 2.0, 2 * N), rng.standard_normal(2 * N)
+    p.auglag_update(mu, y)
+    g = p.gradient(x)
+    al = bo.AugLagFun(bo.FObstacleL1(N), bo.CObstacleRed(N, grid), bo.PairSet("cc", stride=N), mu.copy(), y.copy(), x)
+    dl = np.empty(2 * N)
+    lx = al.gradient(dl, x)
+    assert np.array_equal(g["cx"], al.cx) and np.array_equal(g["s"], al.s) and np.array_equal(g["yupd"], al.yupd)
+    assert np.array_equal(g["dlx"], dl) and abs(g["lx"] - lx) <= KTOL * abs(lx)
+    z, gz = p.prox(x, 0.3)
+    zo = np.empty(2 * N)
+    gzo = bo.GObstacleRedL1(N).prox(zo, x, 0.3)
+    assert np.array_equal(z, zo) and abs(gz - gzo) <= KTOL * abs(gzo)
+    p.close()
+    if grid is None:
+        # the first three outer iterations of the demo-sized solve follow the oracle (the full solve is a long, chaotic
+        # run -- like the demo's own obstacle problems, SURVEY §8d -- and is not compared point for point)
+        N = 16
+        sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=1_000_000, minimum_gamma=bo.EPS)
+        out = bz.alps(bz.SmoothCostObstacleL1(N), bz.NonsmoothCostObstacleRedL1(N), bz.ConstraintObstacleRed(N),
+                      bz.PairSet("cc", stride=N), 2.0 * np.ones(2 * N), np.zeros(2 * N), tol=1e-3, maxit=3, subsolver=sub,
+                      subsolver_maxit=1_000_000, max_inner_total=20000, ctx=gpu_ctx)
+        r = bo.solve(bo.problem_obstacle_red(N), 2.0 * np.ones(2 * N), tol=1e-3, maxit=3)
+        assert out[2] == r.tot_it == 3 and abs(out[3] - r.tot_inner_it) <= 0.25 * r.tot_inner_it
+        assert abs(out[7] - r.norm_res_prim) <= 0.05 * r.norm_res_prim
+        assert np.max(np.abs(out[0] - r.x)) <= 0.05
+
+
 def test_obstacle_2d_gradient(gpu_ctx):
     gy, gx = 24, 40
     N = gy * gx
