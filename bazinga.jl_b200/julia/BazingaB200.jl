@@ -110,7 +110,13 @@ d_kind(D) = error("BazingaB200: D = $(typeof(D)) is not in the GPU oracle catalo
 c_kind(c) = error("BazingaB200: c = $(typeof(c)) is not registered; add a BazingaB200.c_kind method")
 
 # ---- alps(f, g, c, D, x0, y0; ...) -- src/algorithms/alps.jl:7-26 --------------------------------------------
-function alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::AbstractArray, y0::AbstractArray;
+# ---- als(f, g, c, D, x0, y0; ...)  -- src/algorithms/als.jl:7-26 (same keywords, same 10-tuple) ----------------
+alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::AbstractArray, y0::AbstractArray; kwargs...) =
+    solve_on_device(false, f, g, c, D, x0, y0; kwargs...)
+als(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::AbstractArray, y0::AbstractArray; kwargs...) =
+    solve_on_device(true, f, g, c, D, x0, y0; kwargs...)
+
+function solve_on_device(slack::Bool, f, g, c, D, x0, y0;
               tol::Real = 1e-6, tol_prim::Real = tol, tol_dual::Real = tol, inner_tol::Real = cbrt(tol_dual),
               maxit::Int = 100, theta_penalty::Real = 0.8, kappa_penalty::Real = 0.5, kappa_tol::Real = 0.1,
               verbose::Bool = false, subsolver = B200PANOCplus, subsolver_maxit::Int = 1_000_000_000)
@@ -127,7 +133,7 @@ function alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::Abstrac
                        ptr(get(cp, :A, nothing)), ptr(get(cp, :b, nothing)), Int32(1) #= column-major =#,
                        Int32(0), Int32(0), UInt64(0), 0, 0, dlo, dhi, 1, 0, 0,
                        Int32(0), Int32(0), 0,   # no slab decomposition
-                       Int32(0))                # alps (Int32(1): als, bz_als_solve)
+                       Int32(slack))            # 0: alps / bz_alps_solve, 1: als / bz_als_solve (PANOC+ on [x; s])
     prob = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep begin
         check(ccall((:bz_problem_create, lib), Cint, (Ptr{Cvoid}, Ref{ProblemDesc}, Ref{Ptr{Cvoid}}),
@@ -146,14 +152,48 @@ function alps(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::Abstrac
     res = Result()
     x0c = Vector{T}(x0); y0c = Vector{T}(y0)             # x0, y0 are never modified (test_nonconvex_qp.jl:36)
     try
-        check(ccall((:bz_alps_solve, lib), Cint,
-                    (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{Options}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}, Ref{Result}),
-                    prob[], x0c, y0c, opt, x, y, s, mu, res), ctx.handle)
+        if slack
+            check(ccall((:bz_als_solve, lib), Cint,
+                        (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{Options}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}, Ref{Result}),
+                        prob[], x0c, y0c, opt, x, y, s, mu, res), ctx.handle)
+        else
+            check(ccall((:bz_alps_solve, lib), Cint,
+                        (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{Options}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}, Ref{Result}),
+                        prob[], x0c, y0c, opt, x, y, s, mu, res), ctx.handle)
+        end
     finally
         ccall((:bz_problem_destroy, lib), Cint, (Ptr{Cvoid},), prob[])
     end
     return x, y, Int(res.tot_it), Int(res.tot_inner_it), res.elapsed_time, STATUS[res.status + 1],
            res.inner_tol, res.norm_res_prim, s, mu
+end
+
+# ---- the demos' `for i = 1:ntests ... solver(x0)` loops as one launch ----------------------------------------------
+# (demo/rosenbrock.jl:154-177, demo/eitheror.jl:238-271, demo/mpvca.jl:241-281).  `problem` is the demo's problem_name;
+# X0 is nx x ntests (one starting point per column, Julia's layout = instance-major for the C ABI).
+const BATCH_KINDS = Dict("rosenbrock" => (0, 2, 2), "eitheror" => (1, 2, 4), "xor" => (2, 2, 4), "mpvca" => (3, 2, 4),
+                         "eitheror_fullslack" => (4, 6, 4), "xor_fullslack" => (5, 6, 4), "mpvca_slack" => (6, 4, 2),
+                         "mpvca_fullslack" => (7, 6, 4))
+function solve_batch(problem::String, X0::Matrix{Float64}; solver::Symbol = :alps, tol = 1e-8, inner_tol = 1.0, maxit = 100,
+                     subsolver = B200PANOCplus(minimum_gamma = eps(Float64), maxit = 1000), subsolver_maxit = 1000)
+    kind, nx, ny = BATCH_KINDS[problem]
+    size(X0, 1) == nx || error("X0 must be $(nx) x ntests for problem $(problem)")
+    ctx = context(); B = size(X0, 2)
+    opt = Options()
+    ccall((:bz_default_options, lib), Cvoid, (Ref{Options},), opt)
+    opt.tol = tol; opt.inner_tol = inner_tol; opt.maxit = maxit; opt.subsolver_maxit = subsolver_maxit
+    opt.alpha = subsolver.alpha; opt.beta = subsolver.beta; opt.minimum_gamma = subsolver.minimum_gamma
+    opt.max_backtracks = subsolver.max_backtracks; opt.lbfgs_memory = subsolver.memory; opt.sub_maxit = subsolver.maxit
+    Y0 = zeros(ny, B); X = similar(X0); Y = similar(Y0)
+    its = Vector{Int32}(undef, B); inner = Vector{Int64}(undef, B); status = Vector{Int32}(undef, B)
+    nrp = Vector{Float64}(undef, B); ms = Ref{Float64}(0.0)
+    sym = solver == :als ? :bz_batch_solve_als : :bz_batch_solve
+    check(ccall((sym, lib), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Options}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
+                ctx.handle, kind, B, X0, Y0, opt, X, Y, its, inner, status, nrp, ms), ctx.handle)
+    # the columns the demos write to CSV: xfinal, iters, sub_iters, is_solved (demo/eitheror.jl:256-271)
+    return (x = X, y = Y, iters = its, sub_iters = inner, is_solved = status .== 0, norm_res_prim = nrp, kernel_ms = ms[])
 end
 
 end # module
