@@ -12,6 +12,7 @@ from .oracles import (  # noqa: F401
     IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NonsmoothCostObstacleRedL1, NormL0, NormL0Box, NormL1, NormL1Box,
     NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
 )
+from .results import DATA_COLUMNS, STATS_COLUMNS, demo_rows, demo_stats, write_demo_results  # noqa: F401
 from .solver import (  # noqa: F401
     BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, als, alps_batch, als_batch, comm_unique_id,
     default_context, default_subsolver, row_shard,

@@ -190,3 +190,27 @@ def test_slab_decomposed_obstacle_gradient_equals_global_gloo_world2():
     assert np.array_equal(ret[0][2], ret[1][2])                              # rank-order sums: identical bits
     fx = 0.5 * tot[1] - tot[2]
     assert abs((0.5 * tot[0] + fx - al.musqy) - lx) <= 1e-13 * abs(lx)
+
+
+def test_demo_result_files_follow_the_reference_schema(tmp_path):
+    """demo/eitheror.jl:256-273,363-383: column names and order of the per-start CSV and of the stats CSV, the
+    classification of end points by the two minimisers (tolx = 1e-6), max / median columns.  The solves here come from
+    the C oracle (no GPU in this test); the writer is the one the GPU path uses."""
+    import csv
+    from tiny_oracle_binding import tiny_batch
+    v = np.arange(-4.0, 8.0 + 1e-9, 3.0)
+    X0 = np.array([(i, j) for j in v for i in v])
+    out = tiny_batch(1, X0, min_gamma=bo.EPS, sub_maxit=1000, subsolver_maxit=1000)
+    out["kernel_ms"] = 2.5
+    base = str(tmp_path / "eitheror_alps_lbfgs")
+    rows, stats = bz.write_demo_results(base, "eitheror", X0, out)
+    data = list(csv.reader(open(base + ".csv")))
+    assert tuple(data[0]) == ("id", "xinit_1", "xinit_2", "xfinal_1", "xfinal_2", "iters", "sub_iters", "runtime", "is_solved")
+    assert len(data) == 1 + len(X0) and data[1][0] == "1" and float(data[1][1]) == X0[0, 0]
+    st = list(csv.reader(open(base + "_stats.csv")))
+    assert tuple(st[0]) == bz.STATS_COLUMNS and len(st) == 2
+    n, nsolved, it_max, it_med = stats[0], stats[1], stats[2], stats[3]
+    assert n == len(X0) and nsolved == int((out["status"] == 0).sum())
+    assert it_max == out["iters"].max() and it_med == float(np.median(out["iters"]))
+    assert stats[8] + stats[10] + stats[12] == n and stats[8] > 0          # global (2,-2) / local (4,4) / others
+    assert abs(stats[9] + stats[11] + stats[13] - 100.0) <= 1e-9
