@@ -578,22 +578,28 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     o.max_backtracks = opt->max_backtracks; o.mem = opt->lbfgs_memory;
     o.sub_maxit = opt->sub_maxit;
 
-    double *dx0 = nullptr, *dy0 = nullptr, *dx = nullptr, *dy = nullptr, *dnrp = nullptr;
-    int* dit = nullptr; int* dst = nullptr; long long* din = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(dx0); cudaFree(dy0); cudaFree(dx); cudaFree(dy); cudaFree(dnrp);
-        cudaFree(dit); cudaFree(dst); cudaFree(din);
-    };
+    // one grow-only device arena per context, carved into the eight per-instance arrays: no cudaMalloc / cudaFree (and
+    // their implicit synchronisations) on the second and later calls
+    const size_t B = (size_t)batch;
+    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 2 * B * sizeof(int) + 64;
+    auto cleanup = [&]() {};
 #define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
         return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
-    BTRY(cudaMalloc((void**)&dx0, batch * nx * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dy0, batch * ny * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dx, batch * nx * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dy, batch * ny * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dnrp, batch * sizeof(double)));
-    BTRY(cudaMalloc((void**)&dit, batch * sizeof(int)));
-    BTRY(cudaMalloc((void**)&dst, batch * sizeof(int)));
-    BTRY(cudaMalloc((void**)&din, batch * sizeof(long long)));
+    if (ctx->batch_arena_bytes < need) {
+        if (ctx->batch_arena) cudaFree(ctx->batch_arena);
+        ctx->batch_arena = nullptr;
+        ctx->batch_arena_bytes = 0;
+        BTRY(cudaMalloc(&ctx->batch_arena, need));
+        ctx->batch_arena_bytes = need;
+    }
+    double* dx0 = reinterpret_cast<double*>(ctx->batch_arena);
+    double* dy0 = dx0 + B * nx;
+    double* dx = dy0 + B * ny;
+    double* dy = dx + B * nx;
+    double* dnrp = dy + B * ny;
+    long long* din = reinterpret_cast<long long*>(dnrp + B);
+    int* dit = reinterpret_cast<int*>(din + B);
+    int* dst = dit + B;
     BTRY(cudaMemcpyAsync(dx0, x0, batch * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     BTRY(cudaMemcpyAsync(dy0, y0, batch * ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     cudaEvent_t e0, e1;

@@ -439,6 +439,8 @@ struct bz_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     long long n_launches = 0;
+    void* batch_arena = nullptr;          // device scratch of bz_batch_solve (grow-only)
+    size_t batch_arena_bytes = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)

@@ -133,6 +133,7 @@ extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
     cudaSetDevice(ctx->device);
     bz_comm_destroy(ctx);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->batch_arena) cudaFree(ctx->batch_arena);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
