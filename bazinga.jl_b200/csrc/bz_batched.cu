@@ -29,6 +29,38 @@ __device__ __forceinline__ double jmax(double a, double b) {
     return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(a, b);
 }
 
+// a / b given rb = frecip(b), for divisors that are reused many times (mu_i over an inner solve, ys_i over the life of
+// an L-BFGS pair, gamma between halvings).  q = RN(a*rb), the exact remainder r = a - b*q (one FMA) and q' = RN(q + r*rb)
+// give the correctly rounded quotient (Markstein's division-by-FMA theorem; tests/test_host_logic.py runs this very
+// routine, restated in C, against the hardware division on 2e8 operand pairs, adversarial significands and special
+// values included), i.e. the very bits of a / b, in 3 dependent fp64 operations and ONE range test.  A batch runs as long
+// as its slowest instance -- a lone thread of a lone warp that pays every instruction's full latency -- so what this buys
+// is instructions per division, not throughput (r1j: slowest mpvca instance alone 51.1 -> 22.0 ms, either-or 65.0 ->
+// 29.7 ms).  The range test is on q' alone: frecip() poisons rb (NaN) unless 2^-256 <= |b| < 2^256, so a q' with
+// 2^-256 <= |q'| < 2^256 proves a, b, q and every intermediate of the theorem are normal.  Ahead of it, the two
+// numerators that are common and need no arithmetic: +-0 (three in four of the AL gradient's (c(x) + mu y - s)_i vanish
+// on an inactive constraint) and NaN (a diverged instance keeps iterating to its caps and is the slowest of its batch;
+// the IEEE routine's special-value path is its longest).  Everything else is rare and out of line.
+__device__ __forceinline__ bool fmid(double v) {          // 2^-256 <= |v| < 2^256 (false for 0, Inf, NaN)
+    return (unsigned)((__double2hiint(v) & 0x7fffffff) - ((1023 - 256) << 20)) < (512u << 20);
+}
+__device__ __forceinline__ double frecip(double b) {
+    return fmid(b) ? 1.0 / b : __longlong_as_double(0x7ff8000000000000LL);
+}
+__device__ __noinline__ double fdiv_rare(double a, double b, double rb) {
+    const double aa = fabs(a);
+    if (rb == rb ? !(aa > 0.0 && aa < __longlong_as_double(0x7ff0000000000000LL)) : (b != b))
+        return a * rb;                                    // +-Inf over a good b; a NaN divisor
+    return a / b;                                         // tiny or huge operands: the IEEE routine
+}
+__device__ __forceinline__ double fdiv(double a, double b, double rb) {
+    const double q = a * rb;
+    if (a != a || (a == 0.0 && q == 0.0)) return q;       // NaN; +-0 over a good b (q != 0 there means rb is poisoned)
+    const double q2 = fma(fma(-b, q, a), rb, q);
+    if (fmid(q2)) return q2;
+    return fdiv_rare(a, b, rb);
+}
+
 // ---- problem definitions: KIND 0 rosenbrock, 1 either-or, 2 xor, 3 mpvca, and the demos' slack variants
 // 4 eitheror_fullslack, 5 xor_fullslack, 6 mpvca_slack, 7 mpvca_fullslack (x carries explicit slacks, D = {0})
 template <int KIND> struct Prob;
@@ -220,12 +252,12 @@ template <int KIND, int SLACK> struct Al {
     static constexpr int NX = Prob<KIND>::NX;
     static constexpr int NY = Prob<KIND>::NY;
     static constexpr int NV = SLACK ? NX + NY : NX;
-    double mu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;
+    double mu[NY], rmu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;   // rmu = 1 ./ mu (see fdiv)
 
     __device__ void update() {   // AugLagUpdate!
         double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < NY; ++i) { muy[i] = mu[i] * y[i]; acc += muy[i] * y[i]; }
+        for (int i = 0; i < NY; ++i) { muy[i] = mu[i] * y[i]; acc += muy[i] * y[i]; rmu[i] = frecip(mu[i]); }
         musqy = 0.5 * acc;
     }
     __device__ double gradient(const double (&xv)[NV], double (&dlx)[NV]) {   // gradient!(dlx, al, x)
@@ -238,13 +270,13 @@ template <int KIND, int SLACK> struct Al {
 #pragma unroll
             for (int i = 0; i < NY; ++i) {
                 const double t = (cx[i] + muy[i]) - xv[NX + i];
-                acc += (t * t) / mu[i];
+                acc += fdiv(t * t, mu[i], rmu[i]);
             }
             double Fxs = 0.5 * acc;
             Fxs += fx;
             Fxs -= musqy;
 #pragma unroll
-            for (int i = 0; i < NY; ++i) yupd[i] = y[i] + (cx[i] - xv[NX + i]) / mu[i];
+            for (int i = 0; i < NY; ++i) yupd[i] = y[i] + fdiv(cx[i] - xv[NX + i], mu[i], rmu[i]);
             Prob<KIND>::c_jt(x, yupd, jtv);
 #pragma unroll
             for (int j = 0; j < NX; ++j) dlx[j] = dfx[j] + jtv[j];
@@ -259,10 +291,10 @@ template <int KIND, int SLACK> struct Al {
 #pragma unroll
         for (int i = 0; i < NY; ++i) yupd[i] -= s[i];
 #pragma unroll
-        for (int i = 0; i < NY; ++i) acc += (yupd[i] * yupd[i]) / mu[i];
+        for (int i = 0; i < NY; ++i) acc += fdiv(yupd[i] * yupd[i], mu[i], rmu[i]);
         double lx = 0.5 * acc;
 #pragma unroll
-        for (int i = 0; i < NY; ++i) yupd[i] /= mu[i];
+        for (int i = 0; i < NY; ++i) yupd[i] = fdiv(yupd[i], mu[i], rmu[i]);
         fx = Prob<KIND>::f_grad(x, dfx);
         lx += fx;
         lx -= musqy;
@@ -311,7 +343,7 @@ __device__ __forceinline__ double f_model(double fx, const double (&g)[NV], cons
 template <int MM, int NV>
 struct Lbfgs {
     int M, currmem;
-    double H, s[MM][NV], y[MM][NV], ys[MM];
+    double H, s[MM][NV], y[MM][NV], ys[MM], rys[MM];   // rys = 1 ./ ys (see fdiv)
     __device__ void reset() { currmem = 0; H = 1.0; }
     __device__ void update(const double (&sv)[NV], const double (&yv)[NV]) {
         if (M == 0) return;
@@ -322,10 +354,12 @@ struct Lbfgs {
 #pragma unroll
                 for (int j = 0; j < NV; ++j) { s[i][j] = s[i - 1][j]; y[i][j] = y[i - 1][j]; }
                 ys[i] = ys[i - 1];
+                rys[i] = rys[i - 1];
             }
 #pragma unroll
             for (int j = 0; j < NV; ++j) { s[0][j] = sv[j]; y[0][j] = yv[j]; }
             ys[0] = ysv;
+            rys[0] = frecip(ysv);
             currmem = currmem + 1 > M ? M : currmem + 1;
             H = ysv / dotn<NV>(yv, yv);
         }
@@ -337,7 +371,7 @@ struct Lbfgs {
 #pragma unroll
         for (int i = 0; i < MM; ++i) {
             if (i < currmem) {
-                al[i] = dotn<NV>(s[i], d) / ys[i];
+                al[i] = fdiv(dotn<NV>(s[i], d), ys[i], rys[i]);
 #pragma unroll
                 for (int j = 0; j < NV; ++j) d[j] -= al[i] * y[i][j];
             }
@@ -347,7 +381,7 @@ struct Lbfgs {
 #pragma unroll
         for (int i = MM - 1; i >= 0; --i) {
             if (i < currmem) {
-                const double beta = dotn<NV>(y[i], d) / ys[i];
+                const double beta = fdiv(dotn<NV>(y[i], d), ys[i], rys[i]);
                 const double coef = al[i] - beta;
 #pragma unroll
                 for (int j = 0; j < NV; ++j) d[j] += coef * s[i][j];
@@ -378,6 +412,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     for (int j = 0; j < NV; ++j) df[j] = tmpg[j] - grad_x[j];
     const double Lest = sqrt(dotn<NV>(df, df)) / sqrt((double)NV);
     double gamma = a / Lest;
+    double rg = frecip(gamma);   // 1/gamma, kept exact through the halvings (see fdiv)
 #pragma unroll
     for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
     double g_z = al.prox(y, gamma, z);
@@ -386,16 +421,17 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     Lbfgs<MM, NV> H;
     H.M = o.mem;
     H.reset();
-    double f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
+    double f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
     double f_z = al.gradient(z, grad_z);
     while (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
         gamma /= 2;
+        rg *= 2;
 #pragma unroll
         for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
         g_z = al.prox(y, gamma, z);
 #pragma unroll
         for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
-        f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
+        f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
         f_z = al.gradient(z, grad_z);
     }
     double tau = 1.0;
@@ -405,14 +441,14 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         bool isnan_ = false;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const double v = (res[j] / gamma - grad_x[j]) + grad_z[j];
+            const double v = (fdiv(res[j], gamma, rg) - grad_x[j]) + grad_z[j];
             if (v != v) isnan_ = true; else stopnorm = fmax(stopnorm, fabs(v));
         }
         if (isnan_) stopnorm = __longlong_as_double(0x7ff8000000000000LL);
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
-        const double FBE_x = f_model<NV>(f_x, grad_x, res, a / gamma) + g_z;
+        const double FBE_x = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg)) + g_z;
         double nres[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) nres[j] = -res[j];
@@ -423,7 +459,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x[j] = x_d[j]; z_curr[j] = z[j]; }
         tau = 1.0;
-        const double sigma = o.beta * (0.5 / gamma) * (1 - a);
+        const double sigma = o.beta * fdiv(0.5, gamma, rg) * (1 - a);
         const double nr = sqrt(dotn<NV>(res, res));
         const double thresh = FBE_x - sigma * (nr * nr) + 10 * BZ_EPS * (1 + fabs(FBE_x));
         for (int kb = 1; kb <= o.max_backtracks; ++kb) {
@@ -432,10 +468,11 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
             g_z = al.prox(y, gamma, z);
 #pragma unroll
             for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
-            f_up = f_model<NV>(f_x, grad_x, res, a / gamma);
+            f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
             f_z = al.gradient(z, grad_z);
             if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
                 gamma *= 0.5;
+                rg *= 2;
                 H.reset();
                 continue;
             }
@@ -513,7 +550,7 @@ __global__ void __launch_bounds__(TB_THREADS)
             objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;           // f(x) + gSlack.gz, als.jl:78
             Prob<KIND>::c_eval(x, cx);
 #pragma unroll
-            for (int i = 0; i < NY; ++i) al.y[i] = al.y[i] + (cx[i] - s[i]) / al.mu[i];   // als.jl:83
+            for (int i = 0; i < NY; ++i) al.y[i] = al.y[i] + fdiv(cx[i] - s[i], al.mu[i], al.rmu[i]);   // als.jl:83
         } else {
             objx = al.fx + al.gz;
             Prob<KIND>::c_eval(x, cx);
@@ -522,7 +559,7 @@ __global__ void __launch_bounds__(TB_THREADS)
             for (int i = 0; i < NY; ++i) t[i] = cx[i] + al.muy[i];
             Prob<KIND>::proj(t, s);
 #pragma unroll
-            for (int i = 0; i < NY; ++i) al.y[i] = (t[i] - s[i]) / al.mu[i];
+            for (int i = 0; i < NY; ++i) al.y[i] = fdiv(t[i] - s[i], al.mu[i], al.rmu[i]);
         }
         nrp_old = nrp;
         nrp = 0.0;

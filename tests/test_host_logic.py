@@ -214,3 +214,26 @@ def test_demo_result_files_follow_the_reference_schema(tmp_path):
     assert it_max == out["iters"].max() and it_med == float(np.median(out["iters"]))
     assert stats[8] + stats[10] + stats[12] == n and stats[8] > 0          # global (2,-2) / local (4,4) / others
     assert abs(stats[9] + stats[11] + stats[13] - 100.0) <= 1e-9
+
+
+def test_division_by_fma_is_the_ieee_quotient(tmp_path):
+    """bz_batched.cu replaces a / b by two FMAs on a cached reciprocal (fdiv/frecip/fmid).  tests/fdiv_check.c restates
+    those three functions in C; every quotient -- everyday magnitudes, adversarial significands, operands either side
+    of the range test, the whole exponent range, subnormals, zeros, infinities, NaN -- must carry the bits of the
+    hardware division, or the batched kernel could not be bit-identical with the reference arithmetic."""
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fdiv_check.c")
+    exe = str(tmp_path / "fdiv_check")
+    flags = ["-O2", "-ffp-contract=off", "-fopenmp"]
+    try:
+        if " fma " in open("/proc/cpuinfo").read():
+            flags.append("-mfma")           # hardware FMA; without it libm's exact software fma() is used (slower)
+    except OSError:
+        pass
+    subprocess.check_call(["gcc", *flags, src, "-o", exe, "-lm"])
+    per = "20000000" if "-mfma" in flags else "500000"
+    out = subprocess.run([exe, per], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout
+    pairs, bad, fast = (int(out.stdout.split()[i]) for i in (1, 3, 5))
+    assert bad == 0 and pairs >= int(per)
+    assert fast > pairs // 2               # the two-FMA path is the one being exercised
