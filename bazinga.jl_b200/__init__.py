@@ -10,7 +10,8 @@ from ._capi import BazingaError, LIB_PATH, STATUS_SYMBOLS, load_library  # noqa:
 from .oracles import (  # noqa: F401
     ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, ConstraintObstacleRed, FreeSet, IdentityFunction, IndBox, IndFree,
     IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NonsmoothCostObstacleRedL1, NormL0, NormL0Box, NormL1, NormL1Box,
-    NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetXOR, SmoothCostObstacleL1, Zero, ZeroSet,
+    NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetP, SetXOR, SmoothCostObstacleL1, SmoothCostP,
+    ConstraintP, Zero, ZeroSet,
 )
 from .results import DATA_COLUMNS, STATS_COLUMNS, demo_rows, demo_stats, write_demo_results  # noqa: F401
 from .solver import (  # noqa: F401

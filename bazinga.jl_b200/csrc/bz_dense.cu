@@ -146,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
             w = __ldg(a.y + r0 + rowp) + (cxv - sv) / mui;
         } else {
             const double t = cxv + muyi;                             // auglagfun.jl:75
-            sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);             // :76
+            sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t, r0 + rowp);  // :76
             const double u = t - sv;                                 // :77
             lx += (u * u) / mui;                                     // :78 (0.5 applied later)
             w = u / mui;                                             // :79
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(WR_THREADS)
                     w = a.y[gi] + (cxv - sv) / mui;
                 } else {
                     const double t = cxv + a.muy[gi];
-                    sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);
+                    sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t, gi);
                     const double u = t - sv;
                     lx += (u * u) / mui;
                     w = u / mui;

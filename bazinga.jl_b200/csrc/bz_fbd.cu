@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
             const double xj = vx[j];
             if (fresh) vgx[j] = gr;
             const double y = xj - gamma * gr;
-            const double z = (g.snx > 0 && j >= g.snx) ? bz_proj_elem(g.sdk, g.slo, g.shi, y)   // als: proj_D on the slack part
+            const double z = (g.snx > 0 && j >= g.snx) ? bz_proj_elem(g.sdk, g.slo, g.shi, y, j - g.snx)   // als: proj_D on the slack part
                                                       : bz_prox_elem<HEAVY>(g, y, gamma, j, a[2]);
             const double r = xj - z;
             vz[j] = z;

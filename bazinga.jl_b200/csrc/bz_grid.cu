@@ -315,7 +315,7 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
                 w = __ldg(a.y + r0 + j) + (cxv - sv) / mu_j;
             } else {
                 const double t = cxv + muy_j;                            // auglagfun.jl:75
-                sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t);             // :76
+                sv = bz_proj_elem(a.dkind, a.dlo, a.dhi, t, r0 + j);     // :76
                 const double u = t - sv;                                 // :77
                 lx += (u * u) / mu_j;                                    // :78 (0.5 applied later)
                 w = u / mu_j;                                            // :79

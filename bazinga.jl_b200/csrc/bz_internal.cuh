@@ -167,12 +167,14 @@ __host__ __device__ inline void bz_proj_pair(int kind, double x1, double x2, dou
 }
 
 // elementwise sets (zeroSet.jl:17-20, freeSet.jl:17-20, indicatorSet.jl:8-11 -> IndBox clamp)
-__host__ __device__ inline double bz_proj_elem(int kind, double lo, double hi, double v) {
+// `row` is the (global) row index: only SetP (demo/portfolio.jl:55-63: z .= cx; z[1] = max(rho, cx[1]); z[2] = 1) needs it
+__host__ __device__ inline double bz_proj_elem(int kind, double lo, double hi, double v, long long row) {
     if (kind == BZ_D_ZERO) return 0.0;
     if (kind == BZ_D_BOX) return fmin(hi, fmax(lo, v));
+    if (kind == BZ_D_PORTFOLIO) return row == 0 ? fmax(lo, v) : (row == 1 ? 1.0 : v);
     return v;
 }
-__host__ __device__ inline bool bz_d_is_pair(int kind) { return kind >= BZ_D_EITHEROR; }
+__host__ __device__ inline bool bz_d_is_pair(int kind) { return kind >= BZ_D_EITHEROR && kind <= BZ_D_CC; }
 
 // Elementwise prox of the g kinds that do not couple entries.  Returns z and adds this entry's
 // contribution to the value accumulator `acc` (sum |z|, sum z, or a nonzero count).

@@ -283,6 +283,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
 
     // ---- catalogue check (H2: closed catalogue, unknown combinations raise; no CPU fallback)
     const bool d_pair = bz_d_is_pair(d->d_kind);
+    if (d->d_kind == BZ_D_PORTFOLIO && (d->ny != 2 || d->c_kind != BZ_C_DENSE_AFFINE || d->ny_local != 0))
+        return fail(BZ_ERR_ARG, "SetP (portfolio) is [rho, inf) x {1}: it needs ny == 2 and an unsharded dense affine c");
     switch (d->c_kind) {
     case BZ_C_DENSE_AFFINE:
         if (d_pair) return fail(BZ_ERR_UNSUPPORTED, "pair sets with a dense affine c are not in the fused path yet");

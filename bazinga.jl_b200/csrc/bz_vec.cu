@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
                 continue;
             }
             const double t = c + muy[j];
-            const double sv = bz_proj_elem(D.kind, D.lo, D.hi, t);
+            const double sv = bz_proj_elem(D.kind, D.lo, D.hi, t, j);
             const double u = t - sv;
             a[0] += (u * u) / mu[j];
             cx[j] = c; s[j] = sv; yupd[j] = u / mu[j];
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
             out[i1] = s1; out[i2] = s2;
         }
     } else {
-        for (long long j = j0; j < m; j += stride) out[j] = bz_proj_elem(D.kind, D.lo, D.hi, in[j]);
+        for (long long j = j0; j < m; j += stride) out[j] = bz_proj_elem(D.kind, D.lo, D.hi, in[j], j);
     }
 }
 int bz_launch_proj(bz_ctx* ctx, const double* in, double* out, long long m, const BzDParams& D) {
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     } else {
         for (long long j = j0; j < m; j += stride) {
             const double t = cx[j] + muy[j];                      // y .= cx .+ alFun.muy
-            const double sv = bz_proj_elem(D.kind, D.lo, D.hi, t);  // proj!(s, D, y)
+            const double sv = bz_proj_elem(D.kind, D.lo, D.hi, t, j);  // proj!(s, D, y)
             s[j] = sv;
             y[j] = (t - sv) / mu[j];                              // y .-= s; y ./= mu
             mx = bz_nanmax(mx, cx[j] - sv);                       // norm(cx .- s, Inf)
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     } else {
         for (long long j = j0; j < m; j += stride) {
             double sv;
-            if (compute_s) { sv = bz_proj_elem(D.kind, D.lo, D.hi, cx[j]); s[j] = sv; }
+            if (compute_s) { sv = bz_proj_elem(D.kind, D.lo, D.hi, cx[j], j); s[j] = sv; }
             else sv = s[j];
             one(j, sv);
         }

@@ -43,6 +43,16 @@ class Quadratic:
         self.Q, self.q = _f64(Q), _f64(q)
 
 
+class SmoothCostP(Quadratic):
+    """demo/portfolio.jl:33-44 SmoothCostP(Q): f(x) = 0.5 x'Qx, gradient! = mul!(dfx, Q, x) then 0.5 dot(x, dfx)."""
+
+    def __init__(self, Q):
+        Q = _f64(Q)
+        if Q.ndim != 2 or Q.shape[0] != Q.shape[1]:
+            raise ValueError("SmoothCostP: Q must be square")
+        Quadratic.__init__(self, Q, np.zeros(Q.shape[0]))
+
+
 class SmoothCostObstacleL1:
     """demo/obstacle.jl:37-47."""
     f_kind = K.F_OBSTACLE_L1
@@ -201,6 +211,16 @@ class ConstraintBasisPursuit:
             raise ValueError("ConstraintBasisPursuit: size mismatch")
 
 
+class ConstraintP(ConstraintBasisPursuit):
+    """demo/portfolio.jl:46-58 ConstraintP(mu): c(x) = [mu'x; e'x], jtv = mu*v[1] + v[2] -- the dense affine
+    provider with the two rows [mu'; e'] and b = 0."""
+
+    def __init__(self, mu):
+        mu = _f64(mu).reshape(-1)
+        ConstraintBasisPursuit.__init__(self, np.stack([mu, np.ones_like(mu)]), np.zeros(2))
+        self.mu = mu
+
+
 class ConstraintObstacle:
     """demo/obstacle.jl:92-113; ``grid=(gy, gx)`` selects the 2-D 5-point extension (config C4).
     ``slab=(rank, nranks)``: this object describes ONE rank's slab of a grid split by rows over ranks
@@ -245,6 +265,15 @@ class IndicatorSet:
         if not isinstance(f, IndBox):
             raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "IndicatorSet: only IndBox is supported on the GPU path")
         self.lo, self.hi = f.lo, f.hi
+
+
+class SetP:
+    """demo/portfolio.jl:60-69 SetP(rho) = [rho, inf) x {1}: proj! copies cx, then z[1] = max(rho, cx[1]), z[2] = 1."""
+    d_kind = K.D_PORTFOLIO
+
+    def __init__(self, rho):
+        self.lo, self.hi = float(rho), 1.0
+        self.rho = float(rho)
 
 
 def ClosedSet(f):

@@ -81,7 +81,8 @@ typedef enum { /* closed set D: proj!(z,D,v) */
     BZ_D_EITHEROR = 3, /* pairs, src/projections/orConstraints.jl:7-17 */
     BZ_D_XOR = 4,      /* pairs, src/projections/orConstraints.jl:24-36 */
     BZ_D_VC = 5,       /* pairs, src/projections/vanishingConstraints.jl:27-46 */
-    BZ_D_CC = 6        /* pairs, src/projections/complementarityConstraints.jl:8-20 */
+    BZ_D_CC = 6,       /* pairs, src/projections/complementarityConstraints.jl:8-20 */
+    BZ_D_PORTFOLIO = 7 /* demo/portfolio.jl:52-63 SetP = [rho, inf) x {1}: z[1] = max(rho, v[1]), z[2] = 1; d_lo = rho, ny = 2 */
 } bz_d_kind;
 
 typedef enum { BZ_ROW_MAJOR = 0, BZ_COL_MAJOR = 1 /* Julia's native layout */ } bz_layout;

@@ -169,6 +169,18 @@ class BoxSet:
         z[:] = np.minimum(self.hi, np.maximum(self.lo, v))
 
 
+class SetPortfolio:
+    """demo/portfolio.jl:60-69 SetP = [rho, inf) x {1}: z .= cx; z[1] = max(rho, cx[1]); z[2] = 1."""
+
+    def __init__(self, rho):
+        self.rho = float(rho)
+
+    def proj(self, z, v):
+        z[:] = v
+        z[0] = max(self.rho, v[0])
+        z[1] = 1.0
+
+
 class PairSet:
     """Adjacent pairs (1:2),(3:4),... projected by one of the 2-element kernels
     (demo/eitheror.jl:122-126 SetEOR, :128-132 SetXOR; demo/mpvca.jl:146-150 SetMPVCA;
@@ -539,6 +551,20 @@ class CDenseAffine:
 
     def jtprod(self, jtv, x, v):
         jtv[:] = self.A.T @ v
+
+
+class CPortfolio:
+    """demo/portfolio.jl:46-58 ConstraintP: cx = [dot(mu, x); sum(x)], jtv = mu*v[1] + v[2]."""
+
+    def __init__(self, mu):
+        self.mu = np.asarray(mu, dtype=np.float64)
+
+    def eval(self, cx, x):
+        cx[0] = float(self.mu @ x)
+        cx[1] = float(np.sum(x))
+
+    def jtprod(self, jtv, x, v):
+        jtv[:] = self.mu * v[0] + v[1]
 
 
 class CRosenbrock:
@@ -1330,6 +1356,35 @@ def slack_start(name, X):
     if name == "mpvca_fullslack":
         return np.stack([x1, x2, x1, x1 + x2 - 5 * math.sqrt(2), x2, x1 + x2 - 5], axis=1)
     return X
+
+
+def make_portfolio(n, seed=0, factors=None):
+    """Synthetic stand-in for the demo's `portfolio_data/dim200/*/{Q,rho,mu,ub}.csv` (demo/portfolio.jl:71-90; the data
+    files are not part of the reference repository): a factor-model covariance Q = F'F/k + diag(d) (symmetric positive
+    definite), expected returns mu in [0.02, 0.12], a return floor rho at the median of mu and holding caps ub in
+    [0.05, 0.3] (so at least four assets are held).  Entries from the counter-based generator above: the same bits on
+    every machine."""
+    k = factors or max(4, n // 10)
+    F = bz_randn_like(seed, 0, k * n).reshape(k, n)
+    d = 0.05 + 0.1 * np.abs(bz_randn_like(seed, 0, n, stream=3))
+    Q = (F.T @ F) / k + np.diag(d)
+    Q = 0.5 * (Q + Q.T)
+    u = np.abs(bz_randn_like(seed, 0, n, stream=4))
+    mu = 0.02 + 0.1 * (u / (1.0 + u))
+    rho = float(np.median(mu))
+    w = np.abs(bz_randn_like(seed, 0, n, stream=5))
+    ub = 0.05 + 0.25 * (w / (1.0 + w))
+    return Q, rho, mu, ub
+
+
+def problem_portfolio(Q, rho, mu, ub, g="l1", a=100.0, p=0.5):
+    """demo/portfolio.jl:117-166: f = SmoothCostP(Q), c = ConstraintP(mu), D = SetP(rho) and g = NormL1Box(a, u = ub)
+    ('l1'), NormLpPowerBox(0.5, a, u = ub) ('lp') or NormL0Box(a, u = ub) ('l0'); solved with `als`, x0 = ones(n),
+    y0 = zeros(2), PANOCplus(LBFGS(5), maxit = 1000, minimum_gamma = 1e-32)."""
+    n = len(mu)
+    gg = {"l1": lambda: GNormL1Box(a, ub), "lp": lambda: GNormLpBox(p, a, ub), "l0": lambda: GNormL0Box(a, ub)}[g]()
+    return dict(f=FQuadratic(Q, np.zeros(n)), g=gg, c=CPortfolio(mu), D=SetPortfolio(rho), nx=n, ny=2,
+                kw=dict(subsolver=PanocOptions(minimum_gamma=1e-32, maxit=1000)))
 
 
 def problem_basis_pursuit(A, b, g="l1"):

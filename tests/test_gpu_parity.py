@@ -752,3 +752,88 @@ def test_slab_decomposed_obstacle_two_ranks():
     assert sc["same_counts_on_all_ranks"] and sc["same_objective_on_all_ranks"]
     assert d["inner_iterations"] == sc["inner_iterations_single_gpu"] == 10
     assert sc["max_abs_dx"] <= 1e-10 * sc["max_abs_x"]
+
+
+def test_portfolio_slack_gradient_parity(gpu_ctx):
+    """gradient!(dFxs, F::AugLagFunSlack, xs) for demo/portfolio.jl's oracles: f = SmoothCostP(Q) (dense quadratic),
+    c = ConstraintP(mu) (two dense rows), and proj! onto SetP = [rho, inf) x {1} through bz_proj (and inside the
+    alps-form AL gradient, where D enters the kernel)."""
+    n = 200
+    Q, rho, mu_r, ub = bo.make_portfolio(n, seed=3)
+    rng = np.random.default_rng(11)
+    f, c, D, g = bz.SmoothCostP(Q), bz.ConstraintP(mu_r), bz.SetP(rho), bz.NormL1Box(100.0, u=ub)
+    of, oc, oD = bo.FQuadratic(Q, np.zeros(n)), bo.CPortfolio(mu_r), bo.SetPortfolio(rho)
+    mu, y = rng.uniform(0.05, 3.0, 2), rng.standard_normal(2)
+    # als form: [x; s]
+    p = bz.Problem(f, g, c, D, ctx=gpu_ctx, slack=True)
+    xs = np.concatenate([rng.uniform(0, 0.3, n), rng.standard_normal(2)])
+    p.auglag_update(mu, y)
+    gr = p.gradient(xs)
+    F = bo.AugLagFunSlack(of, oc, mu.copy(), y.copy(), xs[:n].copy())
+    d = np.empty(n + 2)
+    Fxs = F.gradient(d, xs)
+    scale = np.linalg.norm(Q, 2) * np.linalg.norm(xs) + np.linalg.norm(F.yupd) * np.sqrt(n) + 1
+    assert np.max(np.abs(gr["dlx"] - d)) <= KTOL * scale and abs(gr["lx"] - Fxs) <= KTOL * (abs(Fxs) + scale)
+    p.close()
+    # alps form: D inside the fused kernel
+    p = bz.Problem(f, g, c, D, ctx=gpu_ctx)
+    p.auglag_update(mu, y)
+    for x in (xs[:n], np.zeros(n), np.full(n, 0.02)):        # mu'x below / above rho
+        gr = p.gradient(x)
+        al = bo.AugLagFun(of, oc, oD, mu.copy(), y.copy(), x.copy())
+        d2 = np.empty(n)
+        lx = al.gradient(d2, x)
+        assert np.max(np.abs(gr["s"] - al.s)) <= KTOL * 10 and gr["s"][1] == 1.0 and gr["s"][0] >= rho
+        assert np.max(np.abs(gr["dlx"] - d2)) <= KTOL * scale and abs(gr["lx"] - lx) <= KTOL * (abs(lx) + scale)
+    p.close()
+    with pytest.raises(bz.BazingaError):                      # SetP is a set in R^2
+        A, _, b = bo.make_basis_pursuit(3, 10)
+        bz.Problem(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.SetP(0.1), ctx=gpu_ctx)
+
+
+def test_portfolio_demo_solves_match_oracle(gpu_ctx):
+    """demo/portfolio.jl:140-203 on a synthetic data set (n = 200 like the demo's dim200): the five als solves (L0, Lp,
+    Lp + L0, L1, L1 + L0) against the numpy restatement.  All must end :first_order at a feasible point.  The convex
+    one (L1) stops its later inner solves at the demo's cap of 1000 iterations (in the oracle as well), so its end point
+    is compared to 5e-3 and its objective to 1 %; the nonconvex ones are compared by support size and objective (which
+    local solution a solve lands in is sensitive to the summation order of Q*x)."""
+    from bazinga_b200 import portfolio as pf
+    n = 200
+    Q, rho, mu, ub = bo.make_portfolio(n, seed=3)
+    rows, outs = pf.solve_portfolio(Q, rho, mu, ub, ctx=gpu_ctx)
+    assert set(rows) == set(pf.KEYS)
+    ref = {}
+    with np.errstate(all="ignore"):
+        for key, g, start in (("l0", "l0", None), ("lp", "lp", None), ("lp0", "l0", "lp"), ("l1", "l1", None), ("l10", "l0", "l1")):
+            P = bo.problem_portfolio(Q, rho, mu, ub, g)
+            x0, y0 = (np.ones(n), np.zeros(2)) if start is None else (ref[start].x, ref[start].y)
+            ref[key] = bo.als(P["f"], P["g"], P["c"], P["D"], x0, y0, **P["kw"])
+    for key in pf.KEYS:
+        out, r = outs[key], ref[key]
+        x = out[0]
+        assert out[5] == r.status == "first_order", key
+        assert out[7] <= 1e-6 and abs(x.sum() - 1) <= 1e-5 and mu @ x >= rho - 1e-5 and np.all(x >= 0), key
+        assert rows[key][6] == int((x > 0).sum()) and abs(rows[key][5] - 0.5 * x @ Q @ x) <= 1e-15
+    assert np.max(np.abs(outs["l1"][0] - ref["l1"].x)) <= 5e-3 and abs(outs["l1"][2] - ref["l1"].tot_it) <= 2
+    o1, r1 = 0.5 * outs["l1"][0] @ Q @ outs["l1"][0], 0.5 * ref["l1"].x @ Q @ ref["l1"].x
+    assert abs(o1 - r1) <= 1e-2 * r1
+    # Lp and Lp + L0 land where the oracle lands; L0 from ones(n) and L1 + L0 are chaotic (a hard threshold on ~n small
+    # entries: 40 inner iterations in, one flipped entry already separates device and oracle) -- support only
+    for key in ("lp", "lp0"):
+        obj, robj = 0.5 * outs[key][0] @ Q @ outs[key][0], 0.5 * ref[key].x @ Q @ ref[key].x
+        assert abs(obj - robj) <= 1e-6 * robj and int((outs[key][0] > 0).sum()) == int((ref[key].x > 0).sum()), (key, obj, robj)
+        assert outs[key][2] == ref[key].tot_it
+    assert int((outs["l0"][0] > 0).sum()) < n // 4
+    assert int((outs["l10"][0] > 0).sum()) <= int((outs["l1"][0] > 0).sum())
+    # the first iterations, before the end points can part ways: two outer iterations of 12 inner iterations each must
+    # reproduce the oracle's iterate (every oracle of the demo is exercised: Q*x, [mu'; e']x, SetP, the three prox)
+    sub = lambda **kw: bz.PANOCplus(directions=bz.LBFGS(5), maxit=12, minimum_gamma=1e-32, **kw)   # noqa: E731
+    f, c, D = bz.SmoothCostP(Q), bz.ConstraintP(mu), bz.SetP(rho)
+    for gname, g in (("l0", bz.NormL0Box(100.0, u=ub)), ("lp", bz.NormLpPowerBox(0.5, 100.0, u=ub)), ("l1", bz.NormL1Box(100.0, u=ub))):
+        out = bz.als(f, g, c, D, np.ones(n), np.zeros(2), maxit=2, subsolver=sub, ctx=gpu_ctx)
+        P = bo.problem_portfolio(Q, rho, mu, ub, gname)
+        with np.errstate(all="ignore"):
+            r = bo.als(P["f"], P["g"], P["c"], P["D"], np.ones(n), np.zeros(2), maxit=2, subsolver=bo.PanocOptions(minimum_gamma=1e-32, maxit=12))
+        assert out[2] == r.tot_it == 2 and out[3] == r.tot_inner_it and out[5] == r.status == "max_iter", gname
+        assert np.max(np.abs(out[0] - r.x)) <= 1e-9 and np.max(np.abs(out[1] - r.y)) <= 1e-7 * (1 + np.max(np.abs(r.y))), gname
+        assert np.max(np.abs(out[8] - r.s)) <= 1e-8 and np.array_equal(out[9], r.mu), gname

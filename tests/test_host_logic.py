@@ -237,3 +237,35 @@ def test_division_by_fma_is_the_ieee_quotient(tmp_path):
     pairs, bad, fast = (int(out.stdout.split()[i]) for i in (1, 3, 5))
     assert bad == 0 and pairs >= int(per)
     assert fast > pairs // 2               # the two-FMA path is the one being exercised
+
+
+def test_portfolio_host_mirror(tmp_path):
+    """demo/portfolio.jl's oracle structs map onto catalogue kinds (SmoothCostP -> dense quadratic, ConstraintP -> the
+    two-row dense affine provider, SetP -> its own set), the CSV reader checks sizes like the reference's @asserts, and
+    the result tables carry push_out_to_data's columns."""
+    from bazinga_b200 import _capi as K
+    from bazinga_b200 import portfolio as pf
+    Q, rho, mu, ub = bo.make_portfolio(12, seed=1)
+    f, c, D = bz.SmoothCostP(Q), bz.ConstraintP(mu), bz.SetP(rho)
+    assert f.f_kind == K.F_QUADRATIC and not f.q.any() and f.Q.shape == (12, 12)
+    assert c.c_kind == K.C_DENSE_AFFINE and c.shape == (2, 12) and np.array_equal(c.A[0], mu) and np.all(c.A[1] == 1) and not c.b.any()
+    assert D.d_kind == K.D_PORTFOLIO and D.lo == rho
+    with pytest.raises(ValueError):
+        bz.SmoothCostP(np.zeros((3, 4)))
+    d = tmp_path / "p1"
+    d.mkdir()
+    np.savetxt(d / "Q.csv", Q, delimiter=",")
+    np.savetxt(d / "rho.csv", [rho], delimiter=",")
+    np.savetxt(d / "mu.csv", mu, delimiter=",")
+    np.savetxt(d / "ub.csv", ub, delimiter=",")
+    Q2, rho2, mu2, ub2 = pf.read_FG_problem_data(str(d))
+    assert np.array_equal(Q2, Q) and rho2 == rho and np.array_equal(mu2, mu) and np.array_equal(ub2, ub)
+    np.savetxt(d / "ub.csv", ub[:-1], delimiter=",")
+    with pytest.raises(ValueError):
+        pf.read_FG_problem_data(str(d))
+    tables = {k: [(1, 5, 100, 0.01, 1e-7, 0.02, 4), (2, 6, 80, 0.02, 2e-7, 0.03, 6)] for k in pf.KEYS}
+    pf.write_portfolio_results(str(tmp_path / "dim12_a100"), tables)
+    head = open(tmp_path / "dim12_a100_lp0.csv").readline().strip().split(",")
+    assert tuple(head) == pf.COLUMNS == ("id", "iters", "subiters", "runtime", "cviolation", "objectiveq", "nnz")
+    s = pf.summary(tables)
+    assert s["l0"]["nnz"] == (4.0, 6.0, 5.0) and s["lp"]["subiters"] == (80.0, 100.0, 90.0)

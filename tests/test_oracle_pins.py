@@ -218,3 +218,47 @@ def test_slack_variant_oracles_agree():
             cx = np.empty(pr["ny"])
             pr["c"].eval(cx, r["x"][i])
             assert np.max(np.abs(cx)) <= 1e-7            # D = {0}: the slacks equal the constraint values
+
+
+def test_portfolio_oracles_and_als_solves():
+    """demo/portfolio.jl: SetP projection (:60-69), ConstraintP eval!/jtprod! (:46-58), SmoothCostP (:33-44), and the
+    demo's solves through als on a synthetic data set (the reference's CSV data is not in its repository): every
+    solve ends :first_order at a feasible point; L0 / Lp solutions are sparse, warm-started L0 keeps the support small."""
+    D = bo.SetPortfolio(0.3)
+    z = np.empty(2)
+    D.proj(z, np.array([0.1, 7.0]))
+    assert z.tolist() == [0.3, 1.0]
+    D.proj(z, np.array([0.9, -2.0]))
+    assert z.tolist() == [0.9, 1.0]
+    z2 = np.empty(2)
+    D.proj(z2, z)
+    assert np.array_equal(z, z2)                                   # idempotent
+    rng = np.random.default_rng(0)
+    n = 60
+    Q, rho, mu, ub = bo.make_portfolio(n, seed=5)
+    assert np.allclose(Q, Q.T) and np.linalg.eigvalsh(Q)[0] > 0 and ub.sum() > 1 and mu.min() < rho < mu.max()
+    c = bo.CPortfolio(mu)
+    x, v = rng.standard_normal(n), rng.standard_normal(2)
+    cx, jtv = np.empty(2), np.empty(n)
+    c.eval(cx, x)
+    c.jtprod(jtv, x, v)
+    assert abs(cx @ v - x @ jtv) <= 1e-12 * (1 + abs(cx @ v))      # <c(x), v> = <x, J'v> for the linear c
+    f = bo.FQuadratic(Q, np.zeros(n))
+    d = np.empty(n)
+    assert abs(f.gradient(d, x) - 0.5 * x @ Q @ x) <= 1e-12 * abs(x @ Q @ x) and np.allclose(d, Q @ x)
+    res = {}
+    for g in ("l0", "lp", "l1"):
+        P = bo.problem_portfolio(Q, rho, mu, ub, g)
+        with np.errstate(all="ignore"):
+            r = bo.als(P["f"], P["g"], P["c"], P["D"], np.ones(n), np.zeros(2), **P["kw"])
+        res[g] = r
+        assert r.status == "first_order" and r.norm_res_prim <= 1e-6
+        assert abs(r.x.sum() - 1) <= 1e-5 and mu @ r.x >= rho - 1e-5
+        assert np.all(r.x >= 0)
+        if g != "l0":     # normL0Box.jl:41-46 keeps x[i] (not u[i]) in its over-the-box branch: L0 iterates may exceed u
+            assert np.all(r.x <= ub + 1e-12)
+    assert (res["l0"].x > 0).sum() < n // 2 and (res["lp"].x > 0).sum() < n // 2
+    P = bo.problem_portfolio(Q, rho, mu, ub, "l0")
+    with np.errstate(all="ignore"):
+        r = bo.als(P["f"], P["g"], P["c"], P["D"], res["lp"].x, res["lp"].y, **P["kw"])     # Lp + L0, portfolio.jl:170-173
+    assert r.status == "first_order" and (r.x > 0).sum() <= (res["lp"].x > 0).sum()
