@@ -99,11 +99,17 @@ g_kind(g::ProximalOperators.IndBox) = (Int32(3), 1.0, Float64(g.lb), Float64(g.u
 g_kind(g::Bazinga.NormL1Box) = (Int32(4), Float64(g.lambda), 0.0, 0.0, Vector{Float64}(g.u))
 g_kind(g::Bazinga.NormL1Nonneg) = (Int32(5), Float64(g.lambda), 0.0, 0.0, nothing)
 g_kind(g::Bazinga.NormL0Box) = (Int32(6), Float64(g.lambda), 0.0, 0.0, Vector{Float64}(g.u))
+g_kind(g::Bazinga.NormLpPowerBox) = (Int32(10), Float64(g.alpha), Float64(g.p), 0.0, Vector{Float64}(g.u))   # g_lo = p
+g_kind(g::Bazinga.NormLpPowerNonneg) = (Int32(11), Float64(g.alpha), Float64(g.p), 0.0, nothing)
 g_kind(g) = error("BazingaB200: g = $(typeof(g)) is not in the GPU oracle catalogue (no CPU fallback)")
 d_kind(::Bazinga.ZeroSet) = (Int32(0), 0.0, 0.0)
 d_kind(::Bazinga.FreeSet) = (Int32(1), 0.0, 0.0)
 d_kind(D::Bazinga.IndicatorSet{<:ProximalOperators.IndBox}) = (Int32(2), Float64(D.f.lb), Float64(D.f.ub))
 d_kind(D) = error("BazingaB200: D = $(typeof(D)) is not in the GPU oracle catalogue (no CPU fallback)")
+# demo structs register themselves the same way, e.g. for demo/portfolio.jl (f, c and D are user structs there):
+#   BazingaB200.f_kind(f::SmoothCostP) = (Int32(2), (A = Matrix{Float64}(f.Q), b = zeros(size(f.Q, 1))))   # :33-44
+#   BazingaB200.c_kind(c::ConstraintP) = (Int32(1), (A = Matrix{Float64}([c.mu'; ones(length(c.mu))']), b = zeros(2)))  # :46-58
+#   BazingaB200.d_kind(D::SetP)        = (Int32(7), Float64(D.rho), 1.0)                                   # :60-69
 # constraint kinds are user structs in the demos/tests; register yours with a method of `c_kind`:
 #   BazingaB200.c_kind(c::ConstraintBasisPursuit) = (Int32(1), (A = c.A, b = c.b))      # demo/basispursuit.jl:38
 #   BazingaB200.c_kind(::IdentityFunction)        = (Int32(0), NamedTuple())            # test/definitions
