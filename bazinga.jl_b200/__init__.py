@@ -9,7 +9,8 @@ Host code here is a thin mirror of the reference's operator/plugin interface ove
 from ._capi import BazingaError, LIB_PATH, STATUS_SYMBOLS, load_library  # noqa: F401
 from .oracles import (  # noqa: F401
     ClosedSet, ConstraintBasisPursuit, ConstraintObstacle, ConstraintObstacleRed, FreeSet, IdentityFunction, IndBox, IndFree,
-    IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NonsmoothCostObstacleRedL1, NormL0, NormL0Box, NormL1, NormL1Box,
+    IndicatorSet, LeastSquares, NonsmoothCostObstacleL1, NonsmoothCostObstacleL2, NonsmoothCostObstacleL2Red, NonsmoothCostObstacleRedL1,
+    SmoothCostObstacleL2, NormL0, NormL0Box, NormL1, NormL1Box,
     NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetP, SetXOR, SmoothCostObstacleL1, SmoothCostP,
     ConstraintP, Zero, ZeroSet,
 )

@@ -12,9 +12,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbazinga_b200.so")
 BZ_ABI_VERSION = 3
 
 # enums (include/bazinga_b200.h)
-F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1 = range(7)
+F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1, F_OBSTACLE_L2 = range(8)
 (G_ZERO, G_NORM_L1, G_NORM_L0, G_IND_BOX, G_NORML1_BOX, G_NORML1_NONNEG, G_NORML0_BOX, G_ROSENBROCK,
- G_NONNEG, G_OBSTACLE_L1, G_NORMLP_BOX, G_NORMLP_NONNEG, G_OBSTACLE_RED_L1) = range(13)
+ G_NONNEG, G_OBSTACLE_L1, G_NORMLP_BOX, G_NORMLP_NONNEG, G_OBSTACLE_RED_L1, G_OBSTACLE_L2) = range(14)
 C_IDENTITY, C_DENSE_AFFINE, C_ROSENBROCK, C_EITHEROR, C_MPVCA, C_OBSTACLE, C_OBSTACLE_RED = range(7)
 D_ZERO, D_FREE, D_BOX, D_EITHEROR, D_XOR, D_VC, D_CC, D_PORTFOLIO = range(8)
 ROW_MAJOR, COL_MAJOR = 0, 1

@@ -80,10 +80,11 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
     };
 
     const bool need_assembly = (mode == MODE_INIT0) || (mode == MODE_INIT1) || fresh;
-    if (mode >= MODE_INITFB && g.kind == BZ_G_OBSTACLE_L1) {
+    if (mode >= MODE_INITFB && (g.kind == BZ_G_OBSTACLE_L1 || g.kind == BZ_G_OBSTACLE_L2)) {
         // demo/obstacle.jl:67-81: soft threshold block 1 by gamma, max(0,.) on blocks 2-3, then
         // complementarity zeroing between blocks 2 and 3 (tie zeroes the block-2 entry)
         const long long N = g.N;
+        const bool l1 = g.kind == BZ_G_OBSTACLE_L1;
         const long long stride = (long long)gridDim.x * blockDim.x;
         const double* __restrict__ Ec = gs.Ec;
         const bool plain = fresh && gs.Ec && !gs.Pf && !gs.Pc && !gs.Ef;   // the stencil provider: grad = Ec
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
                 gr[b] = plain ? __ldcg(Ec + j) : (fresh ? bz_assemble_grad(gs, j, n) : vgx[j]);
                 xv[b] = vx[j];
             }
-            zv[0] = fmax(0.0, (xv[0] - gamma * gr[0]) - gamma);
+            zv[0] = l1 ? fmax(0.0, (xv[0] - gamma * gr[0]) - gamma) : fmax(0.0, xv[0] - gamma * gr[0]);   // L2: no threshold
             zv[1] = fmax(0.0, xv[1] - gamma * gr[1]);
             zv[2] = fmax(0.0, xv[2] - gamma * gr[2]);
             if (zv[1] > zv[2]) zv[2] = 0.0; else zv[1] = 0.0;
-            a[2] += zv[0];
+            if (l1) a[2] += zv[0];               // NonsmoothCostObstacleL2 returns zero (:61)
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
                 const long long j = i + b * N;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
 
 int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
                     const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
-    const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : v.n;
+    const long long items = (g.kind == BZ_G_OBSTACLE_L1 || g.kind == BZ_G_OBSTACLE_L2) ? g.N : v.n;
     static bool once = false;
     if (!once) { prefer_max_smem(k_fstep<false, 1>); prefer_max_smem(k_fstep<false, 4>); prefer_max_smem(k_fstep<true, 1>); once = true; }
     if (bz_g_is_heavy(g.kind))

@@ -299,15 +299,17 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
             return fail(BZ_ERR_ARG, "pair stride must be 1 or ny/2");
         break;
     case BZ_C_OBSTACLE:
-        if (d->f_kind != BZ_F_OBSTACLE_L1 || d->g_kind != BZ_G_OBSTACLE_L1 || d->d_kind != BZ_D_ZERO)
-            return fail(BZ_ERR_UNSUPPORTED, "obstacle c is built for the obstacle_l1 variant only");
+        if (!((d->f_kind == BZ_F_OBSTACLE_L1 && d->g_kind == BZ_G_OBSTACLE_L1) ||
+              (d->f_kind == BZ_F_OBSTACLE_L2 && d->g_kind == BZ_G_OBSTACLE_L2)) || d->d_kind != BZ_D_ZERO)
+            return fail(BZ_ERR_UNSUPPORTED, "obstacle c is built for the obstacle_l1 and obstacle_l2 variants (D = {0})");
         if (d->nx != 3 * d->ny) return fail(BZ_ERR_ARG, "obstacle: nx must be 3*ny");
         if (d->grid_y * d->grid_x != 0 && d->grid_y * d->grid_x != d->ny)
             return fail(BZ_ERR_ARG, "obstacle: grid_y*grid_x must equal ny");
         break;
     case BZ_C_OBSTACLE_RED:
-        if (d->f_kind != BZ_F_OBSTACLE_L1 || d->g_kind != BZ_G_OBSTACLE_RED_L1 || d->d_kind != BZ_D_CC)
-            return fail(BZ_ERR_UNSUPPORTED, "reduced obstacle c is built for the obstacle_l1red variant only (D = CC pairs)");
+        if (!((d->f_kind == BZ_F_OBSTACLE_L1 && d->g_kind == BZ_G_OBSTACLE_RED_L1) ||
+              (d->f_kind == BZ_F_OBSTACLE_L2 && d->g_kind == BZ_G_NONNEG)) || d->d_kind != BZ_D_CC)
+            return fail(BZ_ERR_UNSUPPORTED, "reduced obstacle c is built for the obstacle_l1red and obstacle_l2red variants (D = CC pairs)");
         if (d->nx != d->ny || d->nx % 2) return fail(BZ_ERR_ARG, "obstacle_l1red: nx = ny = 2N");
         if (d->d_pair_stride * 2 != d->ny) return fail(BZ_ERR_ARG, "obstacle_l1red: the CC pairs are (i, i+N)");
         if (d->grid_y * d->grid_x != 0 && d->grid_y * d->grid_x * 2 != d->ny)
@@ -335,7 +337,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         p->n_global = d->nx_global;
         ctx->slab_mode = 1;
     }
-    if (d->g_kind == BZ_G_OBSTACLE_L1 && d->c_kind != BZ_C_OBSTACLE)
+    if ((d->g_kind == BZ_G_OBSTACLE_L1 || d->g_kind == BZ_G_OBSTACLE_L2) && d->c_kind != BZ_C_OBSTACLE)
         return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
     if (d->g_kind == BZ_G_OBSTACLE_RED_L1 && d->c_kind != BZ_C_OBSTACLE_RED)
         return fail(BZ_ERR_UNSUPPORTED, "reduced obstacle g needs the reduced obstacle c");
@@ -366,6 +368,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     p->D.kind = d->d_kind; p->D.lo = d->d_lo; p->D.hi = d->d_hi;
     p->D.stride = d->d_pair_stride > 0 ? d->d_pair_stride : 1;
     p->ob.N = d->c_kind == BZ_C_OBSTACLE_RED ? d->ny / 2 : d->ny; p->ob.gy = d->grid_y; p->ob.gx = d->grid_x;
+    p->ob.l2 = d->f_kind == BZ_F_OBSTACLE_L2 ? 1 : 0;
     if (d->c_kind == BZ_C_OBSTACLE_RED) p->g.N = d->ny / 2;
     if (d->g_u) {
         PTRY(dev_alloc(ctx, &p->g_u, n));
@@ -543,7 +546,7 @@ static BzGradSrc grad_src(bz_problem* p) {
     } else if (d.f_kind == BZ_F_QUADRATIC) {
         gs.Ef = p->Ef;
         gs.fxpart = p->fxpart; gs.nfx = p->nfx; gs.fx_scale = 1.0;
-    } else if (d.f_kind == BZ_F_OBSTACLE_L1) {
+    } else if (d.f_kind == BZ_F_OBSTACLE_L1 || d.f_kind == BZ_F_OBSTACLE_L2) {
         gs.fxpart = p->fxpart; gs.nfx = p->nfx; gs.fx_scale = 0.5;
         gs.fxpart2 = p->fxpart + p->nfx; gs.nfx2 = p->nfx; gs.fx_scale2 = -1.0;
     }

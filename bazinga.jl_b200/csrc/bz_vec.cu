@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
             const long long i = r * g.GX + c, i2 = r2 * g.GX + c;
-            const double x2a = x[N + i];
-            const double cva = (x[i] + bz_stencil_rc(x + N, r, c, g, up, dn)) - x[2 * N + i];
+            const double x1a = x[i], x2a = x[N + i];
+            const double cva = (x1a + bz_stencil_rc(x + N, r, c, g, up, dn)) - x[2 * N + i];
             const double mua = mu[i], muya = muy[i];
-            double x2b = 0.0, cvb = 0.0, mub = 1.0, muyb = 0.0;
+            double x1b = 0.0, x2b = 0.0, cvb = 0.0, mub = 1.0, muyb = 0.0;
             if (two) {
-                x2b = x[N + i2];
-                cvb = (x[i2] + bz_stencil_rc(x + N, r2, c, g, up, dn)) - x[2 * N + i2];
+                x1b = x[i2]; x2b = x[N + i2];
+                cvb = (x1b + bz_stencil_rc(x + N, r2, c, g, up, dn)) - x[2 * N + i2];
                 mub = mu[i2]; muyb = muy[i2];
             }
             {
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
                 const double u = t - 0.0;            // SetObstacle: z .= 0 (demo/obstacle.jl:116-119)
                 a[0] += (u * u) / mua;
                 cx[i] = cva; s[i] = 0.0; yupd[i] = u / mua;
+                if (ob.l2) a[1] += x1a * x1a;        // SmoothCostObstacleL2: 0.5*norm(x[1:2N])^2 - sum(x2)  (:24-26)
                 a[1] += x2a * x2a;                   // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
                 a[2] += x2a;
             }
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
                 const double u = t - 0.0;
                 a[0] += (u * u) / mub;
                 cx[i2] = cvb; s[i2] = 0.0; yupd[i2] = u / mub;
+                if (ob.l2) a[1] += x1b * x1b;
                 a[1] += x2b * x2b;
                 a[2] += x2b;
             }
@@ -251,11 +253,12 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
                 wb = yupd[i2];
                 eb = (x[N + i2] - 1.0) + bz_stencil_rc(yupd, r2, c, g, up, dn);
             }
-            Ec[i] = 0.0 + wa;
+            const double f1a = ob.l2 ? x[i] : 0.0, f1b = (ob.l2 && two) ? x[i2] : 0.0;   // dfx block 1: x1 (L2) or 0 (L1)
+            Ec[i] = f1a + wa;
             Ec[N + i] = ea;
             Ec[2 * N + i] = 0.0 + (-wa);
             if (two) {
-                Ec[i2] = 0.0 + wb;
+                Ec[i2] = f1b + wb;
                 Ec[N + i2] = eb;
                 Ec[2 * N + i2] = 0.0 + (-wb);
             }
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
         for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < g.GX;
              c += (long long)gridDim.x * blockDim.x) {
             const long long i = r * g.GX + c;
-            const double x2 = x[N + i];
-            const double c1 = x[i] + bz_stencil_rc(x + N, r, c, g);   // cx[1:N] = x1 + A x2
+            const double x1 = x[i], x2 = x[N + i];
+            const double c1 = x1 + bz_stencil_rc(x + N, r, c, g);     // cx[1:N] = x1 + A x2
             const double c2 = x2;                                      // cx[N+1:2N] = x2
             const double m1 = mu[i], m2 = mu[N + i];
             const double t1 = c1 + muy[i], t2 = c2 + muy[N + i];
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
             cx[i] = c1; cx[N + i] = c2;
             s[i] = s1; s[N + i] = s2;
             yupd[i] = u1 / m1; yupd[N + i] = u2 / m2;
+            if (ob.l2) a[1] += x1 * x1;          // SmoothCostObstacleL2 (:24-26)
             a[1] += x2 * x2;                     // f = 0.5*sum(x2.^2) - sum(x2)  (:40-42)
             a[2] += x2;
         }
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, 4)
             const long long i = r * g.GX + c;
             const double w1 = yupd[i];
             const double e2 = (x[N + i] - 1.0) + (bz_stencil_rc(yupd, r, c, g) + yupd[N + i]);
-            Ec[i] = 0.0 + w1;
+            Ec[i] = (ob.l2 ? x[i] : 0.0) + w1;
             Ec[N + i] = e2;
         }
     }
@@ -406,14 +410,15 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double a[1] = {0.0};
-    if (g.kind == BZ_G_OBSTACLE_L1) {
+    if (g.kind == BZ_G_OBSTACLE_L1 || g.kind == BZ_G_OBSTACLE_L2) {
         const long long N = g.N;
+        const bool l1 = g.kind == BZ_G_OBSTACLE_L1;    // L2 (demo/obstacle.jl:52-62): no threshold on block 1, value 0
         for (long long i = j0; i < N; i += stride) {
-            double z0 = fmax(0.0, in[i] - gamma);
+            double z0 = l1 ? fmax(0.0, in[i] - gamma) : fmax(0.0, in[i]);
             double z1 = fmax(0.0, in[N + i]), z2 = fmax(0.0, in[2 * N + i]);
             if (z1 > z2) z2 = 0.0; else z1 = 0.0;
             out[i] = z0; out[N + i] = z1; out[2 * N + i] = z2;
-            a[0] += z0;
+            if (l1) a[0] += z0;
         }
     } else {
         for (long long j = j0; j < n; j += stride) out[j] = bz_prox_elem<HEAVY>(g, in[j], gamma, j, a[0]);
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 }
 int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, double* out, long long n,
                    const BzGParams& g, double* part, unsigned int* counter) {
-    const long long items = (g.kind == BZ_G_OBSTACLE_L1) ? g.N : n;
+    const long long items = (g.kind == BZ_G_OBSTACLE_L1 || g.kind == BZ_G_OBSTACLE_L2) ? g.N : n;
     if (bz_g_is_heavy(g.kind))
         k_prox<true><<<bz_vec_grid(ctx, items), BZ_VEC_THREADS, 0, ctx->stream>>>(st, in, gamma, out, n, g, part, counter);
     else

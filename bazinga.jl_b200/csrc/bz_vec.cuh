@@ -23,6 +23,7 @@ struct BzTeam {
 
 struct BzObstacle {      // demo/obstacle.jl ConstraintObstacle (+ 2-D extension)
     long long N, gy, gx; // gy = gx = 0: 1-D SymTridiagonal(2,-1)
+    int l2;              // f = SmoothCostObstacleL2 (adds 0.5||x1||^2: dfx block 1 = x1), else SmoothCostObstacleL1
 };
 
 int bz_vec_grid(const bz_ctx* ctx, long long n);

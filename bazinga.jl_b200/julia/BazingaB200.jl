@@ -110,6 +110,9 @@ d_kind(D) = error("BazingaB200: D = $(typeof(D)) is not in the GPU oracle catalo
 #   BazingaB200.f_kind(f::SmoothCostP) = (Int32(2), (A = Matrix{Float64}(f.Q), b = zeros(size(f.Q, 1))))   # :33-44
 #   BazingaB200.c_kind(c::ConstraintP) = (Int32(1), (A = Matrix{Float64}([c.mu'; ones(length(c.mu))']), b = zeros(2)))  # :46-58
 #   BazingaB200.d_kind(D::SetP)        = (Int32(7), Float64(D.rho), 1.0)                                   # :60-69
+# demo/obstacle.jl: SmoothCostObstacleL1 -> f kind 6, SmoothCostObstacleL2 -> 7; NonsmoothCostObstacleL1 -> g kind 9,
+#   NonsmoothCostObstacleRedL1 -> 12, NonsmoothCostObstacleL2 -> 13, NonsmoothCostObstacleL2Red -> 8 (max(0, x));
+#   ConstraintObstacle -> c kind 5, ConstraintObstacleRed -> 6; SetObstacle -> d kind 0, SetObstacleRed -> 6 with pair stride N
 # constraint kinds are user structs in the demos/tests; register yours with a method of `c_kind`:
 #   BazingaB200.c_kind(c::ConstraintBasisPursuit) = (Int32(1), (A = c.A, b = c.b))      # demo/basispursuit.jl:38
 #   BazingaB200.c_kind(::IdentityFunction)        = (Int32(0), NamedTuple())            # test/definitions

@@ -61,6 +61,14 @@ class SmoothCostObstacleL1:
         self.N = int(N)
 
 
+class SmoothCostObstacleL2:
+    """demo/obstacle.jl:21-35: 0.5||x[1:2N]||^2 - sum(x[N+1:2N]), gradient [x1; x2 - 1; 0]."""
+    f_kind = K.F_OBSTACLE_L2
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
 # ------------------------------------------------------------------ nonsmooth costs g
 class IndFree(Zero):
     """ProximalOperators.IndFree() (test/problems/test_nonconvex_qp.jl:39)."""
@@ -164,6 +172,22 @@ class NormLpPowerNonneg:
 class NonsmoothCostObstacleL1:
     """demo/obstacle.jl:64-81."""
     g_kind = K.G_OBSTACLE_L1
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
+class NonsmoothCostObstacleL2:
+    """demo/obstacle.jl:49-62: max(0, x) on all three blocks, then the complementarity zeroing; value 0."""
+    g_kind = K.G_OBSTACLE_L2
+
+    def __init__(self, N):
+        self.N = int(N)
+
+
+class NonsmoothCostObstacleL2Red:
+    """demo/obstacle.jl:121-126: max(0, x), value 0 (the same prox as demo/mpvca.jl's NonsmoothCostMPVCA)."""
+    g_kind = K.G_NONNEG
 
     def __init__(self, N):
         self.N = int(N)

@@ -45,7 +45,8 @@ typedef enum { /* smooth cost f: f(x), gradient!(dfx,f,x)->fx */
     BZ_F_ROSENBROCK = 3,    /* demo/rosenbrock.jl:39-50 (f_p[0] = w) */
     BZ_F_SQDIST2 = 4,       /* demo/eitheror.jl:58-68 SmoothCostOR (f_p[0..1] = c) */
     BZ_F_LINEAR2 = 5,       /* demo/mpvca.jl:77-87 SmoothCostMPVCA (f_p[0..1] = c) */
-    BZ_F_OBSTACLE_L1 = 6    /* demo/obstacle.jl:37-47 SmoothCostObstacleL1 */
+    BZ_F_OBSTACLE_L1 = 6,   /* demo/obstacle.jl:37-47 SmoothCostObstacleL1 */
+    BZ_F_OBSTACLE_L2 = 7    /* demo/obstacle.jl:21-35 SmoothCostObstacleL2: 0.5||x[1:2N]||^2 - sum(x2), dfx = [x1; x2 - 1; 0] */
 } bz_f_kind;
 
 typedef enum { /* nonsmooth cost g: prox!(z,g,x,gamma)->g(z) */
@@ -61,7 +62,9 @@ typedef enum { /* nonsmooth cost g: prox!(z,g,x,gamma)->g(z) */
     BZ_G_OBSTACLE_L1 = 9,   /* demo/obstacle.jl:64-81 */
     BZ_G_NORMLP_BOX = 10,   /* src/proxoperators/normLpBox.jl:37-97: alpha*sum x^p on [0,u], g_lambda = alpha, g_lo = p */
     BZ_G_NORMLP_NONNEG = 11, /* src/proxoperators/normLpNonneg.jl:36-90: alpha*sum x^p on x >= 0, g_lambda = alpha, g_lo = p */
-    BZ_G_OBSTACLE_RED_L1 = 12 /* demo/obstacle.jl:83-91 NonsmoothCostObstacleRedL1 (nx = 2N) */
+    BZ_G_OBSTACLE_RED_L1 = 12, /* demo/obstacle.jl:83-91 NonsmoothCostObstacleRedL1 (nx = 2N) */
+    BZ_G_OBSTACLE_L2 = 13   /* demo/obstacle.jl:49-62 NonsmoothCostObstacleL2: max(0, x), then the complementarity zeroing; value 0.
+                             * (obstacle_l2red's NonsmoothCostObstacleL2Red, :121-126, is max(0, x): BZ_G_NONNEG) */
 } bz_g_kind;
 
 typedef enum { /* constraint function c: eval!(cx,c,x), jtprod!(jtv,c,x,v) */

@@ -415,6 +415,24 @@ class GObstacleL1:
         return float(np.sum(y[:N]))
 
 
+class GObstacleL2:
+    """demo/obstacle.jl:49-62 NonsmoothCostObstacleL2: y = max(0, x); per i: block 2 > block 3 zeroes block 3, else
+    (tie included) zeroes block 2; returns 0."""
+
+    def __init__(self, N):
+        self.N = N
+
+    def prox(self, y, x, gamma):
+        N = self.N
+        y[:] = np.maximum(0.0, x)
+        a = y[N : 2 * N].copy()
+        b = y[2 * N : 3 * N].copy()
+        gt = a > b
+        y[2 * N : 3 * N] = np.where(gt, 0.0, b)
+        y[N : 2 * N] = np.where(gt, a, 0.0)
+        return 0.0
+
+
 # ----------------------------------------------------------------------------------------------
 # Smooth costs f:  f(x), gradient!(dfx, f, x) -> f(x)
 # ----------------------------------------------------------------------------------------------
@@ -523,6 +541,24 @@ class FObstacleL1:
     def gradient(self, dfx, x):
         N = self.N
         dfx[:] = 0.0
+        dfx[N : 2 * N] = x[N : 2 * N] - 1.0
+        return self.value(x)
+
+
+class FObstacleL2:
+    """demo/obstacle.jl:21-35 SmoothCostObstacleL2: 0.5*norm(x[1:2N])^2 - sum(x[N+1:2N]); dfx = [x1; x2 - 1; 0]."""
+
+    def __init__(self, N):
+        self.N = N
+
+    def value(self, x):
+        N = self.N
+        return 0.5 * float(np.linalg.norm(x[: 2 * N])) ** 2 - float(np.sum(x[N : 2 * N]))
+
+    def gradient(self, dfx, x):
+        N = self.N
+        dfx[:] = 0.0
+        dfx[:N] = x[:N]
         dfx[N : 2 * N] = x[N : 2 * N] - 1.0
         return self.value(x)
 
@@ -683,6 +719,15 @@ def problem_obstacle_red(N, grid=None):
                 nx=2 * N, ny=2 * N,
                 kw=dict(subsolver_maxit=1_000_000,
                         subsolver=PanocOptions(minimum_gamma=EPS, maxit=1_000_000)))
+
+
+def problem_obstacle_l2(N, grid=None, red=False):
+    """demo/obstacle.jl:212-225: 'obstacle_l2' (nx = 3N, ny = N, D = {0}) and 'obstacle_l2red' (nx = ny = 2N, g = max(0, x),
+    D = SetObstacleRed)."""
+    kw = dict(subsolver_maxit=1_000_000, subsolver=PanocOptions(minimum_gamma=EPS, maxit=1_000_000))
+    if red:
+        return dict(f=FObstacleL2(N), g=GNonneg(), c=CObstacleRed(N, grid), D=PairSet("cc", stride=N), nx=2 * N, ny=2 * N, kw=kw)
+    return dict(f=FObstacleL2(N), g=GObstacleL2(N), c=CObstacle(N, grid), D=ZeroSet(), nx=3 * N, ny=N, kw=kw)
 
 
 class AugLagFun:

@@ -837,3 +837,54 @@ def test_portfolio_demo_solves_match_oracle(gpu_ctx):
         assert out[2] == r.tot_it == 2 and out[3] == r.tot_inner_it and out[5] == r.status == "max_iter", gname
         assert np.max(np.abs(out[0] - r.x)) <= 1e-9 and np.max(np.abs(out[1] - r.y)) <= 1e-7 * (1 + np.max(np.abs(r.y))), gname
         assert np.max(np.abs(out[8] - r.s)) <= 1e-8 and np.array_equal(out[9], r.mu), gname
+
+
+@pytest.mark.parametrize("red,grid", [(False, None), (False, (12, 20)), (True, None), (True, (9, 14))])
+def test_obstacle_l2_variants(gpu_ctx, red, grid):
+    """demo/obstacle.jl:21-35,49-62,121-126,212-225: 'obstacle_l2' (f adds 0.5||x1||^2, g has no threshold on block 1
+    and value 0) and 'obstacle_l2red' (g = max(0, x), D = complementarity pairs).  AL-gradient and prox elementwise
+    outputs bit for bit, the sums to 1e-12; a bounded solve from the demo's start follows the oracle."""
+    N = 40 if grid is None else grid[0] * grid[1]
+    nx, ny = (2 * N, 2 * N) if red else (3 * N, N)
+    if red:
+        f, g, c, D = bz.SmoothCostObstacleL2(N), bz.NonsmoothCostObstacleL2Red(N), bz.ConstraintObstacleRed(N, grid), bz.PairSet("cc", stride=N)
+    else:
+        f, g, c, D = bz.SmoothCostObstacleL2(N), bz.NonsmoothCostObstacleL2(N), bz.ConstraintObstacle(N, grid), bz.ZeroSet()
+    P = bo.problem_obstacle_l2(N, grid, red)
+    p = bz.Problem(f, g, c, D, ctx=gpu_ctx)
+    rng = np.random.default_rng(6)
+    x, mu, y = rng.standard_normal(nx), rng.uniform(0.1, 2.0, ny), rng.standard_normal(ny)
+    p.auglag_update(mu, y)
+    gr = p.gradient(x)
+    al = bo.AugLagFun(P["f"], P["c"], P["D"], mu.copy(), y.copy(), x)
+    dl = np.empty(nx)
+    lx = al.gradient(dl, x)
+    assert np.array_equal(gr["cx"], al.cx) and np.array_equal(gr["s"], al.s) and np.array_equal(gr["yupd"], al.yupd)
+    assert np.array_equal(gr["dlx"], dl)
+    assert abs(gr["lx"] - lx) <= KTOL * (abs(lx) + 1) and abs(gr["fx"] - P["f"].value(x)) <= KTOL * (abs(P["f"].value(x)) + N)
+    z, gz = p.prox(x, 0.3)
+    zo = np.empty(nx)
+    gzo = P["g"].prox(zo, x, 0.3)
+    assert np.array_equal(z, zo) and gz == gzo == 0.0
+    if not red:
+        assert np.all((z[N:2 * N] == 0) | (z[2 * N:] == 0))        # complementarity after the prox
+    p.close()
+    if grid is None:
+        Ns = 16
+        Ps = bo.problem_obstacle_l2(Ns, None, red)
+        nxs, nys = Ps["nx"], Ps["ny"]
+        if red:
+            fs, gs_, cs, Ds = bz.SmoothCostObstacleL2(Ns), bz.NonsmoothCostObstacleL2Red(Ns), bz.ConstraintObstacleRed(Ns), bz.PairSet("cc", stride=Ns)
+        else:
+            fs, gs_, cs, Ds = bz.SmoothCostObstacleL2(Ns), bz.NonsmoothCostObstacleL2(Ns), bz.ConstraintObstacle(Ns), bz.ZeroSet()
+        # two outer iterations of 12 inner iterations: before summation-order differences in the scalar reductions
+        # (1e-16 per step, amplified by the line searches) can grow -- the obstacle solves are long and chaotic (SURVEY §8d)
+        sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=12, minimum_gamma=bo.EPS)
+        out = bz.alps(fs, gs_, cs, Ds, 2.0 * np.ones(nxs), np.zeros(nys), tol=1e-3, maxit=2, subsolver=sub, ctx=gpu_ctx)
+        r = bo.alps(Ps["f"], Ps["g"], Ps["c"], Ps["D"], 2.0 * np.ones(nxs), np.zeros(nys), tol=1e-3, maxit=2,
+                    subsolver=bo.PanocOptions(minimum_gamma=bo.EPS, maxit=12))
+        dx, dy = np.max(np.abs(out[0] - r.x)), np.max(np.abs(out[1] - r.y)) / (1 + np.max(np.abs(r.y)))
+        assert out[2] == r.tot_it and out[3] == r.tot_inner_it and out[5] == r.status, (out[2:6], r.tot_it, r.tot_inner_it)
+        assert dx <= 1e-6 and dy <= 1e-6, (dx, dy)
+    with pytest.raises(bz.BazingaError):      # the L2 cost does not go with the L1 prox in the catalogue
+        bz.Problem(bz.SmoothCostObstacleL2(8), bz.NonsmoothCostObstacleL1(8), bz.ConstraintObstacle(8), bz.ZeroSet(), ctx=gpu_ctx)

@@ -262,3 +262,29 @@ def test_portfolio_oracles_and_als_solves():
     with np.errstate(all="ignore"):
         r = bo.als(P["f"], P["g"], P["c"], P["D"], res["lp"].x, res["lp"].y, **P["kw"])     # Lp + L0, portfolio.jl:170-173
     assert r.status == "first_order" and (r.x > 0).sum() <= (res["lp"].x > 0).sum()
+
+
+def test_obstacle_l2_oracles():
+    """demo/obstacle.jl:21-35 (SmoothCostObstacleL2), :49-62 (NonsmoothCostObstacleL2): gradient matches finite
+    differences of the value, the prox is max(0, .) followed by the complementarity zeroing (tie zeroes block 2) and
+    returns 0; a small obstacle_l2 solve ends first-order with complementary blocks 2 and 3."""
+    N = 7
+    rng = np.random.default_rng(3)
+    f = bo.FObstacleL2(N)
+    x = rng.standard_normal(3 * N)
+    d = np.empty(3 * N)
+    fx = f.gradient(d, x)
+    assert abs(fx - (0.5 * np.sum(x[:2 * N] ** 2) - np.sum(x[N:2 * N]))) <= 1e-12 * (1 + abs(fx))
+    for j in (0, N + 2, 2 * N + 1):
+        e = np.zeros(3 * N); e[j] = 1e-6
+        assert abs((f.value(x + e) - f.value(x - e)) / 2e-6 - d[j]) <= 1e-6
+    g = bo.GObstacleL2(N)
+    xin = np.concatenate([rng.standard_normal(N), [1.0, 2.0, -1.0, 0.5, 0.5, 3.0, -2.0], [2.0, 1.0, 4.0, 0.5, -1.0, -3.0, -5.0]])
+    z = np.empty(3 * N)
+    assert g.prox(z, xin, 0.7) == 0.0
+    assert np.array_equal(z[:N], np.maximum(0, xin[:N]))
+    assert z[N:2 * N].tolist() == [0.0, 2.0, 0.0, 0.0, 0.5, 3.0, 0.0] and z[2 * N:].tolist() == [2.0, 0.0, 4.0, 0.5, 0.0, 0.0, 0.0]
+    P = bo.problem_obstacle_l2(8)
+    r = bo.alps(P["f"], P["g"], P["c"], P["D"], 2.0 * np.ones(24), np.zeros(8), tol=1e-4, **P["kw"])
+    assert r.status == "first_order" and r.norm_res_prim <= 1e-4
+    assert np.all((r.x[8:16] == 0) | (r.x[16:] == 0)) and np.all(r.x >= 0)
