@@ -292,11 +292,17 @@ template <int KIND, int SLACK> struct Al {
         Prob<KIND>::proj(yupd, s);
 #pragma unroll
         for (int i = 0; i < NY; ++i) yupd[i] -= s[i];
+        // sum((yupd.^2) ./ mu) and yupd ./= mu (auglagfun.jl:78-79) in one sweep.  On an inactive constraint t = +-0 (three
+        // times in four): (+0)/mu adds nothing to a sum that is never -0, and t/mu = t for mu > 0 -- one test instead of
+        // two divisions (rmu > 0 says mu is positive, finite and not NaN; anything else takes the division).
 #pragma unroll
-        for (int i = 0; i < NY; ++i) acc += fdiv(yupd[i] * yupd[i], mu[i], rmu[i]);
+        for (int i = 0; i < NY; ++i) {
+            const double t = yupd[i];
+            if (t == 0.0 && rmu[i] > 0.0) continue;
+            acc += fdiv(t * t, mu[i], rmu[i]);
+            yupd[i] = fdiv(t, mu[i], rmu[i]);
+        }
         double lx = 0.5 * acc;
-#pragma unroll
-        for (int i = 0; i < NY; ++i) yupd[i] = fdiv(yupd[i], mu[i], rmu[i]);
         fx = Prob<KIND>::f_grad(x, dfx);
         lx += fx;
         lx -= musqy;
