@@ -421,6 +421,8 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     const double Lest = sqrt(dotn<NV>(df, df)) / sqrt((double)NV);
     double gamma = a / Lest;
     double rg = frecip(gamma);   // 1/gamma, kept exact through the halvings (see fdiv)
+    double aog = a / gamma;      // alpha/gamma for f_model: halving gamma doubles the correctly rounded quotient exactly
+                                 // (while it is a normal number: otherwise it is divided afresh)
 #pragma unroll
     for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
     double g_z = al.prox(y, gamma, z);
@@ -429,17 +431,19 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     Lbfgs<MM, NV> H;
     H.M = o.mem;
     H.reset();
-    double f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
+    double f_up = f_model<NV>(f_x, grad_x, res, aog);
     double f_z = al.gradient(z, grad_z);
     while (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
         gamma /= 2;
         rg *= 2;
+        aog *= 2;
+        if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
 #pragma unroll
         for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
         g_z = al.prox(y, gamma, z);
 #pragma unroll
         for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
-        f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
+        f_up = f_model<NV>(f_x, grad_x, res, aog);
         f_z = al.gradient(z, grad_z);
     }
     double tau = 1.0;
@@ -456,7 +460,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
-        const double FBE_x = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg)) + g_z;
+        const double FBE_x = f_model<NV>(f_x, grad_x, res, aog) + g_z;
         double nres[NV];
 #pragma unroll
         for (int j = 0; j < NV; ++j) nres[j] = -res[j];
@@ -476,11 +480,13 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
             g_z = al.prox(y, gamma, z);
 #pragma unroll
             for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
-            f_up = f_model<NV>(f_x, grad_x, res, fdiv(a, gamma, rg));
+            f_up = f_model<NV>(f_x, grad_x, res, aog);
             f_z = al.gradient(z, grad_z);
             if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
                 gamma *= 0.5;
                 rg *= 2;
+                aog *= 2;
+                if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
                 H.reset();
                 continue;
             }
