@@ -238,14 +238,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
 }
 
 int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) {
-    static bool attr_set = false;
+    static BzOncePerDevice once;
     const size_t smem = (size_t)DA_RING_DOUBLES * 8 + DA_MAXSLOTS * 8 + 32 * 8 + 4 * 8 + 2 * 8;
-    if (!attr_set) {
+    if (once.first(ctx->device)) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_dense_algrad<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
 int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs,
                     const BzGParams& g, double* part, unsigned int* counter, int force_mode) {
     const long long items = (g.kind == BZ_G_OBSTACLE_L1 || g.kind == BZ_G_OBSTACLE_L2) ? g.N : v.n;
-    static bool once = false;
-    if (!once) { prefer_max_smem(k_fstep<false, 1>); prefer_max_smem(k_fstep<false, 4>); prefer_max_smem(k_fstep<true, 1>); once = true; }
+    static BzOncePerDevice once;
+    if (once.first(ctx->device)) { prefer_max_smem(k_fstep<false, 1>); prefer_max_smem(k_fstep<false, 4>); prefer_max_smem(k_fstep<true, 1>); }
     if (bz_g_is_heavy(g.kind))
         return bz_launch_pdl(ctx, k_fstep<true, 1>, dim3(fbd_grid(ctx, gs, items)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, g,
                              part, counter, force_mode);
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
 
 int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
                     unsigned int* counter) {
-    static bool once = false;
-    if (!once) { prefer_max_smem(k_dstep); once = true; }
+    static BzOncePerDevice once;
+    if (once.first(ctx->device)) prefer_max_smem(k_dstep);
     return bz_launch_pdl(ctx, k_dstep, dim3(fbd_grid(ctx, gs, v.n)), dim3(BZ_VEC_THREADS), 0, 0, st, v, gs, part,
                          counter);
 }

@@ -417,13 +417,12 @@ static int launch_variant(bz_ctx* ctx, const BzDenseArgs& a, const BzGridGeom& g
     static_assert(CH >= 2 && CH <= 8 && (CH & (CH - 1)) == 0, "wsum holds 8 warp partials per row");
     static_assert(XW <= 16, "lxs holds 16 partials");
     if (g.W > NCH * 64 * CH) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "grid-wide dense pass: slice wider than the variant");
-    static bool attr_set = false;
+    static BzOncePerDevice once;
     static int resident_per_sm = 0;
-    if (!attr_set) {
+    if (once.first(ctx->device)) {
         BZ_CUDA(ctx, cudaFuncSetAttribute(k_grid_algrad<CH, NCH, XW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES));
         BZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident_per_sm, k_grid_algrad<CH, NCH, XW, RB>,
                                                                    (2 * CH + XW + 1) * 32, GR_SMEM_BYTES));
-        attr_set = true;
     }
     // the CTAs of a team wait for each other: the whole grid has to be resident at once
     if ((long long)g.GS * g.T > (long long)resident_per_sm * ctx->num_sms)

@@ -457,6 +457,18 @@ struct bz_ctx {
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);
 
+// Function attributes (dynamic shared memory limit, carve-out) are per DEVICE: a launcher configures its kernels the
+// first time it runs on each device of the process, not once per process.
+struct BzOncePerDevice {
+    unsigned long long mask = 0;
+    bool first(int dev) {
+        const unsigned long long b = 1ULL << (dev & 63);
+        if (mask & b) return false;
+        mask |= b;
+        return true;
+    }
+};
+
 // Programmatic dependent launch (PDL): the kernels of the PANOC+ cycle are launched with
 // programmatic stream serialization, so the next kernel's CTAs are scheduled while the previous
 // kernel drains; each such kernel starts with bz_pdl_wait() (griddepcontrol.wait: everything the

@@ -515,12 +515,11 @@ __global__ void __launch_bounds__(LC_THREADS)
 int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
                     unsigned int* counter, int force_role) {
     const long long per_cta = (long long)LC_THREADS * LC_EPT;
-    static bool once = false;
-    if (!once) {   // same carve-out as the dense passes: no SM reconfiguration inside the cycle
+    static BzOncePerDevice once;
+    if (once.first(ctx->device)) {   // same carve-out as the dense passes: no SM reconfiguration inside the cycle
         cudaFuncSetAttribute(k_lstep_cluster<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_lstep_cluster<LC_EPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_lstep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        once = true;
     }
     if (v.n <= per_cta * LC_MAXCS && !ctx->slab_mode) {   // (slab mode: only the cooperative kernel exchanges across ranks)
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible

@@ -888,3 +888,26 @@ def test_obstacle_l2_variants(gpu_ctx, red, grid):
         assert dx <= 1e-6 and dy <= 1e-6, (dx, dy)
     with pytest.raises(bz.BazingaError):      # the L2 cost does not go with the L1 prox in the catalogue
         bz.Problem(bz.SmoothCostObstacleL2(8), bz.NonsmoothCostObstacleL1(8), bz.ConstraintObstacle(8), bz.ZeroSet(), ctx=gpu_ctx)
+
+
+def test_two_devices_in_one_process():
+    """One host process, one context per device ('a ctx is bound to its device'): kernel attributes
+    (dynamic shared memory limit of the dense kernels) are per device, so the second device must be configured too.
+    The same solve on both devices gives the same bits.  Needs 2 GPUs (skipped on a 1-GPU box)."""
+    import ctypes
+    from bazinga_b200 import _capi as K
+    n = ctypes.c_int(0)
+    K.load_library().bz_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs 2 GPUs in one box")
+    A, _, b = bo.make_basis_pursuit(64, 512, seed=2)
+    outs = []
+    for dev in (0, 1):
+        ctx = bz.Context(dev)
+        sub = bz.PANOCplus(directions=bz.LBFGS(5), maxit=100_000, minimum_gamma=bo.EPS)
+        outs.append(bz.alps(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(512), np.zeros(64),
+                            tol=1e-6, subsolver=sub, subsolver_maxit=100_000, ctx=ctx))
+        X0 = np.array([[1.0, 2.0], [5.0, 1.5], [-3.0, 7.0]])
+        outs[-1] = outs[-1] + (bz.alps_batch("mpvca", X0, ctx=ctx)["x"],)
+    assert outs[0][5] == outs[1][5] == "first_order"
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][3] == outs[1][3] and np.array_equal(outs[0][-1], outs[1][-1])
