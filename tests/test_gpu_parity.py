@@ -911,3 +911,27 @@ def test_two_devices_in_one_process():
         outs[-1] = outs[-1] + (bz.alps_batch("mpvca", X0, ctx=ctx)["x"],)
     assert outs[0][5] == outs[1][5] == "first_order"
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][3] == outs[1][3] and np.array_equal(outs[0][-1], outs[1][-1])
+
+
+def test_widened_rows_against_committed_golden(gpu_ctx):
+    """The CUDA path against tests/golden/oracle_golden_widen.json (committed; written by make_golden_widen.py):
+    obstacle_l2 AL-gradient and prox (elementwise: bit for bit; the value to 1e-12) and the Lp prox sweep (pow: 1e-10)."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden_widen.json")) as fh:
+        gold = json.load(fh)
+    N = 6
+    x = np.linspace(-1.0, 2.0, 3 * N)
+    p = bz.Problem(bz.SmoothCostObstacleL2(N), bz.NonsmoothCostObstacleL2(N), bz.ConstraintObstacle(N), bz.ZeroSet(), ctx=gpu_ctx)
+    p.auglag_update(np.linspace(0.2, 1.5, N), np.linspace(-1.0, 1.0, N))
+    g = p.gradient(x)
+    go = gold["obstacle_l2_N6"]
+    assert np.array_equal(g["dlx"], np.array(go["dlx"])) and abs(g["lx"] - go["lx"]) <= KTOL * abs(go["lx"])
+    z, gz = p.prox(x, 0.25)
+    assert np.array_equal(z, np.array(go["prox"])) and gz == 0.0
+    p.close()
+    gl = gold["lp_prox"]
+    xs = np.array(gl["x"])
+    p = bz.Problem(bz.Zero(), bz.NormLpPowerBox(0.5, 0.3, u=np.full(13, 0.9)), bz.IdentityFunction(), bz.FreeSet(), nx=13, ny=13, ctx=gpu_ctx)
+    z, gz = p.prox(xs, 0.4)
+    assert np.max(np.abs(z - np.array(gl["z"]))) <= 1e-10 and abs(gz - gl["g"]) <= 1e-10
+    p.close()

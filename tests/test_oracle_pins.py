@@ -288,3 +288,28 @@ def test_obstacle_l2_oracles():
     r = bo.alps(P["f"], P["g"], P["c"], P["D"], 2.0 * np.ones(24), np.zeros(8), tol=1e-4, **P["kw"])
     assert r.status == "first_order" and r.norm_res_prim <= 1e-4
     assert np.all((r.x[8:16] == 0) | (r.x[16:] == 0)) and np.all(r.x >= 0)
+
+
+def test_golden_fixtures_widened_rows_frozen():
+    """tests/golden/oracle_golden_widen.json (written by make_golden_widen.py): the synthetic portfolio data set, an Lp
+    portfolio solve, the obstacle_l2 AL-gradient / prox and an Lp prox sweep, recomputed and compared."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_widen", os.path.join(HERE, "golden", "make_golden_widen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(HERE, "golden", "oracle_golden_widen.json")) as fh:
+        gold = json.load(fh)
+    now = mod.build()
+    gp, npf = gold["portfolio40"], now["portfolio40"]
+    for k in ("Q_row0", "mu", "ub"):
+        assert np.array_equal(np.array(gp[k]), np.array(npf[k])), k      # counter-based generator: the same bits everywhere
+    assert gp["rho"] == npf["rho"] and abs(gp["Q_trace"] - npf["Q_trace"]) <= 1e-12 * gp["Q_trace"]
+    assert gp["lp"]["status"] == npf["lp"]["status"] == "first_order" and gp["lp"]["tot_it"] == npf["lp"]["tot_it"]
+    assert abs(gp["lp"]["tot_inner_it"] - npf["lp"]["tot_inner_it"]) <= 0.1 * gp["lp"]["tot_inner_it"] + 5
+    assert gp["lp"]["nnz"] == npf["lp"]["nnz"] and abs(gp["lp"]["objective_q"] - npf["lp"]["objective_q"]) <= 1e-6 * gp["lp"]["objective_q"]
+    assert np.max(np.abs(np.array(gp["lp"]["x"]) - np.array(npf["lp"]["x"]))) <= 1e-6
+    go, no = gold["obstacle_l2_N6"], now["obstacle_l2_N6"]
+    assert abs(go["lx"] - no["lx"]) <= 1e-12 * abs(go["lx"]) and np.max(np.abs(np.array(go["dlx"]) - np.array(no["dlx"]))) <= 1e-12
+    assert np.array_equal(np.array(go["prox"]), np.array(no["prox"]))
+    assert np.max(np.abs(np.array(gold["lp_prox"]["z"]) - np.array(now["lp_prox"]["z"]))) <= 1e-12
+    assert abs(gold["lp_prox"]["g"] - now["lp_prox"]["g"]) <= 1e-12
