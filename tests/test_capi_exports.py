@@ -84,3 +84,21 @@ def test_product_never_imports_the_oracle():
             assert not re.search(r'#include\s+["<][^">]*oracle', txt), path
         elif os.path.basename(path) == "Makefile":
             assert "oracle" not in txt, path
+
+
+def test_catalogue_enums_match_the_python_mirror():
+    """Every enumerator of bz_f_kind / bz_g_kind / bz_c_kind / bz_d_kind in include/bazinga_b200.h has the same value
+    in bazinga_b200._capi (the numbers cross the C ABI inside bz_problem_desc)."""
+    import re
+    from bazinga_b200 import _capi as K
+    text = open(os.path.join(ROOT, "include", "bazinga_b200.h")).read()
+    found = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\bBZ_([FGCD]_[A-Z0-9_]+)\s*=\s*(\d+)", text))
+    assert len(found) >= 8 + 14 + 7 + 8
+    missing = []
+    for name, val in found.items():
+        py = name
+        if not hasattr(K, py):
+            missing.append(name)
+            continue
+        assert getattr(K, py) == val, (name, val, getattr(K, py))
+    assert not missing, missing
