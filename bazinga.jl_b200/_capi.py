@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbazinga_b200.so")
 
-BZ_ABI_VERSION = 3
+BZ_ABI_VERSION = 4
 
 # enums (include/bazinga_b200.h)
 F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1, F_OBSTACLE_L2 = range(8)
@@ -51,6 +51,7 @@ class Options(C.Structure):
         ("alpha", C.c_double), ("beta", C.c_double), ("minimum_gamma", C.c_double),
         ("max_backtracks", C.c_int32), ("lbfgs_memory", C.c_int32),
         ("sub_maxit", C.c_int64), ("max_inner_total", C.c_int64), ("verbose", C.c_int32),
+        ("dual_safeguard", C.c_void_p), ("dual_safeguard_user", C.c_void_p),
     ]
 
 
@@ -62,6 +63,7 @@ class Result(C.Structure):
         ("n_launches", C.c_int64), ("dominant_kernel_ms", C.c_double),
         ("dominant_kernel_launches", C.c_int64),
         ("kind_ms", C.c_double * 4), ("kind_launches", C.c_int64 * 4),
+        ("mu0_min", C.c_double), ("mu0_max", C.c_double), ("inner_tol0", C.c_double),
     ]
 
 
@@ -106,7 +108,11 @@ SYMBOLS = {
     "bz_comm_unique_id": (C.c_int, [_vp]),
     "bz_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "bz_comm_destroy": (C.c_int, [_vp]),
+    "bz_comm_bench_allreduce": (C.c_int, [_vp, C.c_int64, C.c_int, _dp]),
 }
+
+# alps.jl:23,62: dual_safeguard(y, cx) as a host callback (see bz_options.dual_safeguard)
+DUAL_SAFEGUARD_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_void_p)
 
 
 class BazingaError(RuntimeError):

@@ -85,6 +85,31 @@ int bz_comm_allreduce(bz_ctx* ctx, double* dev_buf, long long count, int op) {
     return BZ_OK;
 }
 
+extern "C" int bz_comm_bench_allreduce(bz_ctx* ctx, int64_t count, int reps, double* us_per_call) {
+    if (!ctx || !us_per_call || count < 1 || reps < 1) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->nccl_comm) return bz_fail(ctx, BZ_ERR_COMM, "communicator not initialised");
+    double* buf = nullptr;
+    BZ_CUDA(ctx, cudaMalloc((void**)&buf, (size_t)count * sizeof(double)));
+    cudaMemsetAsync(buf, 0, (size_t)count * sizeof(double), ctx->stream);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = BZ_OK;
+    for (int i = 0; i < 3 && rc == BZ_OK; ++i) rc = bz_comm_allreduce(ctx, buf, count, BZ_COMM_SUM);   // warm-up
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < reps && rc == BZ_OK; ++i) rc = bz_comm_allreduce(ctx, buf, count, BZ_COMM_SUM);
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (rc != BZ_OK) return rc;
+    if (e != cudaSuccess) return bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e));
+    *us_per_call = 1e3 * (double)ms / reps;
+    return BZ_OK;
+}
+
 int bz_shard_alloc(bz_ctx* ctx, BzShard* sh, long long n) {
     sh->n = n;
     BZ_CUDA(ctx, cudaMalloc((void**)&sh->reduced, (size_t)(n + 8) * sizeof(double)));

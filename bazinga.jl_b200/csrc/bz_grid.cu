@@ -31,7 +31,10 @@
 //
 // Co-residency: the grid is <= the number of SMs at 1 CTA/SM and CTAs spin on global memory only after
 // griddepcontrol.wait has returned (the predecessor grid has completed), so every CTA of this grid can
-// be scheduled; dependents are released only once every CTA has started.
+// be scheduled; dependents are released only once every CTA has started.  This holds on a device the process
+// has to itself (the stated requirement, include/bazinga_b200.h); if another tenant (a second context, MPS)
+// holds SMs, part of a team may never start: every cross-CTA wait is bounded by GR_TIMEOUT_NS, after which
+// the launch drains with BzState::err_flag = 4 and the solve returns BZ_ERR_CUDA instead of hanging.
 #include "bz_internal.cuh"
 #include "bz_dense.cuh"
 #include "bz_ptx.cuh"
@@ -40,6 +43,7 @@
 #define GR_PRING 32         // ring of per-row warp-partial sets / published w values (>= GR_MAXSLOTS)
 #define GR_DRING 256        // rows of the global exchange ring
 #define GR_RING_DOUBLES 28624   // 223.6 KB of row slices (16 slots of the C5 slice width 1772)
+#define GR_TIMEOUT_NS 4000000000ULL   // bound on every cross-CTA wait of the exchange (see the exchange warps)
 #define GR_SHARDS 16        // arrival-counter shards per ring position (same-address L2 atomics serialise at ~27 cycles each)
 #define GR_SMEM_BYTES (GR_RING_DOUBLES * 8 + 2 * GR_MAXSLOTS * 8 + 2 * GR_PRING * 8 + GR_PRING * 8 * 8 + GR_PRING * 8 + 16 * 8)
 
@@ -246,6 +250,8 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
         // ------------------------------------------------------------------ exchange warps
         const int e = warp - 2 * CH;
         double lx = 0.0;
+        bool dead = false;
+        const unsigned long long t_start = bz_globaltimer();
         for (int j = e; j < m; j += XW) {
             const double b_j = __ldg(a.b + r0 + j), mu_j = __ldg(a.mu + r0 + j), muy_j = __ldg(a.muy + r0 + j);
             const int pr = j % GR_PRING;
@@ -272,22 +278,28 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
             // The arrival counters are only a HINT that keeps 148 x XW warps from hammering L2 with gather
             // rounds: correctness rests on the self-validating tags below.  CTA c counts on shard c % nshards
             // (same-address L2 atomics from 148 CTAs serialise at ~27 cycles each: 4000 cycles unsharded).
-            if (lane < nshards) {
+            // Every wait on another CTA is bounded (GR_TIMEOUT_NS): a team that is not fully resident -- another tenant
+            // holds SMs of this device -- sets err_flag = 4 and the launch drains instead of spinning forever
+            // (the host then returns BZ_ERR_CUDA).  Once a warp has timed out it stops waiting altogether.
+            if (lane < nshards && !dead) {
                 const unsigned long long* cnt = Dcnt + ((size_t)pos * nshards + lane) * 32;
                 const unsigned long long want = (sq / GR_DRING + 1ULL) * (unsigned long long)((G - lane + nshards - 1) / nshards);
                 unsigned long long have;
+                unsigned int spins = 0;
                 do {
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(have) : "l"(cnt) : "memory");
+                    if (have < want && (++spins & 255u) == 0u && bz_globaltimer() - t_start > GR_TIMEOUT_NS) { dead = true; break; }
                 } while (have < want);
             }
-            __syncwarp();
+            dead = __any_sync(0xffffffffu, dead);
             // gather the G slice dots: lane l owns CTAs l, l+32, ...; all loads of a round are issued
             // before the first is inspected; only entries that failed validation are re-read
             constexpr int NQ = 5;   // G <= 160
             unsigned long long w0[NQ], w1[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q) { w0[q] = ~tag; w1[q] = ~tag; }
-            bool pending = true;
+            bool pending = !dead;
+            unsigned int rounds = 0;
             while (pending) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
@@ -299,7 +311,10 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
                     pending |= (((w0[q] ^ tag) | (w1[q] ^ tag)) >> 32) != 0;
+                if (pending && (++rounds & 255u) == 0u && bz_globaltimer() - t_start > GR_TIMEOUT_NS) { dead = true; break; }
             }
+            dead = __any_sync(0xffffffffu, dead);
+            if (dead && lane == 0) a.st->err_flag = 4;
             double sum = 0.0;
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
@@ -363,6 +378,10 @@ __global__ void __launch_bounds__((2 * CH + XW + 1) * 32, 1)
             if (a.set_after) {
                 a.st->next_op = a.st->after_g;
                 if (a.force_target < 0) bz_toc(a.st, 0);
+            }
+            if (a.st->err_flag == 4) {   // a bounded wait expired: stop the state machine, the host reports the error
+                a.st->next_op = OP_DONE;
+                a.st->inner_status = IST_MAXIT;
             }
             __threadfence();
         }

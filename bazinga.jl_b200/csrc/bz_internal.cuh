@@ -446,7 +446,8 @@ struct bz_ctx {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
-    int slab_mode = 0;          // a slab-decomposed problem lives on this context (cross-rank exchanges in the kernels)
+    void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
+    size_t xpose_bytes = 0;
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu

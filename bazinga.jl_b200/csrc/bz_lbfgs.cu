@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(LC_THREADS)
 }
 
 int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
-                    unsigned int* counter, int force_role) {
+                    unsigned int* counter, int force_role, bool slab) {
     const long long per_cta = (long long)LC_THREADS * LC_EPT;
     static BzOncePerDevice once;
     if (once.first(ctx->device)) {   // same carve-out as the dense passes: no SM reconfiguration inside the cycle
@@ -521,7 +521,7 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
         cudaFuncSetAttribute(k_lstep_cluster<LC_EPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_lstep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    if (v.n <= per_cta * LC_MAXCS && !ctx->slab_mode) {   // (slab mode: only the cooperative kernel exchanges across ranks)
+    if (v.n <= per_cta * LC_MAXCS && !slab) {   // (slab mode: only the cooperative kernel exchanges across ranks)
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
         while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;

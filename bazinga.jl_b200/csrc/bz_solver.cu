@@ -16,7 +16,7 @@
 #include <cstring>
 #include <cstdlib>
 
-static std::string g_last_error;
+static thread_local std::string g_last_error;   // bz_last_error(NULL): per host thread
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -46,8 +46,10 @@ struct bz_problem {
     int c_clusters = 0, c_rpc = 0, f_clusters = 0, f_rpc = 0, nlx = 0, nfx = 0, nfx2 = 0;
     bool c_wide = false, f_wide = false;   // wide path (nx > 16384)
     bool c_grid = false, f_grid = false;   // ... served by the grid-wide single-pass kernel (bz_grid.cu)
-    unsigned long long* gridD = nullptr;   // its exchange ring and tag sequence base
+    unsigned long long* gridD = nullptr;   // its exchange ring and tag sequence base (constraint pass)
     unsigned long long* gseq = nullptr;
+    unsigned long long* gridD_f = nullptr; // ... of the LeastSquares pass
+    unsigned long long* gseq_f = nullptr;
     int c_nlx = 0, f_nlx = 0;              // lx partial counts of the dense passes
     double* part = nullptr;
     unsigned int* counters = nullptr;   // [8]
@@ -134,6 +136,7 @@ extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
     bz_comm_destroy(ctx);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->batch_arena) cudaFree(ctx->batch_arena);
+    if (ctx->xpose_buf) cudaFree(ctx->xpose_buf);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -182,6 +185,8 @@ extern "C" void bz_default_options(bz_options* o) {
     o->sub_maxit = 1000;
     o->max_inner_total = 0;
     o->verbose = 0;
+    o->dual_safeguard = nullptr;        // default_dual_safeguard! on the device
+    o->dual_safeguard_user = nullptr;
 }
 
 static cudaEvent_t ctx_event(bz_ctx* ctx) {
@@ -212,12 +217,17 @@ static int upload_matrix(bz_ctx* ctx, const double* host, int layout, long long 
     if (layout == BZ_ROW_MAJOR) {
         BZ_CUDA(ctx, cudaMemcpyAsync(dst_rowmajor, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     } else {
-        double* tmp = nullptr;
-        BZ_CUDA(ctx, cudaMalloc((void**)&tmp, bytes));
+        // column-major (Julia) input: staged in a grow-only buffer owned by the context and transposed on the device
+        if (ctx->xpose_bytes < bytes) {
+            BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->xpose_buf) cudaFree(ctx->xpose_buf);
+            ctx->xpose_buf = nullptr; ctx->xpose_bytes = 0;
+            BZ_CUDA(ctx, cudaMalloc(&ctx->xpose_buf, bytes));
+            ctx->xpose_bytes = bytes;
+        }
+        double* tmp = static_cast<double*>(ctx->xpose_buf);
         BZ_CUDA(ctx, cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
         BZ_TRY(bz_launch_transpose(ctx, tmp, dst_rowmajor, rows, cols));
-        BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
     }
     return BZ_OK;
 }
@@ -253,6 +263,8 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     if (p->counters) cudaFree(p->counters);
     if (p->gridD) cudaFree(p->gridD);
     if (p->gseq) cudaFree(p->gseq);
+    if (p->gridD_f) cudaFree(p->gridD_f);
+    if (p->gseq_f) cudaFree(p->gseq_f);
     if (p->team.bars) cudaFree(p->team.bars);
     if (p->st) cudaFree(p->st);
     if (p->st_host) cudaFreeHost(p->st_host);
@@ -274,7 +286,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     p->n = d->nx;
     p->m = d->ny;
     p->ml = d->ny_local > 0 ? d->ny_local : d->ny;
-    p->sharded = d->ny_local > 0 && ctx->nranks > 1;
+    // row-sharded: a communicator exists (bz_comm_init; one rank is allowed and exercises the same code path)
+    p->sharded = d->ny_local > 0 && ctx->nccl_comm != nullptr;
     auto fail = [&](int code, const std::string& msg) {
         bz_problem_destroy(p);
         return bz_fail(ctx, code, msg);
@@ -335,7 +348,6 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
             return fail(BZ_ERR_ARG, "slab: nx_global must be 3 * ny_local * slab_nranks (equal slabs)");
         p->slab = true;
         p->n_global = d->nx_global;
-        ctx->slab_mode = 1;
     }
     if ((d->g_kind == BZ_G_OBSTACLE_L1 || d->g_kind == BZ_G_OBSTACLE_L2) && d->c_kind != BZ_C_OBSTACLE)
         return fail(BZ_ERR_UNSUPPORTED, "obstacle g needs the obstacle c");
@@ -372,7 +384,8 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     if (d->c_kind == BZ_C_OBSTACLE_RED) p->g.N = d->ny / 2;
     if (d->g_u) {
         PTRY(dev_alloc(ctx, &p->g_u, n));
-        cudaMemcpyAsync(p->g_u, d->g_u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (cudaMemcpyAsync(p->g_u, d->g_u, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+            return fail(BZ_ERR_CUDA, "copy of g_u to the device failed");
         p->g.u = p->g_u;
     }
     // ---- vectors
@@ -403,9 +416,10 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * p->team.max_ctas * 2));
     p->team.parity = 0;
     PTRY(dev_alloc(ctx, &p->st, 1));
-    BZ_CUDA(ctx, cudaMallocHost((void**)&p->st_host, sizeof(BzState)));
-    BZ_CUDA(ctx, cudaMallocHost((void**)&p->status_host, 2 * sizeof(int)));
-    for (auto& e : p->poll_ev) BZ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+#define PCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
+    PCUDA(cudaMallocHost((void**)&p->st_host, sizeof(BzState)));
+    PCUDA(cudaMallocHost((void**)&p->status_host, 2 * sizeof(int)));
+    for (auto& e : p->poll_ev) PCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     // ---- f data
     if (d->f_kind == BZ_F_LEAST_SQUARES) {
@@ -414,7 +428,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         PTRY(dev_alloc(ctx, &p->fA, (size_t)p->fm * n));
         PTRY(upload_matrix(ctx, d->f_A, d->f_layout, p->fm, n, p->fA));
         PTRY(dev_alloc(ctx, &p->fb, p->fm));
-        cudaMemcpyAsync(p->fb, d->f_b, p->fm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        PCUDA(cudaMemcpyAsync(p->fb, d->f_b, p->fm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         PTRY(dev_alloc(ctx, &p->f_ones, p->fm));
         PTRY(dev_alloc(ctx, &p->f_zeros, p->fm));
         PTRY(dev_alloc(ctx, &p->tm1_f, p->fm));
@@ -430,13 +444,13 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         PTRY(dev_alloc(ctx, &p->fA, (size_t)n * n));
         PTRY(upload_matrix(ctx, d->f_A, d->f_layout, n, n, p->fA));
         PTRY(dev_alloc(ctx, &p->fb, n));
-        cudaMemcpyAsync(p->fb, d->f_b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        PCUDA(cudaMemcpyAsync(p->fb, d->f_b, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
     // ---- c data
     if (d->c_kind == BZ_C_DENSE_AFFINE) {
         if (!d->c_b) return fail(BZ_ERR_ARG, "dense affine c needs c_b");
         PTRY(dev_alloc(ctx, &p->cb, ml));
-        cudaMemcpyAsync(p->cb, d->c_b, ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        PCUDA(cudaMemcpyAsync(p->cb, d->c_b, ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         if (d->c_A_is_device) {
             if (!d->c_A) return fail(BZ_ERR_ARG, "c_A_is_device set but c_A is NULL");
             p->cA = const_cast<double*>(d->c_A);
@@ -460,12 +474,19 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
     }
-    if (p->c_grid || p->f_grid) {
+    // the LeastSquares pass and the constraint pass may pick different team geometries: each has its own exchange
+    // ring, arrival counters and row-sequence bases
+    if (p->c_grid) {
         PTRY(dev_alloc(ctx, &p->gridD, (size_t)BZ_GRID_EXCHANGE_WORDS));
         PTRY(dev_alloc(ctx, &p->gseq, 160));   // one row-sequence base per team
     }
+    if (p->f_grid) {
+        PTRY(dev_alloc(ctx, &p->gridD_f, (size_t)BZ_GRID_EXCHANGE_WORDS));
+        PTRY(dev_alloc(ctx, &p->gseq_f, 160));
+    }
 #undef PTRY
-    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PCUDA(cudaStreamSynchronize(ctx->stream));
+#undef PCUDA
     *out = p;
     return BZ_OK;
 }
@@ -481,6 +502,7 @@ extern "C" int bz_problem_upload_dense(bz_problem* p, const double* c_A, const d
         BZ_TRY(upload_matrix(ctx, c_A, p->desc.c_layout, p->ml, p->n, p->cA));
     }
     BZ_CUDA(ctx, cudaMemcpyAsync(p->cb, c_b, p->ml * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller owns c_A / c_b again when this returns
     return BZ_OK;
 }
 
@@ -578,7 +600,7 @@ static int launch_provider(bz_problem* p, int force_target) {
         a.P = p->Pf; a.lxpart = p->fxpart; a.counter = p->counters + 0; a.set_after = 0;
         a.l2_prefetch_rows = ctx->l2_prefetch_rows;
         a.evict_first = ctx->evict_first;
-        a.D = p->gridD; a.gseq = p->gseq;
+        a.D = p->gridD_f; a.gseq = p->gseq_f;
         if (p->f_grid) BZ_TRY(bz_launch_grid_algrad(ctx, a));
         else if (p->f_wide) { a.yupd = p->tm1_f; BZ_TRY(bz_launch_dense_wide(ctx, a)); }
         else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->f_clusters));
@@ -642,7 +664,7 @@ static int launch_cycle(bz_problem* p) {
     bz_ctx* ctx = p->ctx;
     BzGradSrc gs = grad_src(p);
     BzTeam tm = p->team;
-    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1));
+    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab));
     p->team.parity ^= 1;
     BZ_TRY(launch_provider(p, -1));
     gs = grad_src(p);
@@ -729,14 +751,14 @@ static void collect_dominant(bz_problem* p, bz_result* res) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// alps (src/algorithms/alps.jl:7-117)
+// alps (src/algorithms/alps.jl:7-117) and als (src/algorithms/als.jl:7-120): one outer-loop driver.
+// als runs the same loop on the stacked variable [x; s] with AugLagFunSlack / NonsmoothCostFunSlack; the two
+// differ in three places only (marked `slack`).
 // ---------------------------------------------------------------------------------------------
-extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
-                             double* x, double* y, double* s, double* mu, bz_result* res) {
-    if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_alps_solve: NULL argument");
+static int outer_solve(bz_problem* p, bool slack, const double* x0, const double* y0, const bz_options* o,
+                       double* x, double* y, double* s, double* mu, bz_result* res) {
     bz_ctx* ctx = p->ctx;
-    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (p->slack) return bz_fail(ctx, BZ_ERR_ARG, "bz_alps_solve: the problem was created with slack_formulation (use bz_als_solve)");
+    p->slack_active = false;   // als.jl:38-44: the initial prox / c(x) / proj_D / mu use the plain oracles
     const auto t0 = std::chrono::steady_clock::now();
     const long long launches0 = ctx->n_launches;
     p->dom_events.clear();
@@ -746,6 +768,10 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     const double tol_dual = o->tol_dual >= 0 ? o->tol_dual : tol;
     double inner_tol = o->inner_tol >= 0 ? o->inner_tol : std::cbrt(tol_dual);
     const long long n = p->n, ml = p->ml;
+    typedef void (*safeguard_fn)(double*, const double*, int64_t, void*);
+    const safeguard_fn user_safeguard = reinterpret_cast<safeguard_fn>(o->dual_safeguard);
+    std::vector<double> hy, hcx;
+    if (user_safeguard) { hy.resize(ml); hcx.resize(ml); }
 
     // ---- initialise (alps.jl:31-46)
     BZ_TRY(h2d(p, p->v.z_curr, x0, n));
@@ -773,7 +799,22 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     double objx = h->al_fx + h->g_z;         // objx = f(x) + gFun.gz
     h->objx = objx;
     BZ_TRY(push_state(p));
-    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->cx, p->s, p->mu, ml, p->D, 1, nullptr));
+    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->cx, p->s, p->mu, ml, p->D, 1, nullptr));   // also s = proj_D(cx)
+    res->mu0_min = res->mu0_max = NAN;
+    res->inner_tol0 = inner_tol;
+    if (o->verbose) {   // alps.jl:52-55: the two @info lines report min/max of the initial mu and the inner tolerance
+        std::vector<double> hm(ml);
+        BZ_TRY(d2h(p, hm.data(), p->mu, ml));
+        BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        // Julia's minimum / maximum propagate NaN
+        double lo = hm[0], hi = hm[0];
+        for (long long j = 1; j < ml; ++j) {
+            lo = (lo != lo || hm[j] != hm[j]) ? NAN : std::min(lo, hm[j]);
+            hi = (hi != hi || hm[j] != hm[j]) ? NAN : std::max(hi, hm[j]);
+        }
+        res->mu0_min = lo; res->mu0_max = hi;
+    }
+    if (slack) p->slack_active = true;    // fSlack / gSlack from here on (als.jl:46-47)
 
     int tot_it = 0;
     long long tot_inner = 0;
@@ -783,21 +824,37 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     bool can_stop = solved || tired || broken;
     while (!can_stop) {
         tot_it++;
-        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, 1, 1, p->part, p->counters + 5));
+        if (user_safeguard) {   // dual_safeguard(y, cx), alps.jl:62 -- a host callback, one round trip per OUTER iteration
+            BZ_TRY(d2h(p, hy.data(), p->y, ml));
+            BZ_TRY(d2h(p, hcx.data(), p->cx, ml));
+            BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            user_safeguard(hy.data(), hcx.data(), (int64_t)ml, o->dual_safeguard_user);
+            BZ_TRY(h2d(p, p->y, hy.data(), ml));
+        }
+        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, user_safeguard ? 0 : 1, 1, p->part, p->counters + 5));
         if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));
         long long maxit_inner = o->sub_maxit;
         if (o->max_inner_total > 0)
             maxit_inner = std::max<long long>(1, std::min<long long>(maxit_inner, o->max_inner_total - tot_inner));
+        if (slack) BZ_TRY(d2d(p, p->v.x + n, p->s, ml));         // xSlack = [x; s], als.jl:69-70
         BZ_TRY(panoc_run(p, o, inner_tol, maxit_inner));
-        BZ_TRY(d2d(p, p->v.x, p->v.z, n));                  // x .= sub_sol
-        BZ_TRY(bz_launch_multiplier(ctx, p->st, p->cx, p->muy, p->mu, p->y, p->s, ml, p->D,
-                                    p->sharded ? 0 : 1, p->part, p->counters + 5));
-        if (p->sharded) {   // ||cx - s||_inf over all row blocks, then the same scalar logic on every rank
-            BZ_TRY(bz_comm_allreduce(ctx, &p->st->out[0], 1, BZ_COMM_MAX));
-            BZ_TRY(bz_launch_outer_logic(ctx, p->st));
+        if (slack) {
+            BZ_TRY(d2d(p, p->v.x, p->v.z, n + ml));             // xSlack .= sub_sol; x, s = its two parts
+            BZ_TRY(d2d(p, p->s, p->v.z + n, ml));
+            // y .+= (cx .- s) ./ mu with cx = c(x) as left by the last gradient at the returned point (als.jl:81-87)
+            BZ_TRY(bz_launch_multiplier_als(ctx, p->st, p->cx, p->mu, p->y, p->s, ml, p->part, p->counters + 5));
+        } else {
+            BZ_TRY(d2d(p, p->v.x, p->v.z, n));                  // x .= sub_sol
+            BZ_TRY(bz_launch_multiplier(ctx, p->st, p->cx, p->muy, p->mu, p->y, p->s, ml, p->D,
+                                        p->sharded ? 0 : 1, p->part, p->counters + 5));
+            if (p->sharded) {   // ||cx - s||_inf over all row blocks, then the same scalar logic on every rank
+                BZ_TRY(bz_comm_allreduce(ctx, &p->st->out[0], 1, BZ_COMM_MAX));
+                BZ_TRY(bz_launch_outer_logic(ctx, p->st));
+            }
         }
         BZ_TRY(fetch_state(p));                               // the one sync per outer iteration
         if (h->err_flag == 3) return bz_fail(ctx, BZ_ERR_COMM, "slab mode: a peer rank did not answer a cross-rank exchange");
+        if (h->err_flag == 4) return bz_fail(ctx, BZ_ERR_CUDA, "grid-wide dense pass: a CTA of the team did not arrive (the grid is not co-resident: is the device shared?)");
         if (h->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
         objx = h->objx;
         tot_inner = h->tot_inner_it;
@@ -835,111 +892,20 @@ extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, 
     return BZ_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// als (src/algorithms/als.jl:7-120): the same outer loop on the stacked variable [x; s]
-// ---------------------------------------------------------------------------------------------
-extern "C" int bz_als_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
+extern "C" int bz_alps_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
                              double* x, double* y, double* s, double* mu, bz_result* res) {
+    if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_alps_solve: NULL argument");
+    BZ_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    if (p->slack) return bz_fail(p->ctx, BZ_ERR_ARG, "bz_alps_solve: the problem was created with slack_formulation (use bz_als_solve)");
+    return outer_solve(p, false, x0, y0, o, x, y, s, mu, res);
+}
+
+extern "C" int bz_als_solve(bz_problem* p, const double* x0, const double* y0, const bz_options* o,
+                            double* x, double* y, double* s, double* mu, bz_result* res) {
     if (!p || !x0 || !y0 || !o || !res) return bz_fail(p ? p->ctx : nullptr, BZ_ERR_ARG, "bz_als_solve: NULL argument");
-    bz_ctx* ctx = p->ctx;
-    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!p->slack) return bz_fail(ctx, BZ_ERR_ARG, "bz_als_solve: create the problem with slack_formulation = 1");
-    p->slack_active = false;   // als.jl:38-44: the initial prox / c(x) / proj_D / mu use the plain oracles
-    const auto t0 = std::chrono::steady_clock::now();
-    const long long launches0 = ctx->n_launches;
-    p->dom_events.clear();
-    ctx->ev_used = 0;
-    const double tol = o->tol;
-    const double tol_prim = o->tol_prim >= 0 ? o->tol_prim : tol;
-    const double tol_dual = o->tol_dual >= 0 ? o->tol_dual : tol;
-    double inner_tol = o->inner_tol >= 0 ? o->inner_tol : std::cbrt(tol_dual);
-    const long long n = p->n, ml = p->ml;
-
-    // ---- initialise (alps.jl:31-46)
-    BZ_TRY(h2d(p, p->v.z_curr, x0, n));
-    BZ_TRY(h2d(p, p->y, y0 + (p->sharded ? p->desc.row_begin : 0), ml));
-    BzState* h = p->st_host;
-    memset(h, 0, sizeof(BzState));
-    h->xr = p->xr_host;            // slab mode: peer mapping (zero otherwise)
-    h->n_global = p->n_global;
-    h->next_op = OP_DONE;
-    h->H = 1.0;
-    h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
-    h->theta_penalty = o->theta_penalty; h->kappa_penalty = o->kappa_penalty; h->kappa_tol = o->kappa_tol;
-    h->outer_maxit = o->maxit; h->subsolver_maxit = o->subsolver_maxit;
-    h->n_prox = 1;   // the prox!(x, gFun, x0, eps(T)) of alps.jl:38
-    BZ_TRY(push_state(p));
-    BZ_TRY(bz_launch_prox(ctx, p->st, p->v.z_curr, BZ_EPS, p->v.x, n, p->g, p->part, p->counters + 5));
-    BZ_TRY(bz_launch_fill(ctx, p->mu, ml, 1.0));
-    BZ_TRY(bz_launch_fill(ctx, p->muy, ml, 0.0));
-    BZ_TRY(launch_provider(p, TGT_X));       // cx = c(x), f(x)
-    {
-        BzGradSrc gs = grad_src(p);
-        BZ_TRY(bz_launch_assemble(ctx, p->st, gs, n, p->v.grad_x, p->part, p->counters + 6));
-    }
-    BZ_TRY(fetch_state(p));
-    double objx = h->al_fx + h->g_z;         // objx = f(x) + gFun.gz
-    h->objx = objx;
-    BZ_TRY(push_state(p));
-    BZ_TRY(bz_launch_init_mu(ctx, p->st, p->cx, p->s, p->mu, ml, p->D, 1, nullptr));   // also s = proj_D(cx), als.jl:42
-    p->slack_active = true;    // fSlack / gSlack from here on (als.jl:46-47)
-
-    int tot_it = 0;
-    long long tot_inner = 0;
-    bool solved = false, tired = tot_it >= o->maxit, broken = std::isnan(objx);
-    double norm_res_prim = NAN;
-    long long n_grad = 0, n_prox = 0;
-    bool can_stop = solved || tired || broken;
-    while (!can_stop) {
-        tot_it++;
-        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, 1, 1, p->part, p->counters + 5));
-        if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));
-        long long maxit_inner = o->sub_maxit;
-        if (o->max_inner_total > 0)
-            maxit_inner = std::max<long long>(1, std::min<long long>(maxit_inner, o->max_inner_total - tot_inner));
-        BZ_TRY(d2d(p, p->v.x + n, p->s, ml));                // xSlack = [x; s], als.jl:69-70
-        BZ_TRY(panoc_run(p, o, inner_tol, maxit_inner));
-        BZ_TRY(d2d(p, p->v.x, p->v.z, n + ml));             // xSlack .= sub_sol; x, s = its two parts
-        BZ_TRY(d2d(p, p->s, p->v.z + n, ml));
-        // y .+= (cx .- s) ./ mu with cx = c(x) as left by the last gradient at the returned point (als.jl:81-87)
-        BZ_TRY(bz_launch_multiplier_als(ctx, p->st, p->cx, p->mu, p->y, p->s, ml, p->part, p->counters + 5));
-        BZ_TRY(fetch_state(p));                               // the one sync per outer iteration
-        if (h->err_flag == 3) return bz_fail(ctx, BZ_ERR_COMM, "slab mode: a peer rank did not answer a cross-rank exchange");
-        if (h->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
-        objx = h->objx;
-        tot_inner = h->tot_inner_it;
-        norm_res_prim = h->norm_res_prim;
-        solved = h->solved; tired = h->tired; broken = h->broken;
-        n_grad = h->n_grad; n_prox = h->n_prox;
-        can_stop = solved || tired || broken;
-        if (o->max_inner_total > 0 && tot_inner >= o->max_inner_total) can_stop = true;
-        if (!can_stop && h->scale_mu) BZ_TRY(bz_launch_scale(ctx, p->mu, ml, o->kappa_penalty));
-        inner_tol = h->inner_tol;
-    }
-    BZ_TRY(d2h(p, x, p->v.x, n));
-    BZ_TRY(d2h(p, y, p->y, ml));
-    BZ_TRY(d2h(p, s, p->s, ml));
-    BZ_TRY(d2h(p, mu, p->mu, ml));
-    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    res->tot_it = tot_it;
-    res->tot_inner_it = tot_inner;
-    res->status = solved ? 0 : tired ? 1 : broken ? 2 : 3;
-    res->inner_tol = inner_tol;
-    res->norm_res_prim = norm_res_prim;
-    res->objective = objx;
-    res->n_grad = n_grad;
-    res->n_prox = n_prox;
-    res->n_launches = ctx->n_launches - launches0;
-    res->dominant_kernel_ms = 0.0;
-    res->dominant_kernel_launches = 0;
-    if (ctx->profiling) collect_dominant(p, res);
-    for (int k = 0; k < 4; ++k) {
-        res->kind_ms[k] = 1e-6 * (double)h->tsum[k];
-        res->kind_launches[k] = (int64_t)h->tcnt[k];
-    }
-    res->elapsed_time =
-        std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    return BZ_OK;
+    BZ_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    if (!p->slack) return bz_fail(p->ctx, BZ_ERR_ARG, "bz_als_solve: create the problem with slack_formulation = 1");
+    return outer_solve(p, true, x0, y0, o, x, y, s, mu, res);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -953,6 +919,7 @@ static int set_mu_y(bz_problem* p, const double* mu, const double* y) {
     p->st_host->err_flag = 0;
     BZ_TRY(push_state(p));
     BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, p->ml, 0, 0, p->part, p->counters + 5));
+    if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));   // 0.5*sum(mu.*y.^2) over all row blocks
     BZ_TRY(fetch_state(p));
     if (p->st_host->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
     return BZ_OK;
@@ -1085,7 +1052,7 @@ static int lbfgs_call(bz_problem* p, int skip_update) {
     p->st_host->skip_update = skip_update;
     BZ_TRY(push_state(p));
     BzTeam tm = p->team;
-    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, LROLE_NEWITER));
+    BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, LROLE_NEWITER, p->slab));
     p->team.parity ^= 1;
     return BZ_OK;
 }

@@ -38,6 +38,7 @@ mutable struct Options
     alpha::Float64; beta::Float64; minimum_gamma::Float64
     max_backtracks::Int32; lbfgs_memory::Int32
     sub_maxit::Int64; max_inner_total::Int64; verbose::Int32
+    dual_safeguard::Ptr{Cvoid}; dual_safeguard_user::Ptr{Cvoid}   # alps.jl:23,62 as a host callback (C_NULL = default clamp)
     Options() = new()
 end
 
@@ -47,6 +48,7 @@ mutable struct Result
     n_grad::Int64; n_prox::Int64; n_launches::Int64
     dominant_kernel_ms::Float64; dominant_kernel_launches::Int64
     kind_ms::NTuple{4,Float64}; kind_launches::NTuple{4,Int64}
+    mu0_min::Float64; mu0_max::Float64; inner_tol0::Float64       # verbose: the two @info lines of alps.jl:52-55
     Result() = new()
 end
 
@@ -128,7 +130,8 @@ als(f, g, c::Bazinga.SmoothFunction, D::Bazinga.ClosedSet, x0::AbstractArray, y0
 function solve_on_device(slack::Bool, f, g, c, D, x0, y0;
               tol::Real = 1e-6, tol_prim::Real = tol, tol_dual::Real = tol, inner_tol::Real = cbrt(tol_dual),
               maxit::Int = 100, theta_penalty::Real = 0.8, kappa_penalty::Real = 0.5, kappa_tol::Real = 0.1,
-              verbose::Bool = false, subsolver = B200PANOCplus, subsolver_maxit::Int = 1_000_000_000)
+              verbose::Bool = false, dual_safeguard::Union{Nothing,Function} = nothing,
+              subsolver = B200PANOCplus, subsolver_maxit::Int = 1_000_000_000)
     ctx = context()
     fk, fp = f_kind(f); gk, glam, glo, ghi, gu = g_kind(g); ck, cp = c_kind(c); dk, dlo, dhi = d_kind(D)
     nx, ny = length(x0), length(y0)
@@ -144,7 +147,7 @@ function solve_on_device(slack::Bool, f, g, c, D, x0, y0;
                        Int32(0), Int32(0), 0,   # no slab decomposition
                        Int32(slack))            # 0: alps / bz_alps_solve, 1: als / bz_als_solve (PANOC+ on [x; s])
     prob = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve keep begin
+    GC.@preserve keep begin   # (bz_problem_create copies the oracle data to the device before it returns)
         check(ccall((:bz_problem_create, lib), Cint, (Ptr{Cvoid}, Ref{ProblemDesc}, Ref{Ptr{Cvoid}}),
                     ctx.handle, Ref(desc), prob), ctx.handle)
     end
@@ -156,11 +159,21 @@ function solve_on_device(slack::Bool, f, g, c, D, x0, y0;
     opt.alpha = sub.alpha; opt.beta = sub.beta; opt.minimum_gamma = sub.minimum_gamma
     opt.max_backtracks = sub.max_backtracks; opt.lbfgs_memory = sub.memory; opt.sub_maxit = sub.maxit
     opt.max_inner_total = 0; opt.verbose = verbose
+    # dual_safeguard(y, cx) (alps.jl:23,62): the default clamp runs on the device; a user function becomes a host
+    # callback on unsafe_wrap'ed copies of y and cx, once per outer iteration
+    opt.dual_safeguard = C_NULL; opt.dual_safeguard_user = C_NULL
+    if dual_safeguard !== nothing
+        tramp = (yp::Ptr{Float64}, cp_::Ptr{Float64}, m::Int64, ::Ptr{Cvoid}) ->
+            (dual_safeguard(unsafe_wrap(Array, yp, m), unsafe_wrap(Array, cp_, m)); nothing)
+        cfn = @cfunction($tramp, Cvoid, (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Cvoid}))
+        push!(keep, cfn)
+        opt.dual_safeguard = Base.unsafe_convert(Ptr{Cvoid}, cfn)
+    end
     T = Float64
     x = Vector{T}(undef, nx); y = Vector{T}(undef, ny); s = similar(y); mu = similar(y)
     res = Result()
     x0c = Vector{T}(x0); y0c = Vector{T}(y0)             # x0, y0 are never modified (test_nonconvex_qp.jl:36)
-    try
+    GC.@preserve keep try
         if slack
             check(ccall((:bz_als_solve, lib), Cint,
                         (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{Options}, Ptr{T}, Ptr{T}, Ptr{T}, Ptr{T}, Ref{Result}),
@@ -172,6 +185,10 @@ function solve_on_device(slack::Bool, f, g, c, D, x0, y0;
         end
     finally
         ccall((:bz_problem_destroy, lib), Cint, (Ptr{Cvoid},), prob[])
+    end
+    if verbose                                           # alps.jl:52-55
+        @info "initial penalty parameters μ ∈ [$(res.mu0_min), $(res.mu0_max)]"
+        @info "initial inner tolerance $(res.inner_tol0)"
     end
     return x, y, Int(res.tot_it), Int(res.tot_inner_it), res.elapsed_time, STATUS[res.status + 1],
            res.inner_tol, res.norm_res_prim, s, mu
@@ -196,11 +213,20 @@ function solve_batch(problem::String, X0::Matrix{Float64}; solver::Symbol = :alp
     Y0 = zeros(ny, B); X = similar(X0); Y = similar(Y0)
     its = Vector{Int32}(undef, B); inner = Vector{Int64}(undef, B); status = Vector{Int32}(undef, B)
     nrp = Vector{Float64}(undef, B); ms = Ref{Float64}(0.0)
-    sym = solver == :als ? :bz_batch_solve_als : :bz_batch_solve
-    check(ccall((sym, lib), Cint,
-                (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Options}, Ptr{Float64}, Ptr{Float64},
-                 Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
-                ctx.handle, kind, B, X0, Y0, opt, X, Y, its, inner, status, nrp, ms), ctx.handle)
+    opt.dual_safeguard = C_NULL; opt.dual_safeguard_user = C_NULL
+    # ccall needs a constant (name, library) pair: branch explicitly instead of choosing the symbol at run time
+    rc = if solver == :als
+        ccall((:bz_batch_solve_als, lib), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Options}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
+              ctx.handle, kind, B, X0, Y0, opt, X, Y, its, inner, status, nrp, ms)
+    else
+        ccall((:bz_batch_solve, lib), Cint,
+              (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Options}, Ptr{Float64}, Ptr{Float64},
+               Ptr{Int32}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ref{Float64}),
+              ctx.handle, kind, B, X0, Y0, opt, X, Y, its, inner, status, nrp, ms)
+    end
+    check(rc, ctx.handle)
     # the columns the demos write to CSV: xfinal, iters, sub_iters, is_solved (demo/eitheror.jl:256-271)
     return (x = X, y = Y, iters = its, sub_iters = inner, is_solved = status .== 0, norm_res_prim = nrp, kernel_ms = ms[])
 end

@@ -53,6 +53,12 @@ class Context:
         buf = C.create_string_buffer(unique_id, 128)
         K.check(self.lib.bz_comm_init(self.handle, buf, nranks, rank), self.handle)
 
+    def comm_bench_allreduce(self, count: int, reps: int = 50) -> float:
+        """Average device time (us) of one allreduce(sum) of ``count`` doubles on the library's NCCL communicator."""
+        us = C.c_double()
+        K.check(self.lib.bz_comm_bench_allreduce(self.handle, int(count), int(reps), C.byref(us)), self.handle)
+        return us.value
+
     def randn_fill(self, seed, start, count, stream=0):
         out = np.empty(int(count), dtype=np.float64)
         K.check(self.lib.bz_randn_fill(self.handle, seed, stream, start, int(count), _ptr(out)), self.handle)
@@ -137,8 +143,32 @@ class PANOCplus:
 default_subsolver = PANOCplus   # alps.jl:5
 
 
+def _julia_float(v: float) -> str:
+    """Julia's `print(::Float64)`: shortest round-trip digits, always with a fractional part or an `e` exponent."""
+    if v != v:
+        return "NaN"
+    if v in (float("inf"), float("-inf")):
+        return "Inf" if v > 0 else "-Inf"
+    r = repr(float(v))
+    if "e" in r:
+        m, e = r.split("e")
+        if "." not in m:
+            m += ".0"
+        return f"{m}e{int(e)}"
+    return r
+
+
+def _wrap_dual_safeguard(fn):
+    """alps.jl:23,62 ``dual_safeguard(y, cx)`` (in-place on y) -> the C-ABI host callback of bz_options."""
+    def tramp(yp, cxp, m, _user):
+        y = np.ctypeslib.as_array(yp, shape=(m,))
+        cx = np.ctypeslib.as_array(cxp, shape=(m,))
+        fn(y, cx)
+    return K.DUAL_SAFEGUARD_FN(tramp)
+
+
 def _options(*, tol, tol_prim, tol_dual, inner_tol, maxit, theta_penalty, kappa_penalty, kappa_tol,
-             subsolver_maxit, sub: PANOCplus, max_inner_total=0, verbose=False):
+             subsolver_maxit, sub: PANOCplus, max_inner_total=0, verbose=False, dual_safeguard=None):
     lib = K.load_library()
     o = K.Options()
     lib.bz_default_options(C.byref(o))
@@ -154,6 +184,10 @@ def _options(*, tol, tol_prim, tol_dual, inner_tol, maxit, theta_penalty, kappa_
     o.sub_maxit = sub.maxit
     o.max_inner_total = int(max_inner_total)
     o.verbose = 1 if verbose else 0
+    if dual_safeguard is not None:
+        cb = _wrap_dual_safeguard(dual_safeguard)
+        o._keep_cb = cb                       # the callback object must outlive the solve
+        o.dual_safeguard = C.cast(cb, C.c_void_p)
     return o
 
 
@@ -275,7 +309,11 @@ class Problem:
         if A is None:
             K.check(self.lib.bz_problem_upload_dense(self.handle, None, _ptr(b)), self.ctx.handle)
             return
+        # the library reads A in the layout the problem was created with: normalise, never upload a strided view
         A = np.asarray(A, dtype=np.float64)
+        if A.shape != (self.ny_local, self.nx):
+            raise ValueError("upload_dense: A has the wrong shape")
+        A = np.asfortranarray(A) if self.desc.c_layout == K.COL_MAJOR else np.ascontiguousarray(A)
         K.check(self.lib.bz_problem_upload_dense(self.handle, _ptr(A), _ptr(b)), self.ctx.handle)
 
     def panocplus(self, mu, y, x0, sub: PANOCplus):
@@ -384,10 +422,9 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
     """Drop-in for ``Bazinga.alps`` (src/algorithms/alps.jl:7-26).  Returns the reference's 10-tuple
     ``(x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol, norm_res_prim, s, mu)`` with
     ``status`` in {"first_order", "max_iter", "exception", "unknown"} (the Julia Symbols).
-    x0 and y0 are never modified (test/problems/test_nonconvex_qp.jl:36)."""
-    if dual_safeguard is not None:
-        raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "custom dual_safeguard functions cannot cross the C ABI; "
-                                                   "the default (clamp to ±1e20) runs on the device")
+    x0 and y0 are never modified (test/problems/test_nonconvex_qp.jl:36).  ``dual_safeguard(y, cx)`` (alps.jl:23,62)
+    may be a Python callable that edits ``y`` in place: it runs on the host once per outer iteration; ``None`` keeps
+    ``default_dual_safeguard!`` on the device."""
     sub = subsolver(tol=1.0, verbose=verbose)   # alps.jl:64: constructor call with two kwargs only
     if not isinstance(sub, PANOCplus):
         raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "subsolver must be (a closure over) PANOCplus")
@@ -399,14 +436,15 @@ def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_to
         o = _options(tol=tol, tol_prim=tol_prim, tol_dual=tol_dual, inner_tol=inner_tol, maxit=maxit,
                      theta_penalty=theta_penalty, kappa_penalty=kappa_penalty, kappa_tol=kappa_tol,
                      subsolver_maxit=subsolver_maxit, sub=sub, max_inner_total=max_inner_total,
-                     verbose=verbose)
+                     verbose=verbose, dual_safeguard=dual_safeguard)
         x, y, s, mu, res = p.alps(x0, y0, o)
     finally:
         if own:
             p.close()
-    if verbose:
-        print(f"[bazinga_b200] alps: it={res.tot_it} inner={res.tot_inner_it} status={K.STATUS_SYMBOLS[res.status]} "
-              f"res_prim={res.norm_res_prim:.3e} inner_tol={res.inner_tol:.3e}")
+    if verbose:      # the two @info lines of alps.jl:52-55 (Julia's logger writes them to stderr)
+        import sys
+        print(f"[ Info: initial penalty parameters μ ∈ [{_julia_float(res.mu0_min)}, {_julia_float(res.mu0_max)}]", file=sys.stderr)
+        print(f"[ Info: initial inner tolerance {_julia_float(res.inner_tol0)}", file=sys.stderr)
     out = (x, y, res.tot_it, res.tot_inner_it, res.elapsed_time, K.STATUS_SYMBOLS[res.status], res.inner_tol,
            res.norm_res_prim, s, mu)
     return (out, res) if return_result else out
@@ -420,10 +458,9 @@ def als(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_tol
     variables (PANOCplus on [x; s] with AugLagFunSlack / NonsmoothCostFunSlack).  Returns the reference's 10-tuple
     ``(x, y, tot_it, tot_inner_it, elapsed_time, status, inner_tol, norm_res_prim, s, mu)`` with
     ``status`` in {"first_order", "max_iter", "exception", "unknown"} (the Julia Symbols).
-    x0 and y0 are never modified (test/problems/test_nonconvex_qp.jl:36)."""
-    if dual_safeguard is not None:
-        raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "custom dual_safeguard functions cannot cross the C ABI; "
-                                                   "the default (clamp to ±1e20) runs on the device")
+    x0 and y0 are never modified (test/problems/test_nonconvex_qp.jl:36).  ``dual_safeguard(y, cx)`` (alps.jl:23,62)
+    may be a Python callable that edits ``y`` in place: it runs on the host once per outer iteration; ``None`` keeps
+    ``default_dual_safeguard!`` on the device."""
     sub = subsolver(tol=1.0, verbose=verbose)   # alps.jl:64: constructor call with two kwargs only
     if not isinstance(sub, PANOCplus):
         raise K.BazingaError(K.BZ_ERR_UNSUPPORTED, "subsolver must be (a closure over) PANOCplus")
@@ -436,14 +473,15 @@ def als(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_tol
         o = _options(tol=tol, tol_prim=tol_prim, tol_dual=tol_dual, inner_tol=inner_tol, maxit=maxit,
                      theta_penalty=theta_penalty, kappa_penalty=kappa_penalty, kappa_tol=kappa_tol,
                      subsolver_maxit=subsolver_maxit, sub=sub, max_inner_total=max_inner_total,
-                     verbose=verbose)
+                     verbose=verbose, dual_safeguard=dual_safeguard)
         x, y, s, mu, res = p.als(x0, y0, o)
     finally:
         if own:
             p.close()
-    if verbose:
-        print(f"[bazinga_b200] als: it={res.tot_it} inner={res.tot_inner_it} status={K.STATUS_SYMBOLS[res.status]} "
-              f"res_prim={res.norm_res_prim:.3e} inner_tol={res.inner_tol:.3e}")
+    if verbose:      # the two @info lines of alps.jl:52-55 (Julia's logger writes them to stderr)
+        import sys
+        print(f"[ Info: initial penalty parameters μ ∈ [{_julia_float(res.mu0_min)}, {_julia_float(res.mu0_max)}]", file=sys.stderr)
+        print(f"[ Info: initial inner tolerance {_julia_float(res.inner_tol0)}", file=sys.stderr)
     out = (x, y, res.tot_it, res.tot_inner_it, res.elapsed_time, K.STATUS_SYMBOLS[res.status], res.inner_tol,
            res.norm_res_prim, s, mu)
     return (out, res) if return_result else out

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define BZ_ABI_VERSION 3
+#define BZ_ABI_VERSION 4
 #define BZ_LBFGS_MAX_MEMORY 16
 
 typedef struct bz_ctx bz_ctx;
@@ -149,7 +149,13 @@ typedef struct {
     int32_t max_backtracks, lbfgs_memory;
     int64_t sub_maxit;       /* PANOCplus(maxit = ...) */
     int64_t max_inner_total; /* >0: stop after this many inner iterations in total (bench sampling) */
-    int32_t verbose;
+    int32_t verbose;         /* alps.jl:21,52-55: fills bz_result.mu0_min / mu0_max / inner_tol0 (the two @info lines) */
+    /* alps.jl:23,62 `dual_safeguard(y, cx)`: NULL = default_dual_safeguard! (clamp to +-1e20, on the device).
+     * Otherwise a host callback void f(double* y, const double* cx, int64_t ny_local, void* user) -- a Julia
+     * @cfunction or a ctypes CFUNCTYPE -- called once per OUTER iteration on host copies of y and cx; it edits y
+     * in place.  (One host round trip per outer iteration; the inner loop is untouched.) */
+    void* dual_safeguard;
+    void* dual_safeguard_user;
 } bz_options;
 
 typedef struct {
@@ -168,6 +174,8 @@ typedef struct {
      * backward step, 3 decision step -- summed over the launches that really ran */
     double kind_ms[4];
     int64_t kind_launches[4];
+    /* verbose (alps.jl:52-55): extrema of the initial penalty vector and the initial inner tolerance */
+    double mu0_min, mu0_max, inner_tol0;
 } bz_result;
 
 /* ---- context ------------------------------------------------------------------------------------ */
@@ -261,6 +269,9 @@ int bz_batch_solve_als(bz_ctx* ctx, int kind, int64_t batch, const double* x0, c
 int bz_comm_unique_id(void* id128); /* 128-byte NCCL unique id, generate on rank 0 and broadcast */
 int bz_comm_init(bz_ctx* ctx, const void* id128, int nranks, int rank);
 int bz_comm_destroy(bz_ctx* ctx);
+/* Measurement aid: average device time (us) of one allreduce(sum) of `count` doubles on the library's communicator
+ * and stream -- the collective of the row-sharded AL-gradient (count = nx + 8).  Collective: call on every rank. */
+int bz_comm_bench_allreduce(bz_ctx* ctx, int64_t count, int reps, double* us_per_call);
 
 #ifdef __cplusplus
 }
