@@ -95,6 +95,7 @@ SYMBOLS = {
     "bz_prox": (C.c_int, [_vp, _vp, C.c_double, _vp, _dp]),
     "bz_proj": (C.c_int, [_vp, _vp, _vp]),
     "bz_fb_step": (C.c_int, [_vp, _vp, _vp, C.c_double, _vp, _vp, _dp, _dp, _dp]),
+    "bz_obstacle_fused_step": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "bz_lbfgs_reset": (C.c_int, [_vp, C.c_int]),
     "bz_lbfgs_update": (C.c_int, [_vp, _vp, _vp]),
     "bz_lbfgs_apply": (C.c_int, [_vp, _vp, _vp]),

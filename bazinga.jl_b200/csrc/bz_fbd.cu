@@ -158,24 +158,12 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
         st->n_grad += 1;
         st->mode = MODE_INITFB;
         st->grad_x_fresh = 0;
-        st->next_op = OP_F;
+        st->next_op = st->fused ? OP_X : OP_F;   // fused problems recompute grad_x inside X
     } else {
-        if (fresh) {
-            st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
-            st->n_grad += 1;
-        }
-        const double nrm = sqrt(s1);
-        const double nrm2 = nrm * nrm;                       // norm(res)^2
-        st->dot_gr = s0;
-        st->res_nrm2sq = nrm2;
-        st->f_up = st->f_x - s0 + ((st->alpha / gamma) / 2) * nrm2;   // f_model
-        st->g_z = bz_g_value_scale(g) * s2;
-        st->n_prox += 1;
-        st->grad_x_fresh = 0;
+        bz_f_finish(st, g, gamma, fresh, s0, s1, s2, lx, fx);
         st->grad_target = TGT_Z;
         st->after_g = OP_D;
         st->next_op = OP_G;
-        st->out[0] = st->g_z; st->out[1] = s0; st->out[2] = s1;
     }
     if (force_mode < 0) bz_toc(st, 2);
     __threadfence();
@@ -267,56 +255,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     double fx;
     const double f_z = bz_value_from_sums(gs, st->musqy, sums[0], sums[1], sums[2], fx);
 
-    st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
-    st->n_grad += 1;
-    const int mode = st->mode;
-    const bool cond = (f_z > st->f_up + 10 * BZ_EPS * (1 + fabs(f_z))) && (gamma >= st->gamma_min);
-    bool end_iter = false;
-    double stopn = stop1;
-    if (mode == MODE_INITFB) {          // backtrack_stepsize! (A.4)
-        if (cond) {
-            st->gamma = gamma / 2;
-            st->grad_x_fresh = 0;
-            st->next_op = OP_F;
-        } else {
-            end_iter = true;
-            st->skip_update = 1;
-            st->mode = MODE_ITER;
-        }
-    } else {                            // A.5 loop body at backtrack index k
-        const int k = st->k_bt;
-        if (cond) {
-            st->gamma = gamma * 0.5;
-            st->currmem = 0; st->curridx = 0; st->H = 1.0;       // reset_direction_state!
-            if (k + 1 > st->max_backtracks) {                    // `continue` ran off the loop
-                end_iter = true;
-                stopn = stop2;
-            } else {
-                st->k_bt = k + 1;
-                st->grad_x_fresh = 0;
-                st->next_op = OP_F;
-            }
-        } else if (st->f_up + st->g_z <= st->thresh || k >= st->max_backtracks) {
-            end_iter = true;
-        } else {
-            st->tau = (k >= st->max_backtracks - 1) ? 0.0 : st->tau / 2;
-            st->k_bt = k + 1;
-            st->l_role = LROLE_INTERP;
-            st->next_op = OP_L;
-        }
-        if (end_iter) st->skip_update = 0;
-    }
-    if (end_iter) {
-        st->iter += 1;
-        st->stopnorm = stopn;
-        if (st->iter >= st->maxit || stopn <= st->tol) {
-            st->inner_status = (stopn <= st->tol) ? IST_CONVERGED : IST_MAXIT;
-            st->next_op = OP_DONE;
-        } else {
-            st->l_role = LROLE_NEWITER;
-            st->next_op = OP_L;
-        }
-    }
+    bz_d_decide(st, gamma, f_z, fx, stop1, stop2);
     bz_toc(st, 3);
     __threadfence();
 }

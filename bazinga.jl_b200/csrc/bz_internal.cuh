@@ -19,7 +19,7 @@
 // host can enqueue the fixed kernel cycle [L, G, F, G, D] without knowing which branch is taken
 // (<= 1 host sync per inner iteration; we need far fewer).
 // ---------------------------------------------------------------------------------------------
-enum BzOp : int { OP_L = 0, OP_G = 1, OP_F = 2, OP_D = 3, OP_DONE = 4 };
+enum BzOp : int { OP_L = 0, OP_G = 1, OP_F = 2, OP_D = 3, OP_DONE = 4, OP_X = 5 /* fused G+F+G+D (bz_obfused.cu) */ };
 enum BzMode : int { MODE_INIT0 = 0, MODE_INIT1 = 1, MODE_INITFB = 2, MODE_ITER = 3 };
 enum BzLRole : int { LROLE_NEWITER = 0, LROLE_INTERP = 1 };
 enum BzTarget : int { TGT_X = 0, TGT_Z = 1, TGT_XEPS = 2 };
@@ -60,7 +60,10 @@ struct BzState {
     int max_backtracks;
     int mem;            // L-BFGS memory M
     int currmem, curridx;  // curridx is 1-based like upstream, 0 = empty
+    int slot[BZ_MAXMEM];   // cooperative L kernel: physical history slot of each ring position (a permutation)
+    int spare;             // ... and the free physical slot the next candidate pair is written to
     int err_flag;       // nonpositive mu etc.
+    int fused;          // the problem runs the fused forward-backward kernel X instead of [G, F, G, D] (bz_obfused.cu)
     long long n_global; // slab mode: global nx (0: the local n is the global one)
     long long iter;     // k of the IterativeAlgorithm driver (initial state counts as 1)
     long long maxit;
@@ -82,7 +85,7 @@ struct BzState {
     int tot_it, outer_maxit;
     long long tot_inner_it, subsolver_maxit;
     // generic scalar outputs of the parity entry points
-    double out[8];
+    double out[16];
     // device-side stopwatch per kernel kind (0 G dense, 1 L, 2 F, 3 D): %globaltimer at the start of a
     // launch that really runs and at its last-CTA epilogue (diagnostic breakdown; the roofline number
     // of the dominant kernel uses CUDA events, see bz_solver.cu)
@@ -448,6 +451,7 @@ struct bz_ctx {
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
+    int obstacle_fused = 1;     // obstacle problems run the fused X kernel (env BZ_OBSTACLE_FUSED=0: the unfused cycle, for A/B runs)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)
     int l2_prefetch_rows = 0;   // tuning knob (env BZ_L2_PREFETCH_ROWS), see bz_dense.cu

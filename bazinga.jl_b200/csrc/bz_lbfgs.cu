@@ -22,7 +22,7 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 struct TeamCtx {
     BzTeam tm;
     int idx;
-    double* scratch;   // >= 2*32 + 2 doubles of shared memory
+    double* scratch;   // >= 3*32 + 3 doubles of shared memory (block sums of K <= 3 values, then the team result)
     BzState* st;
     unsigned long long seq0;   // slab mode: cross-rank exchange sequence number at kernel start
     int xidx;                  // ... and the number of exchanges this launch has done
@@ -35,10 +35,10 @@ __device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
     if (nb > 1) {
         const int j = tc.idx++;
         unsigned int* bar = tc.tm.bars + tc.tm.parity * BZ_MAXBAR + j;
-        double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 2;
+        double* sl = tc.tm.slots + ((size_t)(tc.tm.parity * BZ_MAXBAR + j) * tc.tm.max_ctas) * 4;
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) sl[blockIdx.x * 2 + k] = v[k];
+            for (int k = 0; k < K; ++k) sl[blockIdx.x * 4 + k] = v[k];
             __threadfence();
             atomicAdd(bar, 1u);
             while (ld_acquire_u32(bar) < (unsigned int)nb) { }
@@ -48,14 +48,14 @@ __device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 double s = 0.0;
-                for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 2 + k);
+                for (int c = threadIdx.x; c < nb; c += 32) s += __ldcg(sl + c * 4 + k);
                 s = bz_warp_sum(s);
-                if (threadIdx.x == 0) tc.scratch[64 + k] = s;
+                if (threadIdx.x == 0) tc.scratch[96 + k] = s;
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
+        for (int k = 0; k < K; ++k) v[k] = tc.scratch[96 + k];
         __syncthreads();
     }
     if (tc.st->xr.nranks > 1) {
@@ -71,117 +71,164 @@ __device__ inline void team_sum(TeamCtx& tc, double (&v)[K]) {
             for (int k = 0; k < K; ++k) {
                 double acc = g[k];
                 for (int r = 1; r < tc.st->xr.nranks; ++r) acc += g[r * XR_K + k];
-                tc.scratch[64 + k] = acc;
+                tc.scratch[96 + k] = acc;
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = tc.scratch[64 + k];
+        for (int k = 0; k < K; ++k) v[k] = tc.scratch[96 + k];
         __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
-    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
-    __shared__ double scratch[2 * 32 + 4];
-    // the other parity's barrier words are free again: reset them for the launch after this one
-    if (blockIdx.x == 0 && threadIdx.x < BZ_MAXBAR)
-        tm.bars[(1 - tm.parity) * BZ_MAXBAR + threadIdx.x] = 0u;
-    int role = force_role;
-    if (role < 0) {
-        if (__ldcg(&st->next_op) != OP_L) return;
-        role = __ldcg(&st->l_role);
-        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 1);
-    }
-    const long long n = v.n;
+// V entries per access: double2 when n is even (every vector of the state is 256-byte aligned and the history slots
+// are n entries apart), plain doubles otherwise
+template <int V> struct Pk { double v[V]; };
+template <int V> __device__ __forceinline__ Pk<V> ldv(const double* p, long long j);
+template <> __device__ __forceinline__ Pk<1> ldv<1>(const double* p, long long j) { Pk<1> r; r.v[0] = p[j]; return r; }
+template <> __device__ __forceinline__ Pk<2> ldv<2>(const double* p, long long j) {
+    const double2 t = reinterpret_cast<const double2*>(p)[j];
+    Pk<2> r; r.v[0] = t.x; r.v[1] = t.y; return r;
+}
+template <int V> __device__ __forceinline__ void stv(double* p, long long j, const Pk<V>& a);
+template <> __device__ __forceinline__ void stv<1>(double* p, long long j, const Pk<1>& a) { p[j] = a.v[0]; }
+template <> __device__ __forceinline__ void stv<2>(double* p, long long j, const Pk<2>& a) {
+    reinterpret_cast<double2*>(p)[j] = make_double2(a.v[0], a.v[1]);
+}
+
+// Passes over the n-vectors per new iterate with memory M (all 2M+1 dot products stay sequential, in upstream's order):
+//   update      read x, x_prev, res, res_prev; write the candidate pair (s, y) into the SPARE history slot; the same
+//               pass forms <s,y>, <y,y> and <s,-res> -- the first dot product of loop1 if the pair is accepted      6
+//   loop1, 1st  d = -res - alpha*y_new is formed from res (d is never initialised in memory), dot with the next s   4
+//   2M-2 steps  read d, the axpy vector, the next dot vector; write d                                               4 each
+//   last step   d + coef*s fused with  x_prev <- x, res_prev <- res, x_d = x <- x + d, z_curr <- z                 10
+// = 52 at M = 5 (61 before: the pair was recomputed in a second pass, d = -res took a pass of its own, and the last
+// axpy was separate from the end-of-iteration copies).  A rejected pair (<s,y> <= 0) leaves the ring untouched: the
+// physical slots are addressed through BzState::slot[], the spare one is swapped in only on acceptance.
+template <int V>
+__device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, TeamCtx& tc, unsigned int* counter,
+                                               int force_role) {
+    const long long n = v.n, nv = n / V;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-
-    if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
-        const double tau = __ldcg(&st->tau);
-        _Pragma("unroll 4") for (long long j = j0; j < n; j += stride)
-            v.x[j] = tau * v.x_d[j] + (1 - tau) * v.z_curr[j];
-        if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
-            st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-            st->next_op = OP_G;
-            if (force_role < 0) bz_toc(st, 1);
-            __threadfence();
-        }
-        return;
-    }
-
-    TeamCtx tc{tm, 0, scratch, st, st->xr.nranks > 1 ? *st->xr.seq : 0ULL, 0};
     const int M = __ldcg(&st->mem);
     int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
     double H = __ldcg(&st->H);
     const int skip = __ldcg(&st->skip_update);
     double ys[BZ_MAXMEM], al[BZ_MAXMEM];
-    for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; }
+    int slot[BZ_MAXMEM];
+    for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; slot[i] = __ldcg(&st->slot[i]); }
+    int spare = __ldcg(&st->spare);
+    double* const x = v.x;
+    const double* __restrict__ res = v.res;
+    const double* __restrict__ zc = v.z;
+    double* __restrict__ d = v.d;
 
     // ---- update!(H, x - x_prev, res - res_prev)
+    bool have_dot0 = false;
+    double dot0 = 0.0;
     if (!skip && M > 0) {
-        double a[2] = {0.0, 0.0};
-        _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-            const double s = v.x[j] - v.x_prev[j], yv = v.res[j] - v.res_prev[j];
-            a[0] += s * yv;
-            a[1] += yv * yv;
+        const double* __restrict__ xp = v.x_prev;
+        const double* __restrict__ rp = v.res_prev;
+        double* __restrict__ sn = v.sM + (size_t)spare * n;
+        double* __restrict__ yn = v.yM + (size_t)spare * n;
+        double a[3] = {0.0, 0.0, 0.0};
+        for (long long j = j0; j < nv; j += stride) {
+            const Pk<V> xa = ldv<V>(x, j), xb = ldv<V>(xp, j), ra = ldv<V>(res, j), rb = ldv<V>(rp, j);
+            Pk<V> sv, yv;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const double s_ = xa.v[e] - xb.v[e], y_ = ra.v[e] - rb.v[e];
+                sv.v[e] = s_; yv.v[e] = y_;
+                a[0] += s_ * y_;
+                a[1] += y_ * y_;
+                a[2] += s_ * (-ra.v[e]);
+            }
+            stv<V>(sn, j, sv);
+            stv<V>(yn, j, yv);
         }
-        team_sum<2>(tc, a);
+        team_sum<3>(tc, a);
         if (a[0] > 0) {
             curridx += 1;
             if (curridx > M) curridx = 1;
             currmem = currmem + 1 > M ? M : currmem + 1;
             ys[curridx - 1] = a[0];
-            double* sm = v.sM + (size_t)(curridx - 1) * n;
-            double* ym = v.yM + (size_t)(curridx - 1) * n;
-            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-                sm[j] = v.x[j] - v.x_prev[j];
-                ym[j] = v.res[j] - v.res_prev[j];
-            }
+            const int old = slot[curridx - 1];
+            slot[curridx - 1] = spare;
+            spare = old;
             H = a[0] / a[1];
+            dot0 = a[2];
+            have_dot0 = true;
         }
     }
+    auto SM = [&](int ring1) { return v.sM + (size_t)slot[ring1 - 1] * n; };   // 1-based ring position -> history vector
+    auto YM = [&](int ring1) { return v.yM + (size_t)slot[ring1 - 1] * n; };
+    const bool write_d = force_role >= 0;   // the parity entry point bz_lbfgs_apply reads d; the cycle only needs x_d
 
-    // ---- d = H * (-res): two-loop recursion, each axpy fused with the next dot product
-    int idx = curridx;
-    {
-        double a[1] = {0.0};
-        if (currmem > 0) {
-            const double* sm = v.sM + (size_t)(idx - 1) * n;
-            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-                const double dj = -v.res[j];
-                v.d[j] = dj;
-                a[0] += sm[j] * dj;
+    // last pass: d_final = dsrc + coef*sadd (or H*(-res) without history), fused with the end-of-iteration copies
+    auto final_pass = [&](const double* __restrict__ dsrc, const double* __restrict__ sadd, double coef, bool from_res) {
+        double* __restrict__ xpw = v.x_prev;
+        double* __restrict__ rpw = v.res_prev;
+        double* __restrict__ xdw = v.x_d;
+        double* __restrict__ zcw = v.z_curr;
+        for (long long j = j0; j < nv; j += stride) {
+            const Pk<V> xa = ldv<V>(x, j), ra = ldv<V>(res, j), za = ldv<V>(zc, j);
+            Pk<V> da, sa;
+            if (!from_res) { da = ldv<V>(dsrc, j); sa = ldv<V>(sadd, j); }
+            Pk<V> xd, dn;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                dn.v[e] = from_res ? H * (-ra.v[e]) : da.v[e] + coef * sa.v[e];
+                xd.v[e] = xa.v[e] + dn.v[e];
             }
-        } else {
-            _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) v.d[j] = H * (-v.res[j]);
+            stv<V>(xpw, j, xa);
+            stv<V>(rpw, j, ra);
+            stv<V>(xdw, j, xd);
+            stv<V>(x, j, xd);
+            stv<V>(zcw, j, za);
+            if (write_d) stv<V>(d, j, dn);
+        }
+    };
+
+    if (currmem == 0) {
+        final_pass(nullptr, nullptr, 0.0, true);
+    } else {
+        // ---- d = H * (-res): two-loop recursion, each axpy fused with the next dot product
+        int idx = curridx;
+        double a[1] = {0.0};
+        if (!have_dot0) {                     // no (accepted) update in this call: <s_newest, -res> needs its own pass
+            const double* __restrict__ sm = SM(idx);
+            for (long long j = j0; j < nv; j += stride) {
+                const Pk<V> ra = ldv<V>(res, j), sa = ldv<V>(sm, j);
+#pragma unroll
+                for (int e = 0; e < V; ++e) a[0] += sa.v[e] * (-ra.v[e]);
+            }
         }
         for (int t = 0; t < currmem; ++t) {       // loop1!: newest -> oldest
-            team_sum<1>(tc, a);
+            if (t == 0 && have_dot0) a[0] = dot0; else team_sum<1>(tc, a);
             const int i = idx - 1;
             const double alpha_i = a[0] / ys[i];
             al[i] = alpha_i;
             int idx2 = idx - 1;
             if (idx2 == 0) idx2 = M;
-            const double* ym = v.yM + (size_t)i * n;
+            const double* __restrict__ ym = YM(idx);
+            const bool last = t == currmem - 1;
+            int idn = idx2 + 1;
+            if (idn > M) idn = 1;
+            const double* __restrict__ nxt = last ? YM(idn) : SM(idx2);   // last: d .= H .* d, then the first dot of loop2!
+            const double* __restrict__ dsrc = t == 0 ? res : d;            // t = 0: d = -res, read straight from res
             a[0] = 0.0;
-            if (t < currmem - 1) {
-                const double* sm2 = v.sM + (size_t)(idx2 - 1) * n;
-                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-                    const double dj = v.d[j] - alpha_i * ym[j];
-                    v.d[j] = dj;
-                    a[0] += sm2[j] * dj;
+            for (long long j = j0; j < nv; j += stride) {
+                const Pk<V> da = ldv<V>(dsrc, j), ya = ldv<V>(ym, j), na = ldv<V>(nxt, j);
+                Pk<V> dn;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    double dj = (t == 0 ? -da.v[e] : da.v[e]) - alpha_i * ya.v[e];
+                    if (last) dj = H * dj;
+                    dn.v[e] = dj;
+                    a[0] += na.v[e] * dj;
                 }
-            } else {                               // last: also d .= H .* d, then first dot of loop2!
-                int idn = idx2 + 1;
-                if (idn > M) idn = 1;
-                const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-                    double dj = v.d[j] - alpha_i * ym[j];
-                    dj = H * dj;
-                    v.d[j] = dj;
-                    a[0] += ymn[j] * dj;
-                }
+                stv<V>(d, j, dn);
             }
             idx = idx2;
         }
@@ -192,31 +239,27 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
             const int i = idx - 1;
             const double beta = a[0] / ys[i];
             const double coef = al[i] - beta;
-            const double* sm = v.sM + (size_t)i * n;
+            const double* __restrict__ sm = SM(idx);
             a[0] = 0.0;
             if (t < currmem - 1) {
                 int idn = idx + 1;
                 if (idn > M) idn = 1;
-                const double* ymn = v.yM + (size_t)(idn - 1) * n;
-                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-                    const double dj = v.d[j] + coef * sm[j];
-                    v.d[j] = dj;
-                    a[0] += ymn[j] * dj;
+                const double* __restrict__ ymn = YM(idn);
+                for (long long j = j0; j < nv; j += stride) {
+                    const Pk<V> da = ldv<V>(d, j), sa = ldv<V>(sm, j), na = ldv<V>(ymn, j);
+                    Pk<V> dn;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const double dj = da.v[e] + coef * sa.v[e];
+                        dn.v[e] = dj;
+                        a[0] += na.v[e] * dj;
+                    }
+                    stv<V>(d, j, dn);
                 }
             } else {
-                _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) v.d[j] = v.d[j] + coef * sm[j];
+                final_pass(d, sm, coef, false);
             }
         }
-    }
-    // ---- x_prev <- x; res_prev <- res; x_d = x + d; x <- x_d; z_curr <- z
-    _Pragma("unroll 4") for (long long j = j0; j < n; j += stride) {
-        const double xj = v.x[j];
-        v.x_prev[j] = xj;
-        v.res_prev[j] = v.res[j];
-        const double xd = xj + v.d[j];
-        v.x_d[j] = xd;
-        v.x[j] = xd;
-        v.z_curr[j] = v.z[j];
     }
     if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
         const double gamma = st->gamma;
@@ -229,14 +272,61 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
         st->tau = 1.0;
         st->k_bt = 1;
         st->currmem = currmem; st->curridx = curridx; st->H = H;
-        for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; }
+        for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; st->slot[i] = slot[i]; }
+        st->spare = spare;
         st->skip_update = 0;
-        st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-        st->next_op = OP_G;
+        st->grad_x_fresh = 1;
+        bz_goto_fb(st);
         if (st->xr.nranks > 1) *st->xr.seq = tc.seq0 + (unsigned long long)tc.xidx;
         if (force_role < 0) bz_toc(st, 1);
         __threadfence();
     }
+}
+
+__global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
+    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
+    __shared__ double scratch[3 * 32 + 4];
+    // the other parity's barrier words are free again: reset them for the launch after this one
+    if (blockIdx.x == 0 && threadIdx.x < BZ_MAXBAR)
+        tm.bars[(1 - tm.parity) * BZ_MAXBAR + threadIdx.x] = 0u;
+    int role = force_role;
+    if (role < 0) {
+        if (__ldcg(&st->next_op) != OP_L) return;
+        role = __ldcg(&st->l_role);
+        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 1);
+    }
+    const long long n = v.n;
+    const bool vec2 = (n % 2) == 0;
+
+    if (role == LROLE_INTERP) {      // x = tau*x_d + (1-tau)*z_curr   (A.5)
+        const double tau = __ldcg(&st->tau);
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const double* __restrict__ xd = v.x_d;
+        const double* __restrict__ zc = v.z_curr;
+        double* __restrict__ x = v.x;
+        if (vec2) {
+            for (long long j = j0; j < n / 2; j += stride) {
+                const Pk<2> a = ldv<2>(xd, j), b = ldv<2>(zc, j);
+                Pk<2> o;
+                o.v[0] = tau * a.v[0] + (1 - tau) * b.v[0];
+                o.v[1] = tau * a.v[1] + (1 - tau) * b.v[1];
+                stv<2>(x, j, o);
+            }
+        } else {
+            for (long long j = j0; j < n; j += stride) x[j] = tau * xd[j] + (1 - tau) * zc[j];
+        }
+        if (bz_last_cta(counter, gridDim.x) && threadIdx.x == 0) {
+            st->grad_x_fresh = 1;
+            bz_goto_fb(st);
+            if (force_role < 0) bz_toc(st, 1);
+            __threadfence();
+        }
+        return;
+    }
+    TeamCtx tc{tm, 0, scratch, st, st->xr.nranks > 1 ? *st->xr.seq : 0ULL, 0};
+    if (vec2) lstep_newiter<2>(st, v, tc, counter, force_role);
+    else lstep_newiter<1>(st, v, tc, counter, force_role);
 }
 
 
@@ -387,8 +477,8 @@ __global__ void __launch_bounds__(LC_THREADS)
         }
         // (the consumers of this state are later kernels: they see it only after the whole grid is done)
         if (cr.rank == 0 && threadIdx.x == 0) {
-            st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-            st->next_op = OP_G;
+            st->grad_x_fresh = 1;
+            bz_goto_fb(st);
             if (force_role < 0) bz_toc(st, 1);
             __threadfence();
         }
@@ -503,8 +593,8 @@ __global__ void __launch_bounds__(LC_THREADS)
         st->currmem = currmem; st->curridx = curridx; st->H = H;
         for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; }
         st->skip_update = 0;
-        st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
-        st->next_op = OP_G;
+        st->grad_x_fresh = 1;
+        bz_goto_fb(st);
         if (force_role < 0) bz_toc(st, 1);
         __threadfence();
     }

@@ -64,6 +64,7 @@ struct bz_problem {
     bool sharded = false;
     BzShard shard{};
     // slab-decomposed obstacle grid (cross-rank exchange over peer memory)
+    bool fused = false;   // obstacle problems on one GPU: the cycle is [L, X] with the fused kernel of bz_obfused.cu
     bool slab = false;
     unsigned long long* slab_base = nullptr;   // [mailbox | seq | x | z | xeps | yupd]
     size_t slab_bytes = 0;
@@ -125,6 +126,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_WIDE_TWO_PASS")) ctx->wide_two_pass = atoi(e);
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
     if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
+    if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
     return BZ_OK;
@@ -401,19 +403,25 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     double** nvecs[] = {&p->v.x, &p->v.z, &p->v.xeps, &p->v.x_prev, &p->v.x_d, &p->v.z_curr, &p->v.res,
                         &p->v.res_prev, &p->v.grad_x, &p->v.grad_z, &p->v.d, &p->Ec, &p->Ef};
     for (double** q : nvecs) if (!*q) PTRY(dev_alloc(ctx, q, p->nv));
-    PTRY(dev_alloc(ctx, &p->v.sM, (size_t)BZ_MAXMEM * p->nv));
-    PTRY(dev_alloc(ctx, &p->v.yM, (size_t)BZ_MAXMEM * p->nv));
+    // L-BFGS history: BZ_MAXMEM ring slots + one spare (the cooperative L kernel writes the candidate pair there)
+    PTRY(dev_alloc(ctx, &p->v.sM, (size_t)(BZ_MAXMEM + 1) * p->nv));
+    PTRY(dev_alloc(ctx, &p->v.yM, (size_t)(BZ_MAXMEM + 1) * p->nv));
     p->v.n = p->nv;
     double** mvecs[] = {&p->mu, &p->y, &p->muy, &p->cx, &p->s, &p->yupd, &p->tm1, &p->tm2, &p->tm3};
     for (double** q : mvecs) if (!*q) PTRY(dev_alloc(ctx, q, ml));
     const int maxgrid = ctx->num_sms * 8;
-    PTRY(dev_alloc(ctx, &p->part, (size_t)4 * maxgrid));
+    size_t npart = (size_t)4 * maxgrid;
+    if (d->c_kind == BZ_C_OBSTACLE && !p->slab && !p->slack && ctx->obstacle_fused) {
+        p->fused = true;
+        npart = std::max(npart, (size_t)bz_obfused_partials(ctx, p->ob));
+    }
+    PTRY(dev_alloc(ctx, &p->part, npart));
     PTRY(dev_alloc(ctx, &p->lxpart, (size_t)maxgrid));
     PTRY(dev_alloc(ctx, &p->fxpart, (size_t)2 * maxgrid));
     PTRY(dev_alloc(ctx, &p->counters, 8));
     PTRY(dev_alloc(ctx, &p->team.bars, 2 * BZ_MAXBAR));
     p->team.max_ctas = ctx->num_sms * BZ_L_CTAS_PER_SM;
-    PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * p->team.max_ctas * 2));
+    PTRY(dev_alloc(ctx, &p->team.slots, (size_t)2 * BZ_MAXBAR * p->team.max_ctas * 4));
     p->team.parity = 0;
     PTRY(dev_alloc(ctx, &p->st, 1));
 #define PCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
@@ -473,6 +481,14 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         else { dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc); p->c_nlx = p->c_clusters; }
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
+    }
+    {   // a usable L-BFGS state before the first solve (the parity entry points may be called right away)
+        memset(p->st_host, 0, sizeof(BzState));
+        p->st_host->next_op = OP_DONE;
+        p->st_host->H = 1.0;
+        for (int i = 0; i < BZ_MAXMEM; ++i) p->st_host->slot[i] = i;
+        p->st_host->spare = BZ_MAXMEM;
+        PCUDA(cudaMemcpyAsync(p->st, p->st_host, sizeof(BzState), cudaMemcpyHostToDevice, ctx->stream));
     }
     // the LeastSquares pass and the constraint pass may pick different team geometries: each has its own exchange
     // ring, arrival counters and row-sequence bases
@@ -659,11 +675,17 @@ static BzGParams g_params(const bz_problem* p) {
     return g;
 }
 
-// one pass of the fixed cycle [L, G, F, G, D]
+// one pass of the fixed cycle [L, G, F, G, D]; fused problems: [L, X]
 static int launch_cycle(bz_problem* p) {
     bz_ctx* ctx = p->ctx;
     BzGradSrc gs = grad_src(p);
     BzTeam tm = p->team;
+    if (p->fused) {
+        BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab));
+        p->team.parity ^= 1;
+        return bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->muy, p->part, p->counters + 3, 0,
+                                        nullptr, nullptr);
+    }
     BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab));
     p->team.parity ^= 1;
     BZ_TRY(launch_provider(p, -1));
@@ -682,7 +704,16 @@ static int panoc_run(bz_problem* p, const bz_options* o, double tol, long long m
         return bz_fail(ctx, BZ_ERR_ARG, "lbfgs_memory must be in [0, 16]");
     if (maxit < 1) maxit = 1;
     BZ_TRY(bz_launch_panoc_begin(ctx, p->st, tol, maxit, o->alpha, o->beta, o->minimum_gamma,
-                                 o->max_backtracks, o->lbfgs_memory));
+                                 o->max_backtracks, o->lbfgs_memory, p->fused ? 1 : 0));
+    if (p->fused) {
+        // Appendix A.4 with the unfused kernels, once per inner solve: gradient at x, at x .+ 1, the Lipschitz estimate;
+        // from MODE_INITFB on everything is the X kernel
+        for (int k = 0; k < 2; ++k) {
+            BZ_TRY(launch_provider(p, -1));
+            BzGradSrc gs0 = grad_src(p);
+            BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs0, g_params(p), p->part, p->counters + 3, -1));
+        }
+    }
     const int cycles_per_batch = 4;
     int slot = 0, inflight = 0;
     p->status_host[0] = p->status_host[1] = IST_RUNNING;
@@ -699,6 +730,9 @@ static int panoc_run(bz_problem* p, const bz_options* o, double tol, long long m
             if (p->status_host[slot] != IST_RUNNING) break;
         }
     }
+    // fused problems never materialise c(z), s, yupd inside the loop: one unfused AL-gradient at the returned point
+    // leaves the AugLagFun side-effect state the outer step reads (alps.jl:68,74)
+    if (p->fused) BZ_TRY(launch_provider(p, TGT_Z));
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BZ_OK;
 }
@@ -782,6 +816,8 @@ static int outer_solve(bz_problem* p, bool slack, const double* x0, const double
     h->n_global = p->n_global;
     h->next_op = OP_DONE;
     h->H = 1.0;
+    for (int i = 0; i < BZ_MAXMEM; ++i) h->slot[i] = i;
+    h->spare = BZ_MAXMEM;
     h->inner_tol = inner_tol; h->tol_prim = tol_prim; h->tol_dual = tol_dual;
     h->theta_penalty = o->theta_penalty; h->kappa_penalty = o->kappa_penalty; h->kappa_tol = o->kappa_tol;
     h->outer_maxit = o->maxit; h->subsolver_maxit = o->subsolver_maxit;
@@ -1033,6 +1069,29 @@ extern "C" int bz_fb_step(bz_problem* p, const double* x, const double* grad, do
     return BZ_OK;
 }
 
+extern "C" int bz_obstacle_fused_step(bz_problem* p, const double* x, double gamma, double* z, double* res,
+                                      double* grad_x, double* grad_z, double* scalars9) {
+    if (!p || !x) return BZ_ERR_ARG;
+    bz_ctx* ctx = p->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->fused) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_obstacle_fused_step: the problem does not run the fused obstacle kernel");
+    BZ_TRY(h2d(p, p->v.x, x, p->n));
+    BZ_TRY(fetch_state(p));
+    p->st_host->gamma = gamma;
+    BZ_TRY(push_state(p));
+    // grad_x / grad_z are debug outputs of the kernel: staged in x_d / d (free outside a solve)
+    BZ_TRY(bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->muy, p->part, p->counters + 3, 1,
+                                    p->v.x_d, p->v.d));
+    BZ_TRY(fetch_state(p));
+    if (scalars9) for (int k = 0; k < 9; ++k) scalars9[k] = p->st_host->out[k];
+    BZ_TRY(d2h(p, z, p->v.z, p->n));
+    BZ_TRY(d2h(p, res, p->v.res, p->n));
+    BZ_TRY(d2h(p, grad_x, p->v.x_d, p->n));
+    BZ_TRY(d2h(p, grad_z, p->v.d, p->n));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BZ_OK;
+}
+
 extern "C" int bz_lbfgs_reset(bz_problem* p, int memory) {
     if (!p || memory < 0 || memory > BZ_MAXMEM) return BZ_ERR_ARG;
     bz_ctx* ctx = p->ctx;
@@ -1040,6 +1099,8 @@ extern "C" int bz_lbfgs_reset(bz_problem* p, int memory) {
     BZ_TRY(fetch_state(p));
     BzState* h = p->st_host;
     h->mem = memory; h->currmem = 0; h->curridx = 0; h->H = 1.0;
+    for (int i = 0; i < BZ_MAXMEM; ++i) h->slot[i] = i;
+    h->spare = BZ_MAXMEM;
     h->gamma = 1.0; h->alpha = 0.95; h->beta = 0.5;
     BZ_TRY(push_state(p));
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

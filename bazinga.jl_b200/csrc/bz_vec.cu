@@ -686,19 +686,22 @@ int bz_launch_fill(bz_ctx* ctx, double* v, long long m, double value) {
 }
 
 __global__ void k_panoc_begin(BzState* st, double tol, long long maxit, double alpha, double beta,
-                              double gamma_min, int max_backtracks, int mem) {
+                              double gamma_min, int max_backtracks, int mem, int fused) {
+    st->fused = fused;
     st->tol = tol; st->maxit = maxit; st->alpha = alpha; st->beta = beta;
     st->gamma_min = gamma_min; st->max_backtracks = max_backtracks; st->mem = mem;
     st->iter = 0; st->inner_status = IST_RUNNING;
     st->currmem = 0; st->curridx = 0; st->H = 1.0;
+    for (int i = 0; i < BZ_MAXMEM; ++i) st->slot[i] = i;
+    st->spare = BZ_MAXMEM;
     st->tau = 1.0; st->k_bt = 1; st->skip_update = 1;
     st->mode = MODE_INIT0; st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
     st->l_role = LROLE_NEWITER;
     st->next_op = OP_G;
 }
 int bz_launch_panoc_begin(bz_ctx* ctx, BzState* st, double tol, long long maxit, double alpha,
-                          double beta, double gamma_min, int max_backtracks, int mem) {
-    k_panoc_begin<<<1, 1, 0, ctx->stream>>>(st, tol, maxit, alpha, beta, gamma_min, max_backtracks, mem);
+                          double beta, double gamma_min, int max_backtracks, int mem, int fused) {
+    k_panoc_begin<<<1, 1, 0, ctx->stream>>>(st, tol, maxit, alpha, beta, gamma_min, max_backtracks, mem, fused);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;

@@ -5,7 +5,7 @@
 #define BZ_MAXBAR 48          // team barriers per L launch (1 + 2*memory + slack)
 #define BZ_VEC_THREADS 256
 #define BZ_L_THREADS 512
-#define BZ_L_CTAS_PER_SM 3     // co-resident CTAs per SM of the cooperative L kernel (64 regs x 512 thr)
+#define BZ_L_CTAS_PER_SM 2     // co-resident CTAs per SM of the cooperative L kernel (64 regs x 512 thr: the double2 passes need them)
 
 struct BzVecs {
     double *x, *z, *xeps, *x_prev, *x_d, *z_curr, *res, *res_prev, *grad_x, *grad_z, *d;
@@ -16,7 +16,7 @@ struct BzVecs {
 // software grid barrier + all-CTA reduction used by the cooperative L kernel
 struct BzTeam {
     unsigned int* bars;   // [2][BZ_MAXBAR]
-    double* slots;        // [2][BZ_MAXBAR][max_ctas][2]
+    double* slots;        // [2][BZ_MAXBAR][max_ctas][4]
     int max_ctas;
     int parity;
 };
@@ -68,4 +68,9 @@ int bz_launch_outer_logic(bz_ctx* ctx, BzState* st);
 int bz_launch_scale(bz_ctx* ctx, double* v, long long m, double factor);
 int bz_launch_fill(bz_ctx* ctx, double* v, long long m, double value);
 int bz_launch_panoc_begin(bz_ctx* ctx, BzState* st, double tol, long long maxit, double alpha,
-                          double beta, double gamma_min, int max_backtracks, int mem);
+                          double beta, double gamma_min, int max_backtracks, int mem, int fused);
+// fused forward-backward evaluation of the obstacle problems (bz_obfused.cu): [G, F, G, D] in one pass
+int bz_obfused_partials(bz_ctx* ctx, const BzObstacle& ob);
+int bz_launch_obstacle_fused(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzObstacle& ob, const BzGParams& g,
+                             const double* mu, const double* muy, double* part, unsigned int* counter, int force,
+                             double* dbg_gx, double* dbg_gz);

@@ -157,3 +157,85 @@ __device__ inline double bz_assemble_blocked(const BzGradSrc& gs, long long jb, 
     __syncthreads();
     return out;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Scalar logic of the state machine, run by ONE thread once the sums of a step are known.  Shared by the stand-alone
+// F / D kernels (bz_fbd.cu) and the fused obstacle kernel (bz_obfused.cu), so both take the same decisions bit for bit.
+// `fused` problems go L -> X -> (X | L): where the plain cycle asks for a gradient at x followed by F, they ask for X.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bz_goto_fb(BzState* st) {     // "evaluate the AL-gradient at x, then the forward-backward step"
+    if (st->fused) { st->next_op = OP_X; return; }
+    st->grad_target = TGT_X; st->after_g = OP_F;
+    st->next_op = OP_G;
+}
+// forward-backward step done at gamma with s0 = <grad_x, res>, s1 = ||res||^2 (before the sqrt round trip), s2 = g partial sum
+__device__ __forceinline__ void bz_f_finish(BzState* st, const BzGParams& g, double gamma, int fresh, double s0, double s1,
+                                            double s2, double lx, double fx) {
+    if (fresh) {
+        st->f_x = lx; st->al_fx = fx; st->al_lx = lx;
+        st->n_grad += 1;
+    }
+    const double nrm = sqrt(s1);
+    const double nrm2 = nrm * nrm;                       // norm(res)^2
+    st->dot_gr = s0;
+    st->res_nrm2sq = nrm2;
+    st->f_up = st->f_x - s0 + ((st->alpha / gamma) / 2) * nrm2;   // f_model
+    st->g_z = bz_g_value_scale(g) * s2;
+    st->n_prox += 1;
+    st->grad_x_fresh = 0;
+    st->out[0] = st->g_z; st->out[1] = s0; st->out[2] = s1;
+}
+// gradient at z is in: backtrack_stepsize! (A.4), the loop body of A.5, the stop rule A.3
+__device__ __forceinline__ void bz_d_decide(BzState* st, double gamma, double f_z, double fx, double stop1, double stop2) {
+    const int refb = st->fused ? OP_X : OP_F;            // "redo the forward-backward step with the halved gamma"
+    st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
+    st->n_grad += 1;
+    const int mode = st->mode;
+    const bool cond = (f_z > st->f_up + 10 * BZ_EPS * (1 + fabs(f_z))) && (gamma >= st->gamma_min);
+    bool end_iter = false;
+    double stopn = stop1;
+    if (mode == MODE_INITFB) {          // backtrack_stepsize! (A.4)
+        if (cond) {
+            st->gamma = gamma / 2;
+            st->grad_x_fresh = 0;
+            st->next_op = refb;
+        } else {
+            end_iter = true;
+            st->skip_update = 1;
+            st->mode = MODE_ITER;
+        }
+    } else {                            // A.5 loop body at backtrack index k
+        const int k = st->k_bt;
+        if (cond) {
+            st->gamma = gamma * 0.5;
+            st->currmem = 0; st->curridx = 0; st->H = 1.0;       // reset_direction_state!
+            if (k + 1 > st->max_backtracks) {                    // `continue` ran off the loop
+                end_iter = true;
+                stopn = stop2;
+            } else {
+                st->k_bt = k + 1;
+                st->grad_x_fresh = 0;
+                st->next_op = refb;
+            }
+        } else if (st->f_up + st->g_z <= st->thresh || k >= st->max_backtracks) {
+            end_iter = true;
+        } else {
+            st->tau = (k >= st->max_backtracks - 1) ? 0.0 : st->tau / 2;
+            st->k_bt = k + 1;
+            st->l_role = LROLE_INTERP;
+            st->next_op = OP_L;
+        }
+        if (end_iter) st->skip_update = 0;
+    }
+    if (end_iter) {
+        st->iter += 1;
+        st->stopnorm = stopn;
+        if (st->iter >= st->maxit || stopn <= st->tol) {
+            st->inner_status = (stopn <= st->tol) ? IST_CONVERGED : IST_MAXIT;
+            st->next_op = OP_DONE;
+        } else {
+            st->l_role = LROLE_NEWITER;
+            st->next_op = OP_L;
+        }
+    }
+}

@@ -375,6 +375,15 @@ class Problem:
                                     C.byref(gz), C.byref(dot), C.byref(sq)), self.ctx.handle)
         return dict(z=z, res=res, gz=gz.value, dot_grad_res=dot.value, res_sq=sq.value)
 
+    def obstacle_fused_step(self, x, gamma):
+        """One fused forward-backward evaluation (csrc/bz_obfused.cu): dict(z, res, grad_x, grad_z, scalars[9])."""
+        x = _f64(x)
+        z, res, gx, gz = (np.empty(self.nx) for _ in range(4))
+        sc = np.empty(9)
+        K.check(self.lib.bz_obstacle_fused_step(self.handle, _ptr(x), float(gamma), _ptr(z), _ptr(res), _ptr(gx), _ptr(gz),
+                                                _ptr(sc)), self.ctx.handle)
+        return dict(z=z, res=res, grad_x=gx, grad_z=gz, scalars=sc)
+
     def lbfgs_reset(self, memory=5):
         K.check(self.lib.bz_lbfgs_reset(self.handle, int(memory)), self.ctx.handle)
 

@@ -236,6 +236,13 @@ int bz_proj(bz_problem* p, const double* v, double* z);
  * ||res||^2 */
 int bz_fb_step(bz_problem* p, const double* x, const double* grad, double gamma, double* z,
                double* res, double* gz, double* dot_grad_res, double* res_sq);
+/* One fused forward-backward evaluation of an obstacle problem (c kind OBSTACLE on one GPU; csrc/bz_obfused.cu) at x with
+ * step gamma, against the current (mu, y): what PANOCplus computes between two direction steps --
+ * grad_x = gradient!(., alFun, x) (auglagfun.jl:73-86), z = prox!(., g, x - gamma*grad_x, gamma), res = x - z,
+ * grad_z = gradient!(., alFun, z).  scalars9 = {alFun(x), f(x), <grad_x,res>, ||res||^2, g(z), alFun(z), f(z),
+ * ||res/gamma - grad_x + grad_z||_inf, the same norm at gamma/2}.  Output pointers may be NULL. */
+int bz_obstacle_fused_step(bz_problem* p, const double* x, double gamma, double* z, double* res,
+                           double* grad_x, double* grad_z, double* scalars9);
 /* L-BFGS operator: reset / update!(s, y) / d = H*v */
 int bz_lbfgs_reset(bz_problem* p, int memory);
 int bz_lbfgs_update(bz_problem* p, const double* s, const double* y);
