@@ -106,6 +106,7 @@ SYMBOLS = {
                                  _vp, _vp, _vp, _dp]),
     "bz_batch_solve_als": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
                                      _vp, _vp, _vp, _dp]),
+    "bz_fp64_fma_peak": (C.c_int, [_vp, _dp]),
     "bz_comm_unique_id": (C.c_int, [_vp]),
     "bz_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "bz_comm_destroy": (C.c_int, [_vp]),

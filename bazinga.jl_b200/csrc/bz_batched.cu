@@ -222,6 +222,7 @@ template <int KIND, int SLACK> struct Al {
     static constexpr int NY = Prob<KIND>::NY;
     static constexpr int NV = SLACK ? NX + NY : NX;
     double mu[NY], rmu[NY], y[NY], muy[NY], musqy, cx[NY], s[NY], yupd[NY], fx, gz;   // rmu = 1 ./ mu (see fdiv)
+    int ngrad;   // AL-gradient evaluations of this solve so far (the work budget of phase 1, see k_batch_alps)
 
     __device__ void update() {   // AugLagUpdate!
         double acc = 0.0;
@@ -231,6 +232,7 @@ template <int KIND, int SLACK> struct Al {
     }
     __device__ double gradient(const double (&xv)[NV], double (&dlx)[NV]) {   // gradient!(dlx, al, x)
         double dfx[NX], jtv[NX], x[NX], acc = 0.0;
+        ++ngrad;
 #pragma unroll
         for (int j = 0; j < NX; ++j) x[j] = xv[j];
         if constexpr (SLACK != 0) {   // auglagfunslack.jl:77-97
@@ -366,9 +368,13 @@ struct Lbfgs {
 };
 
 // PANOCplus (Appendix A.2-A.5) on a variable of NV entries; returns k, solution in z
-template <int KIND, int MM, int SLACK>
+// WARP = false: one thread runs the solve.  WARP = true: the 32 lanes of a warp run the SAME solve in lock-step (identical
+// registers), except inside the line search, where lane l evaluates the candidate the sequential loop would reach l
+// steps later (see line_search_warp).  budget > 0: give up (return -1) once the solve has used more than `budget`
+// AL-gradients -- phase 1 of the two-phase batch.
+template <int KIND, int MM, int SLACK, bool WARP>
 __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, SLACK>::NV], const TbOpts& o, double tol,
-                               double (&z)[Al<KIND, SLACK>::NV]) {
+                               double (&z)[Al<KIND, SLACK>::NV], int budget) {
     constexpr int NV = Al<KIND, SLACK>::NV;
     const double a = o.alpha;
     double x[NV], grad_x[NV], grad_z[NV], tmpg[NV], y[NV], res[NV];
@@ -425,6 +431,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         }
         if (isnan_) stopnorm = __longlong_as_double(0x7ff8000000000000LL);
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
+        if (budget > 0 && al.ngrad > budget) return -1;      // phase 1: leave this instance to the warp-per-instance pass
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
         const double FBE_x = f_model<NV>(f_x, grad_x, res, aog) + g_z;
@@ -441,27 +448,98 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         const double sigma = o.beta * fdiv(0.5, gamma, rg) * (1 - a);
         const double nr = sqrt(dotn<NV>(res, res));
         const double thresh = FBE_x - sigma * (nr * nr) + 10 * BZ_EPS * (1 + fabs(FBE_x));
-        for (int kb = 1; kb <= o.max_backtracks; ++kb) {
+        if constexpr (!WARP) {
+            for (int kb = 1; kb <= o.max_backtracks; ++kb) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
-            g_z = al.prox(y, gamma, z);
+                for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
+                g_z = al.prox(y, gamma, z);
 #pragma unroll
-            for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
-            f_up = f_model<NV>(f_x, grad_x, res, aog);
-            f_z = al.gradient(z, grad_z);
-            if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
+                for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
+                f_up = f_model<NV>(f_x, grad_x, res, aog);
+                f_z = al.gradient(z, grad_z);
+                if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
+                    gamma *= 0.5;
+                    rg *= 2;
+                    aog *= 2;
+                    if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
+                    H.reset();
+                    continue;
+                }
+                if (f_up + g_z <= thresh || kb >= o.max_backtracks) break;
+                tau = (kb >= o.max_backtracks - 1) ? 0.0 : tau / 2;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) x[j] = tau * x_d[j] + (1 - tau) * z_curr[j];
+                f_x = al.gradient(x, grad_x);
+            }
+        } else {
+            // ---- the same loop, its iterations evaluated speculatively by the lanes of the warp.  Between two gamma-halvings
+            // the candidate of loop index kb + l is a function of (x_d, z_curr, gamma) and of l alone: tau follows the
+            // deterministic schedule below, x = tau*x_d + (1 - tau)*z_curr.  Lane l evaluates it with the very statements of
+            // the sequential loop; the first lane (in loop order) that either halves gamma or stops is what the sequential
+            // loop would have reached, and its registers become everybody's.  A gamma-halving restarts the speculation at the
+            // next loop index from that lane's x.  Bit-identical to the sequential loop by construction.
+            const int lane = threadIdx.x & 31;
+            int kb = 1;
+            while (kb <= o.max_backtracks) {
+                // tau of loop index kb + lane, from the tau of index kb:  tau <- (k >= max_backtracks - 1) ? 0 : tau / 2 at k = kb .. kb+lane-1
+                double tl = tau;
+                for (int q = 0; q < lane; ++q) tl = (kb + q >= o.max_backtracks - 1) ? 0.0 : tl / 2;
+                const int kl = kb + lane;
+                double xl[NV], gxl[NV], fxl = f_x;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) { xl[j] = x[j]; gxl[j] = grad_x[j]; }
+                const bool live = kl <= o.max_backtracks;
+                if (lane > 0 && live) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) xl[j] = tl * x_d[j] + (1 - tl) * z_curr[j];
+                    fxl = al.gradient(xl, gxl);
+                }
+                double zl[NV], rl[NV], gzl[NV], gz_l = 0.0, fup_l = 0.0, fz_l = 0.0;
+                bool halve = false, stop = false;
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) y[j] = xl[j] - gamma * gxl[j];
+                    gz_l = al.prox(y, gamma, zl);
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) rl[j] = xl[j] - zl[j];
+                    fup_l = f_model<NV>(fxl, gxl, rl, aog);
+                    fz_l = al.gradient(zl, gzl);
+                    halve = fz_l > fup_l + 10 * BZ_EPS * (1 + fabs(fz_l)) && gamma >= o.minimum_gamma;
+                    stop = !halve && (fup_l + gz_l <= thresh || kl >= o.max_backtracks);
+                }
+                const unsigned ev = __ballot_sync(0xffffffffu, live && (halve || stop));
+                const int src = __ffs(ev) - 1;        // never empty: the lane of loop index max_backtracks halves or stops
+                const bool was_halve = __shfl_sync(0xffffffffu, halve ? 1 : 0, src) != 0;
+                // the chosen lane's state becomes the warp's (including the AugLagFun side effects of its last gradient!)
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    x[j] = __shfl_sync(0xffffffffu, xl[j], src);
+                    grad_x[j] = __shfl_sync(0xffffffffu, gxl[j], src);
+                    z[j] = __shfl_sync(0xffffffffu, zl[j], src);
+                    res[j] = __shfl_sync(0xffffffffu, rl[j], src);
+                    grad_z[j] = __shfl_sync(0xffffffffu, gzl[j], src);
+                }
+                f_x = __shfl_sync(0xffffffffu, fxl, src);
+                g_z = __shfl_sync(0xffffffffu, gz_l, src);
+                f_up = __shfl_sync(0xffffffffu, fup_l, src);
+                f_z = __shfl_sync(0xffffffffu, fz_l, src);
+                tau = __shfl_sync(0xffffffffu, tl, src);
+                al.fx = __shfl_sync(0xffffffffu, al.fx, src);
+#pragma unroll
+                for (int i = 0; i < Al<KIND, SLACK>::NY; ++i) {
+                    al.cx[i] = __shfl_sync(0xffffffffu, al.cx[i], src);
+                    al.s[i] = __shfl_sync(0xffffffffu, al.s[i], src);
+                    al.yupd[i] = __shfl_sync(0xffffffffu, al.yupd[i], src);
+                }
+                al.ngrad = __shfl_sync(0xffffffffu, al.ngrad, 0);    // (not used in this mode; kept uniform)
+                if (!was_halve) break;
                 gamma *= 0.5;
                 rg *= 2;
                 aog *= 2;
                 if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
                 H.reset();
-                continue;
+                kb += src + 1;
             }
-            if (f_up + g_z <= thresh || kb >= o.max_backtracks) break;
-            tau = (kb >= o.max_backtracks - 1) ? 0.0 : tau / 2;
-#pragma unroll
-            for (int j = 0; j < NV; ++j) x[j] = tau * x_d[j] + (1 - tau) * z_curr[j];
-            f_x = al.gradient(x, grad_x);
         }
         double sv[NV], yv[NV];
 #pragma unroll
@@ -471,13 +549,21 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     }
 }
 
-// one thread = one complete solve: SLACK = 0 `alps` (alps.jl:7-117), SLACK = 1 `als` (als.jl:7-120)
-template <int KIND, int MM, int SLACK>
+// One complete solve per thread (WARP = false) or per warp (WARP = true): SLACK = 0 `alps` (alps.jl:7-117), SLACK = 1 `als`
+// (als.jl:7-120).
+//
+// Two-phase batch (the loop replaced is demo/mpvca.jl:241-281).  A launch lasts as long as its slowest
+// instance, and the slow instances are slow because every PANOC+ iteration exhausts its 20 line-search back-tracks
+// (40 dependent AL-gradients per iteration on one lone lane).  Phase 1 runs every instance on its own thread with a
+// budget of AL-gradient evaluations; an instance that exceeds it is appended to `surv` and abandoned.  Phase 2 re-runs the
+// survivors from scratch, one WARP each, with the line search evaluated speculatively across the lanes: the dependent
+// chain of an iteration shrinks from up to 41 gradients to 3, bit-identical results (same statements, same order).
+template <int KIND, int MM, int SLACK, bool WARP>
 __global__ void __launch_bounds__(TB_THREADS)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
-                 double* __restrict__ nrps) {
+                 double* __restrict__ nrps, int budget, int* __restrict__ surv, int* __restrict__ nsurv) {
     constexpr int NX = Prob<KIND>::NX;
     constexpr int NY = Prob<KIND>::NY;
     constexpr int NV = Al<KIND, SLACK>::NV;
@@ -487,10 +573,17 @@ __global__ void __launch_bounds__(TB_THREADS)
     // branches, each serialised against it (r1j, 65,536 MPVC starts: 38.3 ms in launch order, 21.9 ms this way -- the time
     // of the slowest instance alone; either-or 38.7 -> 36.3 ms).  Results do not depend on the mapping.
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nwarps = (batch + 31) / 32;
-    const long long inst = (t & 31) * nwarps + (t >> 5);
-    if ((t >> 5) >= nwarps || inst >= batch) return;
+    long long inst;
+    if constexpr (WARP) {
+        if ((t >> 5) >= (long long)__ldcg(nsurv)) return;        // whole warp
+        inst = surv[t >> 5];
+    } else {
+        const long long nwarps = (batch + 31) / 32;
+        inst = (t & 31) * nwarps + (t >> 5);
+        if ((t >> 5) >= nwarps || inst >= batch) return;
+    }
     Al<KIND, SLACK> al;
+    al.ngrad = 0;
     double x[NX], cx[NY], s[NY];
     {   // alps.jl:37-45 / als.jl:38-44
         double x0[NX];
@@ -527,7 +620,11 @@ __global__ void __launch_bounds__(TB_THREADS)
 #pragma unroll
             for (int i = 0; i < NY; ++i) v0[NX + i] = s[i];       // xSlack = [x; s], als.jl:69-70
         }
-        const long long sub_it = panocplus<KIND, MM, SLACK>(al, v0, o, inner_tol, z);
+        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget);
+        if (sub_it < 0) {                                         // over the budget: phase 2 takes this instance
+            surv[atomicAdd(nsurv, 1)] = (int)inst;
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < NX; ++j) x[j] = z[j];
         tot_inner += sub_it;
@@ -565,6 +662,7 @@ __global__ void __launch_bounds__(TB_THREADS)
         }
         have_old = true;
     }
+    if (WARP && (threadIdx.x & 31) != 0) return;                  // every lane holds the same result
 #pragma unroll
     for (int j = 0; j < NX; ++j) xs[inst * NX + j] = x[j];
 #pragma unroll
@@ -606,7 +704,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     // one grow-only device arena per context, carved into the eight per-instance arrays: no cudaMalloc / cudaFree (and
     // their implicit synchronisations) on the second and later calls
     const size_t B = (size_t)batch;
-    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 2 * B * sizeof(int) + 64;
+    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 3 * B * sizeof(int) + 64;
     auto cleanup = [&]() {};
 #define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
         return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
@@ -625,6 +723,11 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     long long* din = reinterpret_cast<long long*>(dnrp + B);
     int* dit = reinterpret_cast<int*>(din + B);
     int* dst = dit + B;
+    int* dsurv = dst + B;          // survivors of phase 1 (instance indices), then their count
+    int* dnsurv = dsurv + B;
+    // phase-1 budget of AL-gradients per instance (0: single phase).  The speculative line search covers the whole loop
+    // with one warp when max_backtracks <= 32.
+    const int budget = (ctx->batch_budget > 0 && opt->max_backtracks <= 32 && opt->max_backtracks >= 1) ? ctx->batch_budget : 0;
     BTRY(cudaMemcpyAsync(dx0, x0, batch * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     BTRY(cudaMemcpyAsync(dy0, y0, batch * ny * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     cudaEvent_t e0, e1;
@@ -632,9 +735,15 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     BTRY(cudaEventCreate(&e1));
     const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
     cudaEventRecord(e0, ctx->stream);
+    if (budget > 0) BTRY(cudaMemsetAsync(dnsurv, 0, sizeof(int), ctx->stream));
+    // phase 2: one warp per survivor; the grid covers the worst case (every instance survives), warps beyond the count exit
+    const unsigned grid2 = (unsigned)((batch * 32 + TB_THREADS - 1) / TB_THREADS);
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
-#define TB_LAUNCH(K, MMV) do { if (slack) k_batch_alps<K, MMV, 1><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); \
-                                else k_batch_alps<K, MMV, 0><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp); } while (0)
+#define TB_LAUNCH2(K, MMV, SL) do { \
+        k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv); \
+        if (budget > 0) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
+    } while (0)
+#define TB_LAUNCH(K, MMV) do { if (slack) TB_LAUNCH2(K, MMV, 1); else TB_LAUNCH2(K, MMV, 0); } while (0)
 #define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
     switch (kind) {
     case 0: TB_DISPATCH(0); break;
@@ -648,6 +757,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     }
 #undef TB_DISPATCH
 #undef TB_LAUNCH
+#undef TB_LAUNCH2
     cudaEventRecord(e1, ctx->stream);
     ctx->n_launches++;
     BTRY(cudaGetLastError());
@@ -665,6 +775,47 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     cudaEventDestroy(e1);
     cleanup();
 #undef BTRY
+    return BZ_OK;
+}
+
+// ---- fp64 issue-rate microbenchmark ("measure an FMA microbenchmark"): the denominator of the batched
+// path's secondary roofline.  Every thread runs 8 independent chains of dependent DFMAs.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (double)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456) out[0] = s;      // never true: keeps the chains alive
+}
+extern "C" int bz_fp64_fma_peak(bz_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return BZ_ERR_ARG;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    BZ_CUDA(ctx, cudaMalloc((void**)&d, 64));
+    const int iters = 4096, blocks = ctx->num_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    ctx->n_launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    BZ_CUDA(ctx, cudaGetLastError());
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     return BZ_OK;
 }
 

@@ -451,6 +451,8 @@ struct bz_ctx {
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
+    int batch_budget = 4096;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
+                                // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
     int obstacle_fused = 1;     // obstacle problems run the fused X kernel (env BZ_OBSTACLE_FUSED=0: the unfused cycle, for A/B runs)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)

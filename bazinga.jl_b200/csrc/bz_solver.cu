@@ -126,6 +126,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_WIDE_TWO_PASS")) ctx->wide_two_pass = atoi(e);
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
     if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
+    if (const char* e = getenv("BZ_BATCH_BUDGET")) ctx->batch_budget = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;

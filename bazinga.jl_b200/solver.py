@@ -59,6 +59,12 @@ class Context:
         K.check(self.lib.bz_comm_bench_allreduce(self.handle, int(count), int(reps), C.byref(us)), self.handle)
         return us.value
 
+    def fp64_fma_peak(self) -> float:
+        """fp64 FMA issue peak of the device in TFLOP/s (microbenchmark; the batched path's secondary roofline)."""
+        v = C.c_double()
+        K.check(self.lib.bz_fp64_fma_peak(self.handle, C.byref(v)), self.handle)
+        return v.value
+
     def randn_fill(self, seed, start, count, stream=0):
         out = np.empty(int(count), dtype=np.float64)
         K.check(self.lib.bz_randn_fill(self.handle, seed, stream, start, int(count), _ptr(out)), self.handle)

@@ -573,8 +573,16 @@ def leg_c3(env, args, shared):
                                          "sample": f"all {len(mine)} instances, oracle/tiny_oracle.c with OpenMP ({dt:.2f} s)"}
         leg["problems"][name] = entry
     leg["clocks"] = sampler.stop() if rank == 0 else None
-    leg["bound"] = ("not HBM (9 MB of I/O): fp64 dependent-issue latency of the slowest instance; see profiles/ for the fp64 "
-                    "issue-rate microbenchmark")
+    # secondary roofline: ~250 fp64 flop per inner iteration against the measured fp64 FMA issue peak
+    peak_tf = ctx.fp64_fma_peak()
+    leg["fp64_fma_peak_tflops_measured"] = peak_tf
+    for name, e in leg["problems"].items():
+        for mode in ("strong", "weak"):
+            fl = 250.0 * e[mode]["inner_iterations_per_s"] / 1e12
+            e[mode]["fp64_tflops_model"] = fl
+            e[mode]["frac_of_fp64_peak"] = fl / (peak_tf * world)
+    leg["bound"] = ("not HBM (9 MB of I/O): dependent-issue latency of the slowest instances (a few warps are live at the end of a "
+                    "launch); flop model 250 fp64 flop per inner iteration (SURVEY.md §8d)")
     return leg
 
 

@@ -262,7 +262,9 @@ int bz_randn_fill(bz_ctx* ctx, uint64_t seed, uint64_t stream, uint64_t start, i
  * kind: 0 rosenbrock (demo/rosenbrock.jl; nx 2, ny 2), 1 either-or, 2 xor (demo/eitheror.jl; 2, 4), 3 mpvca
  * (demo/mpvca.jl; 2, 4), and the demos' slack variants 4 eitheror_fullslack, 5 xor_fullslack (6, 4),
  * 6 mpvca_slack (4, 2), 7 mpvca_fullslack (6, 4).  x0 is batch x nx (instance-major), y0 batch x ny.  One full alps solve per
- * instance, on the device, no collectives. */
+ * instance, on the device, no collectives.  Two launches: every instance on its own thread up to a budget of
+ * AL-gradient evaluations, then the few instances over the budget once more, one warp each, with the line search
+ * evaluated across the lanes (same results bit for bit; csrc/bz_batched.cu). */
 int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
                    const bz_options* opt, double* x, double* y, int32_t* tot_it,
                    int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
@@ -271,6 +273,10 @@ int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const
 int bz_batch_solve_als(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
                    const bz_options* opt, double* x, double* y, int32_t* tot_it,
                    int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
+
+/* Measurement aid for the batched path (not HBM-bound): the device's fp64 FMA issue peak in TFLOP/s, from a
+ * microbenchmark of independent dependent-FMA chains. */
+int bz_fp64_fma_peak(bz_ctx* ctx, double* tflops);
 
 /* ---- row-sharded multi-GPU: one process per GPU --------------------------------------- */
 int bz_comm_unique_id(void* id128); /* 128-byte NCCL unique id, generate on rank 0 and broadcast */
