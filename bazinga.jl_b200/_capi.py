@@ -64,6 +64,7 @@ class Result(C.Structure):
         ("dominant_kernel_launches", C.c_int64),
         ("kind_ms", C.c_double * 4), ("kind_launches", C.c_int64 * 4),
         ("mu0_min", C.c_double), ("mu0_max", C.c_double), ("inner_tol0", C.c_double),
+        ("device_ms", C.c_double),
     ]
 
 

@@ -63,6 +63,7 @@ struct BzState {
     int slot[BZ_MAXMEM];   // cooperative L kernel: physical history slot of each ring position (a permutation)
     int spare;             // ... and the free physical slot the next candidate pair is written to
     int err_flag;       // nonpositive mu etc.
+    int rot;            // fused problems: which physical buffers play x/x_prev (bit 0), res/res_prev (bit 1), z/z_curr (bit 2)
     int fused;          // the problem runs the fused forward-backward kernel X instead of [G, F, G, D] (bz_obfused.cu)
     long long n_global; // slab mode: global nx (0: the local n is the global one)
     long long iter;     // k of the IterativeAlgorithm driver (initial state counts as 1)
@@ -447,12 +448,14 @@ struct bz_ctx {
     void* batch_arena = nullptr;          // device scratch of bz_batch_solve (grow-only)
     size_t batch_arena_bytes = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    cudaEvent_t solve_ev0 = nullptr, solve_ev1 = nullptr;   // bz_result.device_ms
     int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
     int batch_budget = 4096;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
+    int obstacle_rotate = 1;    // ... with buffer rotation in the cooperative L kernel (env BZ_OBSTACLE_ROTATE=0: copies)
     int obstacle_fused = 1;     // obstacle problems run the fused X kernel (env BZ_OBSTACLE_FUSED=0: the unfused cycle, for A/B runs)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)
     int evict_first = 1;        // stream A through L2 with evict-first (env BZ_EVICT_FIRST=0 disables)

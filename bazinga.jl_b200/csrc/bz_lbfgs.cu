@@ -105,9 +105,14 @@ template <> __device__ __forceinline__ void stv<2>(double* p, long long j, const
 // = 52 at M = 5 (61 before: the pair was recomputed in a second pass, d = -res took a pass of its own, and the last
 // axpy was separate from the end-of-iteration copies).  A rejected pair (<s,y> <= 0) leaves the ring untouched: the
 // physical slots are addressed through BzState::slot[], the spare one is swapped in only on acceptance.
+// rot != -1: buffer rotation (fused problems, bz_obfused.cu).  The roles (x, x_prev), (res, res_prev), (z, z_curr) are
+// swapped instead of copied at the end of the step: the last pass writes only x_d and the new x (5 vector passes instead
+// of 10, 47 per step at M = 5); BzState::rot records which physical buffer plays which role.
 template <int V>
 __device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, TeamCtx& tc, unsigned int* counter,
-                                               int force_role) {
+                                               int force_role, int rot) {
+    const bool rotate = rot >= 0;
+    const int rb_ = rotate ? rot : 0;
     const long long n = v.n, nv = n / V;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,17 +124,19 @@ __device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, Team
     int slot[BZ_MAXMEM];
     for (int i = 0; i < BZ_MAXMEM; ++i) { ys[i] = __ldcg(&st->ys[i]); al[i] = 0.0; slot[i] = __ldcg(&st->slot[i]); }
     int spare = __ldcg(&st->spare);
-    double* const x = v.x;
-    const double* __restrict__ res = v.res;
-    const double* __restrict__ zc = v.z;
+    double* const x = (rb_ & 1) ? v.x_prev : v.x;
+    double* const x_prev_buf = (rb_ & 1) ? v.x : v.x_prev;
+    const double* __restrict__ res = (rb_ & 2) ? v.res_prev : v.res;
+    const double* const res_prev_buf = (rb_ & 2) ? v.res : v.res_prev;
+    const double* __restrict__ zc = (rb_ & 4) ? v.z_curr : v.z;
     double* __restrict__ d = v.d;
 
     // ---- update!(H, x - x_prev, res - res_prev)
     bool have_dot0 = false;
     double dot0 = 0.0;
     if (!skip && M > 0) {
-        const double* __restrict__ xp = v.x_prev;
-        const double* __restrict__ rp = v.res_prev;
+        const double* __restrict__ xp = x_prev_buf;
+        const double* __restrict__ rp = res_prev_buf;
         double* __restrict__ sn = v.sM + (size_t)spare * n;
         double* __restrict__ yn = v.yM + (size_t)spare * n;
         double a[3] = {0.0, 0.0, 0.0};
@@ -167,9 +174,27 @@ __device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, Team
 
     // last pass: d_final = dsrc + coef*sadd (or H*(-res) without history), fused with the end-of-iteration copies
     auto final_pass = [&](const double* __restrict__ dsrc, const double* __restrict__ sadd, double coef, bool from_res) {
+        double* __restrict__ xdw = v.x_d;
+        if (rotate) {      // the new x goes where x_prev was; x, res, z stay in place and change roles
+            double* __restrict__ xnew = x_prev_buf;
+            for (long long j = j0; j < nv; j += stride) {
+                const Pk<V> xa = ldv<V>(x, j);
+                Pk<V> da, sa, ra;
+                if (!from_res) { da = ldv<V>(dsrc, j); sa = ldv<V>(sadd, j); } else ra = ldv<V>(res, j);
+                Pk<V> xd, dn;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    dn.v[e] = from_res ? H * (-ra.v[e]) : da.v[e] + coef * sa.v[e];
+                    xd.v[e] = xa.v[e] + dn.v[e];
+                }
+                stv<V>(xdw, j, xd);
+                stv<V>(xnew, j, xd);
+                if (write_d) stv<V>(d, j, dn);
+            }
+            return;
+        }
         double* __restrict__ xpw = v.x_prev;
         double* __restrict__ rpw = v.res_prev;
-        double* __restrict__ xdw = v.x_d;
         double* __restrict__ zcw = v.z_curr;
         for (long long j = j0; j < nv; j += stride) {
             const Pk<V> xa = ldv<V>(x, j), ra = ldv<V>(res, j), za = ldv<V>(zc, j);
@@ -274,6 +299,7 @@ __device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, Team
         st->currmem = currmem; st->curridx = curridx; st->H = H;
         for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = ys[i]; st->alphas[i] = al[i]; st->slot[i] = slot[i]; }
         st->spare = spare;
+        if (rotate) st->rot = rb_ ^ 7;          // x <-> x_prev, res <-> res_prev, z <-> z_curr
         st->skip_update = 0;
         st->grad_x_fresh = 1;
         bz_goto_fb(st);
@@ -284,7 +310,7 @@ __device__ __forceinline__ void lstep_newiter(BzState* st, const BzVecs& v, Team
 }
 
 __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
-    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role) {
+    k_lstep(BzState* st, BzVecs v, BzTeam tm, unsigned int* counter, int force_role, int rotate) {
     __shared__ double scratch[3 * 32 + 4];
     // the other parity's barrier words are free again: reset them for the launch after this one
     if (blockIdx.x == 0 && threadIdx.x < BZ_MAXBAR)
@@ -302,9 +328,10 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
         const double tau = __ldcg(&st->tau);
         const long long stride = (long long)gridDim.x * blockDim.x;
         const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const int rot = rotate ? __ldcg(&st->rot) : 0;
         const double* __restrict__ xd = v.x_d;
-        const double* __restrict__ zc = v.z_curr;
-        double* __restrict__ x = v.x;
+        const double* __restrict__ zc = (rot & 4) ? v.z : v.z_curr;
+        double* __restrict__ x = (rot & 1) ? v.x_prev : v.x;
         if (vec2) {
             for (long long j = j0; j < n / 2; j += stride) {
                 const Pk<2> a = ldv<2>(xd, j), b = ldv<2>(zc, j);
@@ -325,8 +352,9 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
         return;
     }
     TeamCtx tc{tm, 0, scratch, st, st->xr.nranks > 1 ? *st->xr.seq : 0ULL, 0};
-    if (vec2) lstep_newiter<2>(st, v, tc, counter, force_role);
-    else lstep_newiter<1>(st, v, tc, counter, force_role);
+    const int rot = rotate ? __ldcg(&st->rot) : -1;
+    if (vec2) lstep_newiter<2>(st, v, tc, counter, force_role, rot);
+    else lstep_newiter<1>(st, v, tc, counter, force_role, rot);
 }
 
 
@@ -603,7 +631,7 @@ __global__ void __launch_bounds__(LC_THREADS)
 }
 
 int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
-                    unsigned int* counter, int force_role, bool slab) {
+                    unsigned int* counter, int force_role, bool slab, bool rotate) {
     const long long per_cta = (long long)LC_THREADS * LC_EPT;
     static BzOncePerDevice once;
     if (once.first(ctx->device)) {   // same carve-out as the dense passes: no SM reconfiguration inside the cycle
@@ -611,7 +639,7 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
         cudaFuncSetAttribute(k_lstep_cluster<LC_EPT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_lstep, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    if (v.n <= per_cta * LC_MAXCS && !slab) {   // (slab mode: only the cooperative kernel exchanges across ranks)
+    if (v.n <= per_cta * LC_MAXCS && !slab && !rotate) {   // (slab mode: only the cooperative kernel exchanges across ranks)
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
         while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;
@@ -622,7 +650,8 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
     const int nb = bz_l_grid(ctx, v.n);
     BzVecs vv = v;
     BzTeam tt = tm;
-    void* args[] = {(void*)&st, (void*)&vv, (void*)&tt, (void*)&counter, (void*)&force_role};
+    int rot_arg = rotate ? 1 : 0;
+    void* args[] = {(void*)&st, (void*)&vv, (void*)&tt, (void*)&counter, (void*)&force_role, (void*)&rot_arg};
     BZ_CUDA(ctx, cudaLaunchCooperativeKernel((void*)k_lstep, dim3(nb), dim3(BZ_L_THREADS), args, 0,
                                              ctx->stream));
     ctx->n_launches++;

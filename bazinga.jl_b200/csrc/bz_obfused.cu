@@ -37,7 +37,7 @@
 #define OF_WARPS (OF_THREADS / 32)
 #define OF_HALO 4
 #define OF_OUT (32 - 2 * OF_HALO)   // 24 output columns per warp
-#define OF_PF 2                      // raw rows in flight ahead of the row being consumed
+#define OF_PF 1                      // raw rows in flight ahead of the row being consumed (one row-time of a warp is several memory latencies)
 #define OF_NSUM 9
 
 struct ObFusedGeom { int ncg, nrc, rows_per_chunk, ctas; };
@@ -55,17 +55,172 @@ __device__ __forceinline__ double of_stencil(double diag, double c, double up, d
     return out;
 }
 
-template <int Q>
-__device__ __forceinline__ void of_shift(double (&q)[Q]) {
-#pragma unroll
-    for (int k = Q - 1; k > 0; --k) q[k] = q[k - 1];
+// The software pipeline of one lane.  Circular delay lines with STATIC indices: the row loop is unrolled six times and
+// step P of a group finds the value of age k (0 = produced in this step) in slot (P-dependent constant + k) mod L, so
+// nothing is ever shifted (a shifting version spent 29 % of its instructions on register moves).
+struct OfPipe {
+    double X1[6], X2[6], X3[6], MU[6], RM[6], MY[6];    // raw rows (x, mu, 1/mu, mu*y): age k = row jc + OF_PF - k
+    double WX[3];                                 // w_x:  age k = row jc - 1 - k
+    double Z1[3], Z2[3], Z3[3];                   // z:    age k = row jc - 2 - k
+    double G1[3], G2[3], G3[3], R1[3], R2[3], R3[3];   // grad_x, res: like z
+    double WZ[3];                                 // w_z:  age k = row jc - 3 - k
+};
+struct OfCtx {
+    const double* __restrict__ x1p; const double* __restrict__ x2p; const double* __restrict__ x3p;
+    const double* __restrict__ mu; const double* __restrict__ rmu; const double* __restrict__ muy;
+    double* __restrict__ zp; double* __restrict__ rp; double* __restrict__ dbg_gx; double* __restrict__ dbg_gz;
+    long long N, GX, GY, col, rb, re;
+    double gamma, gamma_h, rg, rgh, diag;
+    bool colok, own_lane, need2;
+    double a[OF_NSUM];
+    double m1, m2;
+    bool nan1, nan2;
+};
+
+// One row step.  MASKED = false is the steady state of an interior warp: every lane's column is inside the grid, rows
+// jc-4 .. jc+OF_PF are grid rows, and all four stage rows belong to this warp's chunk -- no validity selects, no range
+// tests; the halo lanes accumulate garbage that is discarded at the end (c.own_lane).  MASKED = true is the general step.
+template <int P, bool MASKED, bool L2>
+__device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc) {
+    // L2 = obstacle_l2 (f adds 0.5||x1||^2: dfx block 1 = x1; g without the threshold on block 1 and with value 0), else obstacle_l1
+    constexpr bool l2f = L2, l1g = !L2;
+    constexpr int n0 = (6 - P % 6) % 6, m0 = (3 - P % 3) % 3;
+#define S6(age) ((n0 + (age)) % 6)
+#define S3(age) ((m0 + (age)) % 3)
+    {   // ---- raw row jc + OF_PF (zeros outside the grid)
+        const long long j = jc + OF_PF;
+        const bool ok = MASKED ? (c.colok && j >= 0 && j < c.GY) : true;
+        const long long i = j * c.GX + c.col;
+        s.X1[S6(0)] = ok ? __ldg(c.x1p + i) : 0.0;
+        s.X2[S6(0)] = ok ? __ldg(c.x2p + i) : 0.0;
+        s.X3[S6(0)] = ok ? __ldg(c.x3p + i) : 0.0;
+        s.MU[S6(0)] = ok ? __ldg(c.mu + i) : 1.0;
+        s.RM[S6(0)] = ok ? __ldg(c.rmu + i) : 1.0;      // 1 ./ mu, kept up to date by k_al_update (fdiv: the bits of a / mu)
+        s.MY[S6(0)] = ok ? __ldg(c.muy + i) : 0.0;
+    }
+    {   // ---- stage 1: w_x on row r1 = jc - 1 (x2 rows jc-2, jc-1, jc)                      k_obstacle_c
+        const long long r1 = jc - 1;
+        const double x1 = s.X1[S6(OF_PF + 1)], x2 = s.X2[S6(OF_PF + 1)], x3 = s.X3[S6(OF_PF + 1)];
+        const double mua = s.MU[S6(OF_PF + 1)], rma = s.RM[S6(OF_PF + 1)], muya = s.MY[S6(OF_PF + 1)];
+        const double cva = (x1 + of_stencil(c.diag, x2, s.X2[S6(OF_PF + 2)], s.X2[S6(OF_PF)])) - x3;
+        const double t = cva + muya;
+        const double u = t - 0.0;                      // SetObstacle: proj = 0 (demo/obstacle.jl:116-119)
+        if (MASKED) {
+            const bool ok = c.colok && r1 >= 0 && r1 < c.GY;
+            s.WX[S3(0)] = ok ? fdiv(u, mua, rma) : 0.0;
+            if (c.own_lane && r1 >= c.rb && r1 < c.re) {
+                c.a[0] += fdiv(u * u, mua, rma);
+                if (l2f) c.a[1] += x1 * x1;
+                c.a[1] += x2 * x2;
+                c.a[2] += x2;
+            }
+        } else {
+            s.WX[S3(0)] = fdiv(u, mua, rma);
+            c.a[0] += fdiv(u * u, mua, rma);
+            if (l2f) c.a[1] += x1 * x1;
+            c.a[1] += x2 * x2;
+            c.a[2] += x2;
+        }
+    }
+    {   // ---- stage 2: grad_x, z, res on row r2 = jc - 2 (w_x rows jc-3, jc-2, jc-1)          k_obstacle_jt + k_fstep
+        const long long r2 = jc - 2;
+        const double x1 = s.X1[S6(OF_PF + 2)], x2 = s.X2[S6(OF_PF + 2)], x3 = s.X3[S6(OF_PF + 2)];
+        const double w = s.WX[S3(1)];
+        const double aw = of_stencil(c.diag, w, s.WX[S3(2)], s.WX[S3(0)]);
+        const double g1 = (l2f ? x1 : 0.0) + w;
+        const double g2 = (x2 - 1.0) + aw;
+        const double g3 = 0.0 + (-w);
+        double z1 = l1g ? fmax(0.0, (x1 - c.gamma * g1) - c.gamma) : fmax(0.0, x1 - c.gamma * g1);
+        double z2 = fmax(0.0, x2 - c.gamma * g2);
+        double z3 = fmax(0.0, x3 - c.gamma * g3);
+        if (z2 > z3) z3 = 0.0; else z2 = 0.0;
+        bool st_ok = c.own_lane;
+        if (MASKED) {
+            const bool ok = c.colok && r2 >= 0 && r2 < c.GY;
+            if (!ok) { z1 = 0.0; z2 = 0.0; z3 = 0.0; }
+            st_ok = c.own_lane && r2 >= c.rb && r2 < c.re;
+        }
+        const double q1 = x1 - z1, q2 = x2 - z2, q3 = x3 - z3;
+        s.Z1[S3(0)] = z1; s.Z2[S3(0)] = z2; s.Z3[S3(0)] = z3;
+        s.G1[S3(0)] = g1; s.G2[S3(0)] = g2; s.G3[S3(0)] = g3;
+        s.R1[S3(0)] = q1; s.R2[S3(0)] = q2; s.R3[S3(0)] = q3;
+        if (st_ok) {
+            const long long i = r2 * c.GX + c.col;
+            c.zp[i] = z1; c.zp[c.N + i] = z2; c.zp[2 * c.N + i] = z3;
+            c.rp[i] = q1; c.rp[c.N + i] = q2; c.rp[2 * c.N + i] = q3;
+            if (c.dbg_gx) { c.dbg_gx[i] = g1; c.dbg_gx[c.N + i] = g2; c.dbg_gx[2 * c.N + i] = g3; }
+        }
+        if (!MASKED || st_ok) {
+            if (l1g) c.a[5] += z1;
+            c.a[3] += g1 * q1; c.a[4] += q1 * q1;
+            c.a[3] += g2 * q2; c.a[4] += q2 * q2;
+            c.a[3] += g3 * q3; c.a[4] += q3 * q3;
+        }
+    }
+    {   // ---- stage 3: w_z on row r3 = jc - 3 (z2 rows jc-4, jc-3, jc-2)
+        const long long r3 = jc - 3;
+        const double z1 = s.Z1[S3(1)], z2 = s.Z2[S3(1)], z3 = s.Z3[S3(1)];
+        const double mua = s.MU[S6(OF_PF + 3)], rma = s.RM[S6(OF_PF + 3)], muya = s.MY[S6(OF_PF + 3)];
+        const double cva = (z1 + of_stencil(c.diag, z2, s.Z2[S3(2)], s.Z2[S3(0)])) - z3;
+        const double t = cva + muya;
+        const double u = t - 0.0;
+        if (MASKED) {
+            const bool ok = c.colok && r3 >= 0 && r3 < c.GY;
+            s.WZ[S3(0)] = ok ? fdiv(u, mua, rma) : 0.0;
+            if (c.own_lane && r3 >= c.rb && r3 < c.re) {
+                c.a[6] += fdiv(u * u, mua, rma);
+                if (l2f) c.a[7] += z1 * z1;
+                c.a[7] += z2 * z2;
+                c.a[8] += z2;
+            }
+        } else {
+            s.WZ[S3(0)] = fdiv(u, mua, rma);
+            c.a[6] += fdiv(u * u, mua, rma);
+            if (l2f) c.a[7] += z1 * z1;
+            c.a[7] += z2 * z2;
+            c.a[8] += z2;
+        }
+    }
+    {   // ---- stage 4: grad_z and the stop norm on row r4 = jc - 4 (w_z rows jc-5, jc-4, jc-3)   k_dstep
+        const long long r4 = jc - 4;
+        const double w = s.WZ[S3(1)];
+        const double aw = of_stencil(c.diag, w, s.WZ[S3(2)], s.WZ[S3(0)]);
+        if (!MASKED || (c.own_lane && r4 >= c.rb && r4 < c.re)) {
+            const double h1 = (l2f ? s.Z1[S3(2)] : 0.0) + w;
+            const double h2 = (s.Z2[S3(2)] - 1.0) + aw;
+            const double h3 = 0.0 + (-w);
+            if (c.dbg_gz && c.own_lane) { const long long i = r4 * c.GX + c.col; c.dbg_gz[i] = h1; c.dbg_gz[c.N + i] = h2; c.dbg_gz[2 * c.N + i] = h3; }
+            // NaN-propagating max (Julia's norm(., Inf)): the running maximum ignores NaN, a flag remembers it
+            const double v1 = (fdiv(s.R1[S3(2)], c.gamma, c.rg) - s.G1[S3(2)]) + h1;
+            const double v2 = (fdiv(s.R2[S3(2)], c.gamma, c.rg) - s.G2[S3(2)]) + h2;
+            const double v3 = (fdiv(s.R3[S3(2)], c.gamma, c.rg) - s.G3[S3(2)]) + h3;
+            c.m1 = fmax(c.m1, fmax(fmax(fabs(v1), fabs(v2)), fabs(v3)));
+            c.nan1 |= (v1 != v1) | (v2 != v2) | (v3 != v3);
+            if (c.need2) {   // the norm at gamma/2 is only read when this back-track is the last one allowed (bz_d_decide)
+                const double u1 = (fdiv(s.R1[S3(2)], c.gamma_h, c.rgh) - s.G1[S3(2)]) + h1;
+                const double u2 = (fdiv(s.R2[S3(2)], c.gamma_h, c.rgh) - s.G2[S3(2)]) + h2;
+                const double u3 = (fdiv(s.R3[S3(2)], c.gamma_h, c.rgh) - s.G3[S3(2)]) + h3;
+                c.m2 = fmax(c.m2, fmax(fmax(fabs(u1), fabs(u2)), fabs(u3)));
+                c.nan2 |= (u1 != u1) | (u2 != u2) | (u3 != u3);
+            }
+        }
+    }
+#undef S6
+#undef S3
+}
+
+template <int P, bool L2>
+__device__ __forceinline__ void of_step_any(OfPipe& s, OfCtx& c, long long jc, long long s_lo, long long s_hi) {
+    if (jc >= s_lo && jc < s_hi) of_step<P, false, L2>(s, c, jc);
+    else of_step<P, true, L2>(s, c, jc);
 }
 
 // force: 0 = member of the cycle (predicated on st->next_op == OP_X, runs the decisions), 1 = parity entry point
-// (evaluates at v.x with st->gamma, leaves the eleven scalars in st->out, takes no decision)
+// (evaluates at v.x with st->gamma, leaves the nine scalars in st->out, takes no decision)
+template <bool L2>
 __global__ void __launch_bounds__(OF_THREADS, 3)
     k_obstacle_fused(BzState* st, BzVecs v, BzObstacle ob, BzGParams g, const double* __restrict__ mu,
-                     const double* __restrict__ muy, double* part, unsigned int* counter, ObFusedGeom geo, int force,
+                     const double* __restrict__ rmu, const double* __restrict__ muy, double* part, unsigned int* counter, ObFusedGeom geo, int force,
                      double* __restrict__ dbg_gx, double* __restrict__ dbg_gz) {
     __shared__ double scratch[OF_NSUM * 32];
     bz_pdl_wait();
@@ -74,155 +229,75 @@ __global__ void __launch_bounds__(OF_THREADS, 3)
         if (__ldcg(&st->next_op) != OP_X) return;
         if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 2);
     }
-    const double gamma = __ldcg(&st->gamma);
-    const double gamma_h = gamma * 0.5;
-    const double rg = frecip(gamma), rgh = frecip(gamma_h);
-    const long long N = ob.N;
-    const long long GX = ob.gx == 0 ? N : ob.gx, GY = ob.gx == 0 ? 1 : ob.gy;
-    const double diag = ob.gx == 0 ? 2.0 : 4.0;
-    const bool l2f = ob.l2 != 0;                       // SmoothCostObstacleL2: f adds 0.5||x1||^2, dfx block 1 = x1
-    const bool l1g = g.kind == BZ_G_OBSTACLE_L1;       // NonsmoothCostObstacleL1: threshold gamma on block 1, value sum(z1)
-    const double* __restrict__ x1p = v.x;
-    const double* __restrict__ x2p = v.x + N;
-    const double* __restrict__ x3p = v.x + 2 * N;
-    double* __restrict__ zp = v.z;
-    double* __restrict__ rp = v.res;
+    // buffer rotation (bz_lbfgs.cu): the cooperative L kernel swaps the roles of (x, x_prev), (res, res_prev), (z, z_curr)
+    // instead of copying them; st->rot says which physical buffer plays which role right now
+    const int rot = force ? 0 : __ldcg(&st->rot);
+    const double* xbase = (rot & 1) ? v.x_prev : v.x;
+    OfCtx c;
+    c.gamma = __ldcg(&st->gamma);
+    c.gamma_h = c.gamma * 0.5;
+    c.rg = frecip(c.gamma); c.rgh = frecip(c.gamma_h);
+    c.N = ob.N;
+    c.GX = ob.gx == 0 ? ob.N : ob.gx; c.GY = ob.gx == 0 ? 1 : ob.gy;
+    c.diag = ob.gx == 0 ? 2.0 : 4.0;
+    c.x1p = xbase; c.x2p = xbase + c.N; c.x3p = xbase + 2 * c.N;
+    c.mu = mu; c.rmu = rmu; c.muy = muy;
+    c.zp = (rot & 4) ? v.z_curr : v.z;
+    c.rp = (rot & 2) ? v.res_prev : v.res;
+    c.dbg_gx = dbg_gx; c.dbg_gz = dbg_gz;
+    // stop norm at gamma/2: read by bz_d_decide only when a gamma-halving at this back-track index runs off the loop
+    c.need2 = force || (__ldcg(&st->mode) == MODE_ITER && __ldcg(&st->k_bt) + 1 > __ldcg(&st->max_backtracks));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long wg = (long long)blockIdx.x * OF_WARPS + warp;
     const long long cg = wg % geo.ncg, rc = wg / geo.ncg;
-    const long long c = cg * OF_OUT - OF_HALO + lane;
-    const bool colok = c >= 0 && c < GX;
-    const bool own_lane = lane >= OF_HALO && lane < 32 - OF_HALO && colok;
-    const long long rb = rc * geo.rows_per_chunk;
-    long long re = rb + geo.rows_per_chunk;
-    if (re > GY) re = GY;
-    const bool active = rc < geo.nrc && rb < GY;
-
-    // sums: 0 lx(x) 1 fa(x) 2 fb(x) 3 <grad_x,res> 4 ||res||^2 5 g 6 lx(z) 7 fa(z) 8 fb(z); maxima: stop norm at gamma, gamma/2
-    double a[OF_NSUM];
+    c.col = cg * OF_OUT - OF_HALO + lane;
+    c.colok = c.col >= 0 && c.col < c.GX;
+    c.own_lane = lane >= OF_HALO && lane < 32 - OF_HALO && c.colok;
+    c.rb = rc * geo.rows_per_chunk;
+    c.re = c.rb + geo.rows_per_chunk;
+    if (c.re > c.GY) c.re = c.GY;
+    const bool active = rc < geo.nrc && c.rb < c.GY;
 #pragma unroll
-    for (int k = 0; k < OF_NSUM; ++k) a[k] = 0.0;
-    double m1 = 0.0, m2 = 0.0;
+    for (int k = 0; k < OF_NSUM; ++k) c.a[k] = 0.0;
+    c.m1 = 0.0; c.m2 = 0.0;
+    c.nan1 = false; c.nan2 = false;
 
     if (active) {
-        // delay lines, index 0 = newest.  Raw rows: [0] = row jc + PF (just loaded) ... [PF] = row jc.
-        double X1[OF_PF + 3], X2[OF_PF + 3], X3[OF_PF + 3], MU[OF_PF + 4], MY[OF_PF + 4];
-        double WX[3], Z1[3], Z2[3], Z3[2], G1[3], G2[3], G3[3], R1[3], R2[3], R3[3], WZ[3];
+        OfPipe s;
 #pragma unroll
-        for (int k = 0; k < OF_PF + 3; ++k) { X1[k] = 0.0; X2[k] = 0.0; X3[k] = 0.0; }
+        for (int k = 0; k < 6; ++k) { s.X1[k] = 0.0; s.X2[k] = 0.0; s.X3[k] = 0.0; s.MU[k] = 1.0; s.RM[k] = 1.0; s.MY[k] = 0.0; }
 #pragma unroll
-        for (int k = 0; k < OF_PF + 4; ++k) { MU[k] = 1.0; MY[k] = 0.0; }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { WX[k] = Z1[k] = Z2[k] = G1[k] = G2[k] = G3[k] = R1[k] = R2[k] = R3[k] = WZ[k] = 0.0; }
-        Z3[0] = Z3[1] = 0.0;
-
-        auto load_row = [&](long long j) {            // raw row j into slot 0 (zeros outside the grid)
-            const bool ok = colok && j >= 0 && j < GY;
-            const long long i = j * GX + c;
-            X1[0] = ok ? __ldg(x1p + i) : 0.0;
-            X2[0] = ok ? __ldg(x2p + i) : 0.0;
-            X3[0] = ok ? __ldg(x3p + i) : 0.0;
-            MU[0] = ok ? __ldg(mu + i) : 1.0;
-            MY[0] = ok ? __ldg(muy + i) : 0.0;
-        };
-        // prologue: rows rb-4 .. rb-4+PF-1 into the queue
-#pragma unroll
-        for (int k = 0; k < OF_PF; ++k) {
-            of_shift(X1); of_shift(X2); of_shift(X3); of_shift(MU); of_shift(MY);
-            load_row(rb - 4 + k);
+        for (int k = 0; k < 3; ++k) {
+            s.WX[k] = s.Z1[k] = s.Z2[k] = s.Z3[k] = s.G1[k] = s.G2[k] = s.G3[k] = s.R1[k] = s.R2[k] = s.R3[k] = s.WZ[k] = 0.0;
         }
-        for (long long jc = rb - 4; jc < re + 4; ++jc) {
-            of_shift(X1); of_shift(X2); of_shift(X3); of_shift(MU); of_shift(MY);
-            load_row(jc + OF_PF);
-            of_shift(WX); of_shift(Z1); of_shift(Z2); of_shift(G1); of_shift(G2); of_shift(G3);
-            of_shift(R1); of_shift(R2); of_shift(R3); of_shift(WZ);
-            Z3[1] = Z3[0];
-
-            // ---- stage 1: w_x on row r1 = jc - 1 (x2 rows jc-2, jc-1, jc)            k_obstacle_c
-            {
-                const long long r1 = jc - 1;
-                const bool ok = colok && r1 >= 0 && r1 < GY;
-                const double x1 = X1[OF_PF + 1], x2 = X2[OF_PF + 1], x3 = X3[OF_PF + 1];
-                const double mua = MU[OF_PF + 1], muya = MY[OF_PF + 1];
-                const double cva = (x1 + of_stencil(diag, x2, X2[OF_PF + 2], X2[OF_PF])) - x3;
-                const double t = cva + muya;
-                const double u = t - 0.0;                      // SetObstacle: proj = 0 (demo/obstacle.jl:116-119)
-                WX[0] = ok ? u / mua : 0.0;
-                if (own_lane && r1 >= rb && r1 < re) {
-                    a[0] += (u * u) / mua;
-                    if (l2f) a[1] += x1 * x1;
-                    a[1] += x2 * x2;
-                    a[2] += x2;
-                }
-            }
-            // ---- stage 2: grad_x, z, res on row r2 = jc - 2 (w_x rows jc-3, jc-2, jc-1)  k_obstacle_jt + k_fstep
-            {
-                const long long r2 = jc - 2;
-                const bool ok = colok && r2 >= 0 && r2 < GY;
-                const double x1 = X1[OF_PF + 2], x2 = X2[OF_PF + 2], x3 = X3[OF_PF + 2];
-                const double w = WX[1];
-                const double aw = of_stencil(diag, w, WX[2], WX[0]);
-                const double g1 = (l2f ? x1 : 0.0) + w;
-                const double g2 = (x2 - 1.0) + aw;
-                const double g3 = 0.0 + (-w);
-                double z1 = l1g ? fmax(0.0, (x1 - gamma * g1) - gamma) : fmax(0.0, x1 - gamma * g1);
-                double z2 = fmax(0.0, x2 - gamma * g2);
-                double z3 = fmax(0.0, x3 - gamma * g3);
-                if (z2 > z3) z3 = 0.0; else z2 = 0.0;
-                if (!ok) { z1 = 0.0; z2 = 0.0; z3 = 0.0; }
-                const double q1 = x1 - z1, q2 = x2 - z2, q3 = x3 - z3;
-                Z1[0] = z1; Z2[0] = z2; Z3[0] = z3;
-                G1[0] = g1; G2[0] = g2; G3[0] = g3;
-                R1[0] = q1; R2[0] = q2; R3[0] = q3;
-                if (own_lane && r2 >= rb && r2 < re) {
-                    const long long i = r2 * GX + c;
-                    zp[i] = z1; zp[N + i] = z2; zp[2 * N + i] = z3;
-                    rp[i] = q1; rp[N + i] = q2; rp[2 * N + i] = q3;
-                    if (dbg_gx) { dbg_gx[i] = g1; dbg_gx[N + i] = g2; dbg_gx[2 * N + i] = g3; }
-                    if (l1g) a[5] += z1;
-                    a[3] += g1 * q1; a[4] += q1 * q1;
-                    a[3] += g2 * q2; a[4] += q2 * q2;
-                    a[3] += g3 * q3; a[4] += q3 * q3;
-                }
-            }
-            // ---- stage 3: w_z on row r3 = jc - 3 (z2 rows jc-4, jc-3, jc-2)
-            {
-                const long long r3 = jc - 3;
-                const bool ok = colok && r3 >= 0 && r3 < GY;
-                const double z1 = Z1[1], z2 = Z2[1], z3 = Z3[1];
-                const double mua = MU[OF_PF + 3], muya = MY[OF_PF + 3];
-                const double cva = (z1 + of_stencil(diag, z2, Z2[2], Z2[0])) - z3;
-                const double t = cva + muya;
-                const double u = t - 0.0;
-                WZ[0] = ok ? u / mua : 0.0;
-                if (own_lane && r3 >= rb && r3 < re) {
-                    a[6] += (u * u) / mua;
-                    if (l2f) a[7] += z1 * z1;
-                    a[7] += z2 * z2;
-                    a[8] += z2;
-                }
-            }
-            // ---- stage 4: grad_z and the stop norm on row r4 = jc - 4 (w_z rows jc-5, jc-4, jc-3)   k_dstep
-            {
-                const long long r4 = jc - 4;
-                const double w = WZ[1];
-                const double aw = of_stencil(diag, w, WZ[2], WZ[0]);
-                if (own_lane && r4 >= rb && r4 < re) {
-                    const double h1 = (l2f ? Z1[2] : 0.0) + w;
-                    const double h2 = (Z2[2] - 1.0) + aw;
-                    const double h3 = 0.0 + (-w);
-                    if (dbg_gz) { const long long i = r4 * GX + c; dbg_gz[i] = h1; dbg_gz[N + i] = h2; dbg_gz[2 * N + i] = h3; }
-                    m1 = bz_nanmax(m1, (fdiv(R1[2], gamma, rg) - G1[2]) + h1);
-                    m2 = bz_nanmax(m2, (fdiv(R1[2], gamma_h, rgh) - G1[2]) + h1);
-                    m1 = bz_nanmax(m1, (fdiv(R2[2], gamma, rg) - G2[2]) + h2);
-                    m2 = bz_nanmax(m2, (fdiv(R2[2], gamma_h, rgh) - G2[2]) + h2);
-                    m1 = bz_nanmax(m1, (fdiv(R3[2], gamma, rg) - G3[2]) + h3);
-                    m2 = bz_nanmax(m2, (fdiv(R3[2], gamma_h, rgh) - G3[2]) + h3);
-                }
-            }
+        // steps jc = rb-4-PF .. re+3: the first OF_PF only load (their stages see zeros and own nothing)
+        const long long j_begin = c.rb - 4 - OF_PF, j_end = c.re + 4;
+        // unmasked range: interior warp, stage rows jc-4 .. jc-1 inside [rb, re), loaded row jc+PF a grid row
+        const bool interior = (cg * OF_OUT - OF_HALO >= 0) && (cg * OF_OUT - OF_HALO + 31 < c.GX);
+        long long s_lo = c.rb + 4, s_hi = c.re + 1;
+        if (s_hi > c.GY - OF_PF) s_hi = c.GY - OF_PF;
+        if (!interior) s_hi = s_lo;
+        for (long long jb = j_begin; jb < j_end; jb += 6) {
+            of_step_any<0, L2>(s, c, jb, s_lo, s_hi);
+            if (jb + 1 < j_end) of_step_any<1, L2>(s, c, jb + 1, s_lo, s_hi);
+            if (jb + 2 < j_end) of_step_any<2, L2>(s, c, jb + 2, s_lo, s_hi);
+            if (jb + 3 < j_end) of_step_any<3, L2>(s, c, jb + 3, s_lo, s_hi);
+            if (jb + 4 < j_end) of_step_any<4, L2>(s, c, jb + 4, s_lo, s_hi);
+            if (jb + 5 < j_end) of_step_any<5, L2>(s, c, jb + 5, s_lo, s_hi);
+        }
+        if (!c.own_lane) {           // halo lanes accumulated garbage in the unmasked steps
+#pragma unroll
+            for (int k = 0; k < OF_NSUM; ++k) c.a[k] = 0.0;
+            c.m1 = 0.0; c.m2 = 0.0;
+            c.nan1 = false; c.nan2 = false;
         }
     }
+    double a[OF_NSUM];
+#pragma unroll
+    for (int k = 0; k < OF_NSUM; ++k) a[k] = c.a[k];
+    const double m1 = c.nan1 ? NANQ : c.m1, m2 = c.nan2 ? NANQ : c.m2;
+    const double gamma = c.gamma;
 
     // ---- per-CTA partials (fixed order), then the last CTA sums them and runs the scalar logic
     bz_block_sum<OF_NSUM>(a, scratch);
@@ -239,19 +314,13 @@ __global__ void __launch_bounds__(OF_THREADS, 3)
     }
     if (!bz_last_cta(counter, nb)) return;
     double sums[OF_NSUM];
-    {
-        const double* ptrs[OF_NSUM];
-        int counts[OF_NSUM];
 #pragma unroll
-        for (int k = 0; k < OF_NSUM; ++k) { ptrs[k] = part + (size_t)k * nb; counts[k] = nb; }
-#pragma unroll
-        for (int k = 0; k < OF_NSUM; ++k) {
-            double s = 0.0;
-            for (int i = threadIdx.x; i < counts[k]; i += blockDim.x) s += __ldcg(ptrs[k] + i);
-            sums[k] = s;
-        }
-        bz_block_sum<OF_NSUM>(sums, scratch);
+    for (int k = 0; k < OF_NSUM; ++k) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) t += __ldcg(part + (size_t)k * nb + i);
+        sums[k] = t;
     }
+    bz_block_sum<OF_NSUM>(sums, scratch);
     const double stop1 = bz_final_nanmax(part + (size_t)OF_NSUM * nb, nb, scratch);
     const double stop2 = bz_final_nanmax(part + (size_t)(OF_NSUM + 1) * nb, nb, scratch);
     if (threadIdx.x != 0) return;
@@ -295,8 +364,9 @@ static int of_resident(bz_ctx* ctx) {
     static int per_sm[64] = {0};
     int& r = per_sm[ctx->device & 63];
     if (r == 0) {
-        cudaFuncSetAttribute(k_obstacle_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_obstacle_fused, OF_THREADS, 0) != cudaSuccess || r < 1) r = 1;
+        cudaFuncSetAttribute(k_obstacle_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_obstacle_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_obstacle_fused<false>, OF_THREADS, 0) != cudaSuccess || r < 1) r = 1;
     }
     return r;
 }
@@ -306,9 +376,14 @@ int bz_obfused_partials(bz_ctx* ctx, const BzObstacle& ob) {
 }
 
 int bz_launch_obstacle_fused(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzObstacle& ob, const BzGParams& g,
-                             const double* mu, const double* muy, double* part, unsigned int* counter, int force,
-                             double* dbg_gx, double* dbg_gz) {
+                             const double* mu, const double* rmu, const double* muy, double* part, unsigned int* counter,
+                             int force, double* dbg_gx, double* dbg_gz) {
     const ObFusedGeom geo = of_geometry(ctx, ob, of_resident(ctx));
-    return bz_launch_pdl(ctx, k_obstacle_fused, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, muy, part, counter,
-                         geo, force, dbg_gx, dbg_gz);
+    // obstacle_l1 = (SmoothCostObstacleL1, NonsmoothCostObstacleL1), obstacle_l2 = (..L2, ..L2): the catalogue check of
+    // bz_problem_create admits no other pairing
+    if (ob.l2)
+        return bz_launch_pdl(ctx, k_obstacle_fused<true>, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, rmu, muy, part,
+                             counter, geo, force, dbg_gx, dbg_gz);
+    return bz_launch_pdl(ctx, k_obstacle_fused<false>, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, rmu, muy, part,
+                         counter, geo, force, dbg_gx, dbg_gz);
 }

@@ -37,6 +37,7 @@ struct bz_problem {
     double* g_u = nullptr;
     // AL m-vectors (local rows)
     double *mu = nullptr, *y = nullptr, *muy = nullptr, *cx = nullptr, *s = nullptr, *yupd = nullptr;
+    double* rmu = nullptr;   // 1 ./ mu (fused obstacle kernel), refreshed by every k_al_update
     double *tm1 = nullptr, *tm2 = nullptr, *tm3 = nullptr;
     // n-vectors
     BzVecs v{};
@@ -64,6 +65,7 @@ struct bz_problem {
     bool sharded = false;
     BzShard shard{};
     // slab-decomposed obstacle grid (cross-rank exchange over peer memory)
+    bool rotate = false;  // fused problems large enough for the cooperative L kernel: x/x_prev, res/res_prev, z/z_curr swap roles
     bool fused = false;   // obstacle problems on one GPU: the cycle is [L, X] with the fused kernel of bz_obfused.cu
     bool slab = false;
     unsigned long long* slab_base = nullptr;   // [mailbox | seq | x | z | xeps | yupd]
@@ -127,6 +129,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
     if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
     if (const char* e = getenv("BZ_BATCH_BUDGET")) ctx->batch_budget = atoi(e);
+    if (const char* e = getenv("BZ_OBSTACLE_ROTATE")) ctx->obstacle_rotate = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
@@ -141,6 +144,7 @@ extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
     if (ctx->batch_arena) cudaFree(ctx->batch_arena);
     if (ctx->xpose_buf) cudaFree(ctx->xpose_buf);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
+    if (ctx->solve_ev0) { cudaEventDestroy(ctx->solve_ev0); cudaEventDestroy(ctx->solve_ev1); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BZ_OK;
@@ -257,7 +261,7 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
             if (p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
         cudaFree(p->slab_base);
     }
-    double* frees[] = {p->tm1_f, p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
+    double* frees[] = {p->rmu, p->tm1_f, p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
                        p->s, p->yupd, p->tm1, p->tm2, p->tm3, p->v.x, p->v.z, p->v.xeps, p->v.x_prev,
                        p->v.x_d, p->v.z_curr, p->v.res, p->v.res_prev, p->v.grad_x, p->v.grad_z,
                        p->v.d, p->v.sM, p->v.yM, p->Ec, p->Ef, p->Pc, p->Pf, p->lxpart, p->fxpart,
@@ -414,7 +418,9 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     size_t npart = (size_t)4 * maxgrid;
     if (d->c_kind == BZ_C_OBSTACLE && !p->slab && !p->slack && ctx->obstacle_fused) {
         p->fused = true;
+        p->rotate = p->nv > 32768 && ctx->obstacle_rotate;   // (n <= 32768 runs the cluster L kernel, whose vectors live in registers)
         npart = std::max(npart, (size_t)bz_obfused_partials(ctx, p->ob));
+        PTRY(dev_alloc(ctx, &p->rmu, ml));
     }
     PTRY(dev_alloc(ctx, &p->part, npart));
     PTRY(dev_alloc(ctx, &p->lxpart, (size_t)maxgrid));
@@ -682,9 +688,9 @@ static int launch_cycle(bz_problem* p) {
     BzGradSrc gs = grad_src(p);
     BzTeam tm = p->team;
     if (p->fused) {
-        BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab));
+        BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab, p->rotate));
         p->team.parity ^= 1;
-        return bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->muy, p->part, p->counters + 3, 0,
+        return bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->rmu, p->muy, p->part, p->counters + 3, 0,
                                         nullptr, nullptr);
     }
     BZ_TRY(bz_launch_lstep(ctx, p->st, p->v, tm, p->counters + 2, -1, p->slab));
@@ -730,6 +736,14 @@ static int panoc_run(bz_problem* p, const bz_options* o, double tol, long long m
             inflight--;
             if (p->status_host[slot] != IST_RUNNING) break;
         }
+    }
+    if (p->rotate) {   // buffer rotation: make the host's pointers agree with the roles the device ended with
+        BZ_TRY(fetch_state(p));
+        const int rot = p->st_host->rot;
+        if (rot & 1) std::swap(p->v.x, p->v.x_prev);
+        if (rot & 2) std::swap(p->v.res, p->v.res_prev);
+        if (rot & 4) std::swap(p->v.z, p->v.z_curr);
+        if (rot) BZ_CUDA(ctx, cudaMemsetAsync(&p->st->rot, 0, sizeof(int), ctx->stream));
     }
     // fused problems never materialise c(z), s, yupd inside the loop: one unfused AL-gradient at the returned point
     // leaves the AugLagFun side-effect state the outer step reads (alps.jl:68,74)
@@ -811,6 +825,8 @@ static int outer_solve(bz_problem* p, bool slack, const double* x0, const double
     // ---- initialise (alps.jl:31-46)
     BZ_TRY(h2d(p, p->v.z_curr, x0, n));
     BZ_TRY(h2d(p, p->y, y0 + (p->sharded ? p->desc.row_begin : 0), ml));
+    if (!ctx->solve_ev0) { BZ_CUDA(ctx, cudaEventCreate(&ctx->solve_ev0)); BZ_CUDA(ctx, cudaEventCreate(&ctx->solve_ev1)); }
+    BZ_CUDA(ctx, cudaEventRecord(ctx->solve_ev0, ctx->stream));   // device_ms: the solve between the H2D of x0, y0 and the D2H of the results
     BzState* h = p->st_host;
     memset(h, 0, sizeof(BzState));
     h->xr = p->xr_host;            // slab mode: peer mapping (zero otherwise)
@@ -868,7 +884,7 @@ static int outer_solve(bz_problem* p, bool slack, const double* x0, const double
             user_safeguard(hy.data(), hcx.data(), (int64_t)ml, o->dual_safeguard_user);
             BZ_TRY(h2d(p, p->y, hy.data(), ml));
         }
-        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, user_safeguard ? 0 : 1, 1, p->part, p->counters + 5));
+        BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, ml, user_safeguard ? 0 : 1, 1, p->part, p->counters + 5, p->rmu));
         if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));
         long long maxit_inner = o->sub_maxit;
         if (o->max_inner_total > 0)
@@ -903,11 +919,17 @@ static int outer_solve(bz_problem* p, bool slack, const double* x0, const double
         if (!can_stop && h->scale_mu) BZ_TRY(bz_launch_scale(ctx, p->mu, ml, o->kappa_penalty));
         inner_tol = h->inner_tol;
     }
+    BZ_CUDA(ctx, cudaEventRecord(ctx->solve_ev1, ctx->stream));
     BZ_TRY(d2h(p, x, p->v.x, n));
     BZ_TRY(d2h(p, y, p->y, ml));
     BZ_TRY(d2h(p, s, p->s, ml));
     BZ_TRY(d2h(p, mu, p->mu, ml));
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        float dms = 0.f;
+        cudaEventElapsedTime(&dms, ctx->solve_ev0, ctx->solve_ev1);
+        res->device_ms = dms;
+    }
     res->tot_it = tot_it;
     res->tot_inner_it = tot_inner;
     res->status = solved ? 0 : tired ? 1 : broken ? 2 : 3;
@@ -955,7 +977,7 @@ static int set_mu_y(bz_problem* p, const double* mu, const double* y) {
     BZ_TRY(fetch_state(p));
     p->st_host->err_flag = 0;
     BZ_TRY(push_state(p));
-    BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, p->ml, 0, 0, p->part, p->counters + 5));
+    BZ_TRY(bz_launch_al_update(ctx, p->st, p->mu, p->y, p->muy, p->ml, 0, 0, p->part, p->counters + 5, p->rmu));
     if (p->sharded) BZ_TRY(bz_comm_allreduce(ctx, &p->st->musqy, 1, BZ_COMM_SUM));   // 0.5*sum(mu.*y.^2) over all row blocks
     BZ_TRY(fetch_state(p));
     if (p->st_host->err_flag) return bz_fail(ctx, BZ_ERR_NONPOSITIVE_MU, "parameters `mu` must be positive");
@@ -1081,7 +1103,7 @@ extern "C" int bz_obstacle_fused_step(bz_problem* p, const double* x, double gam
     p->st_host->gamma = gamma;
     BZ_TRY(push_state(p));
     // grad_x / grad_z are debug outputs of the kernel: staged in x_d / d (free outside a solve)
-    BZ_TRY(bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->muy, p->part, p->counters + 3, 1,
+    BZ_TRY(bz_launch_obstacle_fused(ctx, p->st, p->v, p->ob, g_params(p), p->mu, p->rmu, p->muy, p->part, p->counters + 3, 1,
                                     p->v.x_d, p->v.d));
     BZ_TRY(fetch_state(p));
     if (scalars9) for (int k = 0; k < 9; ++k) scalars9[k] = p->st_host->out[k];

@@ -12,6 +12,7 @@
 // This file is compiled with -fmad=false: the reference's Julia broadcasts are not contracted
 // into FMAs, and the discontinuous operators (H4) make that matter.
 #include "bz_vecdev.cuh"
+#include "bz_fdiv.cuh"
 #include <cooperative_groups.h>
 
 
@@ -472,7 +473,7 @@ int bz_launch_proj(bz_ctx* ctx, const double* in, double* out, long long m, cons
 // dual safeguard (safeguards.jl:2-10) + AugLagUpdate! (auglagfun.jl:91-101)
 __global__ void __launch_bounds__(BZ_VEC_THREADS)
     k_al_update(BzState* st, double* mu, double* y, double* muy, long long m, int safeguard,
-                int count_outer, double* part, unsigned int* counter) {
+                int count_outer, double* part, unsigned int* counter, double* rmu) {
     __shared__ double scratch[2 * 32];
     const long long stride = (long long)gridDim.x * blockDim.x;
     double a[1] = {0.0}, bad[1] = {0.0};
@@ -483,6 +484,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
         if (!(mj > 0)) bad[0] = 1.0;      // any(mu .<= 0) (NaN counts as bad here)
         const double my = mj * yj;
         muy[j] = my;
+        if (rmu) rmu[j] = frecip(mj);     // 1 ./ mu for the kernels that divide by mu with fdiv (bz_fdiv.cuh)
         a[0] += my * yj;
     }
     bz_block_sum<1>(a, scratch);
@@ -501,9 +503,9 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     }
 }
 int bz_launch_al_update(bz_ctx* ctx, BzState* st, double* mu, double* y, double* muy, long long m,
-                        int safeguard, int count_outer, double* part, unsigned int* counter) {
+                        int safeguard, int count_outer, double* part, unsigned int* counter, double* rmu) {
     k_al_update<<<bz_vec_grid(ctx, m), BZ_VEC_THREADS, 0, ctx->stream>>>(st, mu, y, muy, m, safeguard,
-                                                                         count_outer, part, counter);
+                                                                         count_outer, part, counter, rmu);
     ctx->n_launches++;
     BZ_CUDA(ctx, cudaGetLastError());
     return BZ_OK;
@@ -694,6 +696,7 @@ __global__ void k_panoc_begin(BzState* st, double tol, long long maxit, double a
     st->currmem = 0; st->curridx = 0; st->H = 1.0;
     for (int i = 0; i < BZ_MAXMEM; ++i) st->slot[i] = i;
     st->spare = BZ_MAXMEM;
+    st->rot = 0;
     st->tau = 1.0; st->k_bt = 1; st->skip_update = 1;
     st->mode = MODE_INIT0; st->grad_target = TGT_X; st->after_g = OP_F; st->grad_x_fresh = 1;
     st->l_role = LROLE_NEWITER;

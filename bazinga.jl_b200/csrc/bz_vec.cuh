@@ -34,7 +34,7 @@ int bz_launch_fstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& 
 int bz_launch_dstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzGradSrc& gs, double* part,
                     unsigned int* counter);
 int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
-                    unsigned int* counter, int force_role, bool slab);
+                    unsigned int* counter, int force_role, bool slab, bool rotate = false);
 int bz_launch_assemble(bz_ctx* ctx, BzState* st, const BzGradSrc& gs, long long n, double* out,
                        double* part, unsigned int* counter);
 
@@ -56,7 +56,7 @@ int bz_launch_prox(bz_ctx* ctx, BzState* st, const double* in, double gamma, dou
                    const BzGParams& g, double* part, unsigned int* counter);
 int bz_launch_proj(bz_ctx* ctx, const double* in, double* out, long long m, const BzDParams& D);
 int bz_launch_al_update(bz_ctx* ctx, BzState* st, double* mu, double* y, double* muy, long long m,
-                        int safeguard, int count_outer, double* part, unsigned int* counter);
+                        int safeguard, int count_outer, double* part, unsigned int* counter, double* rmu = nullptr);
 int bz_launch_multiplier(bz_ctx* ctx, BzState* st, const double* cx, const double* muy,
                          const double* mu, double* y, double* s, long long m, const BzDParams& D,
                          int outer_logic, double* part, unsigned int* counter);
@@ -72,5 +72,5 @@ int bz_launch_panoc_begin(bz_ctx* ctx, BzState* st, double tol, long long maxit,
 // fused forward-backward evaluation of the obstacle problems (bz_obfused.cu): [G, F, G, D] in one pass
 int bz_obfused_partials(bz_ctx* ctx, const BzObstacle& ob);
 int bz_launch_obstacle_fused(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzObstacle& ob, const BzGParams& g,
-                             const double* mu, const double* muy, double* part, unsigned int* counter, int force,
-                             double* dbg_gx, double* dbg_gz);
+                             const double* mu, const double* rmu, const double* muy, double* part, unsigned int* counter,
+                             int force, double* dbg_gx, double* dbg_gz);

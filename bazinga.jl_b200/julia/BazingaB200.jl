@@ -49,6 +49,7 @@ mutable struct Result
     dominant_kernel_ms::Float64; dominant_kernel_launches::Int64
     kind_ms::NTuple{4,Float64}; kind_launches::NTuple{4,Int64}
     mu0_min::Float64; mu0_max::Float64; inner_tol0::Float64       # verbose: the two @info lines of alps.jl:52-55
+    device_ms::Float64
     Result() = new()
 end
 

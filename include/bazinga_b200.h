@@ -176,6 +176,9 @@ typedef struct {
     int64_t kind_launches[4];
     /* verbose (alps.jl:52-55): extrema of the initial penalty vector and the initial inner tolerance */
     double mu0_min, mu0_max, inner_tol0;
+    /* device time of the solve proper (CUDA events on the library's stream): after the H2D of x0, y0, before the D2H
+     * of x, y, s, mu -- elapsed_time minus the host transfers */
+    double device_ms;
 } bz_result;
 
 /* ---- context ------------------------------------------------------------------------------------ */
