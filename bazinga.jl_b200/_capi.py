@@ -91,6 +91,7 @@ SYMBOLS = {
     "bz_panocplus_solve": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(Options), C.c_double, _vp,
                                      C.POINTER(C.c_int64), _dp, _dp]),
     "bz_auglag_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _dp]),
+    "bz_panoc_state": (C.c_int, [_vp, _vp]),
     "bz_auglag_update": (C.c_int, [_vp, _vp, _vp]),
     "bz_auglag_grad": (C.c_int, [_vp, _vp, _vp, _dp, _dp, _vp, _vp, _vp]),
     "bz_prox": (C.c_int, [_vp, _vp, C.c_double, _vp, _dp]),

@@ -1044,6 +1044,16 @@ extern "C" int bz_panocplus_solve(bz_problem* p, const double* mu, const double*
     return BZ_OK;
 }
 
+extern "C" int bz_panoc_state(bz_problem* p, double* out8) {
+    if (!p || !out8) return BZ_ERR_ARG;
+    BZ_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    BZ_TRY(fetch_state(p));
+    const BzState* h = p->st_host;
+    out8[0] = h->gamma; out8[1] = h->tau; out8[2] = h->f_x; out8[3] = h->f_z; out8[4] = h->g_z;
+    out8[5] = h->stopnorm; out8[6] = (double)h->iter; out8[7] = h->H;
+    return BZ_OK;
+}
+
 extern "C" int bz_prox(bz_problem* p, const double* x, double gamma, double* z, double* gz) {
     if (!p || !x) return BZ_ERR_ARG;
     bz_ctx* ctx = p->ctx;

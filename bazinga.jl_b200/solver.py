@@ -334,6 +334,12 @@ class Problem:
                                             _ptr(x), C.byref(it), C.byref(fx), C.byref(gz)), self.ctx.handle)
         return x, it.value, fx.value, gz.value
 
+    def panoc_state(self):
+        """Scalars of the PANOCplus iterate after the last inner solve: dict(gamma, tau, f_x, f_z, g_z, stopnorm, k, H)."""
+        out = np.empty(8)
+        K.check(self.lib.bz_panoc_state(self.handle, _ptr(out)), self.ctx.handle)
+        return dict(gamma=out[0], tau=out[1], f_x=out[2], f_z=out[3], g_z=out[4], stopnorm=out[5], k=int(out[6]), H=out[7])
+
     # ---- per-kernel entry points (names follow the reference's functions)
     def auglag_update(self, mu, y):
         mu, y = _f64(mu), _f64(y)

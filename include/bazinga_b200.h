@@ -223,6 +223,10 @@ int bz_panocplus_solve(bz_problem* p, const double* mu, const double* y, const d
                        const bz_options* opt, double tol, double* x_out, int64_t* sub_it,
                        double* fx, double* gz);
 int bz_auglag_state(bz_problem* p, double* cx, double* s, double* yupd, double* muy, double* musqy);
+/* The PANOCplus iterate's scalars after the last bz_panocplus_solve / solve (what upstream's verbose table and
+ * `state` hold): out8 = {gamma, tau, f_x, f_z, g_z, ||res/gamma - grad_x + grad_z||_inf, k, H}.
+ * With PANOCplus(maxit = k) this is the k-th entry of the oracle's per-iteration trace (tests/golden/panoc_traces.json). */
+int bz_panoc_state(bz_problem* p, double* out8);
 
 /* ---- per-kernel parity entry points ---------------------------------------------------------------- */
 /* AugLagUpdate!(al, mu, y), auglagfun.jl:91-101 (returns BZ_ERR_NONPOSITIVE_MU like the reference) */
