@@ -16,6 +16,6 @@ from .oracles import (  # noqa: F401
 )
 from .results import DATA_COLUMNS, STATS_COLUMNS, demo_rows, demo_stats, write_demo_results  # noqa: F401
 from .solver import (  # noqa: F401
-    BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, alps, als, alps_batch, als_batch, comm_unique_id,
-    default_context, default_subsolver, row_shard,
+    BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, SharedMatrixBatch, alps, als, alps_batch, als_batch,
+    comm_unique_id, default_context, default_subsolver, row_shard,
 )

@@ -109,6 +109,10 @@ SYMBOLS = {
     "bz_batch_solve_als": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
                                      _vp, _vp, _vp, _dp]),
     "bz_fp64_fma_peak": (C.c_int, [_vp, _dp]),
+    "bz_bdense_create": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(_vp)]),
+    "bz_bdense_destroy": (C.c_int, [_vp]),
+    "bz_bdense_auglag_grad": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_double, C.c_double, _vp, _vp, _vp,
+                                        _vp, C.c_int32, _dp]),
     "bz_comm_unique_id": (C.c_int, [_vp]),
     "bz_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "bz_comm_destroy": (C.c_int, [_vp]),

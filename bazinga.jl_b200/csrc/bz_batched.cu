@@ -421,6 +421,8 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
     }
     double tau = 1.0;
     long long k = 1;
+    bool spec = false;     // WARP mode: start the next line search speculatively (see below)
+    (void)spec;
     for (;;) {
         double stopnorm = 0.0;
         bool isnan_ = false;
@@ -478,9 +480,41 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
             // the sequential loop; the first lane (in loop order) that either halves gamma or stops is what the sequential
             // loop would have reached, and its registers become everybody's.  A gamma-halving restarts the speculation at the
             // next loop index from that lane's x.  Bit-identical to the sequential loop by construction.
+            // Speculation costs a broadcast of the winner's registers, so it is only used where it pays: an iteration starts
+            // with the plain sequential step when the previous iteration accepted its first candidate (`spec` false), and
+            // switches to speculation as soon as a candidate is rejected.  `carried` says whether lane 0's (x, f_x, grad_x)
+            // already belong to loop index kb (true at the start and after a gamma-halving) or must be interpolated.
             const int lane = threadIdx.x & 31;
             int kb = 1;
+            bool carried = true, backtracked = false;
             while (kb <= o.max_backtracks) {
+                if (!spec && carried) {
+                    // ---- loop index kb evaluated by every lane alike (identical registers: the sequential statements)
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) y[j] = x[j] - gamma * grad_x[j];
+                    g_z = al.prox(y, gamma, z);
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) res[j] = x[j] - z[j];
+                    f_up = f_model<NV>(f_x, grad_x, res, aog);
+                    f_z = al.gradient(z, grad_z);
+                    if (f_z > f_up + 10 * BZ_EPS * (1 + fabs(f_z)) && gamma >= o.minimum_gamma) {
+                        gamma *= 0.5;
+                        rg *= 2;
+                        aog *= 2;
+                        if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
+                        H.reset();
+                        ++kb;
+                        backtracked = true;
+                        continue;
+                    }
+                    if (f_up + g_z <= thresh || kb >= o.max_backtracks) break;
+                    tau = (kb >= o.max_backtracks - 1) ? 0.0 : tau / 2;      // tau of loop index kb + 1
+                    ++kb;
+                    carried = false;                                          // x of that index is not formed yet
+                    spec = true;
+                    backtracked = true;
+                    continue;
+                }
                 // tau of loop index kb + lane, from the tau of index kb:  tau <- (k >= max_backtracks - 1) ? 0 : tau / 2 at k = kb .. kb+lane-1
                 double tl = tau;
                 for (int q = 0; q < lane; ++q) tl = (kb + q >= o.max_backtracks - 1) ? 0.0 : tl / 2;
@@ -489,7 +523,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
 #pragma unroll
                 for (int j = 0; j < NV; ++j) { xl[j] = x[j]; gxl[j] = grad_x[j]; }
                 const bool live = kl <= o.max_backtracks;
-                if (lane > 0 && live) {
+                if ((lane > 0 || !carried) && live) {
 #pragma unroll
                     for (int j = 0; j < NV; ++j) xl[j] = tl * x_d[j] + (1 - tl) * z_curr[j];
                     fxl = al.gradient(xl, gxl);
@@ -510,6 +544,7 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
                 const unsigned ev = __ballot_sync(0xffffffffu, live && (halve || stop));
                 const int src = __ffs(ev) - 1;        // never empty: the lane of loop index max_backtracks halves or stops
                 const bool was_halve = __shfl_sync(0xffffffffu, halve ? 1 : 0, src) != 0;
+                if (src > 0) backtracked = true;
                 // the chosen lane's state becomes the warp's (including the AugLagFun side effects of its last gradient!)
 #pragma unroll
                 for (int j = 0; j < NV; ++j) {
@@ -532,14 +567,17 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
                     al.yupd[i] = __shfl_sync(0xffffffffu, al.yupd[i], src);
                 }
                 al.ngrad = __shfl_sync(0xffffffffu, al.ngrad, 0);    // (not used in this mode; kept uniform)
+                carried = true;
                 if (!was_halve) break;
                 gamma *= 0.5;
                 rg *= 2;
                 aog *= 2;
                 if (!(fabs(aog) >= 4.5e-308)) aog = a / gamma;
                 H.reset();
+                backtracked = true;
                 kb += src + 1;
             }
+            spec = backtracked;            // the next iteration speculates from its first candidate iff this one back-tracked
         }
         double sv[NV], yv[NV];
 #pragma unroll

@@ -1,0 +1,327 @@
+// Batched shared-A mode of the dense AL-gradient (BASELINE north_star job 2: "tensor-core GEMMs only in the batched
+// shared-A mode where they really are dense contractions"): B <= 8 basis-pursuit instances that share the matrix A
+// (demo/basispursuit.jl:38-49 -- cx .= A*x - b, jtv .= A'*v -- evaluated for a batch of x, b, mu, y):
+//
+//     R = A X          (m x n)(n x 8)      pass 1, DMMA m8n8k4 (fp64 tensor cores; tcgen05 has no fp64 kind)
+//     W = (R - b + mu.*y - proj_D(.)) ./ mu     elementwise, in the epilogue of pass 1 (auglagfun.jl:74-79)
+//     G = A' W         (n x m)(m x 8)      pass 2, DMMA m8n8k4
+//
+// A single instance is a GEMV (0.25 flop/B, bz_dense.cu); eight instances that share A are a skinny GEMM whose cost is
+// still the read of A -- so eight AL-gradients cost what one costs.  This first version reads A once per pass (twice per
+// batched gradient; the single-pass form needs the row-panel exchange of bz_grid.cu widened to 8 x 8 blocks and is the
+// next step): 2 x 537 MB for 8 gradients at 4096 x 16384 instead of 8 x 537 MB.
+//
+// Pass 1: a CTA owns 32 rows; chunks of 128 columns of those rows (32 x 1 KB, cp.async.bulk per row) and of X (8 x 1 KB)
+// stream through a 4-stage shared-memory ring; warp w multiplies the 8-row tile (w & 3) with the 64-column half (w >> 2)
+// of the chunk: 16 DMMAs per chunk, accumulators in registers.  Pass 2: a CTA owns 128 columns; chunks of 32 rows x 128
+// columns stream through the ring, warp w owns 16 columns: 16 DMMAs per chunk (M = columns of A, K = rows, N = batch).
+// Row strides in shared memory are = 4 (mod 16) doubles, which makes every fragment load conflict-free.  No partial
+// results cross CTAs: every output element is produced by one warp in a fixed order (deterministic, no atomics).
+#include "bz_internal.cuh"
+#include "bz_ptx.cuh"
+#include "bz_dense.cuh"
+#include "bz_vec.cuh"
+
+#include <vector>
+
+#define BD_B 8            // batch width = N of m8n8k4
+#define BD_THREADS 256
+#define BD_STAGES 4
+#define BD_RP 32          // pass 1: rows per CTA
+#define BD_KC 128         // pass 1: columns per chunk
+#define BD_CP 128         // pass 2: columns per CTA
+#define BD_RC 32          // pass 2: rows per chunk
+#define BD_PAD 4
+#define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + 2 * BD_RP * BD_B * 8)
+#define BD_SMEM2 (BD_STAGES * (BD_RC * (BD_CP + BD_PAD) + BD_B * (BD_RC + BD_PAD)) * 8 + 64)
+
+struct bz_bdense {
+    bz_ctx* ctx;
+    long long m, n;
+    double* A;                 // row-major m x n
+    double *X, *G;             // [8][n]
+    double *bv, *mu, *y, *cx, *yupd, *W;   // [8][m]
+    double* lxpart;            // [ctas1][8]
+    int ctas1, ctas2;
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- pass 1: R = A X for the CTA's 32 rows, then the elementwise AL stage ------------------------------------------------
+__global__ void __launch_bounds__(BD_THREADS, 1)
+    k_bd_ax(const double* __restrict__ A, long long m, long long n, const double* __restrict__ X,
+            const double* __restrict__ bv, const double* __restrict__ mu, const double* __restrict__ yv, int dkind, double dlo,
+            double dhi, double* __restrict__ cx, double* __restrict__ yupd, double* __restrict__ W, double* __restrict__ lxpart) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LD = BD_KC + BD_PAD;                       // 132 doubles: = 4 (mod 16)
+    constexpr int STAGE = (BD_RP + BD_B) * LD;               // A tile (32 rows) then X chunk (8 rows)
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
+    double* red = reinterpret_cast<double*>(full + 8);       // [2][32][8]: k-half partial tiles, lx partials
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long r0 = (long long)blockIdx.x * BD_RP;
+    const int nchunks = (int)((n + BD_KC - 1) / BD_KC);
+
+    for (int i = tid; i < BD_STAGES * STAGE; i += BD_THREADS) ring[i] = 0.0;   // tails must hold finite values
+    if (tid == 0) {
+        for (int s = 0; s < BD_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t pol = l2_evict_first_policy();
+    auto issue = [&](int c) {                                 // one thread: 32 row segments of A + 8 of X into stage c % S
+        const int s = c % BD_STAGES;
+        const long long c0 = (long long)c * BD_KC;
+        const int valid = (int)((n - c0) < BD_KC ? (n - c0) : BD_KC);
+        double* dst = ring + (size_t)s * STAGE;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], (uint32_t)((BD_RP + BD_B) * valid * 8));
+        for (int r = 0; r < BD_RP; ++r) {
+            long long row = r0 + r;
+            if (row >= m) row = m - 1;                        // rows past the end: a valid row again, its results are dropped
+            bulk_g2s_hint(dst + (size_t)r * LD, A + row * n + c0, (uint32_t)valid * 8u, &full[s], pol);
+        }
+        for (int k = 0; k < BD_B; ++k)
+            bulk_g2s(dst + (size_t)(BD_RP + k) * LD, X + (size_t)k * n + c0, (uint32_t)valid * 8u, &full[s]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < BD_STAGES - 1 && c < nchunks; ++c) issue(c);
+
+    const int mt = warp & 3, kh = warp >> 2;
+    double c0 = 0.0, c1 = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % BD_STAGES;
+        const int nxt = c + BD_STAGES - 1;
+        if (nxt < nchunks) {
+            // the stage of chunk nxt was consumed in iteration c - 1 (barrier below).  A partial last chunk leaves the
+            // tail of the X rows stale: zero it (stale A x 0 = 0; A is finite)
+            const long long cn0 = (long long)nxt * BD_KC;
+            const int valid = (int)((n - cn0) < BD_KC ? (n - cn0) : BD_KC);
+            if (valid < BD_KC) {
+                double* xs = ring + (size_t)(nxt % BD_STAGES) * STAGE + (size_t)BD_RP * LD;
+                for (int i = tid; i < BD_B * (BD_KC - valid); i += BD_THREADS)
+                    xs[(size_t)(i / (BD_KC - valid)) * LD + valid + i % (BD_KC - valid)] = 0.0;
+                __syncthreads();
+            }
+            if (tid == 0) issue(nxt);
+        }
+        mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
+        const double* at = ring + (size_t)s * STAGE + (size_t)(8 * mt + (lane >> 2)) * LD + kh * 64 + (lane & 3);
+        const double* xt = ring + (size_t)s * STAGE + (size_t)(BD_RP + (lane >> 2)) * LD + kh * 64 + (lane & 3);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) dmma_m8n8k4(c0, c1, at[4 * kk], xt[4 * kk]);
+        __syncthreads();
+    }
+    // ---- k-halves: warps 4..7 hand their tiles to warps 0..3 (fixed order: half 0 + half 1)
+    const int row_l = 8 * mt + (lane >> 2), bcol = 2 * (lane & 3);
+    if (kh == 1) { red[row_l * BD_B + bcol] = c0; red[row_l * BD_B + bcol + 1] = c1; }
+    __syncthreads();
+    double lx0 = 0.0, lx1 = 0.0;
+    if (kh == 0) {
+        const double rr[2] = {c0 + red[row_l * BD_B + bcol], c1 + red[row_l * BD_B + bcol + 1]};
+        const long long row = r0 + row_l;
+        if (row < m) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {                     // auglagfun.jl:74-79 for instance k = bcol + e, uncontracted
+                const size_t idx = (size_t)(bcol + e) * m + row;
+                const double mu_j = mu[idx];
+                const double cxv = __dsub_rn(rr[e], bv[idx]);                    // cx = A*x - b
+                const double t = __dadd_rn(cxv, __dmul_rn(mu_j, yv[idx]));       // yupd = cx + mu.*y
+                const double sv = bz_proj_elem(dkind, dlo, dhi, t, row);         // proj!(s, D, yupd)
+                const double u = __dsub_rn(t, sv);
+                const double w = __ddiv_rn(u, mu_j);
+                (e == 0 ? lx0 : lx1) = __ddiv_rn(__dmul_rn(u, u), mu_j);
+                cx[idx] = cxv; yupd[idx] = w; W[idx] = w;
+            }
+        }
+        // sum over the 8 rows of the tile (lanes with equal lane & 3), fixed butterfly order
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            lx0 += __shfl_xor_sync(0xffffffffu, lx0, o);
+            lx1 += __shfl_xor_sync(0xffffffffu, lx1, o);
+        }
+    }
+    __syncthreads();
+    if (kh == 0 && lane < 4) { red[BD_RP * BD_B + mt * BD_B + 2 * lane] = lx0; red[BD_RP * BD_B + mt * BD_B + 2 * lane + 1] = lx1; }
+    __syncthreads();
+    if (tid < BD_B) {
+        const double* q = red + BD_RP * BD_B;
+        lxpart[(size_t)blockIdx.x * BD_B + tid] = ((q[tid] + q[BD_B + tid]) + q[2 * BD_B + tid]) + q[3 * BD_B + tid];
+    }
+}
+
+// ---- pass 2: G = A' W for the CTA's 128 columns ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(BD_THREADS, 1)
+    k_bd_atw(const double* __restrict__ A, long long m, long long n, const double* __restrict__ W, double* __restrict__ G) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LDA = BD_CP + BD_PAD;                      // 132
+    constexpr int LDW = BD_RC + BD_PAD;                      // 36 = 4 (mod 16)
+    constexpr int STAGE = BD_RC * LDA + BD_B * LDW;
+    double* ring = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long c0 = (long long)blockIdx.x * BD_CP;
+    const int cvalid = (int)((n - c0) < BD_CP ? (n - c0) : BD_CP);
+    const int nchunks = (int)((m + BD_RC - 1) / BD_RC);
+
+    for (int i = tid; i < BD_STAGES * STAGE; i += BD_THREADS) ring[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < BD_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t pol = l2_evict_first_policy();
+    auto issue = [&](int c) {
+        const int s = c % BD_STAGES;
+        const long long rr0 = (long long)c * BD_RC;
+        const int rvalid = (int)((m - rr0) < BD_RC ? (m - rr0) : BD_RC);
+        double* dst = ring + (size_t)s * STAGE;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[s], (uint32_t)(BD_RC * cvalid * 8 + BD_B * rvalid * 8));
+        for (int r = 0; r < BD_RC; ++r) {
+            long long row = rr0 + r;
+            if (row >= m) row = m - 1;                        // finite filler; its W entries are zero
+            bulk_g2s_hint(dst + (size_t)r * LDA, A + row * n + c0, (uint32_t)cvalid * 8u, &full[s], pol);
+        }
+        for (int k = 0; k < BD_B; ++k)
+            bulk_g2s(dst + (size_t)BD_RC * LDA + (size_t)k * LDW, W + (size_t)k * m + rr0, (uint32_t)rvalid * 8u, &full[s]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < BD_STAGES - 1 && c < nchunks; ++c) issue(c);
+
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int c = 0; c < nchunks; ++c) {
+        const int s = c % BD_STAGES;
+        const int nxt = c + BD_STAGES - 1;
+        if (nxt < nchunks) {
+            const long long rn0 = (long long)nxt * BD_RC;
+            const int rvalid = (int)((m - rn0) < BD_RC ? (m - rn0) : BD_RC);
+            if (rvalid < BD_RC) {                             // rows past the end contribute A(m-1, :) * 0
+                double* ws = ring + (size_t)(nxt % BD_STAGES) * STAGE + (size_t)BD_RC * LDA;
+                for (int i = tid; i < BD_B * (BD_RC - rvalid); i += BD_THREADS)
+                    ws[(size_t)(i / (BD_RC - rvalid)) * LDW + rvalid + i % (BD_RC - rvalid)] = 0.0;
+                __syncthreads();
+            }
+            if (tid == 0) issue(nxt);
+        }
+        mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
+        const double* tile = ring + (size_t)s * STAGE;
+        const double* wt = tile + (size_t)BD_RC * LDA + (size_t)(lane >> 2) * LDW + (lane & 3);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const double* at = tile + (size_t)(lane & 3) * LDA + 16 * warp + 8 * g + (lane >> 2);
+#pragma unroll
+            for (int kk = 0; kk < BD_RC / 4; ++kk) dmma_m8n8k4(acc[g][0], acc[g][1], at[(size_t)4 * kk * LDA], wt[4 * kk]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const long long col = c0 + 16 * warp + 8 * g + (lane >> 2);
+        if (col < n) {
+            G[(size_t)(2 * (lane & 3)) * n + col] = acc[g][0];
+            G[(size_t)(2 * (lane & 3) + 1) * n + col] = acc[g][1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+extern "C" int bz_bdense_create(bz_ctx* ctx, int64_t m, int64_t n, const double* A, int32_t layout, int32_t gen,
+                                uint64_t gen_seed, bz_bdense** out) {
+    if (!ctx || !out || m < 1 || n < 2 || (n % 2)) return bz_fail(ctx, BZ_ERR_ARG, "bz_bdense_create: need m >= 1 and an even n >= 2");
+    if (!gen && !A) return bz_fail(ctx, BZ_ERR_ARG, "bz_bdense_create: A is NULL");
+    if (!gen && layout != BZ_ROW_MAJOR) return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_bdense_create: row-major A only");
+    *out = nullptr;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    bz_bdense* h = new bz_bdense();
+    h->ctx = ctx; h->m = m; h->n = n;
+    h->ctas1 = (int)((m + BD_RP - 1) / BD_RP);
+    h->ctas2 = (int)((n + BD_CP - 1) / BD_CP);
+    auto fail = [&](cudaError_t e) { bz_bdense_destroy(h); return bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e)); };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&h->A, (size_t)m * n * 8)) != cudaSuccess) return fail(e);
+    double** mv[] = {&h->bv, &h->mu, &h->y, &h->cx, &h->yupd, &h->W};
+    for (double** q : mv) if ((e = cudaMalloc((void**)q, (size_t)BD_B * m * 8)) != cudaSuccess) return fail(e);
+    double** nv[] = {&h->X, &h->G};
+    for (double** q : nv) if ((e = cudaMalloc((void**)q, (size_t)BD_B * n * 8)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc((void**)&h->lxpart, (size_t)h->ctas1 * BD_B * 8)) != cudaSuccess) return fail(e);
+    if (gen) {
+        int rc = bz_launch_randn_fill(ctx, gen_seed, 0, 0, m * n, h->A);
+        if (rc != BZ_OK) { bz_bdense_destroy(h); return rc; }
+    } else if ((e = cudaMemcpyAsync(h->A, A, (size_t)m * n * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return fail(e);
+    if ((e = cudaFuncSetAttribute(k_bd_ax, cudaFuncAttributeMaxDynamicSharedMemorySize, BD_SMEM1)) != cudaSuccess) return fail(e);
+    if ((e = cudaFuncSetAttribute(k_bd_atw, cudaFuncAttributeMaxDynamicSharedMemorySize, BD_SMEM2)) != cudaSuccess) return fail(e);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e);
+    *out = h;
+    return BZ_OK;
+}
+
+extern "C" int bz_bdense_destroy(bz_bdense* h) {
+    if (!h) return BZ_OK;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    double* fr[] = {h->A, h->X, h->G, h->bv, h->mu, h->y, h->cx, h->yupd, h->W, h->lxpart};
+    for (double* q : fr) if (q) cudaFree(q);
+    delete h;
+    return BZ_OK;
+}
+
+extern "C" int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* X, const double* b, const double* mu,
+                                     const double* y, int32_t d_kind, double d_lo, double d_hi, double* dlx, double* lx,
+                                     double* cx, double* yupd, int32_t reps, double* us_per_call) {
+    if (!h || !X || !b || !mu || !y || batch < 1 || batch > BD_B) return BZ_ERR_ARG;
+    bz_ctx* ctx = h->ctx;
+    BZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_kind != BZ_D_ZERO && d_kind != BZ_D_FREE && d_kind != BZ_D_BOX)
+        return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_bdense_auglag_grad: elementwise sets only (ZeroSet, FreeSet, box)");
+    const long long m = h->m, n = h->n;
+    // instances beyond `batch` are padded: x = 0, b = 0, mu = 1, y = 0
+    BZ_CUDA(ctx, cudaMemsetAsync(h->X, 0, (size_t)BD_B * n * 8, ctx->stream));
+    BZ_CUDA(ctx, cudaMemsetAsync(h->bv, 0, (size_t)BD_B * m * 8, ctx->stream));
+    BZ_CUDA(ctx, cudaMemsetAsync(h->y, 0, (size_t)BD_B * m * 8, ctx->stream));
+    BZ_TRY_RC(bz_launch_fill(ctx, h->mu, BD_B * m, 1.0));
+    BZ_CUDA(ctx, cudaMemcpyAsync(h->X, X, (size_t)batch * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpyAsync(h->bv, b, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpyAsync(h->mu, mu, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpyAsync(h->y, y, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (reps < 1) reps = 1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int r = 0; r < reps + 1; ++r) {            // the first launch is a warm-up when reps > 1
+        if (r == 1 || reps == 1) cudaEventRecord(e0, ctx->stream);
+        k_bd_ax<<<h->ctas1, BD_THREADS, BD_SMEM1, ctx->stream>>>(h->A, m, n, h->X, h->bv, h->mu, h->y, d_kind, d_lo, d_hi, h->cx,
+                                                                 h->yupd, h->W, h->lxpart);
+        k_bd_atw<<<h->ctas2, BD_THREADS, BD_SMEM2, ctx->stream>>>(h->A, m, n, h->W, h->G);
+        ctx->n_launches += 2;
+        if (reps == 1) break;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e));
+    if (us_per_call) *us_per_call = 1e3 * (double)ms / reps;
+    if (dlx) BZ_CUDA(ctx, cudaMemcpyAsync(dlx, h->G, (size_t)batch * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cx) BZ_CUDA(ctx, cudaMemcpyAsync(cx, h->cx, (size_t)batch * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (yupd) BZ_CUDA(ctx, cudaMemcpyAsync(yupd, h->yupd, (size_t)batch * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> part((size_t)h->ctas1 * BD_B);
+    BZ_CUDA(ctx, cudaMemcpyAsync(part.data(), h->lxpart, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (lx) {
+        // lx_k = 0.5*sum((t-s)^2 ./ mu) + f(x) - 0.5*sum(mu.*y.^2) with f = Zero (auglagfun.jl:78-82); partials in CTA order
+        for (int k = 0; k < batch; ++k) {
+            double s = 0.0;
+            for (int c = 0; c < h->ctas1; ++c) s += part[(size_t)c * BD_B + k];
+            double musqy = 0.0;
+            for (long long i = 0; i < m; ++i) musqy += (mu[(size_t)k * m + i] * y[(size_t)k * m + i]) * y[(size_t)k * m + i];
+            lx[k] = 0.5 * s - 0.5 * musqy;
+        }
+    }
+    return BZ_OK;
+}

@@ -32,12 +32,13 @@
 // divisions by gamma use the three-FMA quotient of bz_fdiv.cuh (the same bits as the IEEE division).
 #include "bz_vecdev.cuh"
 #include "bz_fdiv.cuh"
+#include <cstdlib>
 
 #define OF_THREADS 128
 #define OF_WARPS (OF_THREADS / 32)
 #define OF_HALO 4
 #define OF_OUT (32 - 2 * OF_HALO)   // 24 output columns per warp
-#define OF_PF 1                      // raw rows in flight ahead of the row being consumed (one row-time of a warp is several memory latencies)
+#define OF_PF 1  /* (documentation only) */                      // raw rows in flight ahead of the row being consumed (one row-time of a warp is several memory latencies)
 #define OF_NSUM 9
 
 struct ObFusedGeom { int ncg, nrc, rows_per_chunk, ctas; };
@@ -55,15 +56,17 @@ __device__ __forceinline__ double of_stencil(double diag, double c, double up, d
     return out;
 }
 
-// The software pipeline of one lane.  Circular delay lines with STATIC indices: the row loop is unrolled six times and
-// step P of a group finds the value of age k (0 = produced in this step) in slot (P-dependent constant + k) mod L, so
-// nothing is ever shifted (a shifting version spent 29 % of its instructions on register moves).
+// The software pipeline of one lane.  Every delay line is a circular buffer of THREE rows with STATIC indices: the row
+// loop is unrolled three times and step P of a group finds the row of age k in slot (P-dependent constant + k) mod 3, so
+// nothing is ever shifted (a shifting version spent 29 % of its instructions on register moves; a six-row version did
+// not fit the instruction cache).  Raw rows are loaded one row ahead into staging registers.
 struct OfPipe {
-    double X1[6], X2[6], X3[6], MU[6], RM[6], MY[6];    // raw rows (x, mu, 1/mu, mu*y): age k = row jc + OF_PF - k
-    double WX[3];                                 // w_x:  age k = row jc - 1 - k
-    double Z1[3], Z2[3], Z3[3];                   // z:    age k = row jc - 2 - k
-    double G1[3], G2[3], G3[3], R1[3], R2[3], R3[3];   // grad_x, res: like z
-    double WZ[3];                                 // w_z:  age k = row jc - 3 - k
+    double X1[3], X2[3], X3[3], MU[3], RM[3], MY[3];   // raw rows jc, jc-1, jc-2 (x, mu, 1/mu, mu*y)
+    double S1, S2, S3, SMU, SRM, SMY;                  // staging: row jc+1, in flight
+    double WX[3];                                       // w_x of rows jc-1, jc-2, jc-3
+    double Z1[3], Z2[3], Z3[3];                         // z of rows jc-2, jc-3, jc-4
+    double G1[3], G2[3], G3[3], R1[3], R2[3], R3[3];    // grad_x, res: like z
+    double WZ[3];                                       // w_z of rows jc-3, jc-4, jc-5
 };
 struct OfCtx {
     const double* __restrict__ x1p; const double* __restrict__ x2p; const double* __restrict__ x3p;
@@ -73,50 +76,61 @@ struct OfCtx {
     double gamma, gamma_h, rg, rgh, diag;
     bool colok, own_lane, need2;
     double a[OF_NSUM];
-    double m1, m2;
-    bool nan1, nan2;
+    double m1, m2, nan1, nan2;     // running maxima (NaN-blind) and NaN detectors: sums of |v|, NaN iff some v was NaN
 };
 
+// fdiv of bz_fdiv.cuh with the range test first: the common quotient costs three FMAs and one integer test
+__device__ __forceinline__ double of_div(double a, double b, double rb) {
+    const double q = a * rb;
+    const double q2 = fma(fma(-b, q, a), rb, q);
+    if (fmid<512>(q2)) return q2;
+    if (a != a || (a == 0.0 && q == 0.0)) return q;
+    return fdiv_rare(a, b, rb);
+}
+
 // One row step.  MASKED = false is the steady state of an interior warp: every lane's column is inside the grid, rows
-// jc-4 .. jc+OF_PF are grid rows, and all four stage rows belong to this warp's chunk -- no validity selects, no range
+// jc-4 .. jc+1 are grid rows, and all four stage rows belong to this warp's chunk -- no validity selects, no range
 // tests; the halo lanes accumulate garbage that is discarded at the end (c.own_lane).  MASKED = true is the general step.
 template <int P, bool MASKED, bool L2>
 __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc) {
     // L2 = obstacle_l2 (f adds 0.5||x1||^2: dfx block 1 = x1; g without the threshold on block 1 and with value 0), else obstacle_l1
     constexpr bool l2f = L2, l1g = !L2;
-    constexpr int n0 = (6 - P % 6) % 6, m0 = (3 - P % 3) % 3;
-#define S6(age) ((n0 + (age)) % 6)
-#define S3(age) ((m0 + (age)) % 3)
-    {   // ---- raw row jc + OF_PF (zeros outside the grid)
-        const long long j = jc + OF_PF;
+    constexpr int n0 = (3 - P % 3) % 3;
+#define SL(age) ((n0 + (age)) % 3)
+    // ---- the row evicted from the raw lines is row jc-3: stage 3 wants its mu, 1/mu, mu*y
+    const double ev_mu = s.MU[SL(0)], ev_rm = s.RM[SL(0)], ev_my = s.MY[SL(0)];
+    s.X1[SL(0)] = s.S1; s.X2[SL(0)] = s.S2; s.X3[SL(0)] = s.S3;            // row jc arrives from staging
+    s.MU[SL(0)] = s.SMU; s.RM[SL(0)] = s.SRM; s.MY[SL(0)] = s.SMY;
+    {   // ---- raw row jc + 1 into staging (zeros outside the grid)
+        const long long j = jc + 1;
         const bool ok = MASKED ? (c.colok && j >= 0 && j < c.GY) : true;
         const long long i = j * c.GX + c.col;
-        s.X1[S6(0)] = ok ? __ldg(c.x1p + i) : 0.0;
-        s.X2[S6(0)] = ok ? __ldg(c.x2p + i) : 0.0;
-        s.X3[S6(0)] = ok ? __ldg(c.x3p + i) : 0.0;
-        s.MU[S6(0)] = ok ? __ldg(c.mu + i) : 1.0;
-        s.RM[S6(0)] = ok ? __ldg(c.rmu + i) : 1.0;      // 1 ./ mu, kept up to date by k_al_update (fdiv: the bits of a / mu)
-        s.MY[S6(0)] = ok ? __ldg(c.muy + i) : 0.0;
+        s.S1 = ok ? __ldg(c.x1p + i) : 0.0;
+        s.S2 = ok ? __ldg(c.x2p + i) : 0.0;
+        s.S3 = ok ? __ldg(c.x3p + i) : 0.0;
+        s.SMU = ok ? __ldg(c.mu + i) : 1.0;
+        s.SRM = ok ? __ldg(c.rmu + i) : 1.0;      // 1 ./ mu, kept up to date by k_al_update (of_div: the bits of a / mu)
+        s.SMY = ok ? __ldg(c.muy + i) : 0.0;
     }
     {   // ---- stage 1: w_x on row r1 = jc - 1 (x2 rows jc-2, jc-1, jc)                      k_obstacle_c
         const long long r1 = jc - 1;
-        const double x1 = s.X1[S6(OF_PF + 1)], x2 = s.X2[S6(OF_PF + 1)], x3 = s.X3[S6(OF_PF + 1)];
-        const double mua = s.MU[S6(OF_PF + 1)], rma = s.RM[S6(OF_PF + 1)], muya = s.MY[S6(OF_PF + 1)];
-        const double cva = (x1 + of_stencil(c.diag, x2, s.X2[S6(OF_PF + 2)], s.X2[S6(OF_PF)])) - x3;
+        const double x1 = s.X1[SL(1)], x2 = s.X2[SL(1)], x3 = s.X3[SL(1)];
+        const double mua = s.MU[SL(1)], rma = s.RM[SL(1)], muya = s.MY[SL(1)];
+        const double cva = (x1 + of_stencil(c.diag, x2, s.X2[SL(2)], s.X2[SL(0)])) - x3;
         const double t = cva + muya;
         const double u = t - 0.0;                      // SetObstacle: proj = 0 (demo/obstacle.jl:116-119)
         if (MASKED) {
             const bool ok = c.colok && r1 >= 0 && r1 < c.GY;
-            s.WX[S3(0)] = ok ? fdiv(u, mua, rma) : 0.0;
+            s.WX[SL(0)] = ok ? of_div(u, mua, rma) : 0.0;
             if (c.own_lane && r1 >= c.rb && r1 < c.re) {
-                c.a[0] += fdiv(u * u, mua, rma);
+                c.a[0] += of_div(u * u, mua, rma);
                 if (l2f) c.a[1] += x1 * x1;
                 c.a[1] += x2 * x2;
                 c.a[2] += x2;
             }
         } else {
-            s.WX[S3(0)] = fdiv(u, mua, rma);
-            c.a[0] += fdiv(u * u, mua, rma);
+            s.WX[SL(0)] = of_div(u, mua, rma);
+            c.a[0] += of_div(u * u, mua, rma);
             if (l2f) c.a[1] += x1 * x1;
             c.a[1] += x2 * x2;
             c.a[2] += x2;
@@ -124,9 +138,9 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     }
     {   // ---- stage 2: grad_x, z, res on row r2 = jc - 2 (w_x rows jc-3, jc-2, jc-1)          k_obstacle_jt + k_fstep
         const long long r2 = jc - 2;
-        const double x1 = s.X1[S6(OF_PF + 2)], x2 = s.X2[S6(OF_PF + 2)], x3 = s.X3[S6(OF_PF + 2)];
-        const double w = s.WX[S3(1)];
-        const double aw = of_stencil(c.diag, w, s.WX[S3(2)], s.WX[S3(0)]);
+        const double x1 = s.X1[SL(2)], x2 = s.X2[SL(2)], x3 = s.X3[SL(2)];
+        const double w = s.WX[SL(1)];
+        const double aw = of_stencil(c.diag, w, s.WX[SL(2)], s.WX[SL(0)]);
         const double g1 = (l2f ? x1 : 0.0) + w;
         const double g2 = (x2 - 1.0) + aw;
         const double g3 = 0.0 + (-w);
@@ -141,9 +155,9 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
             st_ok = c.own_lane && r2 >= c.rb && r2 < c.re;
         }
         const double q1 = x1 - z1, q2 = x2 - z2, q3 = x3 - z3;
-        s.Z1[S3(0)] = z1; s.Z2[S3(0)] = z2; s.Z3[S3(0)] = z3;
-        s.G1[S3(0)] = g1; s.G2[S3(0)] = g2; s.G3[S3(0)] = g3;
-        s.R1[S3(0)] = q1; s.R2[S3(0)] = q2; s.R3[S3(0)] = q3;
+        s.Z1[SL(0)] = z1; s.Z2[SL(0)] = z2; s.Z3[SL(0)] = z3;
+        s.G1[SL(0)] = g1; s.G2[SL(0)] = g2; s.G3[SL(0)] = g3;
+        s.R1[SL(0)] = q1; s.R2[SL(0)] = q2; s.R3[SL(0)] = q3;
         if (st_ok) {
             const long long i = r2 * c.GX + c.col;
             c.zp[i] = z1; c.zp[c.N + i] = z2; c.zp[2 * c.N + i] = z3;
@@ -159,23 +173,22 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     }
     {   // ---- stage 3: w_z on row r3 = jc - 3 (z2 rows jc-4, jc-3, jc-2)
         const long long r3 = jc - 3;
-        const double z1 = s.Z1[S3(1)], z2 = s.Z2[S3(1)], z3 = s.Z3[S3(1)];
-        const double mua = s.MU[S6(OF_PF + 3)], rma = s.RM[S6(OF_PF + 3)], muya = s.MY[S6(OF_PF + 3)];
-        const double cva = (z1 + of_stencil(c.diag, z2, s.Z2[S3(2)], s.Z2[S3(0)])) - z3;
-        const double t = cva + muya;
+        const double z1 = s.Z1[SL(1)], z2 = s.Z2[SL(1)], z3 = s.Z3[SL(1)];
+        const double cva = (z1 + of_stencil(c.diag, z2, s.Z2[SL(2)], s.Z2[SL(0)])) - z3;
+        const double t = cva + ev_my;
         const double u = t - 0.0;
         if (MASKED) {
             const bool ok = c.colok && r3 >= 0 && r3 < c.GY;
-            s.WZ[S3(0)] = ok ? fdiv(u, mua, rma) : 0.0;
+            s.WZ[SL(0)] = ok ? of_div(u, ev_mu, ev_rm) : 0.0;
             if (c.own_lane && r3 >= c.rb && r3 < c.re) {
-                c.a[6] += fdiv(u * u, mua, rma);
+                c.a[6] += of_div(u * u, ev_mu, ev_rm);
                 if (l2f) c.a[7] += z1 * z1;
                 c.a[7] += z2 * z2;
                 c.a[8] += z2;
             }
         } else {
-            s.WZ[S3(0)] = fdiv(u, mua, rma);
-            c.a[6] += fdiv(u * u, mua, rma);
+            s.WZ[SL(0)] = of_div(u, ev_mu, ev_rm);
+            c.a[6] += of_div(u * u, ev_mu, ev_rm);
             if (l2f) c.a[7] += z1 * z1;
             c.a[7] += z2 * z2;
             c.a[8] += z2;
@@ -183,30 +196,30 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     }
     {   // ---- stage 4: grad_z and the stop norm on row r4 = jc - 4 (w_z rows jc-5, jc-4, jc-3)   k_dstep
         const long long r4 = jc - 4;
-        const double w = s.WZ[S3(1)];
-        const double aw = of_stencil(c.diag, w, s.WZ[S3(2)], s.WZ[S3(0)]);
+        const double w = s.WZ[SL(1)];
+        const double aw = of_stencil(c.diag, w, s.WZ[SL(2)], s.WZ[SL(0)]);
         if (!MASKED || (c.own_lane && r4 >= c.rb && r4 < c.re)) {
-            const double h1 = (l2f ? s.Z1[S3(2)] : 0.0) + w;
-            const double h2 = (s.Z2[S3(2)] - 1.0) + aw;
+            const double h1 = (l2f ? s.Z1[SL(2)] : 0.0) + w;
+            const double h2 = (s.Z2[SL(2)] - 1.0) + aw;
             const double h3 = 0.0 + (-w);
             if (c.dbg_gz && c.own_lane) { const long long i = r4 * c.GX + c.col; c.dbg_gz[i] = h1; c.dbg_gz[c.N + i] = h2; c.dbg_gz[2 * c.N + i] = h3; }
-            // NaN-propagating max (Julia's norm(., Inf)): the running maximum ignores NaN, a flag remembers it
-            const double v1 = (fdiv(s.R1[S3(2)], c.gamma, c.rg) - s.G1[S3(2)]) + h1;
-            const double v2 = (fdiv(s.R2[S3(2)], c.gamma, c.rg) - s.G2[S3(2)]) + h2;
-            const double v3 = (fdiv(s.R3[S3(2)], c.gamma, c.rg) - s.G3[S3(2)]) + h3;
-            c.m1 = fmax(c.m1, fmax(fmax(fabs(v1), fabs(v2)), fabs(v3)));
-            c.nan1 |= (v1 != v1) | (v2 != v2) | (v3 != v3);
+            // NaN-propagating max (Julia's norm(., Inf)): the running maximum ignores NaN; a sum of |v| (never Inf - Inf)
+            // is NaN exactly when some v was
+            const double v1 = fabs((of_div(s.R1[SL(2)], c.gamma, c.rg) - s.G1[SL(2)]) + h1);
+            const double v2 = fabs((of_div(s.R2[SL(2)], c.gamma, c.rg) - s.G2[SL(2)]) + h2);
+            const double v3 = fabs((of_div(s.R3[SL(2)], c.gamma, c.rg) - s.G3[SL(2)]) + h3);
+            c.m1 = fmax(c.m1, fmax(fmax(v1, v2), v3));
+            c.nan1 += (v1 + v2) + v3;
             if (c.need2) {   // the norm at gamma/2 is only read when this back-track is the last one allowed (bz_d_decide)
-                const double u1 = (fdiv(s.R1[S3(2)], c.gamma_h, c.rgh) - s.G1[S3(2)]) + h1;
-                const double u2 = (fdiv(s.R2[S3(2)], c.gamma_h, c.rgh) - s.G2[S3(2)]) + h2;
-                const double u3 = (fdiv(s.R3[S3(2)], c.gamma_h, c.rgh) - s.G3[S3(2)]) + h3;
-                c.m2 = fmax(c.m2, fmax(fmax(fabs(u1), fabs(u2)), fabs(u3)));
-                c.nan2 |= (u1 != u1) | (u2 != u2) | (u3 != u3);
+                const double u1 = fabs((of_div(s.R1[SL(2)], c.gamma_h, c.rgh) - s.G1[SL(2)]) + h1);
+                const double u2 = fabs((of_div(s.R2[SL(2)], c.gamma_h, c.rgh) - s.G2[SL(2)]) + h2);
+                const double u3 = fabs((of_div(s.R3[SL(2)], c.gamma_h, c.rgh) - s.G3[SL(2)]) + h3);
+                c.m2 = fmax(c.m2, fmax(fmax(u1, u2), u3));
+                c.nan2 += (u1 + u2) + u3;
             }
         }
     }
-#undef S6
-#undef S3
+#undef SL
 }
 
 template <int P, bool L2>
@@ -220,8 +233,8 @@ __device__ __forceinline__ void of_step_any(OfPipe& s, OfCtx& c, long long jc, l
 template <bool L2>
 __global__ void __launch_bounds__(OF_THREADS, 3)
     k_obstacle_fused(BzState* st, BzVecs v, BzObstacle ob, BzGParams g, const double* __restrict__ mu,
-                     const double* __restrict__ rmu, const double* __restrict__ muy, double* part, unsigned int* counter, ObFusedGeom geo, int force,
-                     double* __restrict__ dbg_gx, double* __restrict__ dbg_gz) {
+                     const double* __restrict__ rmu, const double* __restrict__ muy, double* part, unsigned int* counter,
+                     ObFusedGeom geo, int force, double* __restrict__ dbg_gx, double* __restrict__ dbg_gz) {
     __shared__ double scratch[OF_NSUM * 32];
     bz_pdl_wait();
     bz_pdl_launch_dependents();
@@ -261,42 +274,39 @@ __global__ void __launch_bounds__(OF_THREADS, 3)
 #pragma unroll
     for (int k = 0; k < OF_NSUM; ++k) c.a[k] = 0.0;
     c.m1 = 0.0; c.m2 = 0.0;
-    c.nan1 = false; c.nan2 = false;
+    c.nan1 = 0.0; c.nan2 = 0.0;
 
     if (active) {
         OfPipe s;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { s.X1[k] = 0.0; s.X2[k] = 0.0; s.X3[k] = 0.0; s.MU[k] = 1.0; s.RM[k] = 1.0; s.MY[k] = 0.0; }
-#pragma unroll
         for (int k = 0; k < 3; ++k) {
+            s.X1[k] = 0.0; s.X2[k] = 0.0; s.X3[k] = 0.0; s.MU[k] = 1.0; s.RM[k] = 1.0; s.MY[k] = 0.0;
             s.WX[k] = s.Z1[k] = s.Z2[k] = s.Z3[k] = s.G1[k] = s.G2[k] = s.G3[k] = s.R1[k] = s.R2[k] = s.R3[k] = s.WZ[k] = 0.0;
         }
-        // steps jc = rb-4-PF .. re+3: the first OF_PF only load (their stages see zeros and own nothing)
-        const long long j_begin = c.rb - 4 - OF_PF, j_end = c.re + 4;
-        // unmasked range: interior warp, stage rows jc-4 .. jc-1 inside [rb, re), loaded row jc+PF a grid row
+        s.S1 = s.S2 = s.S3 = 0.0; s.SMU = 1.0; s.SRM = 1.0; s.SMY = 0.0;
+        // steps jc = rb-5 .. re+3: the first one only loads row rb-4 into staging (its stages see zeros and own nothing)
+        const long long j_begin = c.rb - 5, j_end = c.re + 4;
+        // unmasked range: interior warp, stage rows jc-4 .. jc-1 inside [rb, re), loaded row jc+1 a grid row
         const bool interior = (cg * OF_OUT - OF_HALO >= 0) && (cg * OF_OUT - OF_HALO + 31 < c.GX);
         long long s_lo = c.rb + 4, s_hi = c.re + 1;
-        if (s_hi > c.GY - OF_PF) s_hi = c.GY - OF_PF;
+        if (s_hi > c.GY - 1) s_hi = c.GY - 1;
         if (!interior) s_hi = s_lo;
-        for (long long jb = j_begin; jb < j_end; jb += 6) {
+        for (long long jb = j_begin; jb < j_end; jb += 3) {
             of_step_any<0, L2>(s, c, jb, s_lo, s_hi);
             if (jb + 1 < j_end) of_step_any<1, L2>(s, c, jb + 1, s_lo, s_hi);
             if (jb + 2 < j_end) of_step_any<2, L2>(s, c, jb + 2, s_lo, s_hi);
-            if (jb + 3 < j_end) of_step_any<3, L2>(s, c, jb + 3, s_lo, s_hi);
-            if (jb + 4 < j_end) of_step_any<4, L2>(s, c, jb + 4, s_lo, s_hi);
-            if (jb + 5 < j_end) of_step_any<5, L2>(s, c, jb + 5, s_lo, s_hi);
         }
         if (!c.own_lane) {           // halo lanes accumulated garbage in the unmasked steps
 #pragma unroll
             for (int k = 0; k < OF_NSUM; ++k) c.a[k] = 0.0;
             c.m1 = 0.0; c.m2 = 0.0;
-            c.nan1 = false; c.nan2 = false;
+            c.nan1 = 0.0; c.nan2 = 0.0;
         }
     }
     double a[OF_NSUM];
 #pragma unroll
     for (int k = 0; k < OF_NSUM; ++k) a[k] = c.a[k];
-    const double m1 = c.nan1 ? NANQ : c.m1, m2 = c.nan2 ? NANQ : c.m2;
+    const double m1 = (c.nan1 != c.nan1) ? NANQ : c.m1, m2 = (c.nan2 != c.nan2) ? NANQ : c.m2;
     const double gamma = c.gamma;
 
     // ---- per-CTA partials (fixed order), then the last CTA sums them and runs the scalar logic

@@ -436,6 +436,51 @@ class Problem:
             pass
 
 
+class SharedMatrixBatch:
+    """Batched shared-A mode (csrc/bz_bdense.cu): up to 8 dense-affine instances c_k(x) = A x - b_k that share A
+    (demo/basispursuit.jl:38-49 over a batch).  ``gradient`` evaluates gradient!(dlx_k, alFun_k, x_k) (auglagfun.jl:73-86,
+    f = Zero) for the whole batch with A read once per pass, on the fp64 tensor cores."""
+
+    def __init__(self, A=None, *, shape=None, gen_seed=None, ctx: Context | None = None):
+        self.ctx = ctx or default_context()
+        self.lib = self.ctx.lib
+        self.handle = C.c_void_p()
+        if A is not None:
+            A = _f64(A)
+            self.m, self.n = A.shape
+            K.check(self.lib.bz_bdense_create(self.ctx.handle, self.m, self.n, _ptr(A), K.ROW_MAJOR, 0, 0, C.byref(self.handle)),
+                    self.ctx.handle)
+        else:
+            self.m, self.n = shape
+            K.check(self.lib.bz_bdense_create(self.ctx.handle, self.m, self.n, None, K.ROW_MAJOR, 1, int(gen_seed), C.byref(self.handle)),
+                    self.ctx.handle)
+
+    def gradient(self, X, b, mu, y, D=None, reps=1):
+        """X: batch x n; b, mu, y: batch x m.  Returns dict(dlx, lx, cx, yupd, us) with the instance-major layouts of the inputs."""
+        X, b, mu, y = _f64(X), _f64(b), _f64(mu), _f64(y)
+        B = X.shape[0]
+        if X.shape != (B, self.n) or b.shape != (B, self.m) or mu.shape != (B, self.m) or y.shape != (B, self.m):
+            raise ValueError("SharedMatrixBatch.gradient: shapes must be (batch, n) and (batch, m)")
+        D = D or O.ZeroSet()
+        dlx, cx, yupd, lx = np.empty((B, self.n)), np.empty((B, self.m)), np.empty((B, self.m)), np.empty(B)
+        us = C.c_double()
+        K.check(self.lib.bz_bdense_auglag_grad(self.handle, B, _ptr(X), _ptr(b), _ptr(mu), _ptr(y), D.d_kind,
+                                               getattr(D, "lo", 0.0), getattr(D, "hi", 0.0), _ptr(dlx), _ptr(lx), _ptr(cx),
+                                               _ptr(yupd), int(reps), C.byref(us)), self.ctx.handle)
+        return dict(dlx=dlx, lx=lx, cx=cx, yupd=yupd, us=us.value)
+
+    def close(self):
+        if self.handle:
+            self.lib.bz_bdense_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def alps(f, g, c, D, x0, y0, *, tol=1e-6, tol_prim=None, tol_dual=None, inner_tol=None, maxit=100,
          theta_penalty=0.8, kappa_penalty=0.5, kappa_tol=0.1, verbose=False, dual_safeguard=None,
          subsolver=default_subsolver, subsolver_maxit=1_000_000_000, ctx=None, problem=None,

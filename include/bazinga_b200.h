@@ -27,6 +27,7 @@ extern "C" {
 typedef struct bz_ctx bz_ctx;
 typedef struct bz_problem bz_problem;
 typedef struct bz_batch bz_batch;
+typedef struct bz_bdense bz_bdense;
 
 typedef enum {
     BZ_OK = 0,
@@ -280,6 +281,19 @@ int bz_batch_solve(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const
 int bz_batch_solve_als(bz_ctx* ctx, int kind, int64_t batch, const double* x0, const double* y0,
                    const bz_options* opt, double* x, double* y, int32_t* tot_it,
                    int64_t* tot_inner_it, int32_t* status, double* norm_res_prim, double* kernel_ms);
+
+/* ---- batched shared-A mode of the dense AL-gradient (csrc/bz_bdense.cu) ---------------------------------
+ * Up to 8 instances of the dense-affine problem that share the matrix A (demo/basispursuit.jl:38-49 over a batch of
+ * x, b, mu, y): R = A X and G = A' W become skinny GEMMs on the fp64 tensor cores (DMMA m8n8k4), A is read once per
+ * pass for the whole batch.  bz_bdense_auglag_grad replaces `batch` calls of gradient!(dlx_k, alFun_k, x_k)
+ * (auglagfun.jl:73-86, f = Zero): X is batch x n, b / mu / y / cx / yupd are batch x m, dlx is batch x n, all
+ * instance-major; lx has batch entries.  reps > 1 repeats the two kernels and returns their average device time. */
+int bz_bdense_create(bz_ctx* ctx, int64_t m, int64_t n, const double* A, int32_t layout, int32_t gen, uint64_t gen_seed,
+                     bz_bdense** out);
+int bz_bdense_destroy(bz_bdense* h);
+int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* X, const double* b, const double* mu, const double* y,
+                          int32_t d_kind, double d_lo, double d_hi, double* dlx, double* lx, double* cx, double* yupd,
+                          int32_t reps, double* us_per_call);
 
 /* Measurement aid for the batched path (not HBM-bound): the device's fp64 FMA issue peak in TFLOP/s, from a
  * microbenchmark of independent dependent-FMA chains. */
