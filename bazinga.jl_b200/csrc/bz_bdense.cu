@@ -32,12 +32,12 @@
 #define BD_CP 128         // pass 2: columns per CTA
 #define BD_RC 32          // pass 2: rows per chunk
 #define BD_PAD 4
-#define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + 2 * BD_RP * BD_B * 8)
+#define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + 2 * BD_RP * BD_B * 8)   /* ring, 8 barriers, reduction scratch */
 #define BD_SMEM2 (BD_STAGES * (BD_RC * (BD_CP + BD_PAD) + BD_B * (BD_RC + BD_PAD)) * 8 + 64)
 
 struct bz_bdense {
     bz_ctx* ctx;
-    long long m, n;
+    long long m, n, ldm;      // ldm = m rounded up to even: leading dimension of the batch x m device arrays
     double* A;                 // row-major m x n
     double *X, *G;             // [8][n]
     double *bv, *mu, *y, *cx, *yupd, *W;   // [8][m]
@@ -51,9 +51,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void bd_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Both passes: 8 consumer warps + 1 producer warp.  The producer's 32 lanes each issue one row segment of the next A
+// tile (and lanes 0..7 one row of the X / W chunk) as soon as the stage's `empty` barrier says all consumers are done
+// with it; consumers wait on `full`, multiply, and arrive on `empty`.  No block-wide barrier inside the loop (a version
+// with one __syncthreads per chunk and a single issuing thread spent two thirds of its cycles at that barrier: ncu r2d).
+
 // ---- pass 1: R = A X for the CTA's 32 rows, then the elementwise AL stage ------------------------------------------------
-__global__ void __launch_bounds__(BD_THREADS, 1)
-    k_bd_ax(const double* __restrict__ A, long long m, long long n, const double* __restrict__ X,
+// ldm = m rounded up to even: leading dimension of the batch x m arrays (16-byte aligned rows for the bulk copies)
+__global__ void __launch_bounds__(BD_THREADS + 32, 1)
+    k_bd_ax(const double* __restrict__ A, long long m, long long n, long long ldm, const double* __restrict__ X,
             const double* __restrict__ bv, const double* __restrict__ mu, const double* __restrict__ yv, int dkind, double dlo,
             double dhi, double* __restrict__ cx, double* __restrict__ yupd, double* __restrict__ W, double* __restrict__ lxpart) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -61,73 +71,69 @@ __global__ void __launch_bounds__(BD_THREADS, 1)
     constexpr int STAGE = (BD_RP + BD_B) * LD;               // A tile (32 rows) then X chunk (8 rows)
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
-    double* red = reinterpret_cast<double*>(full + 8);       // [2][32][8]: k-half partial tiles, lx partials
+    uint64_t* empty = full + BD_STAGES;
+    double* red = reinterpret_cast<double*>(full + 8);       // [32][8] k-half partial tile, then [4][8] lx partials
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long r0 = (long long)blockIdx.x * BD_RP;
     const int nchunks = (int)((n + BD_KC - 1) / BD_KC);
 
-    for (int i = tid; i < BD_STAGES * STAGE; i += BD_THREADS) ring[i] = 0.0;   // tails must hold finite values
+    for (int i = tid; i < BD_STAGES * STAGE; i += blockDim.x) ring[i] = 0.0;   // tails must hold finite values
     if (tid == 0) {
-        for (int s = 0; s < BD_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < BD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BD_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint64_t pol = l2_evict_first_policy();
-    auto issue = [&](int c) {                                 // one thread: 32 row segments of A + 8 of X into stage c % S
-        const int s = c % BD_STAGES;
-        const long long c0 = (long long)c * BD_KC;
-        const int valid = (int)((n - c0) < BD_KC ? (n - c0) : BD_KC);
-        double* dst = ring + (size_t)s * STAGE;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full[s], (uint32_t)((BD_RP + BD_B) * valid * 8));
-        for (int r = 0; r < BD_RP; ++r) {
-            long long row = r0 + r;
-            if (row >= m) row = m - 1;                        // rows past the end: a valid row again, its results are dropped
-            bulk_g2s_hint(dst + (size_t)r * LD, A + row * n + c0, (uint32_t)valid * 8u, &full[s], pol);
-        }
-        for (int k = 0; k < BD_B; ++k)
-            bulk_g2s(dst + (size_t)(BD_RP + k) * LD, X + (size_t)k * n + c0, (uint32_t)valid * 8u, &full[s]);
-    };
-    if (tid == 0)
-        for (int c = 0; c < BD_STAGES - 1 && c < nchunks; ++c) issue(c);
 
-    const int mt = warp & 3, kh = warp >> 2;
     double c0 = 0.0, c1 = 0.0;
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % BD_STAGES;
-        const int nxt = c + BD_STAGES - 1;
-        if (nxt < nchunks) {
-            // the stage of chunk nxt was consumed in iteration c - 1 (barrier below).  A partial last chunk leaves the
-            // tail of the X rows stale: zero it (stale A x 0 = 0; A is finite)
-            const long long cn0 = (long long)nxt * BD_KC;
-            const int valid = (int)((n - cn0) < BD_KC ? (n - cn0) : BD_KC);
-            if (valid < BD_KC) {
-                double* xs = ring + (size_t)(nxt % BD_STAGES) * STAGE + (size_t)BD_RP * LD;
-                for (int i = tid; i < BD_B * (BD_KC - valid); i += BD_THREADS)
-                    xs[(size_t)(i / (BD_KC - valid)) * LD + valid + i % (BD_KC - valid)] = 0.0;
-                __syncthreads();
+    const int mt = warp & 3, kh = (warp >> 2) & 1;
+    if (warp == BD_THREADS / 32) {
+        // ------------------------------------------------------------------ producer warp
+        const uint64_t pol = l2_evict_first_policy();
+        long long row = r0 + lane;
+        if (row >= m) row = m - 1;                            // rows past the end: a valid row again, its results are dropped
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % BD_STAGES;
+            if (c >= BD_STAGES) mbar_wait(&empty[s], (uint32_t)(((c / BD_STAGES) - 1) & 1));
+            const long long cc0 = (long long)c * BD_KC;
+            const int valid = (int)((n - cc0) < BD_KC ? (n - cc0) : BD_KC);
+            double* dst = ring + (size_t)s * STAGE;
+            if (valid < BD_KC) {     // a partial last chunk: stale X beyond `valid` must read as zero (stale A x 0 = 0; A is finite)
+                for (int i = lane; i < BD_B * (BD_KC - valid); i += 32)
+                    dst[(size_t)(BD_RP + i / (BD_KC - valid)) * LD + valid + i % (BD_KC - valid)] = 0.0;
             }
-            if (tid == 0) issue(nxt);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((BD_RP + BD_B) * valid * 8));
+            __syncwarp();
+            bulk_g2s_hint(dst + (size_t)lane * LD, A + row * n + cc0, (uint32_t)valid * 8u, &full[s], pol);
+            if (lane < BD_B) bulk_g2s(dst + (size_t)(BD_RP + lane) * LD, X + (size_t)lane * n + cc0, (uint32_t)valid * 8u, &full[s]);
         }
-        mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
-        const double* at = ring + (size_t)s * STAGE + (size_t)(8 * mt + (lane >> 2)) * LD + kh * 64 + (lane & 3);
-        const double* xt = ring + (size_t)s * STAGE + (size_t)(BD_RP + (lane >> 2)) * LD + kh * 64 + (lane & 3);
+    } else {
+        // ------------------------------------------------------------------ consumer warps: tile (mt) x k-half (kh)
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % BD_STAGES;
+            mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
+            const double* at = ring + (size_t)s * STAGE + (size_t)(8 * mt + (lane >> 2)) * LD + kh * 64 + (lane & 3);
+            const double* xt = ring + (size_t)s * STAGE + (size_t)(BD_RP + (lane >> 2)) * LD + kh * 64 + (lane & 3);
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) dmma_m8n8k4(c0, c1, at[4 * kk], xt[4 * kk]);
-        __syncthreads();
+            for (int kk = 0; kk < 16; ++kk) dmma_m8n8k4(c0, c1, at[4 * kk], xt[4 * kk]);
+            __syncwarp();
+            if (lane == 0) bd_arrive(&empty[s]);
+        }
     }
     // ---- k-halves: warps 4..7 hand their tiles to warps 0..3 (fixed order: half 0 + half 1)
     const int row_l = 8 * mt + (lane >> 2), bcol = 2 * (lane & 3);
-    if (kh == 1) { red[row_l * BD_B + bcol] = c0; red[row_l * BD_B + bcol + 1] = c1; }
+    const bool consumer = warp < BD_THREADS / 32;
+    if (consumer && kh == 1) { red[row_l * BD_B + bcol] = c0; red[row_l * BD_B + bcol + 1] = c1; }
     __syncthreads();
     double lx0 = 0.0, lx1 = 0.0;
-    if (kh == 0) {
+    if (consumer && kh == 0) {
         const double rr[2] = {c0 + red[row_l * BD_B + bcol], c1 + red[row_l * BD_B + bcol + 1]};
         const long long row = r0 + row_l;
         if (row < m) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {                     // auglagfun.jl:74-79 for instance k = bcol + e, uncontracted
-                const size_t idx = (size_t)(bcol + e) * m + row;
+                const size_t idx = (size_t)(bcol + e) * ldm + row;
                 const double mu_j = mu[idx];
                 const double cxv = __dsub_rn(rr[e], bv[idx]);                    // cx = A*x - b
                 const double t = __dadd_rn(cxv, __dmul_rn(mu_j, yv[idx]));       // yupd = cx + mu.*y
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1)
         }
     }
     __syncthreads();
-    if (kh == 0 && lane < 4) { red[BD_RP * BD_B + mt * BD_B + 2 * lane] = lx0; red[BD_RP * BD_B + mt * BD_B + 2 * lane + 1] = lx1; }
+    if (consumer && kh == 0 && lane < 4) { red[BD_RP * BD_B + mt * BD_B + 2 * lane] = lx0; red[BD_RP * BD_B + mt * BD_B + 2 * lane + 1] = lx1; }
     __syncthreads();
     if (tid < BD_B) {
         const double* q = red + BD_RP * BD_B;
@@ -155,76 +161,74 @@ __global__ void __launch_bounds__(BD_THREADS, 1)
 }
 
 // ---- pass 2: G = A' W for the CTA's 128 columns ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(BD_THREADS, 1)
-    k_bd_atw(const double* __restrict__ A, long long m, long long n, const double* __restrict__ W, double* __restrict__ G) {
+__global__ void __launch_bounds__(BD_THREADS + 32, 1)
+    k_bd_atw(const double* __restrict__ A, long long m, long long n, long long ldm, const double* __restrict__ W,
+             double* __restrict__ G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int LDA = BD_CP + BD_PAD;                      // 132
     constexpr int LDW = BD_RC + BD_PAD;                      // 36 = 4 (mod 16)
     constexpr int STAGE = BD_RC * LDA + BD_B * LDW;
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
+    uint64_t* empty = full + BD_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c0 = (long long)blockIdx.x * BD_CP;
     const int cvalid = (int)((n - c0) < BD_CP ? (n - c0) : BD_CP);
     const int nchunks = (int)((m + BD_RC - 1) / BD_RC);
 
-    for (int i = tid; i < BD_STAGES * STAGE; i += BD_THREADS) ring[i] = 0.0;
+    for (int i = tid; i < BD_STAGES * STAGE; i += blockDim.x) ring[i] = 0.0;
     if (tid == 0) {
-        for (int s = 0; s < BD_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < BD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BD_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint64_t pol = l2_evict_first_policy();
-    auto issue = [&](int c) {
-        const int s = c % BD_STAGES;
-        const long long rr0 = (long long)c * BD_RC;
-        const int rvalid = (int)((m - rr0) < BD_RC ? (m - rr0) : BD_RC);
-        double* dst = ring + (size_t)s * STAGE;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&full[s], (uint32_t)(BD_RC * cvalid * 8 + BD_B * rvalid * 8));
-        for (int r = 0; r < BD_RC; ++r) {
-            long long row = rr0 + r;
-            if (row >= m) row = m - 1;                        // finite filler; its W entries are zero
-            bulk_g2s_hint(dst + (size_t)r * LDA, A + row * n + c0, (uint32_t)cvalid * 8u, &full[s], pol);
-        }
-        for (int k = 0; k < BD_B; ++k)
-            bulk_g2s(dst + (size_t)BD_RC * LDA + (size_t)k * LDW, W + (size_t)k * m + rr0, (uint32_t)rvalid * 8u, &full[s]);
-    };
-    if (tid == 0)
-        for (int c = 0; c < BD_STAGES - 1 && c < nchunks; ++c) issue(c);
 
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    for (int c = 0; c < nchunks; ++c) {
-        const int s = c % BD_STAGES;
-        const int nxt = c + BD_STAGES - 1;
-        if (nxt < nchunks) {
-            const long long rn0 = (long long)nxt * BD_RC;
-            const int rvalid = (int)((m - rn0) < BD_RC ? (m - rn0) : BD_RC);
-            if (rvalid < BD_RC) {                             // rows past the end contribute A(m-1, :) * 0
-                double* ws = ring + (size_t)(nxt % BD_STAGES) * STAGE + (size_t)BD_RC * LDA;
-                for (int i = tid; i < BD_B * (BD_RC - rvalid); i += BD_THREADS)
-                    ws[(size_t)(i / (BD_RC - rvalid)) * LDW + rvalid + i % (BD_RC - rvalid)] = 0.0;
-                __syncthreads();
+    if (warp == BD_THREADS / 32) {
+        const uint64_t pol = l2_evict_first_policy();
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % BD_STAGES;
+            if (c >= BD_STAGES) mbar_wait(&empty[s], (uint32_t)(((c / BD_STAGES) - 1) & 1));
+            const long long rr0 = (long long)c * BD_RC;
+            const int rvalid = (int)((m - rr0) < BD_RC ? (m - rr0) : BD_RC);
+            const int rcopy = (rvalid + 1) & ~1;              // whole 16-byte units: W rows are padded to ldm (the pad entry is zero)
+            double* dst = ring + (size_t)s * STAGE;
+            if (rcopy < BD_RC) {                              // rows past the end contribute A(m-1, :) * 0
+                for (int i = lane; i < BD_B * (BD_RC - rcopy); i += 32)
+                    dst[(size_t)BD_RC * LDA + (size_t)(i / (BD_RC - rcopy)) * LDW + rcopy + i % (BD_RC - rcopy)] = 0.0;
             }
-            if (tid == 0) issue(nxt);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(BD_RC * cvalid * 8 + BD_B * rcopy * 8));
+            __syncwarp();
+            long long row = rr0 + lane;
+            if (row >= m) row = m - 1;                        // finite filler; its W entries are zero
+            bulk_g2s_hint(dst + (size_t)lane * LDA, A + row * n + c0, (uint32_t)cvalid * 8u, &full[s], pol);
+            if (lane < BD_B)
+                bulk_g2s(dst + (size_t)BD_RC * LDA + (size_t)lane * LDW, W + (size_t)lane * ldm + rr0, (uint32_t)rcopy * 8u, &full[s]);
         }
-        mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
-        const double* tile = ring + (size_t)s * STAGE;
-        const double* wt = tile + (size_t)BD_RC * LDA + (size_t)(lane >> 2) * LDW + (lane & 3);
+    } else {
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % BD_STAGES;
+            mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
+            const double* tile = ring + (size_t)s * STAGE;
+            const double* wt = tile + (size_t)BD_RC * LDA + (size_t)(lane >> 2) * LDW + (lane & 3);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const double* at = tile + (size_t)(lane & 3) * LDA + 16 * warp + 8 * g + (lane >> 2);
+#pragma unroll
+                for (int kk = 0; kk < BD_RC / 4; ++kk) dmma_m8n8k4(acc[g][0], acc[g][1], at[(size_t)4 * kk * LDA], wt[4 * kk]);
+            }
+            __syncwarp();
+            if (lane == 0) bd_arrive(&empty[s]);
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-            const double* at = tile + (size_t)(lane & 3) * LDA + 16 * warp + 8 * g + (lane >> 2);
-#pragma unroll
-            for (int kk = 0; kk < BD_RC / 4; ++kk) dmma_m8n8k4(acc[g][0], acc[g][1], at[(size_t)4 * kk * LDA], wt[4 * kk]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const long long col = c0 + 16 * warp + 8 * g + (lane >> 2);
-        if (col < n) {
-            G[(size_t)(2 * (lane & 3)) * n + col] = acc[g][0];
-            G[(size_t)(2 * (lane & 3) + 1) * n + col] = acc[g][1];
+            const long long col = c0 + 16 * warp + 8 * g + (lane >> 2);
+            if (col < n) {
+                G[(size_t)(2 * (lane & 3)) * n + col] = acc[g][0];
+                G[(size_t)(2 * (lane & 3) + 1) * n + col] = acc[g][1];
+            }
         }
     }
 }
@@ -238,14 +242,17 @@ extern "C" int bz_bdense_create(bz_ctx* ctx, int64_t m, int64_t n, const double*
     *out = nullptr;
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
     bz_bdense* h = new bz_bdense();
-    h->ctx = ctx; h->m = m; h->n = n;
+    h->ctx = ctx; h->m = m; h->n = n; h->ldm = (m + 1) & ~1LL;
     h->ctas1 = (int)((m + BD_RP - 1) / BD_RP);
     h->ctas2 = (int)((n + BD_CP - 1) / BD_CP);
     auto fail = [&](cudaError_t e) { bz_bdense_destroy(h); return bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e)); };
     cudaError_t e;
     if ((e = cudaMalloc((void**)&h->A, (size_t)m * n * 8)) != cudaSuccess) return fail(e);
     double** mv[] = {&h->bv, &h->mu, &h->y, &h->cx, &h->yupd, &h->W};
-    for (double** q : mv) if ((e = cudaMalloc((void**)q, (size_t)BD_B * m * 8)) != cudaSuccess) return fail(e);
+    for (double** q : mv) {
+        if ((e = cudaMalloc((void**)q, (size_t)BD_B * h->ldm * 8)) != cudaSuccess) return fail(e);
+        cudaMemsetAsync(*q, 0, (size_t)BD_B * h->ldm * 8, ctx->stream);
+    }
     double** nv[] = {&h->X, &h->G};
     for (double** q : nv) if ((e = cudaMalloc((void**)q, (size_t)BD_B * n * 8)) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc((void**)&h->lxpart, (size_t)h->ctas1 * BD_B * 8)) != cudaSuccess) return fail(e);
@@ -278,24 +285,25 @@ extern "C" int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* 
     BZ_CUDA(ctx, cudaSetDevice(ctx->device));
     if (d_kind != BZ_D_ZERO && d_kind != BZ_D_FREE && d_kind != BZ_D_BOX)
         return bz_fail(ctx, BZ_ERR_UNSUPPORTED, "bz_bdense_auglag_grad: elementwise sets only (ZeroSet, FreeSet, box)");
-    const long long m = h->m, n = h->n;
+    const long long m = h->m, n = h->n, ldm = h->ldm;
     // instances beyond `batch` are padded: x = 0, b = 0, mu = 1, y = 0
     BZ_CUDA(ctx, cudaMemsetAsync(h->X, 0, (size_t)BD_B * n * 8, ctx->stream));
-    BZ_CUDA(ctx, cudaMemsetAsync(h->bv, 0, (size_t)BD_B * m * 8, ctx->stream));
-    BZ_CUDA(ctx, cudaMemsetAsync(h->y, 0, (size_t)BD_B * m * 8, ctx->stream));
-    BZ_TRY_RC(bz_launch_fill(ctx, h->mu, BD_B * m, 1.0));
+    BZ_CUDA(ctx, cudaMemsetAsync(h->bv, 0, (size_t)BD_B * ldm * 8, ctx->stream));
+    BZ_CUDA(ctx, cudaMemsetAsync(h->y, 0, (size_t)BD_B * ldm * 8, ctx->stream));
+    BZ_CUDA(ctx, cudaMemsetAsync(h->W, 0, (size_t)BD_B * ldm * 8, ctx->stream));
+    BZ_TRY_RC(bz_launch_fill(ctx, h->mu, BD_B * ldm, 1.0));
     BZ_CUDA(ctx, cudaMemcpyAsync(h->X, X, (size_t)batch * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    BZ_CUDA(ctx, cudaMemcpyAsync(h->bv, b, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    BZ_CUDA(ctx, cudaMemcpyAsync(h->mu, mu, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    BZ_CUDA(ctx, cudaMemcpyAsync(h->y, y, (size_t)batch * m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpy2DAsync(h->bv, ldm * 8, b, m * 8, m * 8, batch, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpy2DAsync(h->mu, ldm * 8, mu, m * 8, m * 8, batch, cudaMemcpyHostToDevice, ctx->stream));
+    BZ_CUDA(ctx, cudaMemcpy2DAsync(h->y, ldm * 8, y, m * 8, m * 8, batch, cudaMemcpyHostToDevice, ctx->stream));
     if (reps < 1) reps = 1;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int r = 0; r < reps + 1; ++r) {            // the first launch is a warm-up when reps > 1
         if (r == 1 || reps == 1) cudaEventRecord(e0, ctx->stream);
-        k_bd_ax<<<h->ctas1, BD_THREADS, BD_SMEM1, ctx->stream>>>(h->A, m, n, h->X, h->bv, h->mu, h->y, d_kind, d_lo, d_hi, h->cx,
-                                                                 h->yupd, h->W, h->lxpart);
-        k_bd_atw<<<h->ctas2, BD_THREADS, BD_SMEM2, ctx->stream>>>(h->A, m, n, h->W, h->G);
+        k_bd_ax<<<h->ctas1, BD_THREADS + 32, BD_SMEM1, ctx->stream>>>(h->A, m, n, ldm, h->X, h->bv, h->mu, h->y, d_kind, d_lo, d_hi,
+                                                                      h->cx, h->yupd, h->W, h->lxpart);
+        k_bd_atw<<<h->ctas2, BD_THREADS + 32, BD_SMEM2, ctx->stream>>>(h->A, m, n, ldm, h->W, h->G);
         ctx->n_launches += 2;
         if (reps == 1) break;
     }
@@ -308,8 +316,8 @@ extern "C" int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* 
     if (e != cudaSuccess) return bz_fail(ctx, BZ_ERR_CUDA, cudaGetErrorString(e));
     if (us_per_call) *us_per_call = 1e3 * (double)ms / reps;
     if (dlx) BZ_CUDA(ctx, cudaMemcpyAsync(dlx, h->G, (size_t)batch * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cx) BZ_CUDA(ctx, cudaMemcpyAsync(cx, h->cx, (size_t)batch * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (yupd) BZ_CUDA(ctx, cudaMemcpyAsync(yupd, h->yupd, (size_t)batch * m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cx) BZ_CUDA(ctx, cudaMemcpy2DAsync(cx, m * 8, h->cx, ldm * 8, m * 8, batch, cudaMemcpyDeviceToHost, ctx->stream));
+    if (yupd) BZ_CUDA(ctx, cudaMemcpy2DAsync(yupd, m * 8, h->yupd, ldm * 8, m * 8, batch, cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<double> part((size_t)h->ctas1 * BD_B);
     BZ_CUDA(ctx, cudaMemcpyAsync(part.data(), h->lxpart, part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     BZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

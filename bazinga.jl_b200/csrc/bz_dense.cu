@@ -53,7 +53,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     const long long r0 = (long long)q * a.rows_per_cluster;
     long long r1 = r0 + a.rows_per_cluster;
     if (r1 > a.m) r1 = a.m;
-    const int nrows = (int)(r1 - r0);
+    const int nrows = r1 > r0 ? (int)(r1 - r0) : 0;
+    const bool is_spec = a.ls.enabled && q >= a.ls.dense_clusters;   // a cluster of the speculative L step: owns no rows
 
     // ring of whole row slices: slot stride rounded to an even number of doubles (16 B)
     const int stride = ((W + 1) & ~1) > 0 ? ((W + 1) & ~1) : 2;
@@ -112,6 +113,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         target = __ldcg(&a.st->grad_target);
         if (blockIdx.x == 0 && tid == 0 && a.set_after) bz_tic(a.st, 0);
     }
+    if (is_spec) {
+        // ---- speculative L step of the NEXT iteration beside G(z) (bz_lspec.cuh); nothing here touches the dense pass
+        if (a.force_target < 0 && target == TGT_Z) {
+            const int mode = __ldcg(&a.st->mode);
+            const int rank_ls = (int)blockIdx.x - 2 * a.ls.dense_clusters;
+            int cs = 1;
+            while (cs < LS_MAXCS && (long long)cs * LS_THREADS * 8 < a.ls.v.n) cs *= 2;
+            if ((mode == MODE_INITFB || mode == MODE_ITER) && rank_ls < cs) {
+                if ((long long)cs * LS_THREADS * 8 >= a.ls.v.n) ls_body<8>(a.st, a.ls, rank_ls, cs, wsum);
+                else ls_body<16>(a.st, a.ls, rank_ls, cs, wsum);
+            }
+        }
+    } else {
     const double* __restrict__ xsrc = a.src[target];
     const double* __restrict__ sslack = xsrc + a.n;   // als: the slack part of the stacked input
     if (!BULK)
@@ -227,11 +241,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
     if (rank == 0 && tid == 0) a.lxpart[q] = lx;
     // (no closing cluster barrier: every store into this CTA's shared memory has been waited for
     // above, and the last store this CTA issued targets a peer that is still waiting for it)
+    }   // !is_spec
 
     if (bz_last_cta(a.counter, gridDim.x)) {
-        if (tid == 0 && a.set_after) {
-            a.st->next_op = a.st->after_g;
-            if (a.force_target < 0) bz_toc(a.st, 0);
+        if (tid == 0) {
+            if (a.is_cpass) a.st->npc_c = a.ls.enabled ? a.ls.dense_clusters : (int)(gridDim.x >> 1);
+            if (a.ls.enabled) a.st->lspec_seq += 32ULL;
+            if (a.set_after) {
+                a.st->next_op = a.st->after_g;
+                if (a.force_target < 0) bz_toc(a.st, 0);
+            }
             __threadfence();
         }
     }
@@ -248,7 +267,8 @@ int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) 
     }
     const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
-    const dim3 grid(2 * nclusters), block(DA_THREADS);
+    // with a speculative L step on board: `nclusters` row clusters + ceil(LS_MAXCS / 2) clusters for the L step
+    const dim3 grid(2 * (nclusters + (args.ls.enabled ? LS_MAXCS / 2 : 0))), block(DA_THREADS);
     if (args.slack)
         return bulk ? bz_launch_pdl(ctx, k_dense_algrad<true, true>, grid, block, smem, 0, args)
                     : bz_launch_pdl(ctx, k_dense_algrad<false, true>, grid, block, smem, 0, args);

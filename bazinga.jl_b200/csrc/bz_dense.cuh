@@ -1,6 +1,7 @@
 // Launch interfaces of bz_dense.cu
 #pragma once
 #include "bz_internal.cuh"
+#include "bz_lspec.cuh"
 
 #define DA_THREADS 512
 #define DA_CHUNK 1024   // doubles per ring slot (8 KB)
@@ -35,6 +36,8 @@ struct BzDenseArgs {
     // proj_D:  lx += (cx + mu*y - s)^2/mu,  yupd = y + (cx - s)/mu
     int slack;
     const double* y;       // m multipliers (slack mode only)
+    int is_cpass;          // the constraint pass (not the LeastSquares pass): records its partial-row count in BzState::npc_c
+    BzLSpec ls;            // speculative L step riding on this launch (k_dense_algrad only; ls.enabled = 0: none)
     // grid-wide single-pass kernel (bz_grid.cu) only
     unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters
     unsigned long long* gseq;  // [teams] sequence base of the exchange tags, advanced by the team's row count per launch

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
         if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 2);
     }
     const long long n = v.n;
+    bz_gs_sync_counts(gs, st);
     const bool blocked = bz_gs_blocked(gs);
     const double gamma = __ldcg(&st->gamma);
     const int fresh = (mode >= MODE_INITFB) ? __ldcg(&st->grad_x_fresh) : 0;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
     if (__ldcg(&st->next_op) != OP_D) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 3);
     const long long n = v.n;
+    bz_gs_sync_counts(gs, st);
     const double gamma = __ldcg(&st->gamma);
     const double gamma_h = gamma * 0.5;
     double m1 = 0.0, m2 = 0.0;
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS)
                unsigned int* counter) {
     __shared__ double scratch[4 * 32];
     __shared__ double asm_sm[2 * BZ_VEC_THREADS];
+    bz_gs_sync_counts(gs, st);
     if (bz_gs_blocked(gs)) {
         for (long long jb = (long long)blockIdx.x * BZ_ASM_COLS; jb < n; jb += (long long)gridDim.x * BZ_ASM_COLS) {
             const double gr = bz_assemble_blocked(gs, jb, n, asm_sm);

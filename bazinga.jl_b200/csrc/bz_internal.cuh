@@ -63,6 +63,11 @@ struct BzState {
     int slot[BZ_MAXMEM];   // cooperative L kernel: physical history slot of each ring position (a permutation)
     int spare;             // ... and the free physical slot the next candidate pair is written to
     int err_flag;       // nonpositive mu etc.
+    // speculative L step (bz_lspec.cuh): shadow results of the L step that ran beside G(z), and the hand-shake with D / L
+    int spec_ok, spec_commit, sp_currmem, sp_curridx, sp_pair;
+    int npc_c;          // partial rows the last dense constraint pass wrote (0: the host-side count applies)
+    unsigned long long lspec_seq;
+    double sp_H, sp_ys[BZ_MAXMEM], sp_alphas[BZ_MAXMEM];
     int rot;            // fused problems: which physical buffers play x/x_prev (bit 0), res/res_prev (bit 1), z/z_curr (bit 2)
     int fused;          // the problem runs the fused forward-backward kernel X instead of [G, F, G, D] (bz_obfused.cu)
     long long n_global; // slab mode: global nx (0: the local n is the global one)
@@ -455,6 +460,7 @@ struct bz_ctx {
     size_t xpose_bytes = 0;
     int batch_budget = 4096;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
+    int lspec = 1;              // dense problems (n <= 16384, f = Zero): the L step runs speculatively beside G(z) (env BZ_LSPEC=0: off)
     int obstacle_rotate = 1;    // ... with buffer rotation in the cooperative L kernel (env BZ_OBSTACLE_ROTATE=0: copies)
     int obstacle_fused = 1;     // obstacle problems run the fused X kernel (env BZ_OBSTACLE_FUSED=0: the unfused cycle, for A/B runs)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)

@@ -47,10 +47,10 @@ __device__ __forceinline__ double of_shl(double v) { return __shfl_up_sync(0xfff
 __device__ __forceinline__ double of_shr(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }   // value of lane + 1
 
 // diag*v - left - right - up - down, the operation order of bz_stencil_rc (missing neighbours are exact zeros)
-__device__ __forceinline__ double of_stencil(double diag, double c, double up, double dn) {
+__device__ __forceinline__ double of_stencil(double diag, double c, double left, double right, double up, double dn) {
     double out = diag * c;
-    out -= of_shl(c);
-    out -= of_shr(c);
+    out -= left;
+    out -= right;
     out -= up;
     out -= dn;
     return out;
@@ -101,6 +101,12 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     const double ev_mu = s.MU[SL(0)], ev_rm = s.RM[SL(0)], ev_my = s.MY[SL(0)];
     s.X1[SL(0)] = s.S1; s.X2[SL(0)] = s.S2; s.X3[SL(0)] = s.S3;            // row jc arrives from staging
     s.MU[SL(0)] = s.SMU; s.RM[SL(0)] = s.SRM; s.MY[SL(0)] = s.SMY;
+    // ---- all horizontal neighbours of this step at once: the four stencil centres (x2 of row jc-1, w_x of row jc-2, z2 of
+    // row jc-3, w_z of row jc-4) were produced in EARLIER steps, so their eight shuffles are issued back to back here and
+    // their latency is paid once (shuffles issued where they are used cost 63 % of all stall cycles: ncu r2d)
+    const double cx2 = s.X2[SL(1)], cwx = s.WX[SL(1)], cz2 = s.Z2[SL(1)], cwz = s.WZ[SL(1)];
+    const double lx2 = of_shl(cx2), rx2 = of_shr(cx2), lwx = of_shl(cwx), rwx = of_shr(cwx);
+    const double lz2 = of_shl(cz2), rz2 = of_shr(cz2), lwz = of_shl(cwz), rwz = of_shr(cwz);
     {   // ---- raw row jc + 1 into staging (zeros outside the grid)
         const long long j = jc + 1;
         const bool ok = MASKED ? (c.colok && j >= 0 && j < c.GY) : true;
@@ -116,7 +122,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         const long long r1 = jc - 1;
         const double x1 = s.X1[SL(1)], x2 = s.X2[SL(1)], x3 = s.X3[SL(1)];
         const double mua = s.MU[SL(1)], rma = s.RM[SL(1)], muya = s.MY[SL(1)];
-        const double cva = (x1 + of_stencil(c.diag, x2, s.X2[SL(2)], s.X2[SL(0)])) - x3;
+        const double cva = (x1 + of_stencil(c.diag, x2, lx2, rx2, s.X2[SL(2)], s.X2[SL(0)])) - x3;
         const double t = cva + muya;
         const double u = t - 0.0;                      // SetObstacle: proj = 0 (demo/obstacle.jl:116-119)
         if (MASKED) {
@@ -140,7 +146,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         const long long r2 = jc - 2;
         const double x1 = s.X1[SL(2)], x2 = s.X2[SL(2)], x3 = s.X3[SL(2)];
         const double w = s.WX[SL(1)];
-        const double aw = of_stencil(c.diag, w, s.WX[SL(2)], s.WX[SL(0)]);
+        const double aw = of_stencil(c.diag, w, lwx, rwx, s.WX[SL(2)], s.WX[SL(0)]);
         const double g1 = (l2f ? x1 : 0.0) + w;
         const double g2 = (x2 - 1.0) + aw;
         const double g3 = 0.0 + (-w);
@@ -174,7 +180,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     {   // ---- stage 3: w_z on row r3 = jc - 3 (z2 rows jc-4, jc-3, jc-2)
         const long long r3 = jc - 3;
         const double z1 = s.Z1[SL(1)], z2 = s.Z2[SL(1)], z3 = s.Z3[SL(1)];
-        const double cva = (z1 + of_stencil(c.diag, z2, s.Z2[SL(2)], s.Z2[SL(0)])) - z3;
+        const double cva = (z1 + of_stencil(c.diag, z2, lz2, rz2, s.Z2[SL(2)], s.Z2[SL(0)])) - z3;
         const double t = cva + ev_my;
         const double u = t - 0.0;
         if (MASKED) {
@@ -197,7 +203,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
     {   // ---- stage 4: grad_z and the stop norm on row r4 = jc - 4 (w_z rows jc-5, jc-4, jc-3)   k_dstep
         const long long r4 = jc - 4;
         const double w = s.WZ[SL(1)];
-        const double aw = of_stencil(c.diag, w, s.WZ[SL(2)], s.WZ[SL(0)]);
+        const double aw = of_stencil(c.diag, w, lwz, rwz, s.WZ[SL(2)], s.WZ[SL(0)]);
         if (!MASKED || (c.own_lane && r4 >= c.rb && r4 < c.re)) {
             const double h1 = (l2f ? s.Z1[SL(2)] : 0.0) + w;
             const double h2 = (s.Z2[SL(2)] - 1.0) + aw;

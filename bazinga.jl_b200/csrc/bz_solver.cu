@@ -65,6 +65,9 @@ struct bz_problem {
     bool sharded = false;
     BzShard shard{};
     // slab-decomposed obstacle grid (cross-rank exchange over peer memory)
+    bool lspec = false;   // dense problems: the L step of the next iteration runs speculatively beside G(z) (bz_lspec.cuh)
+    int c_clusters_z = 0, c_rpc_z = 0;      // ... on this many row clusters (the rest of the SMs carry the L step)
+    unsigned long long* lspec_buf = nullptr;
     bool rotate = false;  // fused problems large enough for the cooperative L kernel: x/x_prev, res/res_prev, z/z_curr swap roles
     bool fused = false;   // obstacle problems on one GPU: the cycle is [L, X] with the fused kernel of bz_obfused.cu
     bool slab = false;
@@ -129,6 +132,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
     if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
     if (const char* e = getenv("BZ_BATCH_BUDGET")) ctx->batch_budget = atoi(e);
+    if (const char* e = getenv("BZ_LSPEC")) ctx->lspec = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_ROTATE")) ctx->obstacle_rotate = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
@@ -270,6 +274,8 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     if (p->counters) cudaFree(p->counters);
     if (p->gridD) cudaFree(p->gridD);
     if (p->gseq) cudaFree(p->gseq);
+    if (p->lspec_buf) cudaFree(p->lspec_buf);
+    if (p->v.xs) cudaFree(p->v.xs);
     if (p->gridD_f) cudaFree(p->gridD_f);
     if (p->gseq_f) cudaFree(p->gseq_f);
     if (p->team.bars) cudaFree(p->team.bars);
@@ -488,6 +494,23 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         else { dense_partition(ctx, ml, &p->c_clusters, &p->c_rpc); p->c_nlx = p->c_clusters; }
         PTRY(dev_alloc(ctx, &p->Pc, (size_t)p->c_clusters * n));
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
+        // speculative L step beside G(z): plain alps on one GPU with the cluster kernels (n <= 16384) and f = Zero
+        if (ctx->lspec && !p->c_wide && !p->c_grid && !p->sharded && !p->slack && d->f_kind == BZ_F_ZERO &&
+            p->nv <= (long long)LS_MAXCS * LS_THREADS * 16) {
+            const int maxc = ctx->num_sms / 2, extra = LS_MAXCS / 2;
+            if (maxc > extra) {
+                p->lspec = true;
+                p->c_clusters_z = p->c_clusters;
+                p->c_rpc_z = p->c_rpc;
+                if (p->c_clusters + extra > maxc) {          // give up a few row clusters so that the whole grid stays co-resident
+                    const int want = maxc - extra;
+                    p->c_rpc_z = (int)((ml + want - 1) / want);
+                    p->c_clusters_z = (int)((ml + p->c_rpc_z - 1) / p->c_rpc_z);
+                }
+                PTRY(dev_alloc(ctx, &p->v.xs, p->nv));
+                PTRY(dev_alloc(ctx, &p->lspec_buf, (size_t)32 * LS_MAXCS * 2 * 2));
+            }
+        }
     }
     {   // a usable L-BFGS state before the first solve (the parity entry points may be called right away)
         memset(p->st_host, 0, sizeof(BzState));
@@ -607,7 +630,7 @@ static BzGradSrc grad_src(bz_problem* p) {
     return gs;
 }
 
-static int launch_provider(bz_problem* p, int force_target) {
+static int launch_provider(bz_problem* p, int force_target, bool gz_slot = false) {
     bz_ctx* ctx = p->ctx;
     const bz_problem_desc& d = p->desc;
     const double* srcbuf[3];
@@ -649,9 +672,16 @@ static int launch_provider(bz_problem* p, int force_target) {
         if (timed) { e0 = ctx_event(ctx); e1 = ctx_event(ctx); cudaEventRecord(e0, ctx->stream); }
         a.D = p->gridD; a.gseq = p->gseq;
         a.slack = p->slack_active ? 1 : 0; a.y = p->y;
+        a.is_cpass = 1;
+        int nclus = p->c_clusters;
+        if (gz_slot && p->lspec && force_target < 0) {       // the second provider launch of a cycle: G(z) + speculative L
+            a.ls.enabled = 1; a.ls.dense_clusters = p->c_clusters_z; a.ls.v = p->v; a.ls.xs = p->v.xs; a.ls.xbuf = p->lspec_buf;
+            a.rows_per_cluster = p->c_rpc_z;
+            nclus = p->c_clusters_z;
+        }
         if (p->c_grid) BZ_TRY(bz_launch_grid_algrad(ctx, a));
         else if (p->c_wide) BZ_TRY(bz_launch_dense_wide(ctx, a));
-        else BZ_TRY(bz_launch_dense_algrad(ctx, a, p->c_clusters));
+        else BZ_TRY(bz_launch_dense_algrad(ctx, a, nclus));
         if (timed) { cudaEventRecord(e1, ctx->stream); p->dom_events.push_back({e0, e1}); }
         if (p->sharded)
             BZ_TRY(bz_shard_allreduce(ctx, &p->shard, p->Pc, p->c_clusters, p->lxpart, p->c_nlx, p->n));
@@ -698,7 +728,7 @@ static int launch_cycle(bz_problem* p) {
     BZ_TRY(launch_provider(p, -1));
     gs = grad_src(p);
     BZ_TRY(bz_launch_fstep(ctx, p->st, p->v, gs, g_params(p), p->part, p->counters + 3, -1));
-    BZ_TRY(launch_provider(p, -1));
+    BZ_TRY(launch_provider(p, -1, true));
     BZ_TRY(bz_launch_dstep(ctx, p->st, p->v, gs, p->part, p->counters + 4));
     return BZ_OK;
 }

@@ -9,7 +9,8 @@
 
 struct BzVecs {
     double *x, *z, *xeps, *x_prev, *x_d, *z_curr, *res, *res_prev, *grad_x, *grad_z, *d;
-    double *sM, *yM;   // mem x n ring buffers
+    double *sM, *yM;   // mem x n ring buffers (+ one spare slot)
+    double* xs;        // shadow x + d of the speculative L step (bz_lspec.cuh), or nullptr
     long long n;
 };
 

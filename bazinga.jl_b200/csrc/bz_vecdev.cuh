@@ -130,6 +130,12 @@ __device__ __forceinline__ double bz_sum_group(const double* __restrict__ P, int
 }
 
 __device__ __forceinline__ bool bz_gs_blocked(const BzGradSrc& gs) { return gs.Pf || gs.Pc; }
+// the dense constraint pass records how many partial rows it wrote (it runs on fewer row clusters when the speculative
+// L step rides along, bz_lspec.cuh): consumers take the count from the state
+__device__ __forceinline__ void bz_gs_sync_counts(BzGradSrc& gs, const BzState* st) {
+    const int npc = __ldcg(&st->npc_c);
+    if (gs.Pc && npc > 0) { gs.npc = npc; gs.nlx = npc; }
+}
 
 __device__ inline double bz_assemble_blocked(const BzGradSrc& gs, long long jb, long long n, double* sm) {
     const int col = threadIdx.x & (BZ_ASM_COLS - 1), grp = threadIdx.x / BZ_ASM_COLS;
@@ -188,6 +194,8 @@ __device__ __forceinline__ void bz_f_finish(BzState* st, const BzGParams& g, dou
 // gradient at z is in: backtrack_stepsize! (A.4), the loop body of A.5, the stop rule A.3
 __device__ __forceinline__ void bz_d_decide(BzState* st, double gamma, double f_z, double fx, double stop1, double stop2) {
     const int refb = st->fused ? OP_X : OP_F;            // "redo the forward-backward step with the halved gamma"
+    const int spec = st->spec_ok;                        // an L step was speculated beside this G(z) (bz_lspec.cuh)
+    st->spec_ok = 0; st->spec_commit = 0;
     st->f_z = f_z; st->al_fx = fx; st->al_lx = f_z;
     st->n_grad += 1;
     const int mode = st->mode;
@@ -236,6 +244,7 @@ __device__ __forceinline__ void bz_d_decide(BzState* st, double gamma, double f_
         } else {
             st->l_role = LROLE_NEWITER;
             st->next_op = OP_L;
+            st->spec_commit = spec;                      // the speculation assumed exactly this verdict: L only commits it
         }
     }
 }
