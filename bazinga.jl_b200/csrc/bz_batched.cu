@@ -13,6 +13,7 @@
 
 #define TB_MAXMEM 8
 #define TB_THREADS 64
+#define TB_HEAVY 10          // AL-gradients per inner iteration that make an instance a "heavy back-tracker"
 
 namespace {
 
@@ -374,7 +375,7 @@ struct Lbfgs {
 // AL-gradients -- phase 1 of the two-phase batch.
 template <int KIND, int MM, int SLACK, bool WARP>
 __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, SLACK>::NV], const TbOpts& o, double tol,
-                               double (&z)[Al<KIND, SLACK>::NV], int budget) {
+                               double (&z)[Al<KIND, SLACK>::NV], int budget, long long its_before) {
     constexpr int NV = Al<KIND, SLACK>::NV;
     const double a = o.alpha;
     double x[NV], grad_x[NV], grad_z[NV], tmpg[NV], y[NV], res[NV];
@@ -433,7 +434,10 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         }
         if (isnan_) stopnorm = __longlong_as_double(0x7ff8000000000000LL);
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
-        if (budget > 0 && al.ngrad > budget) return -1;      // phase 1: leave this instance to the warp-per-instance pass
+        // phase 1: a heavy back-tracker (more than TB_HEAVY AL-gradients per iteration so far) past its budget is left to
+        // the warp-per-instance kernel, where its line searches run across the lanes.  Instances that merely iterate
+        // long (few back-tracks) stay: one lone lane is the fastest place for them.
+        if (budget > 0 && al.ngrad > budget && (long long)al.ngrad > TB_HEAVY * (its_before + k)) return -1;
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
         const double FBE_x = f_model<NV>(f_x, grad_x, res, aog) + g_z;
@@ -601,7 +605,9 @@ __global__ void __launch_bounds__(TB_THREADS)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
-                 double* __restrict__ nrps, int budget, int* __restrict__ surv, int* __restrict__ nsurv) {
+                 double* __restrict__ nrps, int budget, int* surv, int* queue) {
+    // queue[0]: survivors pushed so far (slots reserved), queue[1]: next slot to pop, queue[2]: phase 1 has finished.
+    // surv[slot] is -1 until the pushing thread has stored the instance index.
     constexpr int NX = Prob<KIND>::NX;
     constexpr int NY = Prob<KIND>::NY;
     constexpr int NV = Al<KIND, SLACK>::NV;
@@ -612,13 +618,33 @@ __global__ void __launch_bounds__(TB_THREADS)
     // of the slowest instance alone; either-or 38.7 -> 36.3 ms).  Results do not depend on the mapping.
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long inst;
-    if constexpr (WARP) {
-        if ((t >> 5) >= (long long)__ldcg(nsurv)) return;        // whole warp
-        inst = surv[t >> 5];
-    } else {
+    if constexpr (!WARP) {
         const long long nwarps = (batch + 31) / 32;
         inst = (t & 31) * nwarps + (t >> 5);
         if ((t >> 5) >= nwarps || inst >= batch) return;
+    }
+    // WARP: a persistent warp of the concurrent phase-2 kernel; it pops survivors until phase 1 is over and the queue is dry
+    for (;;) {
+    if constexpr (WARP) {
+        int idx = 0;
+        if ((threadIdx.x & 31) == 0) {
+            for (;;) {
+                const int tail = *(volatile int*)&queue[0], head = *(volatile int*)&queue[1];
+                if (head < tail) {
+                    if (atomicCAS(&queue[1], head, head + 1) == head) { idx = head; break; }
+                    continue;
+                }
+                if (*(volatile int*)&queue[2]) {
+                    if (*(volatile int*)&queue[1] >= *(volatile int*)&queue[0]) { idx = -1; break; }
+                    continue;
+                }
+                __nanosleep(400);
+            }
+            if (idx >= 0) while ((inst = *(volatile int*)&surv[idx]) < 0) __nanosleep(100);
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx < 0) return;
+        inst = __shfl_sync(0xffffffffu, (int)inst, 0);
     }
     Al<KIND, SLACK> al;
     al.ngrad = 0;
@@ -658,9 +684,11 @@ __global__ void __launch_bounds__(TB_THREADS)
 #pragma unroll
             for (int i = 0; i < NY; ++i) v0[NX + i] = s[i];       // xSlack = [x; s], als.jl:69-70
         }
-        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget);
-        if (sub_it < 0) {                                         // over the budget: phase 2 takes this instance
-            surv[atomicAdd(nsurv, 1)] = (int)inst;
+        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget, tot_inner);
+        if (sub_it < 0) {                                         // a heavy back-tracker over the budget: the warp kernel takes it
+            const int slot = atomicAdd(&queue[0], 1);
+            __threadfence();
+            *(volatile int*)&surv[slot] = (int)inst;
             return;
         }
 #pragma unroll
@@ -700,16 +728,21 @@ __global__ void __launch_bounds__(TB_THREADS)
         }
         have_old = true;
     }
-    if (WARP && (threadIdx.x & 31) != 0) return;                  // every lane holds the same result
+    if (!WARP || (threadIdx.x & 31) == 0) {                       // WARP: every lane holds the same result
 #pragma unroll
-    for (int j = 0; j < NX; ++j) xs[inst * NX + j] = x[j];
+        for (int j = 0; j < NX; ++j) xs[inst * NX + j] = x[j];
 #pragma unroll
-    for (int i = 0; i < NY; ++i) ys[inst * NY + i] = al.y[i];
-    tot_its[inst] = tot_it;
-    tot_inners[inst] = tot_inner;
-    statuses[inst] = solved ? 0 : tired ? 1 : broken ? 2 : 3;
-    nrps[inst] = nrp;
+        for (int i = 0; i < NY; ++i) ys[inst * NY + i] = al.y[i];
+        tot_its[inst] = tot_it;
+        tot_inners[inst] = tot_inner;
+        statuses[inst] = solved ? 0 : tired ? 1 : broken ? 2 : 3;
+        nrps[inst] = nrp;
+    }
+    if constexpr (!WARP) return;
+    }   // for (;;): next survivor
 }
+
+__global__ void k_batch_phase1_done(int* queue) { *(volatile int*)&queue[2] = 1; }
 
 }  // namespace
 
@@ -742,7 +775,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     // one grow-only device arena per context, carved into the eight per-instance arrays: no cudaMalloc / cudaFree (and
     // their implicit synchronisations) on the second and later calls
     const size_t B = (size_t)batch;
-    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 3 * B * sizeof(int) + 64;
+    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 3 * B * sizeof(int) + 128;
     auto cleanup = [&]() {};
 #define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
         return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
@@ -761,7 +794,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     long long* din = reinterpret_cast<long long*>(dnrp + B);
     int* dit = reinterpret_cast<int*>(din + B);
     int* dst = dit + B;
-    int* dsurv = dst + B;          // survivors of phase 1 (instance indices), then their count
+    int* dsurv = dst + B;          // survivors of phase 1 (instance indices, -1 = not stored yet), then the queue words
     int* dnsurv = dsurv + B;
     // phase-1 budget of AL-gradients per instance (0: single phase).  The speculative line search covers the whole loop
     // with one warp when max_backtracks <= 32.
@@ -773,13 +806,23 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     BTRY(cudaEventCreate(&e1));
     const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
     cudaEventRecord(e0, ctx->stream);
-    if (budget > 0) BTRY(cudaMemsetAsync(dnsurv, 0, sizeof(int), ctx->stream));
-    // phase 2: one warp per survivor; the grid covers the worst case (every instance survives), warps beyond the count exit
-    const unsigned grid2 = (unsigned)((batch * 32 + TB_THREADS - 1) / TB_THREADS);
+    // Two kernels run side by side.  The warp-per-instance kernel goes first, on a second stream: two CTAs per SM of
+    // persistent warps that pop survivors from the queue as phase 1 produces them (and leave half of every SM to phase 1).
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (budget > 0) {
+        if (!ctx->stream2) BTRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        BTRY(cudaMemsetAsync(dsurv, 0xff, B * sizeof(int), ctx->stream));
+        BTRY(cudaMemsetAsync(dnsurv, 0, 4 * sizeof(int), ctx->stream));
+        BTRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        BTRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        BTRY(cudaEventRecord(ev_fork, ctx->stream));
+        BTRY(cudaStreamWaitEvent(ctx->stream2, ev_fork, 0));
+    }
+    const unsigned grid2 = (unsigned)(2 * ctx->num_sms);
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
 #define TB_LAUNCH2(K, MMV, SL) do { \
+        if (budget > 0) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
         k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv); \
-        if (budget > 0) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
     } while (0)
 #define TB_LAUNCH(K, MMV) do { if (slack) TB_LAUNCH2(K, MMV, 1); else TB_LAUNCH2(K, MMV, 0); } while (0)
 #define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
@@ -796,6 +839,12 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
 #undef TB_DISPATCH
 #undef TB_LAUNCH
 #undef TB_LAUNCH2
+    if (budget > 0) {
+        k_batch_phase1_done<<<1, 1, 0, ctx->stream>>>(dnsurv);          // after phase 1 (stream order): the queue gets no more entries
+        cudaEventRecord(ev_join, ctx->stream2);
+        cudaStreamWaitEvent(ctx->stream, ev_join, 0);
+        ctx->n_launches++;
+    }
     cudaEventRecord(e1, ctx->stream);
     ctx->n_launches++;
     BTRY(cudaGetLastError());
@@ -811,6 +860,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     if (kernel_ms) *kernel_ms = ms;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
     cleanup();
 #undef BTRY
     return BZ_OK;

@@ -7,6 +7,8 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <map>
+#include <unordered_map>
 
 #include "../../include/bazinga_b200.h"
 
@@ -441,6 +443,7 @@ struct bz_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // bz_batch_solve: the warp-per-instance kernel runs beside phase 1
     std::string err;
     bool profiling = false;
     // NCCL (loaded lazily with dlopen; see bz_comm.cu)
@@ -456,9 +459,16 @@ struct bz_ctx {
     cudaEvent_t solve_ev0 = nullptr, solve_ev1 = nullptr;   // bz_result.device_ms
     int prof_stride = 8;        // bracket every n-th dominant-kernel launch with CUDA events
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
+    // Device-memory cache of the context: bz_problem_destroy parks its blocks here and the next bz_problem_create of the
+    // same shapes takes them back, so a create / solve / destroy cycle (what one `alps(f, g, c, D, x0, y0)` call is) pays
+    // no cudaMalloc / cudaFree (both synchronise the device and cost milliseconds for the 0.5 GB matrix of config C2).
+    std::multimap<size_t, void*> pool;             // free blocks by size
+    std::unordered_map<void*, size_t> pool_live;   // blocks handed out (size)
+    size_t pool_bytes = 0;                         // bytes parked in `pool`
+    std::vector<void*> pinned_pool;                // parked pinned host blocks of BZ_PINNED_BLOCK bytes
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
-    int batch_budget = 4096;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
+    int batch_budget = 1024;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
     int lspec = 1;              // dense problems (n <= 16384, f = Zero): the L step runs speculatively beside G(z) (env BZ_LSPEC=0: off)
     int obstacle_rotate = 1;    // ... with buffer rotation in the cooperative L kernel (env BZ_OBSTACLE_ROTATE=0: copies)
@@ -472,6 +482,12 @@ struct bz_ctx {
 };
 
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg);
+#define BZ_POOL_MAX_BYTES (8ULL << 30)     // park at most this much; larger blocks (the 68.7 GB matrix of C5) go back to the driver
+#define BZ_POOL_MAX_BLOCK (2ULL << 30)
+#define BZ_PINNED_BLOCK 4096
+cudaError_t bz_pool_alloc(bz_ctx* ctx, void** ptr, size_t bytes);
+void bz_pool_free(bz_ctx* ctx, void* ptr);
+void bz_pool_release(bz_ctx* ctx);
 
 // Function attributes (dynamic shared memory limit, carve-out) are per DEVICE: a launcher configures its kernels the
 // first time it runs on each device of the process, not once per process.

@@ -59,22 +59,26 @@ __device__ __forceinline__ double of_stencil(double diag, double c, double left,
 // The software pipeline of one lane.  Every delay line is a circular buffer of THREE rows with STATIC indices: the row
 // loop is unrolled three times and step P of a group finds the row of age k in slot (P-dependent constant + k) mod 3, so
 // nothing is ever shifted (a shifting version spent 29 % of its instructions on register moves; a six-row version did
-// not fit the instruction cache).  Raw rows are loaded one row ahead into staging registers.
+// not fit the instruction cache).  Raw rows are loaded one row ahead into staging registers.  Registers are the scarce
+// resource (a first version spilled its loop bounds and stalled on local-memory loads, ncu r2d): indices are 32-bit,
+// the stop norm keeps res/gamma - grad_x (3 values per row) instead of res and grad_x (6), the debug outputs and the
+// rarely needed second stop norm are compile-time variants.
+template <bool NEED2>
 struct OfPipe {
     double X1[3], X2[3], X3[3], MU[3], RM[3], MY[3];   // raw rows jc, jc-1, jc-2 (x, mu, 1/mu, mu*y)
     double S1, S2, S3, SMU, SRM, SMY;                  // staging: row jc+1, in flight
     double WX[3];                                       // w_x of rows jc-1, jc-2, jc-3
     double Z1[3], Z2[3], Z3[3];                         // z of rows jc-2, jc-3, jc-4
-    double G1[3], G2[3], G3[3], R1[3], R2[3], R3[3];    // grad_x, res: like z
+    double T1[3], T2[3], T3[3];                         // res/gamma - grad_x of the same rows
+    double U1[NEED2 ? 3 : 1], U2[NEED2 ? 3 : 1], U3[NEED2 ? 3 : 1];   // res/(gamma/2) - grad_x (NEED2 only)
     double WZ[3];                                       // w_z of rows jc-3, jc-4, jc-5
 };
 struct OfCtx {
-    const double* __restrict__ x1p; const double* __restrict__ x2p; const double* __restrict__ x3p;
-    const double* __restrict__ mu; const double* __restrict__ rmu; const double* __restrict__ muy;
+    const double* __restrict__ x; const double* __restrict__ mu; const double* __restrict__ rmu; const double* __restrict__ muy;
     double* __restrict__ zp; double* __restrict__ rp; double* __restrict__ dbg_gx; double* __restrict__ dbg_gz;
-    long long N, GX, GY, col, rb, re;
+    int N, GX, GY, col, rb, re;
     double gamma, gamma_h, rg, rgh, diag;
-    bool colok, own_lane, need2;
+    bool colok, own_lane;
     double a[OF_NSUM];
     double m1, m2, nan1, nan2;     // running maxima (NaN-blind) and NaN detectors: sums of |v|, NaN iff some v was NaN
 };
@@ -91,35 +95,35 @@ __device__ __forceinline__ double of_div(double a, double b, double rb) {
 // One row step.  MASKED = false is the steady state of an interior warp: every lane's column is inside the grid, rows
 // jc-4 .. jc+1 are grid rows, and all four stage rows belong to this warp's chunk -- no validity selects, no range
 // tests; the halo lanes accumulate garbage that is discarded at the end (c.own_lane).  MASKED = true is the general step.
-template <int P, bool MASKED, bool L2>
-__device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc) {
-    // L2 = obstacle_l2 (f adds 0.5||x1||^2: dfx block 1 = x1; g without the threshold on block 1 and with value 0), else obstacle_l1
+// L2 = obstacle_l2 (f adds 0.5||x1||^2: dfx block 1 = x1; g without the threshold on block 1 and with value 0), else
+// obstacle_l1.  NEED2: also the stop norm at gamma/2.  DEBUG: store grad_x / grad_z (parity entry point).
+template <int P, bool MASKED, bool L2, bool NEED2, bool DEBUG>
+__device__ __forceinline__ void of_step(OfPipe<NEED2>& s, OfCtx& c, const int jc) {
     constexpr bool l2f = L2, l1g = !L2;
     constexpr int n0 = (3 - P % 3) % 3;
 #define SL(age) ((n0 + (age)) % 3)
+    const int base = jc * c.GX + c.col;                // element index of (row jc, this lane's column)
     // ---- the row evicted from the raw lines is row jc-3: stage 3 wants its mu, 1/mu, mu*y
     const double ev_mu = s.MU[SL(0)], ev_rm = s.RM[SL(0)], ev_my = s.MY[SL(0)];
     s.X1[SL(0)] = s.S1; s.X2[SL(0)] = s.S2; s.X3[SL(0)] = s.S3;            // row jc arrives from staging
     s.MU[SL(0)] = s.SMU; s.RM[SL(0)] = s.SRM; s.MY[SL(0)] = s.SMY;
     // ---- all horizontal neighbours of this step at once: the four stencil centres (x2 of row jc-1, w_x of row jc-2, z2 of
-    // row jc-3, w_z of row jc-4) were produced in EARLIER steps, so their eight shuffles are issued back to back here and
-    // their latency is paid once (shuffles issued where they are used cost 63 % of all stall cycles: ncu r2d)
+    // row jc-3, w_z of row jc-4) were produced in EARLIER steps, so their eight shuffles are issued back to back here
     const double cx2 = s.X2[SL(1)], cwx = s.WX[SL(1)], cz2 = s.Z2[SL(1)], cwz = s.WZ[SL(1)];
     const double lx2 = of_shl(cx2), rx2 = of_shr(cx2), lwx = of_shl(cwx), rwx = of_shr(cwx);
     const double lz2 = of_shl(cz2), rz2 = of_shr(cz2), lwz = of_shl(cwz), rwz = of_shr(cwz);
     {   // ---- raw row jc + 1 into staging (zeros outside the grid)
-        const long long j = jc + 1;
-        const bool ok = MASKED ? (c.colok && j >= 0 && j < c.GY) : true;
-        const long long i = j * c.GX + c.col;
-        s.S1 = ok ? __ldg(c.x1p + i) : 0.0;
-        s.S2 = ok ? __ldg(c.x2p + i) : 0.0;
-        s.S3 = ok ? __ldg(c.x3p + i) : 0.0;
+        const bool ok = MASKED ? (c.colok && jc + 1 >= 0 && jc + 1 < c.GY) : true;
+        const int i = base + c.GX;
+        s.S1 = ok ? __ldg(c.x + i) : 0.0;
+        s.S2 = ok ? __ldg(c.x + c.N + i) : 0.0;
+        s.S3 = ok ? __ldg(c.x + 2 * c.N + i) : 0.0;
         s.SMU = ok ? __ldg(c.mu + i) : 1.0;
         s.SRM = ok ? __ldg(c.rmu + i) : 1.0;      // 1 ./ mu, kept up to date by k_al_update (of_div: the bits of a / mu)
         s.SMY = ok ? __ldg(c.muy + i) : 0.0;
     }
     {   // ---- stage 1: w_x on row r1 = jc - 1 (x2 rows jc-2, jc-1, jc)                      k_obstacle_c
-        const long long r1 = jc - 1;
+        const int r1 = jc - 1;
         const double x1 = s.X1[SL(1)], x2 = s.X2[SL(1)], x3 = s.X3[SL(1)];
         const double mua = s.MU[SL(1)], rma = s.RM[SL(1)], muya = s.MY[SL(1)];
         const double cva = (x1 + of_stencil(c.diag, x2, lx2, rx2, s.X2[SL(2)], s.X2[SL(0)])) - x3;
@@ -143,7 +147,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         }
     }
     {   // ---- stage 2: grad_x, z, res on row r2 = jc - 2 (w_x rows jc-3, jc-2, jc-1)          k_obstacle_jt + k_fstep
-        const long long r2 = jc - 2;
+        const int r2 = jc - 2;
         const double x1 = s.X1[SL(2)], x2 = s.X2[SL(2)], x3 = s.X3[SL(2)];
         const double w = s.WX[SL(1)];
         const double aw = of_stencil(c.diag, w, lwx, rwx, s.WX[SL(2)], s.WX[SL(0)]);
@@ -162,13 +166,20 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         }
         const double q1 = x1 - z1, q2 = x2 - z2, q3 = x3 - z3;
         s.Z1[SL(0)] = z1; s.Z2[SL(0)] = z2; s.Z3[SL(0)] = z3;
-        s.G1[SL(0)] = g1; s.G2[SL(0)] = g2; s.G3[SL(0)] = g3;
-        s.R1[SL(0)] = q1; s.R2[SL(0)] = q2; s.R3[SL(0)] = q3;
+        // what the stop norm needs of this row: res/gamma - grad_x  (k_dstep: (r/gamma - gx) + gz)
+        s.T1[SL(0)] = of_div(q1, c.gamma, c.rg) - g1;
+        s.T2[SL(0)] = of_div(q2, c.gamma, c.rg) - g2;
+        s.T3[SL(0)] = of_div(q3, c.gamma, c.rg) - g3;
+        if (NEED2) {
+            s.U1[SL(0) % (NEED2 ? 3 : 1)] = of_div(q1, c.gamma_h, c.rgh) - g1;
+            s.U2[SL(0) % (NEED2 ? 3 : 1)] = of_div(q2, c.gamma_h, c.rgh) - g2;
+            s.U3[SL(0) % (NEED2 ? 3 : 1)] = of_div(q3, c.gamma_h, c.rgh) - g3;
+        }
         if (st_ok) {
-            const long long i = r2 * c.GX + c.col;
+            const int i = base - 2 * c.GX;
             c.zp[i] = z1; c.zp[c.N + i] = z2; c.zp[2 * c.N + i] = z3;
             c.rp[i] = q1; c.rp[c.N + i] = q2; c.rp[2 * c.N + i] = q3;
-            if (c.dbg_gx) { c.dbg_gx[i] = g1; c.dbg_gx[c.N + i] = g2; c.dbg_gx[2 * c.N + i] = g3; }
+            if (DEBUG) { c.dbg_gx[i] = g1; c.dbg_gx[c.N + i] = g2; c.dbg_gx[2 * c.N + i] = g3; }
         }
         if (!MASKED || st_ok) {
             if (l1g) c.a[5] += z1;
@@ -178,7 +189,7 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         }
     }
     {   // ---- stage 3: w_z on row r3 = jc - 3 (z2 rows jc-4, jc-3, jc-2)
-        const long long r3 = jc - 3;
+        const int r3 = jc - 3;
         const double z1 = s.Z1[SL(1)], z2 = s.Z2[SL(1)], z3 = s.Z3[SL(1)];
         const double cva = (z1 + of_stencil(c.diag, z2, lz2, rz2, s.Z2[SL(2)], s.Z2[SL(0)])) - z3;
         const double t = cva + ev_my;
@@ -201,25 +212,22 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
         }
     }
     {   // ---- stage 4: grad_z and the stop norm on row r4 = jc - 4 (w_z rows jc-5, jc-4, jc-3)   k_dstep
-        const long long r4 = jc - 4;
+        const int r4 = jc - 4;
         const double w = s.WZ[SL(1)];
         const double aw = of_stencil(c.diag, w, lwz, rwz, s.WZ[SL(2)], s.WZ[SL(0)]);
         if (!MASKED || (c.own_lane && r4 >= c.rb && r4 < c.re)) {
             const double h1 = (l2f ? s.Z1[SL(2)] : 0.0) + w;
             const double h2 = (s.Z2[SL(2)] - 1.0) + aw;
             const double h3 = 0.0 + (-w);
-            if (c.dbg_gz && c.own_lane) { const long long i = r4 * c.GX + c.col; c.dbg_gz[i] = h1; c.dbg_gz[c.N + i] = h2; c.dbg_gz[2 * c.N + i] = h3; }
+            if (DEBUG) { if (c.own_lane) { const int i = base - 4 * c.GX; c.dbg_gz[i] = h1; c.dbg_gz[c.N + i] = h2; c.dbg_gz[2 * c.N + i] = h3; } }
             // NaN-propagating max (Julia's norm(., Inf)): the running maximum ignores NaN; a sum of |v| (never Inf - Inf)
             // is NaN exactly when some v was
-            const double v1 = fabs((of_div(s.R1[SL(2)], c.gamma, c.rg) - s.G1[SL(2)]) + h1);
-            const double v2 = fabs((of_div(s.R2[SL(2)], c.gamma, c.rg) - s.G2[SL(2)]) + h2);
-            const double v3 = fabs((of_div(s.R3[SL(2)], c.gamma, c.rg) - s.G3[SL(2)]) + h3);
+            const double v1 = fabs(s.T1[SL(2)] + h1), v2 = fabs(s.T2[SL(2)] + h2), v3 = fabs(s.T3[SL(2)] + h3);
             c.m1 = fmax(c.m1, fmax(fmax(v1, v2), v3));
             c.nan1 += (v1 + v2) + v3;
-            if (c.need2) {   // the norm at gamma/2 is only read when this back-track is the last one allowed (bz_d_decide)
-                const double u1 = fabs((of_div(s.R1[SL(2)], c.gamma_h, c.rgh) - s.G1[SL(2)]) + h1);
-                const double u2 = fabs((of_div(s.R2[SL(2)], c.gamma_h, c.rgh) - s.G2[SL(2)]) + h2);
-                const double u3 = fabs((of_div(s.R3[SL(2)], c.gamma_h, c.rgh) - s.G3[SL(2)]) + h3);
+            if (NEED2) {   // the norm at gamma/2 is only read when this back-track is the last one allowed (bz_d_decide)
+                const double u1 = fabs(s.U1[SL(2) % (NEED2 ? 3 : 1)] + h1), u2 = fabs(s.U2[SL(2) % (NEED2 ? 3 : 1)] + h2),
+                             u3 = fabs(s.U3[SL(2) % (NEED2 ? 3 : 1)] + h3);
                 c.m2 = fmax(c.m2, fmax(fmax(u1, u2), u3));
                 c.nan2 += (u1 + u2) + u3;
             }
@@ -228,48 +236,39 @@ __device__ __forceinline__ void of_step(OfPipe& s, OfCtx& c, const long long jc)
 #undef SL
 }
 
-template <int P, bool L2>
-__device__ __forceinline__ void of_step_any(OfPipe& s, OfCtx& c, long long jc, long long s_lo, long long s_hi) {
-    if (jc >= s_lo && jc < s_hi) of_step<P, false, L2>(s, c, jc);
-    else of_step<P, true, L2>(s, c, jc);
+template <int P, bool L2, bool NEED2, bool DEBUG>
+__device__ __forceinline__ void of_step_any(OfPipe<NEED2>& s, OfCtx& c, int jc, int s_lo, int s_hi) {
+    if (jc >= s_lo && jc < s_hi) of_step<P, false, L2, NEED2, DEBUG>(s, c, jc);
+    else of_step<P, true, L2, NEED2, DEBUG>(s, c, jc);
 }
 
 // force: 0 = member of the cycle (predicated on st->next_op == OP_X, runs the decisions), 1 = parity entry point
 // (evaluates at v.x with st->gamma, leaves the nine scalars in st->out, takes no decision)
-template <bool L2>
-__global__ void __launch_bounds__(OF_THREADS, 3)
-    k_obstacle_fused(BzState* st, BzVecs v, BzObstacle ob, BzGParams g, const double* __restrict__ mu,
-                     const double* __restrict__ rmu, const double* __restrict__ muy, double* part, unsigned int* counter,
-                     ObFusedGeom geo, int force, double* __restrict__ dbg_gx, double* __restrict__ dbg_gz) {
-    __shared__ double scratch[OF_NSUM * 32];
-    bz_pdl_wait();
-    bz_pdl_launch_dependents();
-    if (!force) {
-        if (__ldcg(&st->next_op) != OP_X) return;
-        if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 2);
-    }
+template <bool L2, bool NEED2, bool DEBUG>
+__device__ __forceinline__ void of_kernel_body(BzState* st, const BzVecs& v, const BzObstacle& ob, const BzGParams& g,
+                                               const double* __restrict__ mu, const double* __restrict__ rmu,
+                                               const double* __restrict__ muy, double* part, unsigned int* counter,
+                                               const ObFusedGeom& geo, int force, double* __restrict__ dbg_gx,
+                                               double* __restrict__ dbg_gz, double* scratch) {
     // buffer rotation (bz_lbfgs.cu): the cooperative L kernel swaps the roles of (x, x_prev), (res, res_prev), (z, z_curr)
     // instead of copying them; st->rot says which physical buffer plays which role right now
     const int rot = force ? 0 : __ldcg(&st->rot);
-    const double* xbase = (rot & 1) ? v.x_prev : v.x;
     OfCtx c;
     c.gamma = __ldcg(&st->gamma);
     c.gamma_h = c.gamma * 0.5;
     c.rg = frecip(c.gamma); c.rgh = frecip(c.gamma_h);
-    c.N = ob.N;
-    c.GX = ob.gx == 0 ? ob.N : ob.gx; c.GY = ob.gx == 0 ? 1 : ob.gy;
+    c.N = (int)ob.N;
+    c.GX = (int)(ob.gx == 0 ? ob.N : ob.gx); c.GY = (int)(ob.gx == 0 ? 1 : ob.gy);
     c.diag = ob.gx == 0 ? 2.0 : 4.0;
-    c.x1p = xbase; c.x2p = xbase + c.N; c.x3p = xbase + 2 * c.N;
+    c.x = (rot & 1) ? v.x_prev : v.x;
     c.mu = mu; c.rmu = rmu; c.muy = muy;
     c.zp = (rot & 4) ? v.z_curr : v.z;
     c.rp = (rot & 2) ? v.res_prev : v.res;
     c.dbg_gx = dbg_gx; c.dbg_gz = dbg_gz;
-    // stop norm at gamma/2: read by bz_d_decide only when a gamma-halving at this back-track index runs off the loop
-    c.need2 = force || (__ldcg(&st->mode) == MODE_ITER && __ldcg(&st->k_bt) + 1 > __ldcg(&st->max_backtracks));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long wg = (long long)blockIdx.x * OF_WARPS + warp;
-    const long long cg = wg % geo.ncg, rc = wg / geo.ncg;
+    const int wg = (int)blockIdx.x * OF_WARPS + warp;
+    const int cg = wg % geo.ncg, rc = wg / geo.ncg;
     c.col = cg * OF_OUT - OF_HALO + lane;
     c.colok = c.col >= 0 && c.col < c.GX;
     c.own_lane = lane >= OF_HALO && lane < 32 - OF_HALO && c.colok;
@@ -283,24 +282,26 @@ __global__ void __launch_bounds__(OF_THREADS, 3)
     c.nan1 = 0.0; c.nan2 = 0.0;
 
     if (active) {
-        OfPipe s;
+        OfPipe<NEED2> s;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             s.X1[k] = 0.0; s.X2[k] = 0.0; s.X3[k] = 0.0; s.MU[k] = 1.0; s.RM[k] = 1.0; s.MY[k] = 0.0;
-            s.WX[k] = s.Z1[k] = s.Z2[k] = s.Z3[k] = s.G1[k] = s.G2[k] = s.G3[k] = s.R1[k] = s.R2[k] = s.R3[k] = s.WZ[k] = 0.0;
+            s.WX[k] = s.Z1[k] = s.Z2[k] = s.Z3[k] = s.T1[k] = s.T2[k] = s.T3[k] = s.WZ[k] = 0.0;
         }
+#pragma unroll
+        for (int k = 0; k < (NEED2 ? 3 : 1); ++k) { s.U1[k] = 0.0; s.U2[k] = 0.0; s.U3[k] = 0.0; }
         s.S1 = s.S2 = s.S3 = 0.0; s.SMU = 1.0; s.SRM = 1.0; s.SMY = 0.0;
         // steps jc = rb-5 .. re+3: the first one only loads row rb-4 into staging (its stages see zeros and own nothing)
-        const long long j_begin = c.rb - 5, j_end = c.re + 4;
+        const int j_begin = c.rb - 5, j_end = c.re + 4;
         // unmasked range: interior warp, stage rows jc-4 .. jc-1 inside [rb, re), loaded row jc+1 a grid row
         const bool interior = (cg * OF_OUT - OF_HALO >= 0) && (cg * OF_OUT - OF_HALO + 31 < c.GX);
-        long long s_lo = c.rb + 4, s_hi = c.re + 1;
+        int s_lo = c.rb + 4, s_hi = c.re + 1;
         if (s_hi > c.GY - 1) s_hi = c.GY - 1;
         if (!interior) s_hi = s_lo;
-        for (long long jb = j_begin; jb < j_end; jb += 3) {
-            of_step_any<0, L2>(s, c, jb, s_lo, s_hi);
-            if (jb + 1 < j_end) of_step_any<1, L2>(s, c, jb + 1, s_lo, s_hi);
-            if (jb + 2 < j_end) of_step_any<2, L2>(s, c, jb + 2, s_lo, s_hi);
+        for (int jb = j_begin; jb < j_end; jb += 3) {
+            of_step_any<0, L2, NEED2, DEBUG>(s, c, jb, s_lo, s_hi);
+            if (jb + 1 < j_end) of_step_any<1, L2, NEED2, DEBUG>(s, c, jb + 1, s_lo, s_hi);
+            if (jb + 2 < j_end) of_step_any<2, L2, NEED2, DEBUG>(s, c, jb + 2, s_lo, s_hi);
         }
         if (!c.own_lane) {           // halo lanes accumulated garbage in the unmasked steps
 #pragma unroll
@@ -359,6 +360,27 @@ __global__ void __launch_bounds__(OF_THREADS, 3)
     __threadfence();
 }
 
+// MINB resident CTAs per SM: 3 (168 registers) or 2 (255 registers, nothing spilled); chosen at launch (BZ_OF_OCC)
+template <bool L2, int MINB>
+__global__ void __launch_bounds__(OF_THREADS, MINB)
+    k_obstacle_fused(BzState* st, BzVecs v, BzObstacle ob, BzGParams g, const double* __restrict__ mu,
+                     const double* __restrict__ rmu, const double* __restrict__ muy, double* part, unsigned int* counter,
+                     ObFusedGeom geo, int force, double* __restrict__ dbg_gx, double* __restrict__ dbg_gz) {
+    __shared__ double scratch[OF_NSUM * 32];
+    bz_pdl_wait();
+    bz_pdl_launch_dependents();
+    if (force) {      // parity entry point: both stop norms, grad_x / grad_z written out
+        of_kernel_body<L2, true, true>(st, v, ob, g, mu, rmu, muy, part, counter, geo, 1, dbg_gx, dbg_gz, scratch);
+        return;
+    }
+    if (__ldcg(&st->next_op) != OP_X) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) bz_tic(st, 2);
+    // stop norm at gamma/2: read by bz_d_decide only when a gamma-halving at this back-track index runs off the loop
+    const bool need2 = __ldcg(&st->mode) == MODE_ITER && __ldcg(&st->k_bt) + 1 > __ldcg(&st->max_backtracks);
+    if (need2) of_kernel_body<L2, true, false>(st, v, ob, g, mu, rmu, muy, part, counter, geo, 0, nullptr, nullptr, scratch);
+    else of_kernel_body<L2, false, false>(st, v, ob, g, mu, rmu, muy, part, counter, geo, 0, nullptr, nullptr, scratch);
+}
+
 // chunks of rows x groups of 24 columns -> warps; the grid is sized to ONE wave of resident CTAs when the problem is big
 static ObFusedGeom of_geometry(const bz_ctx* ctx, const BzObstacle& ob, int resident_per_sm) {
     const long long GX = ob.gx == 0 ? ob.N : ob.gx, GY = ob.gx == 0 ? 1 : ob.gy;
@@ -376,13 +398,22 @@ static ObFusedGeom of_geometry(const bz_ctx* ctx, const BzObstacle& ob, int resi
     return g;
 }
 
+static int of_occ() {
+    static int occ = 0;
+    if (occ == 0) { const char* e = getenv("BZ_OF_OCC"); occ = (e && atoi(e) == 2) ? 2 : 3; }
+    return occ;
+}
 static int of_resident(bz_ctx* ctx) {
     static int per_sm[64] = {0};
     int& r = per_sm[ctx->device & 63];
     if (r == 0) {
-        cudaFuncSetAttribute(k_obstacle_fused<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_obstacle_fused<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_obstacle_fused<false>, OF_THREADS, 0) != cudaSuccess || r < 1) r = 1;
+        cudaFuncSetAttribute(k_obstacle_fused<false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_obstacle_fused<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_obstacle_fused<false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_obstacle_fused<true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaError_t e = of_occ() == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_obstacle_fused<false, 2>, OF_THREADS, 0)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, k_obstacle_fused<false, 3>, OF_THREADS, 0);
+        if (e != cudaSuccess || r < 1) r = 1;
     }
     return r;
 }
@@ -397,9 +428,9 @@ int bz_launch_obstacle_fused(bz_ctx* ctx, BzState* st, const BzVecs& v, const Bz
     const ObFusedGeom geo = of_geometry(ctx, ob, of_resident(ctx));
     // obstacle_l1 = (SmoothCostObstacleL1, NonsmoothCostObstacleL1), obstacle_l2 = (..L2, ..L2): the catalogue check of
     // bz_problem_create admits no other pairing
-    if (ob.l2)
-        return bz_launch_pdl(ctx, k_obstacle_fused<true>, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, rmu, muy, part,
-                             counter, geo, force, dbg_gx, dbg_gz);
-    return bz_launch_pdl(ctx, k_obstacle_fused<false>, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, rmu, muy, part,
-                         counter, geo, force, dbg_gx, dbg_gz);
+#define OF_LAUNCH(L2V, OCC) bz_launch_pdl(ctx, k_obstacle_fused<L2V, OCC>, dim3(geo.ctas), dim3(OF_THREADS), 0, 0, st, v, ob, g, mu, rmu, \
+                                          muy, part, counter, geo, force, dbg_gx, dbg_gz)
+    if (of_occ() == 2) return ob.l2 ? OF_LAUNCH(true, 2) : OF_LAUNCH(false, 2);
+    return ob.l2 ? OF_LAUNCH(true, 3) : OF_LAUNCH(false, 3);
+#undef OF_LAUNCH
 }

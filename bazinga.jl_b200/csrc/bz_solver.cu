@@ -18,6 +18,40 @@
 
 static thread_local std::string g_last_error;   // bz_last_error(NULL): per host thread
 
+cudaError_t bz_pool_alloc(bz_ctx* ctx, void** ptr, size_t bytes) {
+    auto it = ctx->pool.find(bytes);
+    if (it != ctx->pool.end()) {
+        *ptr = it->second;
+        ctx->pool.erase(it);
+        ctx->pool_bytes -= bytes;
+    } else {
+        cudaError_t e = cudaMalloc(ptr, bytes);
+        if (e != cudaSuccess && !ctx->pool.empty()) {      // out of memory with blocks parked: give them back and retry
+            cudaGetLastError();
+            bz_pool_release(ctx);
+            e = cudaMalloc(ptr, bytes);
+        }
+        if (e != cudaSuccess) return e;
+    }
+    ctx->pool_live[*ptr] = bytes;
+    return cudaSuccess;
+}
+void bz_pool_free(bz_ctx* ctx, void* ptr) {
+    if (!ptr) return;
+    auto it = ctx->pool_live.find(ptr);
+    if (it == ctx->pool_live.end()) { cudaFree(ptr); return; }
+    const size_t bytes = it->second;
+    ctx->pool_live.erase(it);
+    if (bytes > BZ_POOL_MAX_BLOCK || ctx->pool_bytes + bytes > BZ_POOL_MAX_BYTES) { cudaFree(ptr); return; }
+    ctx->pool.emplace(bytes, ptr);
+    ctx->pool_bytes += bytes;
+}
+void bz_pool_release(bz_ctx* ctx) {
+    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+}
+
 int bz_fail(bz_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     g_last_error = msg;
@@ -147,8 +181,11 @@ extern "C" int bz_ctx_destroy(bz_ctx* ctx) {
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->batch_arena) cudaFree(ctx->batch_arena);
     if (ctx->xpose_buf) cudaFree(ctx->xpose_buf);
+    bz_pool_release(ctx);
+    for (void* q : ctx->pinned_pool) cudaFreeHost(q);
     if (ctx->timer0) { cudaEventDestroy(ctx->timer0); cudaEventDestroy(ctx->timer1); }
     if (ctx->solve_ev0) { cudaEventDestroy(ctx->solve_ev0); cudaEventDestroy(ctx->solve_ev1); }
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BZ_OK;
@@ -216,7 +253,7 @@ template <typename T>
 static int dev_alloc(bz_ctx* ctx, T** ptr, size_t count) {
     *ptr = nullptr;
     if (count == 0) count = 1;
-    BZ_CUDA(ctx, cudaMalloc((void**)ptr, count * sizeof(T)));
+    BZ_CUDA(ctx, bz_pool_alloc(ctx, (void**)ptr, count * sizeof(T)));
     BZ_CUDA(ctx, cudaMemsetAsync(*ptr, 0, count * sizeof(T), ctx->stream));
     return BZ_OK;
 }
@@ -257,31 +294,33 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     if (!p) return BZ_OK;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
-    if (p->own_cA) cudaFree(p->cA);
+    bz_ctx* ctx = p->ctx;
+    if (p->own_cA) bz_pool_free(ctx, p->cA);
     if (p->slab_base) {   // x, z, xeps, yupd live inside the exported slab
         p->v.x = p->v.z = p->v.xeps = nullptr;
         p->yupd = nullptr;
         for (int r = 0; r < XR_MAXR; ++r)
             if (p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
-        cudaFree(p->slab_base);
+        ctx->pool_live.erase(p->slab_base);
+        cudaFree(p->slab_base);      // (exported through cudaIpc: never recycled)
     }
     double* frees[] = {p->rmu, p->tm1_f, p->cb, p->fA, p->fb, p->f_ones, p->f_zeros, p->g_u, p->mu, p->y, p->muy, p->cx,
                        p->s, p->yupd, p->tm1, p->tm2, p->tm3, p->v.x, p->v.z, p->v.xeps, p->v.x_prev,
                        p->v.x_d, p->v.z_curr, p->v.res, p->v.res_prev, p->v.grad_x, p->v.grad_z,
                        p->v.d, p->v.sM, p->v.yM, p->Ec, p->Ef, p->Pc, p->Pf, p->lxpart, p->fxpart,
                        p->part, p->team.slots};
-    for (double* f : frees) if (f) cudaFree(f);
-    if (p->counters) cudaFree(p->counters);
-    if (p->gridD) cudaFree(p->gridD);
-    if (p->gseq) cudaFree(p->gseq);
-    if (p->lspec_buf) cudaFree(p->lspec_buf);
-    if (p->v.xs) cudaFree(p->v.xs);
-    if (p->gridD_f) cudaFree(p->gridD_f);
-    if (p->gseq_f) cudaFree(p->gseq_f);
-    if (p->team.bars) cudaFree(p->team.bars);
-    if (p->st) cudaFree(p->st);
-    if (p->st_host) cudaFreeHost(p->st_host);
-    if (p->status_host) cudaFreeHost(p->status_host);
+    for (double* f : frees) bz_pool_free(ctx, f);
+    bz_pool_free(ctx, p->counters);
+    bz_pool_free(ctx, p->gridD);
+    bz_pool_free(ctx, p->gseq);
+    bz_pool_free(ctx, p->lspec_buf);
+    bz_pool_free(ctx, p->v.xs);
+    bz_pool_free(ctx, p->gridD_f);
+    bz_pool_free(ctx, p->gseq_f);
+    bz_pool_free(ctx, p->team.bars);
+    bz_pool_free(ctx, p->st);
+    if (p->st_host) ctx->pinned_pool.push_back(p->st_host);
+    if (p->status_host) ctx->pinned_pool.push_back(p->status_host);
     for (auto& e : p->poll_ev) if (e) cudaEventDestroy(e);
     bz_shard_free(p->ctx, &p->shard);
     delete p;
@@ -422,7 +461,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     for (double** q : mvecs) if (!*q) PTRY(dev_alloc(ctx, q, ml));
     const int maxgrid = ctx->num_sms * 8;
     size_t npart = (size_t)4 * maxgrid;
-    if (d->c_kind == BZ_C_OBSTACLE && !p->slab && !p->slack && ctx->obstacle_fused) {
+    if (d->c_kind == BZ_C_OBSTACLE && !p->slab && !p->slack && ctx->obstacle_fused && p->nv < (1LL << 31)) {   // (32-bit element indices)
         p->fused = true;
         p->rotate = p->nv > 32768 && ctx->obstacle_rotate;   // (n <= 32768 runs the cluster L kernel, whose vectors live in registers)
         npart = std::max(npart, (size_t)bz_obfused_partials(ctx, p->ob));
@@ -438,8 +477,11 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     p->team.parity = 0;
     PTRY(dev_alloc(ctx, &p->st, 1));
 #define PCUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } while (0)
-    PCUDA(cudaMallocHost((void**)&p->st_host, sizeof(BzState)));
-    PCUDA(cudaMallocHost((void**)&p->status_host, 2 * sizeof(int)));
+    static_assert(sizeof(BzState) <= BZ_PINNED_BLOCK, "pinned blocks hold a BzState");
+    for (void** q : {(void**)&p->st_host, (void**)&p->status_host}) {
+        if (!ctx->pinned_pool.empty()) { *q = ctx->pinned_pool.back(); ctx->pinned_pool.pop_back(); }
+        else PCUDA(cudaMallocHost(q, BZ_PINNED_BLOCK));
+    }
     for (auto& e : p->poll_ev) PCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     // ---- f data
