@@ -809,20 +809,32 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     // Two kernels run side by side.  The warp-per-instance kernel goes first, on a second stream: two CTAs per SM of
     // persistent warps that pop survivors from the queue as phase 1 produces them (and leave half of every SM to phase 1).
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    const bool concurrent = budget > 0 && ctx->batch_concurrent;     // else: phase 2 after phase 1 on the same stream
     if (budget > 0) {
-        if (!ctx->stream2) BTRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         BTRY(cudaMemsetAsync(dsurv, 0xff, B * sizeof(int), ctx->stream));
         BTRY(cudaMemsetAsync(dnsurv, 0, 4 * sizeof(int), ctx->stream));
+    }
+    if (concurrent) {
+        if (!ctx->stream2) BTRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         BTRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         BTRY(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         BTRY(cudaEventRecord(ev_fork, ctx->stream));
         BTRY(cudaStreamWaitEvent(ctx->stream2, ev_fork, 0));
     }
-    const unsigned grid2 = (unsigned)(2 * ctx->num_sms);
+    const unsigned grid2 = (unsigned)((concurrent ? 2 : 4) * ctx->num_sms);
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
+    // (lazy module loading: the first launch of a kernel may wait for running kernels to finish -- fatal when the running
+    // kernel is the persistent one that waits for the kernel being loaded.  Both are loaded before either is launched.)
 #define TB_LAUNCH2(K, MMV, SL) do { \
-        if (budget > 0) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
+        if (concurrent) { cudaFuncAttributes fa__; \
+            cudaFuncGetAttributes(&fa__, k_batch_alps<K, MMV, SL, true>); cudaFuncGetAttributes(&fa__, k_batch_alps<K, MMV, SL, false>); \
+            cudaFuncGetAttributes(&fa__, k_batch_phase1_done); } \
+        if (concurrent) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
         k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv); \
+        if (budget > 0 && !concurrent) { \
+            k_batch_phase1_done<<<1, 1, 0, ctx->stream>>>(dnsurv); \
+            k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); \
+            ctx->n_launches += 2; } \
     } while (0)
 #define TB_LAUNCH(K, MMV) do { if (slack) TB_LAUNCH2(K, MMV, 1); else TB_LAUNCH2(K, MMV, 0); } while (0)
 #define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
@@ -839,7 +851,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
 #undef TB_DISPATCH
 #undef TB_LAUNCH
 #undef TB_LAUNCH2
-    if (budget > 0) {
+    if (concurrent) {
         k_batch_phase1_done<<<1, 1, 0, ctx->stream>>>(dnsurv);          // after phase 1 (stream order): the queue gets no more entries
         cudaEventRecord(ev_join, ctx->stream2);
         cudaStreamWaitEvent(ctx->stream, ev_join, 0);

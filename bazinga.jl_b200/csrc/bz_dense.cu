@@ -118,11 +118,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
         if (a.force_target < 0 && target == TGT_Z) {
             const int mode = __ldcg(&a.st->mode);
             const int rank_ls = (int)blockIdx.x - 2 * a.ls.dense_clusters;
-            int cs = 1;
-            while (cs < LS_MAXCS && (long long)cs * LS_THREADS * 8 < a.ls.v.n) cs *= 2;
+            const int cs = a.ls.cs;
             if ((mode == MODE_INITFB || mode == MODE_ITER) && rank_ls < cs) {
-                if ((long long)cs * LS_THREADS * 8 >= a.ls.v.n) ls_body<8>(a.st, a.ls, rank_ls, cs, wsum);
-                else ls_body<16>(a.st, a.ls, rank_ls, cs, wsum);
+                // (the ring is unused in these CTAs: its first doubles are the reduction scratch)
+                if ((long long)cs * LS_THREADS * 8 >= a.ls.v.n) ls_body<8>(a.st, a.ls, rank_ls, cs, ring);
+                else ls_body<16>(a.st, a.ls, rank_ls, cs, ring);
             }
         }
     } else {
@@ -267,8 +267,8 @@ int bz_launch_dense_algrad(bz_ctx* ctx, const BzDenseArgs& args, int nclusters) 
     }
     const bool bulk = (args.n % 2 == 0) && (args.lda % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(args.A) & 15) == 0);
-    // with a speculative L step on board: `nclusters` row clusters + ceil(LS_MAXCS / 2) clusters for the L step
-    const dim3 grid(2 * (nclusters + (args.ls.enabled ? LS_MAXCS / 2 : 0))), block(DA_THREADS);
+    // with a speculative L step on board: `nclusters` row clusters + ceil(cs / 2) clusters for the L step
+    const dim3 grid(2 * (nclusters + (args.ls.enabled ? (args.ls.cs + 1) / 2 : 0))), block(DA_THREADS);
     if (args.slack)
         return bulk ? bz_launch_pdl(ctx, k_dense_algrad<true, true>, grid, block, smem, 0, args)
                     : bz_launch_pdl(ctx, k_dense_algrad<false, true>, grid, block, smem, 0, args);

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(BZ_L_THREADS, BZ_L_CTAS_PER_SM)
 // ---------------------------------------------------------------------------------------------
 // cluster version
 // ---------------------------------------------------------------------------------------------
-#define LC_THREADS 256
+#define LC_THREADS 512     // (the speculative copy of this kernel, bz_lspec.cuh, must use the same numbers)
 #define LC_EPT 16          // max elements per thread
 #define LC_MAXCS 8         // portable cluster size
 
@@ -420,7 +420,7 @@ __device__ __forceinline__ void lc_st_async(void* local_data, uint64_t* local_ba
 }
 
 struct ClusterRed {
-    double* wpart;     // [2][8] warp partials (K <= 2)
+    double* wpart;     // [2 parities][K <= 2][16] warp partials
     double* slots;     // [2 parities][LC_MAXCS][2]
     uint64_t* bars;    // [2 parities]: all senders' stores of a round complete their tx here
     uint32_t rank, cs;
@@ -441,10 +441,10 @@ __device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
     const int par = cr.round & 1;
     const uint32_t phase = (uint32_t)((cr.round >> 1) & 1);
     cr.round++;
-    double* wp = cr.wpart + par * 16;
+    double* wp = cr.wpart + par * 32;
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) wp[k * 8 + warp] = v[k];
+        for (int k = 0; k < K; ++k) wp[k * 16 + warp] = v[k];
     }
     __syncthreads();
     double* sl = cr.slots + par * (LC_MAXCS * 2);
@@ -454,8 +454,9 @@ __device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
         double bs[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double* w = wp + k * 8;
-            bs[k] = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+            const double* w = wp + k * 16;
+            bs[k] = (((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]))) +
+                    (((w[8] + w[9]) + (w[10] + w[11])) + ((w[12] + w[13]) + (w[14] + w[15])));
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) lc_st_async(&sl[cr.rank * 2 + k], bar, threadIdx.x, bs[k]);
@@ -472,7 +473,7 @@ __device__ inline void cluster_sum(ClusterRed& cr, double (&v)[K]) {
 template <int EPT>
 __global__ void __launch_bounds__(LC_THREADS)
     k_lstep_cluster(BzState* st, BzVecs v, int force_role) {
-    __shared__ double wpart[2 * 2 * 8];
+    __shared__ double wpart[2 * 2 * 16];
     __shared__ double slots[2 * LC_MAXCS * 2];
     __shared__ uint64_t bars[2];
     bz_pdl_wait();
@@ -683,7 +684,7 @@ int bz_launch_lstep(bz_ctx* ctx, BzState* st, const BzVecs& v, const BzTeam& tm,
     if (v.n <= per_cta * LC_MAXCS && !slab && !rotate) {   // (slab mode: only the cooperative kernel exchanges across ranks)
         // smallest power-of-two cluster that keeps <= 8 elements per thread when possible
         int cs = 1;
-        while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;
+        while (cs < LC_MAXCS && (long long)cs * LC_THREADS * 8 < v.n) cs *= 2;      // n = 16384: four CTAs of 512 threads
         if ((long long)cs * LC_THREADS * 8 >= v.n)
             return bz_launch_pdl(ctx, k_lstep_cluster<8>, dim3(cs), dim3(LC_THREADS), 0, cs, st, v, force_role);
         return bz_launch_pdl(ctx, k_lstep_cluster<LC_EPT>, dim3(cs), dim3(LC_THREADS), 0, cs, st, v, force_role);

@@ -2,8 +2,8 @@
 //
 // A PANOC+ iteration is the chain  L -> G(x) -> F -> G(z) -> D  and the next L needs nothing that G(z) or D compute
 // except D's verdict: its inputs (x, x_prev, res, res_prev, the L-BFGS history, gamma and the scalars F left) are all
-// final once F has run.  So while the 70 row clusters of k_dense_algrad stream A for G(z), four spare clusters of the
-// same launch (8 CTAs; an HBM-bound pass does not need all 148 SMs) run the L step of the NEXT iteration on the
+// final once F has run.  So while 72 row clusters of k_dense_algrad stream A for G(z), two spare clusters of the
+// same launch (4 CTAs at n = 16384) run the L step of the NEXT iteration on the
 // assumption that D will accept the iterate, writing into shadow storage only:
 //     x + d              -> BzLSpec::xs
 //     (s, y) candidate   -> the spare history slot BZ_MAXMEM
@@ -20,12 +20,13 @@
 #include "bz_internal.cuh"
 #include "bz_vec.cuh"
 
-#define LS_THREADS 256
+#define LS_THREADS 512     // = LC_THREADS of bz_lbfgs.cu
 #define LS_MAXCS 8
 
 struct BzLSpec {
     int enabled;               // this launch carries the speculative L step (G(z) of a dense, n <= 16384 problem)
     int dense_clusters;        // row clusters of the dense pass; clusters beyond them run the L step
+    int cs;                    // CTAs of the L step (the cluster size k_lstep_cluster would use for this n)
     BzVecs v;
     double* xs;                // shadow x + d
     unsigned long long* xbuf;  // exchange: [32 rounds][LS_MAXCS][2 values][2 words]
@@ -52,17 +53,18 @@ __device__ inline void ls_sum(double (&v)[K], double* wpart, unsigned long long*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = bz_warp_sum(v[k]);
-    double* wp = wpart + (round & 1) * 16;
+    double* wp = wpart + (round & 1) * 32;
     if (threadIdx.x < LS_THREADS && lane == 0) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) wp[k * 8 + warp] = v[k];
+        for (int k = 0; k < K; ++k) wp[k * 16 + warp] = v[k];
     }
     __syncthreads();
     const unsigned long long tag = ((seq + (unsigned long long)round + 1ULL) & 0xffffffffULL) << 32;
     unsigned long long* base = xbuf + (size_t)(round & 31) * (LS_MAXCS * 2 * 2);
     if (threadIdx.x < K) {
-        const double* w = wp + threadIdx.x * 8;
-        const double bs = ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+        const double* w = wp + threadIdx.x * 16;
+        const double bs = (((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]))) +
+                          (((w[8] + w[9]) + (w[10] + w[11])) + ((w[12] + w[13]) + (w[14] + w[15])));
         ls_post(base + ((size_t)rank * 2 + threadIdx.x) * 2, tag, bs);
     }
     double s[K];

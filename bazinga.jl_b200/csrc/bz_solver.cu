@@ -101,6 +101,7 @@ struct bz_problem {
     // slab-decomposed obstacle grid (cross-rank exchange over peer memory)
     bool lspec = false;   // dense problems: the L step of the next iteration runs speculatively beside G(z) (bz_lspec.cuh)
     int c_clusters_z = 0, c_rpc_z = 0;      // ... on this many row clusters (the rest of the SMs carry the L step)
+    int lspec_cs = 0;                       // CTAs of the speculative L step
     unsigned long long* lspec_buf = nullptr;
     bool rotate = false;  // fused problems large enough for the cooperative L kernel: x/x_prev, res/res_prev, z/z_curr swap roles
     bool fused = false;   // obstacle problems on one GPU: the cycle is [L, X] with the fused kernel of bz_obfused.cu
@@ -166,6 +167,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_GRID_VARIANT")) ctx->grid_variant = atoi(e);
     if (const char* e = getenv("BZ_GRID_TEAM")) ctx->grid_team = atoi(e);
     if (const char* e = getenv("BZ_BATCH_BUDGET")) ctx->batch_budget = atoi(e);
+    if (const char* e = getenv("BZ_BATCH_CONCURRENT")) ctx->batch_concurrent = atoi(e);
     if (const char* e = getenv("BZ_LSPEC")) ctx->lspec = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_ROTATE")) ctx->obstacle_rotate = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
@@ -539,9 +541,12 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         // speculative L step beside G(z): plain alps on one GPU with the cluster kernels (n <= 16384) and f = Zero
         if (ctx->lspec && !p->c_wide && !p->c_grid && !p->sharded && !p->slack && d->f_kind == BZ_F_ZERO &&
             p->nv <= (long long)LS_MAXCS * LS_THREADS * 16) {
-            const int maxc = ctx->num_sms / 2, extra = LS_MAXCS / 2;
+            int cs = 1;
+            while (cs < LS_MAXCS && (long long)cs * LS_THREADS * 8 < p->nv) cs *= 2;     // the cluster size of k_lstep_cluster
+            const int maxc = ctx->num_sms / 2, extra = (cs + 1) / 2;
             if (maxc > extra) {
                 p->lspec = true;
+                p->lspec_cs = cs;
                 p->c_clusters_z = p->c_clusters;
                 p->c_rpc_z = p->c_rpc;
                 if (p->c_clusters + extra > maxc) {          // give up a few row clusters so that the whole grid stays co-resident
@@ -717,7 +722,7 @@ static int launch_provider(bz_problem* p, int force_target, bool gz_slot = false
         a.is_cpass = 1;
         int nclus = p->c_clusters;
         if (gz_slot && p->lspec && force_target < 0) {       // the second provider launch of a cycle: G(z) + speculative L
-            a.ls.enabled = 1; a.ls.dense_clusters = p->c_clusters_z; a.ls.v = p->v; a.ls.xs = p->v.xs; a.ls.xbuf = p->lspec_buf;
+            a.ls.enabled = 1; a.ls.dense_clusters = p->c_clusters_z; a.ls.cs = p->lspec_cs; a.ls.v = p->v; a.ls.xs = p->v.xs; a.ls.xbuf = p->lspec_buf;
             a.rows_per_cluster = p->c_rpc_z;
             nclus = p->c_clusters_z;
         }
