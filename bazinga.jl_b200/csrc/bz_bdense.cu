@@ -11,10 +11,11 @@
 // batched gradient; the single-pass form needs the row-panel exchange of bz_grid.cu widened to 8 x 8 blocks and is the
 // next step): 2 x 537 MB for 8 gradients at 4096 x 16384 instead of 8 x 537 MB.
 //
-// Pass 1: a CTA owns 32 rows; chunks of 128 columns of those rows (32 x 1 KB, cp.async.bulk per row) and of X (8 x 1 KB)
-// stream through a 4-stage shared-memory ring; warp w multiplies the 8-row tile (w & 3) with the 64-column half (w >> 2)
-// of the chunk: 16 DMMAs per chunk, accumulators in registers.  Pass 2: a CTA owns 128 columns; chunks of 32 rows x 128
-// columns stream through the ring, warp w owns 16 columns: 16 DMMAs per chunk (M = columns of A, K = rows, N = batch).
+// Pass 1: a CTA owns 16 rows; chunks of 128 columns of those rows (16 x 1 KB, cp.async.bulk per row) and of X (8 x 1 KB)
+// stream through a 4-stage shared-memory ring; warp w multiplies the 8-row tile (w & 1) with the 32-column quarter (w >> 1)
+// of the chunk: 8 DMMAs per chunk on two independent accumulator pairs.  Pass 2: a CTA owns 64 columns; chunks of 32 rows
+// x 64 columns stream through the ring, warp w owns 8 columns: 8 DMMAs per chunk (M = columns of A, K = rows, N = batch).
+// Two CTAs per SM in both passes.
 // Row strides in shared memory are = 4 (mod 16) doubles, which makes every fragment load conflict-free.  No partial
 // results cross CTAs: every output element is produced by one warp in a fixed order (deterministic, no atomics).
 #include "bz_internal.cuh"
@@ -27,12 +28,12 @@
 #define BD_B 8            // batch width = N of m8n8k4
 #define BD_THREADS 256
 #define BD_STAGES 4
-#define BD_RP 32          // pass 1: rows per CTA
+#define BD_RP 16          // pass 1: rows per CTA (two 8-row tiles; 4 x 25 KB of ring -> two CTAs per SM, 256 CTAs at m = 4096)
 #define BD_KC 128         // pass 1: columns per chunk
-#define BD_CP 128         // pass 2: columns per CTA
+#define BD_CP 64          // pass 2: columns per CTA (eight 8-column groups; two CTAs per SM, 256 CTAs at n = 16384)
 #define BD_RC 32          // pass 2: rows per chunk
 #define BD_PAD 4
-#define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + 2 * BD_RP * BD_B * 8)   /* ring, 8 barriers, reduction scratch */
+#define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + (3 * BD_RP * BD_B + 2 * BD_B) * 8)   /* ring, 8 barriers, reduction scratch */
 #define BD_SMEM2 (BD_STAGES * (BD_RC * (BD_CP + BD_PAD) + BD_B * (BD_RC + BD_PAD)) * 8 + 64)
 
 struct bz_bdense {
@@ -62,7 +63,7 @@ __device__ __forceinline__ void bd_arrive(uint64_t* bar) {
 
 // ---- pass 1: R = A X for the CTA's 32 rows, then the elementwise AL stage ------------------------------------------------
 // ldm = m rounded up to even: leading dimension of the batch x m arrays (16-byte aligned rows for the bulk copies)
-__global__ void __launch_bounds__(BD_THREADS + 32, 1)
+__global__ void __launch_bounds__(BD_THREADS + 32, 2)
     k_bd_ax(const double* __restrict__ A, long long m, long long n, long long ldm, const double* __restrict__ X,
             const double* __restrict__ bv, const double* __restrict__ mu, const double* __restrict__ yv, int dkind, double dlo,
             double dhi, double* __restrict__ cx, double* __restrict__ yupd, double* __restrict__ W, double* __restrict__ lxpart) {
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
     double* ring = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
     uint64_t* empty = full + BD_STAGES;
-    double* red = reinterpret_cast<double*>(full + 8);       // [32][8] k-half partial tile, then [4][8] lx partials
+    double* red = reinterpret_cast<double*>(full + 8);       // [3][16][8] k-quarter partial tiles, then [2][8] lx partials
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long r0 = (long long)blockIdx.x * BD_RP;
     const int nchunks = (int)((n + BD_KC - 1) / BD_KC);
@@ -84,12 +85,15 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
     }
     __syncthreads();
 
+    // two independent accumulator pairs per warp (even / odd k-steps): one dependent chain of DMMAs per chunk left the
+    // tensor pipe 85 % idle (ncu r2d); the pairs are added in fixed order at the end
+    double ca[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     double c0 = 0.0, c1 = 0.0;
-    const int mt = warp & 3, kh = (warp >> 2) & 1;
+    const int mt = warp & 1, kq = (warp >> 1) & 3;
     if (warp == BD_THREADS / 32) {
         // ------------------------------------------------------------------ producer warp
         const uint64_t pol = l2_evict_first_policy();
-        long long row = r0 + lane;
+        long long row = r0 + (lane & (BD_RP - 1));
         if (row >= m) row = m - 1;                            // rows past the end: a valid row again, its results are dropped
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % BD_STAGES;
@@ -105,30 +109,41 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
             __syncwarp();
             if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((BD_RP + BD_B) * valid * 8));
             __syncwarp();
-            bulk_g2s_hint(dst + (size_t)lane * LD, A + row * n + cc0, (uint32_t)valid * 8u, &full[s], pol);
-            if (lane < BD_B) bulk_g2s(dst + (size_t)(BD_RP + lane) * LD, X + (size_t)lane * n + cc0, (uint32_t)valid * 8u, &full[s]);
+            if (lane < BD_RP) bulk_g2s_hint(dst + (size_t)lane * LD, A + row * n + cc0, (uint32_t)valid * 8u, &full[s], pol);
+            else if (lane < BD_RP + BD_B)
+                bulk_g2s(dst + (size_t)lane * LD, X + (size_t)(lane - BD_RP) * n + cc0, (uint32_t)valid * 8u, &full[s]);
         }
     } else {
-        // ------------------------------------------------------------------ consumer warps: tile (mt) x k-half (kh)
+        // ------------------------------------------------------------------ consumer warps: tile (mt) x k-quarter (kq)
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % BD_STAGES;
             mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
-            const double* at = ring + (size_t)s * STAGE + (size_t)(8 * mt + (lane >> 2)) * LD + kh * 64 + (lane & 3);
-            const double* xt = ring + (size_t)s * STAGE + (size_t)(BD_RP + (lane >> 2)) * LD + kh * 64 + (lane & 3);
+            const double* at = ring + (size_t)s * STAGE + (size_t)(8 * mt + (lane >> 2)) * LD + kq * 32 + (lane & 3);
+            const double* xt = ring + (size_t)s * STAGE + (size_t)(BD_RP + (lane >> 2)) * LD + kq * 32 + (lane & 3);
+            double af[8], xf[8];
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) dmma_m8n8k4(c0, c1, at[4 * kk], xt[4 * kk]);
+            for (int kk = 0; kk < 8; ++kk) { af[kk] = at[4 * kk]; xf[kk] = xt[4 * kk]; }     // all fragment loads first
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) dmma_m8n8k4(ca[kk & 1][0], ca[kk & 1][1], af[kk], xf[kk]);
             __syncwarp();
             if (lane == 0) bd_arrive(&empty[s]);
         }
+        c0 = ca[0][0] + ca[1][0];
+        c1 = ca[0][1] + ca[1][1];
     }
-    // ---- k-halves: warps 4..7 hand their tiles to warps 0..3 (fixed order: half 0 + half 1)
+    // ---- k-quarters: the warps of quarters 1..3 hand their tiles to the warps of quarter 0 (fixed order 0 + 1 + 2 + 3)
     const int row_l = 8 * mt + (lane >> 2), bcol = 2 * (lane & 3);
     const bool consumer = warp < BD_THREADS / 32;
-    if (consumer && kh == 1) { red[row_l * BD_B + bcol] = c0; red[row_l * BD_B + bcol + 1] = c1; }
+    if (consumer && kq > 0) {
+        red[((kq - 1) * BD_RP + row_l) * BD_B + bcol] = c0;
+        red[((kq - 1) * BD_RP + row_l) * BD_B + bcol + 1] = c1;
+    }
     __syncthreads();
     double lx0 = 0.0, lx1 = 0.0;
-    if (consumer && kh == 0) {
-        const double rr[2] = {c0 + red[row_l * BD_B + bcol], c1 + red[row_l * BD_B + bcol + 1]};
+    if (consumer && kq == 0) {
+        const double rr[2] = {((c0 + red[row_l * BD_B + bcol]) + red[(BD_RP + row_l) * BD_B + bcol]) + red[(2 * BD_RP + row_l) * BD_B + bcol],
+                              ((c1 + red[row_l * BD_B + bcol + 1]) + red[(BD_RP + row_l) * BD_B + bcol + 1]) +
+                                  red[(2 * BD_RP + row_l) * BD_B + bcol + 1]};
         const long long row = r0 + row_l;
         if (row < m) {
 #pragma unroll
@@ -152,16 +167,16 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
         }
     }
     __syncthreads();
-    if (consumer && kh == 0 && lane < 4) { red[BD_RP * BD_B + mt * BD_B + 2 * lane] = lx0; red[BD_RP * BD_B + mt * BD_B + 2 * lane + 1] = lx1; }
+    if (consumer && kq == 0 && lane < 4) { red[3 * BD_RP * BD_B + mt * BD_B + 2 * lane] = lx0; red[3 * BD_RP * BD_B + mt * BD_B + 2 * lane + 1] = lx1; }
     __syncthreads();
     if (tid < BD_B) {
-        const double* q = red + BD_RP * BD_B;
-        lxpart[(size_t)blockIdx.x * BD_B + tid] = ((q[tid] + q[BD_B + tid]) + q[2 * BD_B + tid]) + q[3 * BD_B + tid];
+        const double* q = red + 3 * BD_RP * BD_B;
+        lxpart[(size_t)blockIdx.x * BD_B + tid] = q[tid] + q[BD_B + tid];
     }
 }
 
 // ---- pass 2: G = A' W for the CTA's 128 columns ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(BD_THREADS + 32, 1)
+__global__ void __launch_bounds__(BD_THREADS + 32, 2)
     k_bd_atw(const double* __restrict__ A, long long m, long long n, long long ldm, const double* __restrict__ W,
              double* __restrict__ G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
     }
     __syncthreads();
 
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // [even / odd k-step][2]: the warp's 8-column group
     if (warp == BD_THREADS / 32) {
         const uint64_t pol = l2_evict_first_policy();
         for (int c = 0; c < nchunks; ++c) {
@@ -213,22 +228,21 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 1)
             mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
             const double* tile = ring + (size_t)s * STAGE;
             const double* wt = tile + (size_t)BD_RC * LDA + (size_t)(lane >> 2) * LDW + (lane & 3);
+            double wf[BD_RC / 4], af[BD_RC / 4];
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const double* at = tile + (size_t)(lane & 3) * LDA + 16 * warp + 8 * g + (lane >> 2);
-#pragma unroll
-                for (int kk = 0; kk < BD_RC / 4; ++kk) dmma_m8n8k4(acc[g][0], acc[g][1], at[(size_t)4 * kk * LDA], wt[4 * kk]);
+            for (int kk = 0; kk < BD_RC / 4; ++kk) {
+                wf[kk] = wt[4 * kk];
+                af[kk] = tile[(size_t)(4 * kk + (lane & 3)) * LDA + 8 * warp + (lane >> 2)];
             }
+#pragma unroll
+            for (int kk = 0; kk < BD_RC / 4; ++kk) dmma_m8n8k4(acc[kk & 1][0], acc[kk & 1][1], af[kk], wf[kk]);
             __syncwarp();
             if (lane == 0) bd_arrive(&empty[s]);
         }
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const long long col = c0 + 16 * warp + 8 * g + (lane >> 2);
-            if (col < n) {
-                G[(size_t)(2 * (lane & 3)) * n + col] = acc[g][0];
-                G[(size_t)(2 * (lane & 3) + 1) * n + col] = acc[g][1];
-            }
+        const long long col = c0 + 8 * warp + (lane >> 2);
+        if (col < n) {
+            G[(size_t)(2 * (lane & 3)) * n + col] = acc[0][0] + acc[1][0];
+            G[(size_t)(2 * (lane & 3) + 1) * n + col] = acc[0][1] + acc[1][1];
         }
     }
 }

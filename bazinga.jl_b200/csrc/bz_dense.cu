@@ -251,6 +251,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
                 a.st->next_op = a.st->after_g;
                 if (a.force_target < 0) bz_toc(a.st, 0);
             }
+            if (a.st->err_flag == 4) {   // a bounded wait of the speculative L step expired: stop, the host reports the error
+                a.st->next_op = OP_DONE;
+                a.st->inner_status = IST_MAXIT;
+            }
             __threadfence();
         }
     }

@@ -37,19 +37,28 @@ __device__ __forceinline__ void ls_post(unsigned long long* slot, unsigned long 
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(tag | (bits & 0xffffffffULL)),
                  "l"(tag | (bits >> 32)) : "memory");
 }
-__device__ __forceinline__ double ls_take(const unsigned long long* slot, unsigned long long tag) {
+// the wait for a sibling CTA is bounded (a device shared with another tenant may never make the whole grid resident):
+// after ~4 s the speculation is abandoned, err_flag = 4 stops the state machine and the host reports BZ_ERR_CUDA
+__device__ __forceinline__ double ls_take(BzState* st, const unsigned long long* slot, unsigned long long tag) {
     unsigned long long w0, w1;
-    do {
+    unsigned int spins = 0;
+    const unsigned long long t0 = bz_globaltimer();
+    for (;;) {
         asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
-    } while ((((w0 ^ tag) | (w1 ^ tag)) >> 32) != 0);
+        if ((((w0 ^ tag) | (w1 ^ tag)) >> 32) == 0) break;
+        if ((++spins & 1023u) == 0u && (bz_globaltimer() - t0 > 4000000000ULL || *(volatile int*)&st->err_flag == 4)) {
+            st->err_flag = 4;
+            return __longlong_as_double(0x7ff8000000000000LL);
+        }
+    }
     return __longlong_as_double((long long)((w0 & 0xffffffffULL) | (w1 << 32)));
 }
 
 // sum of K values per thread over the cs CTAs; the trees of cluster_sum (bz_lbfgs.cu): warp butterfly, eight warp sums
 // pairwise, CTA sums in rank order
 template <int K>
-__device__ inline void ls_sum(double (&v)[K], double* wpart, unsigned long long* xbuf, unsigned long long seq, int& round,
-                              int rank, int cs) {
+__device__ inline void ls_sum(BzState* st, double (&v)[K], double* wpart, unsigned long long* xbuf, unsigned long long seq,
+                              int& round, int rank, int cs) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = bz_warp_sum(v[k]);
@@ -71,7 +80,7 @@ __device__ inline void ls_sum(double (&v)[K], double* wpart, unsigned long long*
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double acc = 0.0;
-        for (int c = 0; c < cs; ++c) acc += ls_take(base + ((size_t)c * 2 + k) * 2, tag);
+        for (int c = 0; c < cs; ++c) acc += ls_take(st, base + ((size_t)c * 2 + k) * 2, tag);
         s[k] = acc;
     }
 #pragma unroll
@@ -121,7 +130,7 @@ __device__ inline void ls_body(BzState* st, const BzLSpec& ls, int rank, int cs,
             yv[k] = LS_OK(k) ? __dsub_rn(rv[k], v.res_prev[j]) : 0.0;
         }
         LS_FOR(k) { a[0] = __dadd_rn(a[0], __dmul_rn(sv[k], yv[k])); a[1] = __dadd_rn(a[1], __dmul_rn(yv[k], yv[k])); }
-        ls_sum<2>(a, wpart, ls.xbuf, seq, round, rank, cs);
+        ls_sum<2>(st, a, wpart, ls.xbuf, seq, round, rank, cs);
         if (a[0] > 0) {
             curridx += 1;
             if (curridx > M) curridx = 1;
@@ -168,7 +177,7 @@ __device__ inline void ls_body(BzState* st, const BzLSpec& ls, int rank, int cs,
         double na[EPT], nb[EPT];
         LS_FOR(e) { na[e] = 0.0; nb[e] = 0.0; }
         load_step(kk + 1, na, nb);
-        ls_sum<1>(a, wpart, ls.xbuf, seq, round, rank, cs);
+        ls_sum<1>(st, a, wpart, ls.xbuf, seq, round, rank, cs);
         const int i = hist_index(kk);
         if (kk < currmem) {
             const double alpha_i = __ddiv_rn(a[0], ys[i]);
@@ -190,7 +199,7 @@ __device__ inline void ls_body(BzState* st, const BzLSpec& ls, int rank, int cs,
         st->sp_currmem = currmem; st->sp_curridx = curridx; st->sp_H = H;
         st->sp_pair = pair_accepted;
         for (int i = 0; i < BZ_MAXMEM; ++i) { st->sp_ys[i] = ys[i]; st->sp_alphas[i] = al[i]; }
-        st->spec_ok = 1;
+        st->spec_ok = (*(volatile int*)&st->err_flag == 4) ? 0 : 1;
     }
 #undef LS_FOR
 #undef LS_J

@@ -11,6 +11,12 @@
  *
  * Threading: a bz_ctx is not thread-safe (the reference is single-threaded and mutates its oracle
  * structs, src/utilities/auglagfun.jl:11-26).  Use one ctx per host thread / per GPU.
+ *
+ * Device: the library expects to have the GPU to itself (one process per GPU).  Three kernels make CTAs of one launch
+ * wait for each other and are sized to be co-resident on an idle device: the grid-wide dense pass for nx > 16384, the
+ * speculative L step that rides on the dense pass, and the slab mode's cross-rank exchanges.  Every such wait is
+ * bounded (about 4 s): on a shared device a solve fails with BZ_ERR_CUDA / BZ_ERR_COMM instead of hanging, and the
+ * problem object must then be destroyed.
  */
 #ifndef BAZINGA_B200_H
 #define BAZINGA_B200_H
