@@ -353,7 +353,7 @@ def run_headline(env, args):
                 "traffic_source": "profiles/r1_dense_traffic.json (ncu --set full capture of the same kernel and shape; not re-measured in this run)",
                 "algorithmic_bytes_per_launch": bgrad, "launches_timed": dom_launches,
                 "avg_launch_us": (1e3 * dom_ms / dom_launches) if dom_launches else None,
-                "events_bracket_every_nth_launch": 8,
+                "events_bracket_every_nth_launch": 32,
                 "kernel_share_of_step": ((dom_ms / dom_launches) * grads / ms) if (ms > 0 and dom_launches) else None}
     # iteration-level roofline: bytes = N_grad * B_grad + N_it * 8n(4 mem + 17)  (SURVEY §8d), this rank's step
     it_bytes = grads * bgrad + its * algorithmic_bytes_per_iteration_vectors(n)
@@ -570,6 +570,13 @@ def leg_c3(env, args, shared):
             if world == 1:
                 entry["cpu_baseline"] = {"value": len(mine) / dt, "unit": "solves/s", "cores": os.cpu_count() or 1, "kind": "port",
                                          "sample": f"all {len(mine)} instances, oracle/tiny_oracle.c with OpenMP ({dt:.2f} s)"}
+        if rank == 0:      # the residual bound of a launch: its longest dependent chain = the longest-iterating instance run ALONE
+            mine, out, _ = keep["strong"]
+            worst = int(np.argmax(out["sub_iters"]))
+            bz.alps_batch(name, mine[worst:worst + 1], ctx=ctx)
+            alone = min(bz.alps_batch(name, mine[worst:worst + 1], ctx=ctx)["kernel_ms"] for _ in range(2))
+            entry["longest_instance_alone"] = {"inner_iterations": int(out["sub_iters"][worst]), "kernel_ms": alone,
+                                               "note": "one instance, one launch: the dependent chain no partitioning over GPUs can shorten"}
         leg["problems"][name] = entry
     leg["clocks"] = sampler.stop() if rank == 0 else None
     # secondary roofline: ~250 fp64 flop per inner iteration against the measured fp64 FMA issue peak
