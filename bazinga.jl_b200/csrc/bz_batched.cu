@@ -13,6 +13,7 @@
 
 #define TB_MAXMEM 8
 #define TB_THREADS 64
+#define TB_QUEUE_TIMEOUT_NS 20000000000ull   // 20 s without a survivor or the end-of-phase-1 flag: the persistent warps give up
 #define TB_HEAVY 10          // AL-gradients per inner iteration that make an instance a "heavy back-tracker"
 
 namespace {
@@ -628,6 +629,9 @@ __global__ void __launch_bounds__(TB_THREADS)
     if constexpr (WARP) {
         int idx = 0;
         if ((threadIdx.x & 31) == 0) {
+            // bounded wait: if phase 1 never reports (a failed launch, a device that cannot co-schedule the two kernels),
+            // the warp gives up after TB_QUEUE_TIMEOUT_NS, raises queue[3] and the host returns BZ_ERR_CUDA
+            unsigned long long t_start = 0;
             for (;;) {
                 const int tail = *(volatile int*)&queue[0], head = *(volatile int*)&queue[1];
                 if (head < tail) {
@@ -639,6 +643,10 @@ __global__ void __launch_bounds__(TB_THREADS)
                     continue;
                 }
                 __nanosleep(400);
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t_start == 0) t_start = now;
+                else if (now - t_start > TB_QUEUE_TIMEOUT_NS) { *(volatile int*)&queue[3] = 1; idx = -1; break; }
             }
             if (idx >= 0) while ((inst = *(volatile int*)&surv[idx]) < 0) __nanosleep(100);
         }
@@ -866,6 +874,8 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     BTRY(cudaMemcpyAsync(tot_it, dit, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaMemcpyAsync(status, dst, batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaMemcpyAsync(tot_inner_it, din, batch * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    int qwords[4] = {0, 0, 0, 0};
+    if (budget > 0) BTRY(cudaMemcpyAsync(qwords, dnsurv, sizeof(qwords), cudaMemcpyDeviceToHost, ctx->stream));
     BTRY(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -875,6 +885,8 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     if (ev_fork) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); }
     cleanup();
 #undef BTRY
+    if (qwords[3]) return bz_fail(ctx, BZ_ERR_CUDA, "bz_batch_solve: the warp-per-instance kernel timed out waiting for phase 1 "
+                                  "(the two kernels were not co-scheduled); set BZ_BATCH_CONCURRENT=0");
     return BZ_OK;
 }
 

@@ -468,7 +468,7 @@ struct bz_ctx {
     std::vector<void*> pinned_pool;                // parked pinned host blocks of BZ_PINNED_BLOCK bytes
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
-    int batch_concurrent = 0;   // run the warp-per-instance kernel beside phase 1 on a second stream (env BZ_BATCH_CONCURRENT=1)
+    int batch_concurrent = 1;   // run the warp-per-instance kernel beside phase 1 on a second stream (env BZ_BATCH_CONCURRENT=0: one after the other)
     int batch_budget = 1024;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
     int lspec = 1;              // dense problems (n <= 16384, f = Zero): the L step runs speculatively beside G(z) (env BZ_LSPEC=0: off)
