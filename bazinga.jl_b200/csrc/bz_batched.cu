@@ -14,6 +14,10 @@
 #define TB_MAXMEM 8
 #define TB_THREADS 64
 #define TB_QUEUE_TIMEOUT_NS 20000000000ull   // 20 s without a survivor or the end-of-phase-1 flag: the persistent warps give up
+#define TB_CKPT 24           // doubles per hand-over record (x, s, y, mu, inner_tol, nrp, counters)
+#ifndef TB_MINB
+#define TB_MINB 5            // CTAs per SM the thread-per-solve kernel is compiled for: 168 registers instead of 224, a few spills,
+#endif                       // 10 instead of 8 warps per SM beside the warp-per-instance kernel (either-or grid 21-24 -> 16-17 ms)
 #define TB_HEAVY 10          // AL-gradients per inner iteration that make an instance a "heavy back-tracker"
 
 namespace {
@@ -372,13 +376,14 @@ struct Lbfgs {
 // PANOCplus (Appendix A.2-A.5) on a variable of NV entries; returns k, solution in z
 // WARP = false: one thread runs the solve.  WARP = true: the 32 lanes of a warp run the SAME solve in lock-step (identical
 // registers), except inside the line search, where lane l evaluates the candidate the sequential loop would reach l
-// steps later (see line_search_warp).  budget > 0: give up (return -1) once the solve has used more than `budget`
-// AL-gradients -- phase 1 of the two-phase batch.
+// steps later (see line_search_warp).  budget > 0: give up (return -1) once THIS inner solve has used more than `budget`
+// AL-gradients at more than TB_HEAVY per iteration -- phase 1 of the two-phase batch.
 template <int KIND, int MM, int SLACK, bool WARP>
 __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, SLACK>::NV], const TbOpts& o, double tol,
-                               double (&z)[Al<KIND, SLACK>::NV], int budget, long long its_before) {
+                               double (&z)[Al<KIND, SLACK>::NV], int budget) {
     constexpr int NV = Al<KIND, SLACK>::NV;
     const double a = o.alpha;
+    const int ng0 = al.ngrad;
     double x[NV], grad_x[NV], grad_z[NV], tmpg[NV], y[NV], res[NV];
     double x_prev[NV], res_prev[NV], x_d[NV], z_curr[NV], d[NV];
 #pragma unroll
@@ -435,10 +440,12 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
         }
         if (isnan_) stopnorm = __longlong_as_double(0x7ff8000000000000LL);
         if (k >= o.sub_maxit || stopnorm <= tol) { al.gz = g_z; return k; }
-        // phase 1: a heavy back-tracker (more than TB_HEAVY AL-gradients per iteration so far) past its budget is left to
-        // the warp-per-instance kernel, where its line searches run across the lanes.  Instances that merely iterate
-        // long (few back-tracks) stay: one lone lane is the fastest place for them.
-        if (budget > 0 && al.ngrad > budget && (long long)al.ngrad > TB_HEAVY * (its_before + k)) return -1;
+        // phase 1: an inner solve that back-tracks heavily (more than TB_HEAVY AL-gradients per iteration so far) and is past
+        // its budget is left to the warp-per-instance kernel, where its line searches run across the lanes.  The test is
+        // local to this inner solve: the heavy solves of the demos come late (outer iteration 30 of 32 on the slowest
+        // either-or start), after thousands of cheap iterations that would hide them in a whole-solve average.  Solves that
+        // merely iterate long (few back-tracks) stay: one lone lane is the fastest place for them.
+        if (budget > 0 && al.ngrad - ng0 > budget && (long long)(al.ngrad - ng0) > TB_HEAVY * k) return -1;
 #pragma unroll
         for (int j = 0; j < NV; ++j) { x_prev[j] = x[j]; res_prev[j] = res[j]; }
         const double FBE_x = f_model<NV>(f_x, grad_x, res, aog) + g_z;
@@ -598,16 +605,28 @@ __device__ long long panocplus(Al<KIND, SLACK>& al, const double (&x0)[Al<KIND, 
 // Two-phase batch (the loop replaced is demo/mpvca.jl:241-281).  A launch lasts as long as its slowest
 // instance, and the slow instances are slow because every PANOC+ iteration exhausts its 20 line-search back-tracks
 // (40 dependent AL-gradients per iteration on one lone lane).  Phase 1 runs every instance on its own thread with a
-// budget of AL-gradient evaluations; an instance that exceeds it is appended to `surv` and abandoned.  Phase 2 re-runs the
-// survivors from scratch, one WARP each, with the line search evaluated speculatively across the lanes: the dependent
-// chain of an iteration shrinks from up to 41 gradients to 3, bit-identical results (same statements, same order).
+// budget of AL-gradient evaluations per inner solve; an instance whose inner solve exceeds it records the state at the top
+// of that outer iteration (TB_CKPT doubles), is appended to `surv` and abandoned.  Phase 2 resumes the survivors from that
+// record, one WARP each, with the line search evaluated speculatively across the lanes: the dependent chain of an iteration
+// shrinks from up to 41 gradients to 3, bit-identical results (same statements, same order; an outer iteration starts a
+// fresh PANOC+ solve, so nothing but the record crosses the hand-over).
+// Every thread of phase 1 reports here before it returns; the last one tells the warp-per-instance kernel that the queue gets
+// no more entries (queue[2]).  (A separate one-thread kernel behind phase 1 used to do this -- and could not be scheduled
+// when the persistent kernel's CTAs had taken every register of every SM: a dead-lock.)  The fence orders a thread's push
+// before its count, so whoever sees the flag sees every push.
+__device__ __forceinline__ void tb_phase1_exit(int* queue, long long total) {
+    __threadfence();
+    if (atomicAdd(&queue[5], 1) == (int)(total - 1)) *(volatile int*)&queue[2] = 1;
+}
+
 template <int KIND, int MM, int SLACK, bool WARP>
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, WARP ? 1 : TB_MINB)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
-                 double* __restrict__ nrps, int budget, int* surv, int* queue) {
-    // queue[0]: survivors pushed so far (slots reserved), queue[1]: next slot to pop, queue[2]: phase 1 has finished.
+                 double* __restrict__ nrps, int budget, int* surv, int* queue, double* ckpt) {
+    // queue[0]: survivors pushed so far (slots reserved), queue[1]: next slot to pop, queue[2]: phase 1 has finished,
+    // queue[3]: a persistent warp gave up waiting, queue[5]: threads of phase 1 that have returned.
     // surv[slot] is -1 until the pushing thread has stored the instance index.
     constexpr int NX = Prob<KIND>::NX;
     constexpr int NY = Prob<KIND>::NY;
@@ -622,7 +641,7 @@ __global__ void __launch_bounds__(TB_THREADS)
     if constexpr (!WARP) {
         const long long nwarps = (batch + 31) / 32;
         inst = (t & 31) * nwarps + (t >> 5);
-        if ((t >> 5) >= nwarps || inst >= batch) return;
+        if ((t >> 5) >= nwarps || inst >= batch) { tb_phase1_exit(queue, (long long)gridDim.x * blockDim.x); return; }
     }
     // WARP: a persistent warp of the concurrent phase-2 kernel; it pops survivors until phase 1 is over and the queue is dry
     for (;;) {
@@ -648,7 +667,7 @@ __global__ void __launch_bounds__(TB_THREADS)
                 if (t_start == 0) t_start = now;
                 else if (now - t_start > TB_QUEUE_TIMEOUT_NS) { *(volatile int*)&queue[3] = 1; idx = -1; break; }
             }
-            if (idx >= 0) while ((inst = *(volatile int*)&surv[idx]) < 0) __nanosleep(100);
+            if (idx >= 0) { while ((inst = *(volatile int*)&surv[idx]) < 0) __nanosleep(100); __threadfence(); }
         }
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx < 0) return;
@@ -657,14 +676,34 @@ __global__ void __launch_bounds__(TB_THREADS)
     Al<KIND, SLACK> al;
     al.ngrad = 0;
     double x[NX], cx[NY], s[NY];
+    double inner_tol = o.inner_tol;
+    int tot_it = 0;
+    bool have_old = false;
+    long long tot_inner = 0;
+    double nrp = __longlong_as_double(0x7ff8000000000000LL), nrp_old = nrp;
+    double objx = 0.0;
+    double dtmp[NX];
+    if constexpr (WARP) {
+        // resume at the top of the outer iteration phase 1 gave up in: everything the loop carries across iterations
+        // (x, s, y, mu, inner_tol, the previous violation, the counters) was recorded by the thread that pushed the instance
+        const double* ck = ckpt + (size_t)inst * TB_CKPT;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) x[j] = __ldcg(ck + j);
+#pragma unroll
+        for (int i = 0; i < NY; ++i) { s[i] = __ldcg(ck + 6 + i); al.y[i] = __ldcg(ck + 10 + i); al.mu[i] = __ldcg(ck + 14 + i); }
+        inner_tol = __ldcg(ck + 18);
+        nrp = __ldcg(ck + 19);
+        tot_it = (int)__ldcg(ck + 20);
+        tot_inner = (long long)__ldcg(ck + 21);
+        have_old = __ldcg(ck + 22) != 0.0;
+    } else {
     {   // alps.jl:37-45 / als.jl:38-44
         double x0[NX];
 #pragma unroll
         for (int j = 0; j < NX; ++j) x0[j] = x0s[inst * NX + j];
         al.gz = Prob<KIND>::prox(x0, BZ_EPS, x);
     }
-    double dtmp[NX];
-    double objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;
+    objx = Prob<KIND>::f_grad(x, dtmp) + al.gz;
     Prob<KIND>::c_eval(x, cx);
     Prob<KIND>::proj(cx, s);
 #pragma unroll
@@ -675,11 +714,8 @@ __global__ void __launch_bounds__(TB_THREADS)
         al.mu[i] = jmax(1e-8, (m != m) ? m : fmin(m, 1e8));
         al.y[i] = y0s[inst * NY + i];
     }
-    double inner_tol = o.inner_tol;
-    int tot_it = 0;
-    bool solved = false, tired = tot_it >= o.maxit, broken = objx != objx, have_old = false;
-    long long tot_inner = 0;
-    double nrp = __longlong_as_double(0x7ff8000000000000LL), nrp_old = nrp;
+    }
+    bool solved = false, tired = tot_it >= o.maxit, broken = objx != objx;
     while (!(solved || tired || broken)) {
         tot_it++;
 #pragma unroll
@@ -692,11 +728,24 @@ __global__ void __launch_bounds__(TB_THREADS)
 #pragma unroll
             for (int i = 0; i < NY; ++i) v0[NX + i] = s[i];       // xSlack = [x; s], als.jl:69-70
         }
-        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget, tot_inner);
+        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget);
         if (sub_it < 0) {                                         // a heavy back-tracker over the budget: the warp kernel takes it
+            // ... from the top of THIS outer iteration: x, s, mu, inner_tol and the counters have not moved since, y is
+            // the clamped y (clamping again changes nothing)
+            double* ck = ckpt + (size_t)inst * TB_CKPT;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) __stcg(ck + j, x[j]);
+#pragma unroll
+            for (int i = 0; i < NY; ++i) { __stcg(ck + 6 + i, s[i]); __stcg(ck + 10 + i, al.y[i]); __stcg(ck + 14 + i, al.mu[i]); }
+            __stcg(ck + 18, inner_tol);
+            __stcg(ck + 19, nrp);
+            __stcg(ck + 20, (double)(tot_it - 1));
+            __stcg(ck + 21, (double)tot_inner);
+            __stcg(ck + 22, have_old ? 1.0 : 0.0);
             const int slot = atomicAdd(&queue[0], 1);
             __threadfence();
             *(volatile int*)&surv[slot] = (int)inst;
+            tb_phase1_exit(queue, (long long)gridDim.x * blockDim.x);
             return;
         }
 #pragma unroll
@@ -746,11 +795,10 @@ __global__ void __launch_bounds__(TB_THREADS)
         statuses[inst] = solved ? 0 : tired ? 1 : broken ? 2 : 3;
         nrps[inst] = nrp;
     }
-    if constexpr (!WARP) return;
+    if constexpr (!WARP) { tb_phase1_exit(queue, (long long)gridDim.x * blockDim.x); return; }
     }   // for (;;): next survivor
 }
 
-__global__ void k_batch_phase1_done(int* queue) { *(volatile int*)&queue[2] = 1; }
 
 }  // namespace
 
@@ -783,7 +831,7 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     // one grow-only device arena per context, carved into the eight per-instance arrays: no cudaMalloc / cudaFree (and
     // their implicit synchronisations) on the second and later calls
     const size_t B = (size_t)batch;
-    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1) * sizeof(double) + B * sizeof(long long) + 3 * B * sizeof(int) + 128;
+    const size_t need = B * (2 * (size_t)nx + 2 * (size_t)ny + 1 + TB_CKPT) * sizeof(double) + B * sizeof(long long) + 3 * B * sizeof(int) + 128;
     auto cleanup = [&]() {};
 #define BTRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); \
         return bz_fail(ctx, BZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } } while (0)
@@ -799,7 +847,8 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     double* dx = dy0 + B * ny;
     double* dy = dx + B * nx;
     double* dnrp = dy + B * ny;
-    long long* din = reinterpret_cast<long long*>(dnrp + B);
+    double* dck = dnrp + B;        // hand-over records of the instances phase 1 gives up on (TB_CKPT doubles each)
+    long long* din = reinterpret_cast<long long*>(dck + B * TB_CKPT);
     int* dit = reinterpret_cast<int*>(din + B);
     int* dst = dit + B;
     int* dsurv = dst + B;          // survivors of phase 1 (instance indices, -1 = not stored yet), then the queue words
@@ -814,14 +863,16 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     BTRY(cudaEventCreate(&e1));
     const unsigned grid = (unsigned)((batch + TB_THREADS - 1) / TB_THREADS);
     cudaEventRecord(e0, ctx->stream);
-    // Two kernels run side by side.  The warp-per-instance kernel goes first, on a second stream: two CTAs per SM of
-    // persistent warps that pop survivors from the queue as phase 1 produces them (and leave half of every SM to phase 1).
+    // Two kernels run side by side.  Phase 1 goes first and takes the SMs; the warp-per-instance kernel follows on a second
+    // stream: its persistent warps move in as CTAs of phase 1 retire (the median solve is short, so that is early) and pop
+    // survivors from the queue as phase 1 produces them.  Phase 1 never waits for it, so nothing can dead-lock; launched the
+    // other way round, the persistent kernel held 45 % of every SM's registers from the start and pushed phase 1 into a
+    // third wave (either-or grid 27 ms instead of 17), and a phase-1 launch that had to grow the device's local-memory
+    // reservation waited for an idle device that never came.
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     const bool concurrent = budget > 0 && ctx->batch_concurrent;     // else: phase 2 after phase 1 on the same stream
-    if (budget > 0) {
-        BTRY(cudaMemsetAsync(dsurv, 0xff, B * sizeof(int), ctx->stream));
-        BTRY(cudaMemsetAsync(dnsurv, 0, 4 * sizeof(int), ctx->stream));
-    }
+    if (budget > 0) BTRY(cudaMemsetAsync(dsurv, 0xff, B * sizeof(int), ctx->stream));
+    BTRY(cudaMemsetAsync(dnsurv, 0, 16 * sizeof(int), ctx->stream));      // (words 8..15: scratch queue of the empty launches below)
     if (concurrent) {
         if (!ctx->stream2) BTRY(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
         BTRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -829,20 +880,28 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
         BTRY(cudaEventRecord(ev_fork, ctx->stream));
         BTRY(cudaStreamWaitEvent(ctx->stream2, ev_fork, 0));
     }
-    const unsigned grid2 = (unsigned)((concurrent ? 2 : 4) * ctx->num_sms);
+    const int p2ctas = ctx->batch_p2ctas > 0 ? ctx->batch_p2ctas : (concurrent ? 2 : 4);
+    const unsigned grid2 = (unsigned)(p2ctas * ctx->num_sms);
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
     // (lazy module loading: the first launch of a kernel may wait for running kernels to finish -- fatal when the running
     // kernel is the persistent one that waits for the kernel being loaded.  Both are loaded before either is launched.)
 #define TB_LAUNCH2(K, MMV, SL) do { \
-        if (concurrent) { cudaFuncAttributes fa__; \
-            cudaFuncGetAttributes(&fa__, k_batch_alps<K, MMV, SL, true>); cudaFuncGetAttributes(&fa__, k_batch_alps<K, MMV, SL, false>); \
-            cudaFuncGetAttributes(&fa__, k_batch_phase1_done); } \
-        if (concurrent) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); ctx->n_launches++; } \
-        k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv); \
+        if (concurrent) { const unsigned bit__ = 1u << ((K) * 4 + ((MMV) > 5 ? 2 : 0) + (SL)); \
+            if (!(ctx->batch_presized & bit__)) { \
+                /* once per kernel pair and context: an empty launch of each (no instances; a scratch queue that says */ \
+                /* "phase 1 is over").  It loads the modules and grows the device's local-memory reservation to the    */ \
+                /* larger stack frame now -- a launch that has to grow it waits for an idle device, and with the other  */ \
+                /* kernel of the pair already running and waiting for it that is a dead-lock.                         */ \
+                cudaMemsetAsync(dnsurv + 8, 1, 4 * sizeof(int), ctx->stream);   /* tail = head, "phase 1 is over" != 0 */ \
+                k_batch_alps<K, MMV, SL, false><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck); \
+                k_batch_alps<K, MMV, SL, true><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck); \
+                BTRY(cudaStreamSynchronize(ctx->stream)); \
+                ctx->batch_presized |= bit__; ctx->n_launches += 2; } } \
+        k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv, dck); \
+        if (concurrent) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck); ctx->n_launches++; } \
         if (budget > 0 && !concurrent) { \
-            k_batch_phase1_done<<<1, 1, 0, ctx->stream>>>(dnsurv); \
-            k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv); \
-            ctx->n_launches += 2; } \
+            k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck); \
+            ctx->n_launches++; } \
     } while (0)
 #define TB_LAUNCH(K, MMV) do { if (slack) TB_LAUNCH2(K, MMV, 1); else TB_LAUNCH2(K, MMV, 0); } while (0)
 #define TB_DISPATCH(K) do { if (o.mem <= 5) TB_LAUNCH(K, 5); else TB_LAUNCH(K, TB_MAXMEM); } while (0)
@@ -860,10 +919,8 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
 #undef TB_LAUNCH
 #undef TB_LAUNCH2
     if (concurrent) {
-        k_batch_phase1_done<<<1, 1, 0, ctx->stream>>>(dnsurv);          // after phase 1 (stream order): the queue gets no more entries
         cudaEventRecord(ev_join, ctx->stream2);
         cudaStreamWaitEvent(ctx->stream, ev_join, 0);
-        ctx->n_launches++;
     }
     cudaEventRecord(e1, ctx->stream);
     ctx->n_launches++;

@@ -469,7 +469,9 @@ struct bz_ctx {
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
     int batch_concurrent = 1;   // run the warp-per-instance kernel beside phase 1 on a second stream (env BZ_BATCH_CONCURRENT=0: one after the other)
-    int batch_budget = 1024;    // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
+    unsigned batch_presized = 0; // bz_batch_solve: kernel pairs whose modules / local-memory reservation are in place
+    int batch_p2ctas = 0;       // CTAs per SM of the warp-per-instance kernel (env BZ_BATCH_P2CTAS; 0 = 4)
+    int batch_budget = 400;     // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
     int lspec = 1;              // dense problems (n <= 16384, f = Zero): the L step runs speculatively beside G(z) (env BZ_LSPEC=0: off)
     int obstacle_rotate = 1;    // ... with buffer rotation in the cooperative L kernel (env BZ_OBSTACLE_ROTATE=0: copies)
