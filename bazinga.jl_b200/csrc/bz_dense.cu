@@ -126,7 +126,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DA_THREADS, 1)
             }
         }
     } else {
-    const double* __restrict__ xsrc = a.src[target];
+    // (a speculated L step that D has confirmed leaves the new x in the shadow buffer until the F step that follows this
+    // launch copies it into place, bz_lspec.cuh)
+    const double* __restrict__ xsrc = (a.x_shadow && a.force_target < 0 && target == TGT_X && __ldcg(&a.st->spec_commit))
+                                          ? a.x_shadow : a.src[target];
     const double* __restrict__ sslack = xsrc + a.n;   // als: the slack part of the stacked input
     if (!BULK)
         for (int r = 0; r < npre; ++r) issue_row(r, r);

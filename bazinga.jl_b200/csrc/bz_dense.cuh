@@ -37,6 +37,7 @@ struct BzDenseArgs {
     int slack;
     const double* y;       // m multipliers (slack mode only)
     int is_cpass;          // the constraint pass (not the LeastSquares pass): records its partial-row count in BzState::npc_c
+    const double* x_shadow; // problems that speculate the L step: where x + d waits while BzState::spec_commit is set (else null)
     BzLSpec ls;            // speculative L step riding on this launch (k_dense_algrad only; ls.enabled = 0: none)
     // grid-wide single-pass kernel (bz_grid.cu) only
     unsigned long long* D;     // exchange ring: GR_DRING x 160 x 2 words, then GR_DRING arrival counters

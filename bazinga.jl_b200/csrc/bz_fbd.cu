@@ -58,6 +58,25 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
     double* __restrict__ vgx = v.grad_x;
     double* __restrict__ vz = v.z;
     double* __restrict__ vres = v.res;
+    // A speculated L step that D confirmed (bz_lspec.cuh, bz_d_decide) is still to be copied into place: the new x waits
+    // in the shadow buffer (the dense pass before this kernel read it there), the candidate pair in the spare history
+    // slot.  Entry j is moved by the thread that then steps it, before any restrict-qualified access to the same arrays.
+    const bool commit = (mode >= MODE_INITFB) && force_mode < 0 && v.xs != nullptr && __ldcg(&st->spec_commit) != 0;
+    const int c_pair = commit ? __ldcg(&st->sp_pair) : 0;
+    const int c_idx = commit ? __ldcg(&st->curridx) : 0;      // (= sp_curridx: D has put the scalars in place)
+    auto commit_elem = [&](long long j) -> double {
+        const double xo = v.x[j], ro = v.res[j], zo = v.z[j], xn = __ldcg(v.xs + j);
+        double sj = 0.0, yj = 0.0;
+        if (c_pair) { sj = __ldcg(v.sM + (size_t)BZ_MAXMEM * n + j); yj = __ldcg(v.yM + (size_t)BZ_MAXMEM * n + j); }
+        v.x_prev[j] = xo;
+        v.res_prev[j] = ro;
+        v.x_d[j] = xn;
+        v.x[j] = xn;
+        v.z_curr[j] = zo;
+        if (c_pair) { v.sM[(size_t)(c_idx > 0 ? c_idx - 1 : 0) * n + j] = sj; v.yM[(size_t)(c_idx > 0 ? c_idx - 1 : 0) * n + j] = yj; }
+        asm volatile("" ::: "memory");
+        return xn;
+    };
     auto elem = [&](long long j, double gr) {
         if (mode == MODE_INIT0) {
             const double xj = vx[j];
@@ -67,7 +86,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
             const double df = gr - vgx[j];
             a[0] += df * df;
         } else {
-            const double xj = vx[j];
+            const double xj = commit ? commit_elem(j) : vx[j];
             if (fresh) vgx[j] = gr;
             const double y = xj - gamma * gr;
             const double z = (g.snx > 0 && j >= g.snx) ? bz_proj_elem(g.sdk, g.slo, g.shi, y, j - g.snx)   // als: proj_D on the slack part
@@ -162,6 +181,7 @@ __global__ void __launch_bounds__(BZ_VEC_THREADS, MINB)
         st->next_op = st->fused ? OP_X : OP_F;   // fused problems recompute grad_x inside X
     } else {
         bz_f_finish(st, g, gamma, fresh, s0, s1, s2, lx, fx);
+        st->spec_commit = 0;                 // (every CTA read it before it got here)
         st->grad_target = TGT_Z;
         st->after_g = OP_D;
         st->next_op = OP_G;

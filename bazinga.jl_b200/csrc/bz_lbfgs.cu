@@ -559,47 +559,6 @@ __global__ void __launch_bounds__(LC_THREADS)
     }
 
     const int M = __ldcg(&st->mem);
-    if (force_role < 0 && __ldcg(&st->spec_commit)) {
-        // ---- the step was computed speculatively beside G(z) (bz_lspec.cuh) and D confirmed its assumption: copy the
-        // shadow into place.  Same element -> thread mapping as below, no reductions.
-        const int pair = __ldcg(&st->sp_pair), sidx = __ldcg(&st->sp_curridx);
-        const double* sc = v.sM + (size_t)BZ_MAXMEM * n;
-        const double* yc = v.yM + (size_t)BZ_MAXMEM * n;
-        double* sm = v.sM + (size_t)(sidx > 0 ? sidx - 1 : 0) * n;
-        double* ym = v.yM + (size_t)(sidx > 0 ? sidx - 1 : 0) * n;
-        LC_FOR(k) {
-            const long long j = LC_J(k);
-            if (j < n) {
-                const double xj = v.x[j], rj = v.res[j], zj = v.z[j], xn = __ldcg(v.xs + j);
-                v.x_prev[j] = xj;
-                v.res_prev[j] = rj;
-                v.x_d[j] = xn;
-                v.x[j] = xn;
-                v.z_curr[j] = zj;
-                if (pair) { sm[j] = __ldcg(sc + j); ym[j] = __ldcg(yc + j); }
-            }
-        }
-        if (cr.rank == 0 && threadIdx.x == 0) {
-            const double gamma = st->gamma;
-            const double FBE_x =
-                (st->f_x - st->dot_gr + ((st->alpha / gamma) / 2) * st->res_nrm2sq) + st->g_z;
-            const double sigma = st->beta * (0.5 / gamma) * (1 - st->alpha);
-            st->FBE_x = FBE_x;
-            st->sigma = sigma;
-            st->thresh = FBE_x - sigma * st->res_nrm2sq + 10 * BZ_EPS * (1 + fabs(FBE_x));
-            st->tau = 1.0;
-            st->k_bt = 1;
-            st->currmem = st->sp_currmem; st->curridx = st->sp_curridx; st->H = st->sp_H;
-            for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = st->sp_ys[i]; st->alphas[i] = st->sp_alphas[i]; }
-            st->skip_update = 0;
-            st->spec_commit = 0;
-            st->grad_x_fresh = 1;
-            bz_goto_fb(st);
-            bz_toc(st, 1);
-            __threadfence();
-        }
-        return;
-    }
     int currmem = __ldcg(&st->currmem), curridx = __ldcg(&st->curridx);
     double H = __ldcg(&st->H);
     const int skip = __ldcg(&st->skip_update);

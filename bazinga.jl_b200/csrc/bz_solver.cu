@@ -541,6 +541,7 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         if (p->sharded) PTRY(bz_shard_alloc(ctx, &p->shard, n));
         // speculative L step beside G(z): plain alps on one GPU with the cluster kernels (n <= 16384) and f = Zero
         if (ctx->lspec && !p->c_wide && !p->c_grid && !p->sharded && !p->slack && d->f_kind == BZ_F_ZERO &&
+            d->g_kind != BZ_G_OBSTACLE_L1 && d->g_kind != BZ_G_OBSTACLE_L2 &&     // (their F step is not the elementwise one that commits)
             p->nv <= (long long)LS_MAXCS * LS_THREADS * 16) {
             int cs = 1;
             while (cs < LS_MAXCS && (long long)cs * LS_THREADS * 8 < p->nv) cs *= 2;     // the cluster size of k_lstep_cluster
@@ -721,6 +722,7 @@ static int launch_provider(bz_problem* p, int force_target, bool gz_slot = false
         a.D = p->gridD; a.gseq = p->gseq;
         a.slack = p->slack_active ? 1 : 0; a.y = p->y;
         a.is_cpass = 1;
+        a.x_shadow = p->lspec ? p->v.xs : nullptr;
         int nclus = p->c_clusters;
         if (gz_slot && p->lspec && force_target < 0) {       // the second provider launch of a cycle: G(z) + speculative L
             a.ls.enabled = 1; a.ls.dense_clusters = p->c_clusters_z; a.ls.cs = p->lspec_cs; a.ls.v = p->v; a.ls.xs = p->v.xs; a.ls.xbuf = p->lspec_buf;

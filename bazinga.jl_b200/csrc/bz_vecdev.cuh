@@ -241,10 +241,28 @@ __device__ __forceinline__ void bz_d_decide(BzState* st, double gamma, double f_
         if (st->iter >= st->maxit || stopn <= st->tol) {
             st->inner_status = (stopn <= st->tol) ? IST_CONVERGED : IST_MAXIT;
             st->next_op = OP_DONE;
+        } else if (spec && !cond) {
+            // The L step of the next iteration was computed beside this G(z) on exactly this verdict (bz_lspec.cuh): its
+            // scalars go into place here, the L kernel is skipped, G reads x + d from the shadow buffer and the F step
+            // behind it copies the vectors into place (spec_commit stays set until then).  (cond: the line search ran off
+            // its loop on a gamma-halving, which resets the history the speculation used -- the plain L kernel runs.)
+            const double gm = st->gamma;
+            const double FBE_x = (st->f_x - st->dot_gr + ((st->alpha / gm) / 2) * st->res_nrm2sq) + st->g_z;
+            const double sigma = st->beta * (0.5 / gm) * (1 - st->alpha);
+            st->FBE_x = FBE_x;
+            st->sigma = sigma;
+            st->thresh = FBE_x - sigma * st->res_nrm2sq + 10 * BZ_EPS * (1 + fabs(FBE_x));
+            st->tau = 1.0;
+            st->k_bt = 1;
+            st->currmem = st->sp_currmem; st->curridx = st->sp_curridx; st->H = st->sp_H;
+            for (int i = 0; i < BZ_MAXMEM; ++i) { st->ys[i] = st->sp_ys[i]; st->alphas[i] = st->sp_alphas[i]; }
+            st->skip_update = 0;
+            st->spec_commit = 1;
+            st->grad_x_fresh = 1;
+            bz_goto_fb(st);
         } else {
             st->l_role = LROLE_NEWITER;
             st->next_op = OP_L;
-            st->spec_commit = spec;                      // the speculation assumed exactly this verdict: L only commits it
         }
     }
 }
