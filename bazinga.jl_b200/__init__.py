@@ -14,6 +14,7 @@ from .oracles import (  # noqa: F401
     NormL1Nonneg, NormLpPowerBox, NormLpPowerNonneg, PairSet, Quadratic, SetEOR, SetMPVCA, SetP, SetXOR, SmoothCostObstacleL1, SmoothCostP,
     ConstraintP, Zero, ZeroSet,
 )
+from .matrixprox import NuclearNorm, Rank, SchattenNormLpPower, check_and_reshape_as_matrix  # noqa: F401
 from .results import DATA_COLUMNS, STATS_COLUMNS, demo_rows, demo_stats, write_demo_results  # noqa: F401
 from .solver import (  # noqa: F401
     BATCH_KINDS, Context, LBFGS, NoAcceleration, PANOCplus, Problem, SharedMatrixBatch, alps, als, alps_batch, als_batch,

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libbazinga_b200.so")
 
-BZ_ABI_VERSION = 4
+BZ_ABI_VERSION = 5
 
 # enums (include/bazinga_b200.h)
 F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBSTACLE_L1, F_OBSTACLE_L2 = range(8)
@@ -18,6 +18,7 @@ F_ZERO, F_LEAST_SQUARES, F_QUADRATIC, F_ROSENBROCK, F_SQDIST2, F_LINEAR2, F_OBST
 C_IDENTITY, C_DENSE_AFFINE, C_ROSENBROCK, C_EITHEROR, C_MPVCA, C_OBSTACLE, C_OBSTACLE_RED = range(7)
 D_ZERO, D_FREE, D_BOX, D_EITHEROR, D_XOR, D_VC, D_CC, D_PORTFOLIO = range(8)
 ROW_MAJOR, COL_MAJOR = 0, 1
+MATPROX_RANK, MATPROX_NUCLEAR, MATPROX_SCHATTEN_LP = range(3)
 
 BZ_OK, BZ_ERR_ARG, BZ_ERR_CUDA, BZ_ERR_UNSUPPORTED, BZ_ERR_COMM, BZ_ERR_NONPOSITIVE_MU = 0, -1, -2, -3, -4, -5
 STATUS_SYMBOLS = ("first_order", "max_iter", "exception", "unknown")   # alps.jl:105-113
@@ -109,6 +110,7 @@ SYMBOLS = {
     "bz_batch_solve_als": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp, C.POINTER(Options), _vp, _vp, _vp,
                                      _vp, _vp, _vp, _dp]),
     "bz_fp64_fma_peak": (C.c_int, [_vp, _dp]),
+    "bz_prox_matrix": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "bz_bdense_create": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int32, C.c_int32, C.c_uint64, C.POINTER(_vp)]),
     "bz_bdense_destroy": (C.c_int, [_vp]),
     "bz_bdense_auglag_grad": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_int32, C.c_double, C.c_double, _vp, _vp, _vp,

@@ -232,4 +232,20 @@ function solve_batch(problem::String, X0::Matrix{Float64}; solver::Symbol = :alp
     return (x = X, y = Y, iters = its, sub_iters = inner, is_solved = status .== 0, norm_res_prim = nrp, kernel_ms = ms[])
 end
 
+# ---- matrix prox operators (src/proxoperators/rank.jl, nuclearNorm.jl, schattenNormLp.jl) ---------------------------
+# `prox!(Y, f, X, gamma)` for f::Bazinga.Rank / NuclearNorm / SchattenNormLpPower on the device (bz_prox_matrix: one-sided
+# Jacobi instead of LAPACK's svd).  A Julia Matrix is column-major, which is the layout the entry point takes.
+matprox_params(f::Bazinga.Rank) = (Cint(0), Float64(f.lambda), 0.5)
+matprox_params(f::Bazinga.NuclearNorm) = (Cint(1), Float64(f.lambda), 0.5)
+matprox_params(f::Bazinga.SchattenNormLpPower) = (Cint(2), Float64(f.alpha), Float64(f.p))
+function prox_matrix!(Y::Matrix{Float64}, f, X::Matrix{Float64}, gamma::Real)
+    kind, lambda, p = matprox_params(f)
+    ctx = context(); gz = Ref{Float64}(0.0)
+    check(ccall((:bz_prox_matrix, lib), Cint,
+                (Ptr{Cvoid}, Cint, Float64, Float64, Float64, Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64},
+                 Ptr{Float64}, Ptr{Int32}),
+                ctx.handle, kind, lambda, p, Float64(gamma), size(X, 1), size(X, 2), 1, X, Y, gz, C_NULL, C_NULL), ctx.handle)
+    return gz[]
+end
+
 end # module

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BZ_ABI_VERSION 4
+#define BZ_ABI_VERSION 5
 #define BZ_LBFGS_MAX_MEMORY 16
 
 typedef struct bz_ctx bz_ctx;
@@ -300,6 +300,20 @@ int bz_bdense_destroy(bz_bdense* h);
 int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* X, const double* b, const double* mu, const double* y,
                           int32_t d_kind, double d_lo, double d_hi, double* dlx, double* lx, double* cx, double* yupd,
                           int32_t reps, double* us_per_call);
+
+/* ---- matrix prox operators: src/proxoperators/rank.jl:28-33 `prox!(Y, f::Rank, X, gamma)`,
+ * nuclearNorm.jl:29-34 `prox!(Y, f::NuclearNorm, X, gamma)`, schattenNormLp.jl:36-42 `prox!(Y, f::SchattenNormLpPower, X,
+ * gamma)` (with solve_lp_quasi_norm_subproblem, :60-97).  The reference factorises with LAPACK (`svd(X)`); here a one-sided
+ * Jacobi iteration, one CTA per matrix of the batch (csrc/bz_matprox.cu).
+ *   X, Y    batch matrices of rows x cols doubles each, columns contiguous (Julia's layout, and what
+ *           check_and_reshape_as_matrix makes of a vector, rank.jl:36-44); rows, cols in 1..64
+ *   lambda  Rank / NuclearNorm: lambda >= 0;  Schatten: alpha >= 0 and 0 < p < 1 (the reference's constructor errors)
+ *   gz      batch values: what the reference's prox! returns (lambda*count, lambda*sum, alpha*sum sigma^p of the result)
+ *   sigma   (may be NULL) batch x cols: singular values of every X, descending, zeros beyond min(rows, cols)
+ *   sweeps  (may be NULL) batch: Jacobi sweeps used */
+typedef enum { BZ_MATPROX_RANK = 0, BZ_MATPROX_NUCLEAR = 1, BZ_MATPROX_SCHATTEN_LP = 2 } bz_matprox_kind;
+int bz_prox_matrix(bz_ctx* ctx, int kind, double lambda, double p, double gamma, int rows, int cols, int64_t batch,
+                   const double* X, double* Y, double* gz, double* sigma, int32_t* sweeps);
 
 /* Measurement aid for the batched path (not HBM-bound): the device's fp64 FMA issue peak in TFLOP/s, from a
  * microbenchmark of independent dependent-FMA chains. */

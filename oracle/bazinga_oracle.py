@@ -372,6 +372,97 @@ class GNormLpNonneg:
         return self.alpha * float(np.sum(z**self.p))
 
 
+def _schatten_subproblem(x, p, a, gamma):
+    """src/proxoperators/schattenNormLp.jl:60-97 solve_lp_quasi_norm_subproblem: the scalar problem of normLpBox.jl without
+    the upper bound, tolerance 1e-14, perturbation 0.1."""
+    alpha = a * gamma
+    if x <= 0:
+        return 0.0
+    zbar = (1 / (alpha * p * (1 - p))) ** (1 / (p - 2))
+    psi_zbar = zbar + alpha * p * zbar ** (p - 1)
+    if psi_zbar >= x:
+        return 0.0
+    z = zbar + 0.1
+    it = 0
+    while it < 1000:
+        dphi = z - x + alpha * p * z ** (p - 1)
+        if abs(dphi) <= 1e-14:
+            break
+        it += 1
+        ddphi = 1 + alpha * p * (p - 1) * z ** (p - 2)
+        z -= dphi / ddphi
+    phi_0 = 0.5 * x**2
+    phi_z = 0.5 * (z - x) ** 2 + alpha * z**p
+    return 0.0 if phi_0 <= phi_z else z
+
+
+def check_and_reshape_as_matrix(x):
+    """src/proxoperators/rank.jl:36-44 (column-major reshape of a vector of n^2 entries)"""
+    x = np.asarray(x, dtype=np.float64)
+    n = int(round(np.sqrt(x.size)))
+    if n * n != x.size:
+        raise ValueError("do not know how to reshape passed vector x")
+    return x.reshape((n, n), order="F")
+
+
+class GRank:
+    """src/proxoperators/rank.jl:11-33 (LAPACK through numpy.linalg.svd, as Julia's `svd`)."""
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        self.lam = float(lam)
+
+    def __call__(self, X):
+        return self.lam * int(np.linalg.matrix_rank(np.asarray(X, dtype=np.float64)))   # rank.jl:24-26
+
+    def prox(self, Y, X, gamma):
+        U, S, Vt = np.linalg.svd(X, full_matrices=False)          # rank.jl:29
+        over = S > np.sqrt(2 * gamma * self.lam)                  # :30
+        Y[...] = U @ (np.diag(S * over) @ Vt)                     # :31
+        return self.lam * float(np.sum(over))                     # :32
+
+
+class GNuclearNorm:
+    """src/proxoperators/nuclearNorm.jl:11-34."""
+
+    def __init__(self, lam=1.0):
+        if lam < 0:
+            raise ValueError("parameter λ must be nonnegative")
+        self.lam = float(lam)
+
+    def __call__(self, X):
+        return self.lam * float(np.sum(np.linalg.svd(X, compute_uv=False)))   # nuclearNorm.jl:24-27
+
+    def prox(self, Y, X, gamma):
+        U, S, Vt = np.linalg.svd(X, full_matrices=False)          # nuclearNorm.jl:30
+        S = np.maximum(0.0, S - self.lam * gamma)                 # :31
+        Y[...] = U @ (np.diag(S) @ Vt)                            # :32
+        return self.lam * float(np.sum(S))                        # :33
+
+
+class GSchattenNormLpPower:
+    """src/proxoperators/schattenNormLp.jl:14-42."""
+
+    def __init__(self, p, alpha=1.0):
+        if p <= 0:
+            raise ValueError("p must be positive")
+        if p >= 1:
+            raise ValueError("p must be smaller than one")
+        if alpha < 0:
+            raise ValueError("alpha must be nonnegative")
+        self.p, self.alpha = float(p), float(alpha)
+
+    def __call__(self, X):
+        return self.alpha * float(np.sum(np.linalg.svd(X, compute_uv=False) ** self.p))   # :32-34
+
+    def prox(self, Y, X, gamma):
+        U, S, Vt = np.linalg.svd(X, full_matrices=False)          # schattenNormLp.jl:37-38
+        S = np.array([_schatten_subproblem(float(v), self.p, self.alpha, gamma) for v in S])   # :39
+        Y[...] = U @ (np.diag(S) @ Vt)                            # :40
+        return self.alpha * float(np.sum(S**self.p))              # :41
+
+
 class GRosenbrock:
     """demo/rosenbrock.jl:55-64: soft threshold on x[1] only."""
 

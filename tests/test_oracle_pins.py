@@ -313,3 +313,31 @@ def test_golden_fixtures_widened_rows_frozen():
     assert np.array_equal(np.array(go["prox"]), np.array(no["prox"]))
     assert np.max(np.abs(np.array(gold["lp_prox"]["z"]) - np.array(now["lp_prox"]["z"]))) <= 1e-12
     assert abs(gold["lp_prox"]["g"] - now["lp_prox"]["g"]) <= 1e-12
+
+
+def test_matrix_prox_restatement_properties():
+    """rank.jl / nuclearNorm.jl / schattenNormLp.jl restated on numpy's LAPACK svd: closed forms on diagonal input, the
+    prox minimises lambda*g(Y) + ||Y - X||^2 / (2 gamma) against random competitors, and the reference's constructor errors."""
+    import pytest
+    rng = np.random.default_rng(11)
+    d = np.array([3.0, 1.0, 0.2])
+    Y = np.empty((3, 3))
+    assert bo.GNuclearNorm(0.5).prox(Y, np.diag(d), 1.0) == 1.5 and np.allclose(np.diag(Y), [2.5, 0.5, 0.0])
+    assert bo.GRank(0.5).prox(Y, np.diag(d), 1.0) == 0.5 and np.allclose(np.diag(Y), [3.0, 0.0, 0.0])   # strict > at the tie
+    assert bo.GRank(2.0)(np.diag(d)) == 6.0
+    X = rng.standard_normal((6, 6))
+    for g in (bo.GNuclearNorm(0.7), bo.GRank(0.7), bo.GSchattenNormLpPower(0.5, 0.8)):
+        gamma = 0.4
+        Y = np.empty_like(X)
+        gy = g.prox(Y, X, gamma)
+        # (a singular value the prox set to zero comes back from svd(Y) as ~1e-16, and its square root is 1e-8)
+        assert abs(gy - g(Y)) <= 1e-6 * max(1.0, abs(gy))
+        best = gy + np.sum((Y - X) ** 2) / (2 * gamma)
+        for _ in range(200):
+            Z = Y + 0.05 * rng.standard_normal(X.shape)
+            assert g(Z) + np.sum((Z - X) ** 2) / (2 * gamma) >= best - 1e-9
+    for bad in (lambda: bo.GRank(-1.0), lambda: bo.GNuclearNorm(-1.0), lambda: bo.GSchattenNormLpPower(0.0),
+                lambda: bo.GSchattenNormLpPower(1.0), lambda: bo.GSchattenNormLpPower(0.5, -1.0),
+                lambda: bo.check_and_reshape_as_matrix(np.zeros(35))):
+        with pytest.raises(ValueError):
+            bad()
