@@ -457,7 +457,8 @@ struct bz_ctx {
     size_t batch_arena_bytes = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     cudaEvent_t solve_ev0 = nullptr, solve_ev1 = nullptr;   // bz_result.device_ms
-    int prof_stride = 32;       // bracket every n-th dominant-kernel launch with CUDA events (an event between two kernels costs their PDL overlap)
+    int prof_stride = 31;       // bracket every n-th dominant-kernel launch with CUDA events (an event between two kernels costs their PDL
+                                // overlap); odd, so that the two launches of an iteration -- G(x), G(z) beside the speculative L -- are sampled alike
     int force_wide = 0;         // testing: use the two-pass wide dense path for every shape (env BZ_FORCE_WIDE)
     // Device-memory cache of the context: bz_problem_destroy parks its blocks here and the next bz_problem_create of the
     // same shapes takes them back, so a create / solve / destroy cycle (what one `alps(f, g, c, D, x0, y0)` call is) pays

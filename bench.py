@@ -353,7 +353,8 @@ def run_headline(env, args):
                 "traffic_source": "profiles/r1_dense_traffic.json (ncu --set full capture of the same kernel and shape; not re-measured in this run)",
                 "algorithmic_bytes_per_launch": bgrad, "launches_timed": dom_launches,
                 "avg_launch_us": (1e3 * dom_ms / dom_launches) if dom_launches else None,
-                "events_bracket_every_nth_launch": 32,
+                "events_bracket_every_nth_launch": 31,
+                "launches_sampled": "every 31st launch of the kernel: G(x) on all row clusters and G(z) on two clusters fewer beside the speculative L step alternate, so both are sampled alike",
                 "kernel_share_of_step": ((dom_ms / dom_launches) * grads / ms) if (ms > 0 and dom_launches) else None}
     # iteration-level roofline: bytes = N_grad * B_grad + N_it * 8n(4 mem + 17)  (SURVEY §8d), this rank's step
     it_bytes = grads * bgrad + its * algorithmic_bytes_per_iteration_vectors(n)
