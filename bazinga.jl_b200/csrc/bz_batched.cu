@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(TB_THREADS, WARP ? 1 : TB_MINB)
     k_batch_alps(long long batch, const double* __restrict__ x0s, const double* __restrict__ y0s,
                  TbOpts o, double* __restrict__ xs, double* __restrict__ ys, int* __restrict__ tot_its,
                  long long* __restrict__ tot_inners, int* __restrict__ statuses,
-                 double* __restrict__ nrps, int budget, int* surv, int* queue, double* ckpt) {
+                 double* __restrict__ nrps, int budget, int* surv, int* queue, double* ckpt, int drain) {
     // queue[0]: survivors pushed so far (slots reserved), queue[1]: next slot to pop, queue[2]: phase 1 has finished,
     // queue[3]: a persistent warp gave up waiting, queue[5]: threads of phase 1 that have returned.
     // surv[slot] is -1 until the pushing thread has stored the instance index.
@@ -728,7 +728,18 @@ __global__ void __launch_bounds__(TB_THREADS, WARP ? 1 : TB_MINB)
 #pragma unroll
             for (int i = 0; i < NY; ++i) v0[NX + i] = s[i];       // xSlack = [x; s], als.jl:69-70
         }
-        const long long sub_it = panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget);
+        // End game of phase 1: once no more than `drain` of its threads are still at work (the persistent kernel has that many
+        // warps, nearly all idle by then), a solve moves to a warp of its own at its next outer iteration.  The long solves
+        // that are left share warps with each other and run one after the other wherever they disagree; alone they run at
+        // the speed of their dependent chain (the 200 longest either-or starts: 13.8 ms together, 9.6 ms for the slowest alone).
+        bool move = false;
+        if constexpr (!WARP) {
+            if (budget > 0 && drain > 0 && tot_it > 1) {
+                const long long total = (long long)gridDim.x * blockDim.x;
+                move = total - (long long)*(volatile int*)&queue[5] <= (long long)drain;
+            }
+        }
+        const long long sub_it = move ? -1 : panocplus<KIND, MM, SLACK, WARP>(al, v0, o, inner_tol, z, WARP ? 0 : budget);
         if (sub_it < 0) {                                         // a heavy back-tracker over the budget: the warp kernel takes it
             // ... from the top of THIS outer iteration: x, s, mu, inner_tol and the counters have not moved since, y is
             // the clamped y (clamping again changes nothing)
@@ -882,6 +893,8 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
     }
     const int p2ctas = ctx->batch_p2ctas > 0 ? ctx->batch_p2ctas : (concurrent ? 2 : 4);
     const unsigned grid2 = (unsigned)(p2ctas * ctx->num_sms);
+    // phase 1 hands its last solves to the persistent warps (one each) once fewer of its threads are left than there are such warps
+    const int drain = (concurrent && ctx->batch_drain != 0) ? (ctx->batch_drain > 0 ? ctx->batch_drain : (int)(grid2 * (TB_THREADS / 32))) : 0;
     // L-BFGS history is a register-resident shift register sized at compile time: 5 (the demos') or 8
     // (lazy module loading: the first launch of a kernel may wait for running kernels to finish -- fatal when the running
     // kernel is the persistent one that waits for the kernel being loaded.  Both are loaded before either is launched.)
@@ -893,14 +906,14 @@ static int batch_solve(bz_ctx* ctx, int slack, int kind, int64_t batch, const do
                 /* larger stack frame now -- a launch that has to grow it waits for an idle device, and with the other  */ \
                 /* kernel of the pair already running and waiting for it that is a dead-lock.                         */ \
                 cudaMemsetAsync(dnsurv + 8, 1, 4 * sizeof(int), ctx->stream);   /* tail = head, "phase 1 is over" != 0 */ \
-                k_batch_alps<K, MMV, SL, false><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck); \
-                k_batch_alps<K, MMV, SL, true><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck); \
+                k_batch_alps<K, MMV, SL, false><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck, 0); \
+                k_batch_alps<K, MMV, SL, true><<<1, TB_THREADS, 0, ctx->stream>>>(0, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv + 8, dck, 0); \
                 BTRY(cudaStreamSynchronize(ctx->stream)); \
                 ctx->batch_presized |= bit__; ctx->n_launches += 2; } } \
-        k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv, dck); \
-        if (concurrent) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck); ctx->n_launches++; } \
+        k_batch_alps<K, MMV, SL, false><<<grid, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, budget, dsurv, dnsurv, dck, drain); \
+        if (concurrent) { k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream2>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck, 0); ctx->n_launches++; } \
         if (budget > 0 && !concurrent) { \
-            k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck); \
+            k_batch_alps<K, MMV, SL, true><<<grid2, TB_THREADS, 0, ctx->stream>>>(batch, dx0, dy0, o, dx, dy, dit, din, dst, dnrp, 0, dsurv, dnsurv, dck, 0); \
             ctx->n_launches++; } \
     } while (0)
 #define TB_LAUNCH(K, MMV) do { if (slack) TB_LAUNCH2(K, MMV, 1); else TB_LAUNCH2(K, MMV, 0); } while (0)

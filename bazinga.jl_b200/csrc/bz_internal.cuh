@@ -470,6 +470,7 @@ struct bz_ctx {
     void* xpose_buf = nullptr;  // grow-only staging buffer for column-major (Julia) matrix uploads
     size_t xpose_bytes = 0;
     int batch_concurrent = 1;   // run the warp-per-instance kernel beside phase 1 on a second stream (env BZ_BATCH_CONCURRENT=0: one after the other)
+    int batch_drain = -1;       // phase-1 threads left at which the remaining solves move to persistent warps (env BZ_BATCH_DRAIN; -1 = as many as there are such warps, 0 = never)
     unsigned batch_presized = 0; // bz_batch_solve: kernel pairs whose modules / local-memory reservation are in place
     int batch_p2ctas = 0;       // CTAs per SM of the warp-per-instance kernel (env BZ_BATCH_P2CTAS; 0 = 4)
     int batch_budget = 400;     // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance

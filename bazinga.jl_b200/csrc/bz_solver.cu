@@ -169,6 +169,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_BATCH_BUDGET")) ctx->batch_budget = atoi(e);
     if (const char* e = getenv("BZ_BATCH_CONCURRENT")) ctx->batch_concurrent = atoi(e);
     if (const char* e = getenv("BZ_BATCH_P2CTAS")) ctx->batch_p2ctas = atoi(e);
+    if (const char* e = getenv("BZ_BATCH_DRAIN")) ctx->batch_drain = atoi(e);
     if (const char* e = getenv("BZ_LSPEC")) ctx->lspec = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_ROTATE")) ctx->obstacle_rotate = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);

@@ -1,4 +1,4 @@
-# phase-2 grid size / concurrency sweep of the batched launch (65,536-start demo grids and the tail instances alone)
-for c in 1 0; do for p in 1 2 4; do
-  VARIANT="conc$c p2ctas$p" BZ_BATCH_CONCURRENT=$c BZ_BATCH_P2CTAS=$p python scripts/c3_quick.py
+# end-game sweep of the batched launch: phase-1 threads left at which the remaining solves move to persistent warps
+for d in 0 -1 200 1200 2400 4800; do for p in 2 4; do
+  VARIANT="drain$d p2ctas$p" BZ_BATCH_DRAIN=$d BZ_BATCH_P2CTAS=$p python scripts/c3_quick.py
 done; done
