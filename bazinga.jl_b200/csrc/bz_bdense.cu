@@ -30,11 +30,16 @@
 #define BD_STAGES 4
 #define BD_RP 16          // pass 1: rows per CTA (two 8-row tiles; 4 x 25 KB of ring -> two CTAs per SM, 256 CTAs at m = 4096)
 #define BD_KC 128         // pass 1: columns per chunk
-#define BD_CP 64          // pass 2: columns per CTA (eight 8-column groups; two CTAs per SM, 256 CTAs at n = 16384)
+#ifndef BD_CP
+#define BD_CP 64          // pass 2: columns per CTA (eight 8-column groups; two CTAs per SM, 256 CTAs at n = 16384).  -DBD_CP=128 (sixteen
+#endif                    // groups, one CTA per SM, six stages, 1 KB row pieces) was measured: 292 us per batched gradient against 291
+#define BD2_THREADS (BD_CP * 4)
+#define BD2_MINB (BD_CP > 64 ? 1 : 2)
+#define BD2_STAGES (BD_CP > 64 ? 6 : 4)
 #define BD_RC 32          // pass 2: rows per chunk
 #define BD_PAD 4
 #define BD_SMEM1 (BD_STAGES * ((BD_RP + BD_B) * (BD_KC + BD_PAD)) * 8 + 64 + (3 * BD_RP * BD_B + 2 * BD_B) * 8)   /* ring, 8 barriers, reduction scratch */
-#define BD_SMEM2 (BD_STAGES * (BD_RC * (BD_CP + BD_PAD) + BD_B * (BD_RC + BD_PAD)) * 8 + 64)
+#define BD_SMEM2 (BD2_STAGES * (BD_RC * (BD_CP + BD_PAD) + BD_B * (BD_RC + BD_PAD)) * 8 + 64)
 
 struct bz_bdense {
     bz_ctx* ctx;
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 2)
 }
 
 // ---- pass 2: G = A' W for the CTA's 128 columns ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(BD_THREADS + 32, 2)
+__global__ void __launch_bounds__(BD2_THREADS + 32, BD2_MINB)
     k_bd_atw(const double* __restrict__ A, long long m, long long n, long long ldm, const double* __restrict__ W,
              double* __restrict__ G) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -184,26 +189,26 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 2)
     constexpr int LDW = BD_RC + BD_PAD;                      // 36 = 4 (mod 16)
     constexpr int STAGE = BD_RC * LDA + BD_B * LDW;
     double* ring = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD_STAGES * STAGE);
-    uint64_t* empty = full + BD_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + BD2_STAGES * STAGE);
+    uint64_t* empty = full + BD2_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c0 = (long long)blockIdx.x * BD_CP;
     const int cvalid = (int)((n - c0) < BD_CP ? (n - c0) : BD_CP);
     const int nchunks = (int)((m + BD_RC - 1) / BD_RC);
 
-    for (int i = tid; i < BD_STAGES * STAGE; i += blockDim.x) ring[i] = 0.0;
+    for (int i = tid; i < BD2_STAGES * STAGE; i += blockDim.x) ring[i] = 0.0;
     if (tid == 0) {
-        for (int s = 0; s < BD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BD_THREADS / 32); }
+        for (int s = 0; s < BD2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BD2_THREADS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};   // [even / odd k-step][2]: the warp's 8-column group
-    if (warp == BD_THREADS / 32) {
+    if (warp == BD2_THREADS / 32) {
         const uint64_t pol = l2_evict_first_policy();
         for (int c = 0; c < nchunks; ++c) {
-            const int s = c % BD_STAGES;
-            if (c >= BD_STAGES) mbar_wait(&empty[s], (uint32_t)(((c / BD_STAGES) - 1) & 1));
+            const int s = c % BD2_STAGES;
+            if (c >= BD2_STAGES) mbar_wait(&empty[s], (uint32_t)(((c / BD2_STAGES) - 1) & 1));
             const long long rr0 = (long long)c * BD_RC;
             const int rvalid = (int)((m - rr0) < BD_RC ? (m - rr0) : BD_RC);
             const int rcopy = (rvalid + 1) & ~1;              // whole 16-byte units: W rows are padded to ldm (the pad entry is zero)
@@ -224,8 +229,8 @@ __global__ void __launch_bounds__(BD_THREADS + 32, 2)
         }
     } else {
         for (int c = 0; c < nchunks; ++c) {
-            const int s = c % BD_STAGES;
-            mbar_wait(&full[s], (uint32_t)((c / BD_STAGES) & 1));
+            const int s = c % BD2_STAGES;
+            mbar_wait(&full[s], (uint32_t)((c / BD2_STAGES) & 1));
             const double* tile = ring + (size_t)s * STAGE;
             const double* wt = tile + (size_t)BD_RC * LDA + (size_t)(lane >> 2) * LDW + (lane & 3);
             double wf[BD_RC / 4], af[BD_RC / 4];
@@ -317,7 +322,7 @@ extern "C" int bz_bdense_auglag_grad(bz_bdense* h, int32_t batch, const double* 
         if (r == 1 || reps == 1) cudaEventRecord(e0, ctx->stream);
         k_bd_ax<<<h->ctas1, BD_THREADS + 32, BD_SMEM1, ctx->stream>>>(h->A, m, n, ldm, h->X, h->bv, h->mu, h->y, d_kind, d_lo, d_hi,
                                                                       h->cx, h->yupd, h->W, h->lxpart);
-        k_bd_atw<<<h->ctas2, BD_THREADS + 32, BD_SMEM2, ctx->stream>>>(h->A, m, n, ldm, h->W, h->G);
+        k_bd_atw<<<h->ctas2, BD2_THREADS + 32, BD_SMEM2, ctx->stream>>>(h->A, m, n, ldm, h->W, h->G);
         ctx->n_launches += 2;
         if (reps == 1) break;
     }
