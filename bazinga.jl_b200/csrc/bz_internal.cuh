@@ -436,6 +436,19 @@ __device__ inline void bz_xr_allreduce(BzState* st, double* v, int K, unsigned i
     *st->xr.seq = s + 1ULL;
 }
 
+// Slab mode (the grid rows are split over the ranks): every stencil pass starts with a
+// cross-rank barrier -- after it the previous kernel of EVERY rank is complete, so the neighbours' boundary
+// rows may be read through the peer mapping.  Exchange number s; CTA (0,0) posts, every CTA waits.
+__device__ inline void bz_xr_barrier_all(BzState* st, unsigned long long s) {
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0) { double z[1] = {0.0}; bz_xr_post(st->xr, s, z, 1); }
+        double g[XR_MAXR * XR_K];
+        bz_xr_gather(st, s, 1, g);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side objects
 // ---------------------------------------------------------------------------------------------
@@ -476,6 +489,7 @@ struct bz_ctx {
     int batch_budget = 400;     // bz_batch_solve: AL-gradients an instance may use on its own thread before the warp-per-instance
                                 // pass takes it over (env BZ_BATCH_BUDGET; 0 = single phase)
     int lspec = 1;              // dense problems (n <= 16384, f = Zero): the L step runs speculatively beside G(z) (env BZ_LSPEC=0: off)
+    int slab_fused = 1;         // slab-decomposed obstacle grids run the fused kernel too, halo rows read from the neighbours (env BZ_SLAB_FUSED=0: the unfused cycle)
     int obstacle_rotate = 1;    // ... with buffer rotation in the cooperative L kernel (env BZ_OBSTACLE_ROTATE=0: copies)
     int obstacle_fused = 1;     // obstacle problems run the fused X kernel (env BZ_OBSTACLE_FUSED=0: the unfused cycle, for A/B runs)
     int pdl = 1;                // programmatic dependent launch inside the cycle (env BZ_PDL=0 disables)

@@ -77,6 +77,11 @@ struct OfCtx {
     const double* __restrict__ x; const double* __restrict__ mu; const double* __restrict__ rmu; const double* __restrict__ muy;
     double* __restrict__ zp; double* __restrict__ rp; double* __restrict__ dbg_gx; double* __restrict__ dbg_gz;
     int N, GX, GY, col, rb, re;
+    // slab mode (grid rows split over the ranks, bz_internal.cuh): rows ylo .. yhi-1 exist -- 4 rows beyond the slab on a side
+    // with a neighbour, whose raw rows (x, mu, 1/mu, mu*y at the same offsets of ITS slab) are read through the peer mapping
+    int ylo, yhi;
+    const double* x_up; const double* mu_up; const double* rmu_up; const double* muy_up;
+    const double* x_dn; const double* mu_dn; const double* rmu_dn; const double* muy_dn;
     double gamma, gamma_h, rg, rgh, diag;
     bool colok, own_lane;
     double a[OF_NSUM];
@@ -113,14 +118,27 @@ __device__ __forceinline__ void of_step(OfPipe<NEED2>& s, OfCtx& c, const int jc
     const double lx2 = of_shl(cx2), rx2 = of_shr(cx2), lwx = of_shl(cwx), rwx = of_shr(cwx);
     const double lz2 = of_shl(cz2), rz2 = of_shr(cz2), lwz = of_shl(cwz), rwz = of_shr(cwz);
     {   // ---- raw row jc + 1 into staging (zeros outside the grid)
-        const bool ok = MASKED ? (c.colok && jc + 1 >= 0 && jc + 1 < c.GY) : true;
+        const bool ok = MASKED ? (c.colok && jc + 1 >= c.ylo && jc + 1 < c.yhi) : true;
         const int i = base + c.GX;
+        if (MASKED && ok && (jc + 1 < 0 || jc + 1 >= c.GY)) {
+            // a row of the neighbouring rank's slab (after the cross-rank barrier at the top of the kernel); uncached loads
+            const bool up = jc + 1 < 0;
+            const int ih = (up ? jc + 1 + c.GY : jc + 1 - c.GY) * c.GX + c.col;
+            const double* hx = up ? c.x_up : c.x_dn;
+            s.S1 = __ldcv(hx + ih);
+            s.S2 = __ldcv(hx + c.N + ih);
+            s.S3 = __ldcv(hx + 2 * c.N + ih);
+            s.SMU = __ldcv((up ? c.mu_up : c.mu_dn) + ih);
+            s.SRM = __ldcv((up ? c.rmu_up : c.rmu_dn) + ih);
+            s.SMY = __ldcv((up ? c.muy_up : c.muy_dn) + ih);
+        } else {
         s.S1 = ok ? __ldg(c.x + i) : 0.0;
         s.S2 = ok ? __ldg(c.x + c.N + i) : 0.0;
         s.S3 = ok ? __ldg(c.x + 2 * c.N + i) : 0.0;
         s.SMU = ok ? __ldg(c.mu + i) : 1.0;
         s.SRM = ok ? __ldg(c.rmu + i) : 1.0;      // 1 ./ mu, kept up to date by k_al_update (of_div: the bits of a / mu)
         s.SMY = ok ? __ldg(c.muy + i) : 0.0;
+        }
     }
     {   // ---- stage 1: w_x on row r1 = jc - 1 (x2 rows jc-2, jc-1, jc)                      k_obstacle_c
         const int r1 = jc - 1;
@@ -130,7 +148,7 @@ __device__ __forceinline__ void of_step(OfPipe<NEED2>& s, OfCtx& c, const int jc
         const double t = cva + muya;
         const double u = t - 0.0;                      // SetObstacle: proj = 0 (demo/obstacle.jl:116-119)
         if (MASKED) {
-            const bool ok = c.colok && r1 >= 0 && r1 < c.GY;
+            const bool ok = c.colok && r1 >= c.ylo && r1 < c.yhi;
             s.WX[SL(0)] = ok ? of_div(u, mua, rma) : 0.0;
             if (c.own_lane && r1 >= c.rb && r1 < c.re) {
                 c.a[0] += of_div(u * u, mua, rma);
@@ -160,7 +178,7 @@ __device__ __forceinline__ void of_step(OfPipe<NEED2>& s, OfCtx& c, const int jc
         if (z2 > z3) z3 = 0.0; else z2 = 0.0;
         bool st_ok = c.own_lane;
         if (MASKED) {
-            const bool ok = c.colok && r2 >= 0 && r2 < c.GY;
+            const bool ok = c.colok && r2 >= c.ylo && r2 < c.yhi;
             if (!ok) { z1 = 0.0; z2 = 0.0; z3 = 0.0; }
             st_ok = c.own_lane && r2 >= c.rb && r2 < c.re;
         }
@@ -195,7 +213,7 @@ __device__ __forceinline__ void of_step(OfPipe<NEED2>& s, OfCtx& c, const int jc
         const double t = cva + ev_my;
         const double u = t - 0.0;
         if (MASKED) {
-            const bool ok = c.colok && r3 >= 0 && r3 < c.GY;
+            const bool ok = c.colok && r3 >= c.ylo && r3 < c.yhi;
             s.WZ[SL(0)] = ok ? of_div(u, ev_mu, ev_rm) : 0.0;
             if (c.own_lane && r3 >= c.rb && r3 < c.re) {
                 c.a[6] += of_div(u * u, ev_mu, ev_rm);
@@ -265,6 +283,29 @@ __device__ __forceinline__ void of_kernel_body(BzState* st, const BzVecs& v, con
     c.zp = (rot & 4) ? v.z_curr : v.z;
     c.rp = (rot & 2) ? v.res_prev : v.res;
     c.dbg_gx = dbg_gx; c.dbg_gz = dbg_gz;
+    c.ylo = 0; c.yhi = c.GY;
+    c.x_up = c.x_dn = c.mu_up = c.mu_dn = c.rmu_up = c.rmu_dn = c.muy_up = c.muy_dn = nullptr;
+    const BzXr& xr = st->xr;
+    const bool slab = !force && xr.nranks > 1;
+    unsigned long long xseq = 0ULL;
+    if (slab) {
+        // after this barrier the L kernel (or the outer-step kernels) of EVERY rank is complete: the neighbours' x, mu,
+        // 1/mu, mu*y rows may be read.  The reductions at the end are the second rendezvous: no rank leaves this kernel --
+        // and overwrites x in its next L step -- before every rank has finished reading.
+        xseq = *xr.seq;
+        bz_xr_barrier_all(st, xseq);
+        const double* base = xr.slab[xr.rank];
+        if (xr.rank > 0) {
+            const double* nb = xr.slab[xr.rank - 1];
+            c.x_up = nb + (c.x - base); c.mu_up = nb + (mu - base); c.rmu_up = nb + (rmu - base); c.muy_up = nb + (muy - base);
+            c.ylo = -OF_HALO;
+        }
+        if (xr.rank + 1 < xr.nranks) {
+            const double* nb = xr.slab[xr.rank + 1];
+            c.x_dn = nb + (c.x - base); c.mu_dn = nb + (mu - base); c.rmu_dn = nb + (rmu - base); c.muy_dn = nb + (muy - base);
+            c.yhi = c.GY + OF_HALO;
+        }
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wg = (int)blockIdx.x * OF_WARPS + warp;
@@ -341,6 +382,14 @@ __device__ __forceinline__ void of_kernel_body(BzState* st, const BzVecs& v, con
     const double stop1 = bz_final_nanmax(part + (size_t)OF_NSUM * nb, nb, scratch);
     const double stop2 = bz_final_nanmax(part + (size_t)(OF_NSUM + 1) * nb, nb, scratch);
     if (threadIdx.x != 0) return;
+    double stop1x = stop1, stop2x = stop2;
+    if (slab) {      // sums and stop norms over the ranks, added / compared in rank order: the same bits everywhere
+        *xr.seq = xseq + 1ULL;                 // (the barrier at the top was exchange xseq)
+        bz_xr_allreduce(st, sums, 8, 0u);
+        double tail[3] = {sums[8], stop1, stop2};
+        bz_xr_allreduce(st, tail, 3, 6u);      // entries 1, 2: NaN-propagating max
+        sums[8] = tail[0]; stop1x = tail[1]; stop2x = tail[2];
+    }
     // AL values (auglagfun.jl:78-82): lx = 0.5*sum((t-s)^2/mu) + f - 0.5*sum(mu y^2); f = 0.5*fa - fb (demo/obstacle.jl:24-26,40-42)
     const double musqy = st->musqy;
     double fx_x = 0.5 * sums[1]; fx_x = fx_x + (-1.0) * sums[2];
@@ -355,7 +404,7 @@ __device__ __forceinline__ void of_kernel_body(BzState* st, const BzVecs& v, con
     }
     const int fresh = st->grad_x_fresh;
     bz_f_finish(st, g, gamma, fresh, sums[3], sums[4], sums[5], lx_x, fx_x);
-    bz_d_decide(st, gamma, lx_z, fx_z, stop1, stop2);
+    bz_d_decide(st, gamma, lx_z, fx_z, stop1x, stop2x);
     bz_toc(st, 2);
     __threadfence();
 }

@@ -172,6 +172,7 @@ extern "C" int bz_ctx_create(int device, bz_ctx** out) {
     if (const char* e = getenv("BZ_BATCH_DRAIN")) ctx->batch_drain = atoi(e);
     if (const char* e = getenv("BZ_LSPEC")) ctx->lspec = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_ROTATE")) ctx->obstacle_rotate = atoi(e);
+    if (const char* e = getenv("BZ_SLAB_FUSED")) ctx->slab_fused = atoi(e);
     if (const char* e = getenv("BZ_OBSTACLE_FUSED")) ctx->obstacle_fused = atoi(e);
     if (const char* e = getenv("BZ_PROF_STRIDE")) ctx->prof_stride = atoi(e) > 0 ? atoi(e) : 1;
     *out = ctx;
@@ -300,9 +301,9 @@ extern "C" int bz_problem_destroy(bz_problem* p) {
     cudaStreamSynchronize(p->ctx->stream);
     bz_ctx* ctx = p->ctx;
     if (p->own_cA) bz_pool_free(ctx, p->cA);
-    if (p->slab_base) {   // x, z, xeps, yupd live inside the exported slab
-        p->v.x = p->v.z = p->v.xeps = nullptr;
-        p->yupd = nullptr;
+    if (p->slab_base) {   // x, z, xeps, yupd, mu, 1 ./ mu, mu .* y live inside the exported slab
+        p->v.x = p->v.z = p->v.xeps = p->v.x_prev = p->v.z_curr = nullptr;
+        p->yupd = p->mu = p->rmu = p->muy = nullptr;
         for (int r = 0; r < XR_MAXR; ++r)
             if (p->peer_ptr[r]) cudaIpcCloseMemHandle(p->peer_ptr[r]);
         ctx->pool_live.erase(p->slab_base);
@@ -449,10 +450,14 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
         // one exportable allocation: mailbox ring, sequence word, and the vectors whose boundary rows the
         // neighbouring ranks read through the peer mapping (same layout on every rank)
         const size_t head = (size_t)XR_MAIL_WORDS + 8;
-        p->slab_bytes = (head + 3 * (size_t)n + (size_t)ml) * sizeof(double);
+        // (mu, 1 ./ mu, mu .* y too: the fused forward-backward kernel recomputes a radius-4 neighbourhood from raw rows)
+        // (x_prev and z_curr too: with buffer rotation they take the roles of x and z on every other iteration)
+        p->slab_bytes = (head + 5 * (size_t)n + 4 * (size_t)ml) * sizeof(double);
         PTRY(dev_alloc(ctx, &p->slab_base, p->slab_bytes / sizeof(double)));
         double* vecs = reinterpret_cast<double*>(p->slab_base + head);
         p->v.x = vecs; p->v.z = vecs + n; p->v.xeps = vecs + 2 * n; p->yupd = vecs + 3 * n;
+        p->mu = vecs + 3 * n + ml; p->rmu = vecs + 3 * n + 2 * ml; p->muy = vecs + 3 * n + 3 * ml;
+        p->v.x_prev = vecs + 3 * n + 4 * ml; p->v.z_curr = vecs + 4 * n + 4 * ml;
     }
     double** nvecs[] = {&p->v.x, &p->v.z, &p->v.xeps, &p->v.x_prev, &p->v.x_d, &p->v.z_curr, &p->v.res,
                         &p->v.res_prev, &p->v.grad_x, &p->v.grad_z, &p->v.d, &p->Ec, &p->Ef};
@@ -465,11 +470,13 @@ extern "C" int bz_problem_create(bz_ctx* ctx, const bz_problem_desc* d, bz_probl
     for (double** q : mvecs) if (!*q) PTRY(dev_alloc(ctx, q, ml));
     const int maxgrid = ctx->num_sms * 8;
     size_t npart = (size_t)4 * maxgrid;
-    if (d->c_kind == BZ_C_OBSTACLE && !p->slab && !p->slack && ctx->obstacle_fused && p->nv < (1LL << 31)) {   // (32-bit element indices)
+    if (d->c_kind == BZ_C_OBSTACLE && (!p->slab || ctx->slab_fused) && !p->slack && ctx->obstacle_fused && p->nv < (1LL << 31)) {   // (32-bit element indices)
         p->fused = true;
-        p->rotate = p->nv > 32768 && ctx->obstacle_rotate;   // (n <= 32768 runs the cluster L kernel, whose vectors live in registers)
+        // (n <= 32768 runs the cluster L kernel, whose vectors live in registers.  In slab mode the ranks rotate in lock-step
+        // and both buffers of a pair are inside the exported slab, so a neighbour finds the current x at the same offset.)
+        p->rotate = p->nv > 32768 && ctx->obstacle_rotate;
         npart = std::max(npart, (size_t)bz_obfused_partials(ctx, p->ob));
-        PTRY(dev_alloc(ctx, &p->rmu, ml));
+        if (!p->rmu) PTRY(dev_alloc(ctx, &p->rmu, ml));
     }
     PTRY(dev_alloc(ctx, &p->part, npart));
     PTRY(dev_alloc(ctx, &p->lxpart, (size_t)maxgrid));

@@ -132,18 +132,6 @@ __device__ __forceinline__ double bz_stencil_rc(const double* __restrict__ v, lo
     return out;
 }
 
-// Slab mode (the grid rows are split over the ranks): every stencil pass starts with a
-// cross-rank barrier -- after it the previous kernel of EVERY rank is complete, so the neighbours' boundary
-// rows may be read through the peer mapping.  Exchange number s; CTA (0,0) posts, every CTA waits.
-__device__ inline void bz_xr_barrier_all(BzState* st, unsigned long long s) {
-    if (threadIdx.x == 0) {
-        if (blockIdx.x == 0 && blockIdx.y == 0) { double z[1] = {0.0}; bz_xr_post(st->xr, s, z, 1); }
-        double g[XR_MAXR * XR_K];
-        bz_xr_gather(st, s, 1, g);
-        __threadfence_system();
-    }
-    __syncthreads();
-}
 // boundary rows of the neighbours' copy of local vector `v` (a vector inside the exported slab), block offset
 // `off` (0 or N), grid GY x GX: up = last row of rank-1, dn = first row of rank+1
 __device__ __forceinline__ void bz_xr_halo(const BzXr& xr, const double* v, long long off, const StencilGeom& g,
