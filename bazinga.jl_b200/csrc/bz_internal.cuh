@@ -38,7 +38,7 @@ enum BzInnerStatus : int { IST_RUNNING = 0, IST_CONVERGED = 1, IST_MAXIT = 2 };
 // machines of the ranks in lock-step.
 // ---------------------------------------------------------------------------------------------
 #define XR_MAXR 8
-#define XR_K 8
+#define XR_K 12    /* values per exchange: the fused obstacle kernel all-gathers 9 sums + 2 stop norms at once */
 #define XR_RING 64
 #define XR_MAIL_WORDS (XR_RING * XR_MAXR * XR_K * 2)
 struct BzXr {
@@ -385,8 +385,9 @@ __device__ inline double bz_sum_parts(const double* part, int n) {
 
 
 // ---- cross-rank exchange (see BzXr).  err_flag = 3: a peer did not answer within ~4 s.
-__device__ __forceinline__ void bz_xr_post(const BzXr& xr, unsigned long long s, const double* v, int K) {
-    __threadfence_system();   // what this GPU wrote before the post is visible to a peer that sees the post
+// fence = false: for a post that only carries scalars -- nothing this GPU's kernel wrote is read by a peer that sees it
+__device__ __forceinline__ void bz_xr_post(const BzXr& xr, unsigned long long s, const double* v, int K, bool fence = true) {
+    if (fence) __threadfence_system();   // what this GPU wrote before the post is visible to a peer that sees the post
     const unsigned long long tag = ((s + 1ULL) & 0xffffffffULL) << 32;
     const size_t off = (((size_t)(s % XR_RING) * XR_MAXR + xr.rank) * XR_K) * 2;
     for (int p = 0; p < xr.nranks; ++p) {
@@ -418,10 +419,10 @@ __device__ inline void bz_xr_gather(BzState* st, unsigned long long s, int K, do
 }
 // All-reduce of K <= XR_K scalars by ONE thread per GPU (the thread that holds the local totals).
 // ismax bit k set: NaN-propagating max (Julia's), else sum; both in rank order.
-__device__ inline void bz_xr_allreduce(BzState* st, double* v, int K, unsigned int ismax) {
+__device__ inline void bz_xr_allreduce(BzState* st, double* v, int K, unsigned int ismax, bool fence = true) {
     if (st->xr.nranks <= 1) return;
     const unsigned long long s = *st->xr.seq;
-    bz_xr_post(st->xr, s, v, K);
+    bz_xr_post(st->xr, s, v, K, fence);
     double g[XR_MAXR * XR_K];
     bz_xr_gather(st, s, K, g);
     for (int k = 0; k < K; ++k) {

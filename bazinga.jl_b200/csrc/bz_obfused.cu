@@ -383,12 +383,17 @@ __device__ __forceinline__ void of_kernel_body(BzState* st, const BzVecs& v, con
     const double stop2 = bz_final_nanmax(part + (size_t)(OF_NSUM + 1) * nb, nb, scratch);
     if (threadIdx.x != 0) return;
     double stop1x = stop1, stop2x = stop2;
-    if (slab) {      // sums and stop norms over the ranks, added / compared in rank order: the same bits everywhere
+    if (slab) {      // sums and stop norms over the ranks in ONE exchange, added / compared in rank order: the same bits everywhere
         *xr.seq = xseq + 1ULL;                 // (the barrier at the top was exchange xseq)
-        bz_xr_allreduce(st, sums, 8, 0u);
-        double tail[3] = {sums[8], stop1, stop2};
-        bz_xr_allreduce(st, tail, 3, 6u);      // entries 1, 2: NaN-propagating max
-        sums[8] = tail[0]; stop1x = tail[1]; stop2x = tail[2];
+        double all[OF_NSUM + 2];
+#pragma unroll
+        for (int k = 0; k < OF_NSUM; ++k) all[k] = sums[k];
+        all[OF_NSUM] = stop1; all[OF_NSUM + 1] = stop2;
+        // (no system-scope fence: z and res, all this kernel wrote, are read by no peer before its next fenced barrier)
+        bz_xr_allreduce(st, all, OF_NSUM + 2, (1u << OF_NSUM) | (1u << (OF_NSUM + 1)), false);   // the last two: NaN-propagating max
+#pragma unroll
+        for (int k = 0; k < OF_NSUM; ++k) sums[k] = all[k];
+        stop1x = all[OF_NSUM]; stop2x = all[OF_NSUM + 1];
     }
     // AL values (auglagfun.jl:78-82): lx = 0.5*sum((t-s)^2/mu) + f - 0.5*sum(mu y^2); f = 0.5*fa - fb (demo/obstacle.jl:24-26,40-42)
     const double musqy = st->musqy;

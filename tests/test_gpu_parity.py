@@ -721,11 +721,13 @@ def test_wide_path_whole_solve(two_pass, monkeypatch):
 
 
 # ------------------------------------------------------------------------------- slab-decomposed obstacle grid
-def test_slab_decomposed_obstacle_two_ranks():
-    """SURVEY.md §8e, third mode: the obstacle grid split by rows over two ranks (one process each), boundary rows
-    and every reduction scalar exchanged over peer-mapped memory from inside the kernels.  On a one-GPU box both
-    ranks share cuda:0 (time-sliced processes); with two GPUs each rank gets its own.  One AL-gradient must equal
-    the un-decomposed kernels' bit for bit, the scalars must be identical on all ranks, and a short solve must
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_slab_decomposed_obstacle_ranks(nranks):
+    """SURVEY.md §8e, third mode: the obstacle grid split by rows over the ranks (one process each), halo rows
+    and every reduction scalar exchanged over peer-mapped memory from inside the kernels (the fused forward-backward
+    kernel and the rotating L kernel since round 2).  With fewer GPUs than ranks the ranks share cuda:0 (time-sliced
+    processes).  Four ranks put two of them in the middle, with a neighbour on either side.  One AL-gradient must
+    equal the un-decomposed kernels' bit for bit, the scalars must be identical on all ranks, and a short solve must
     follow the un-decomposed one."""
     import json
     import socket
@@ -737,10 +739,10 @@ def test_slab_decomposed_obstacle_two_ranks():
     port = sk.getsockname()[1]
     sk.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(root, "scripts", "bench_obstacle_slab.py"),
            "--side", "32", "--inner", "10", "--check"]
-    if torch.cuda.device_count() < 2:
+    if torch.cuda.device_count() < nranks:
         cmd.append("--same-device")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{"config"')]
