@@ -658,8 +658,21 @@ def leg_c4(env, args, shared):
         # convergence of the decomposed solve at a size that converges in seconds: same solution as the un-decomposed one
         cs = args.c4_check_side
         if cs and cs % world == 0:
-            rc, _, xc = one(ctx, cs, world, args.c4_check_cap, tol=1e-4, warm=0)
+            # (i) the first 12 iterations, before rounding differences of the reductions can move a decision: the decomposed
+            # iterate must be the un-decomposed one to rounding
+            rp, _, xp = one(ctx, cs, world, 12, tol=1e-4, warm=0)
             Nl = (cs // world) * cs
+            xps = env.gather(xp)
+            if rank == 0:
+                r1p, _, x1p = one(ctx, cs, 1, 12, tol=1e-4, warm=0)
+                xpg = np.concatenate([np.concatenate([q[b * Nl:(b + 1) * Nl] for q in xps]) for b in range(3)])
+                leg["prefix_check"] = {"grid": [cs, cs], "inner_iterations": int(rp.tot_inner_it), "n_grad_slab": int(rp.n_grad),
+                                       "n_grad_single": int(r1p.n_grad), "x_max_abs_diff": float(np.max(np.abs(xpg - x1p))),
+                                       "x_max_abs": float(np.max(np.abs(x1p))),
+                                       "objective_rel_diff": abs(rp.objective - r1p.objective) / max(1e-300, abs(r1p.objective))}
+            env.barrier()
+            # (ii) the whole solve
+            rc, _, xc = one(ctx, cs, world, args.c4_check_cap, tol=1e-4, warm=0)
             xs = env.gather(xc)
             chk = None
             if rank == 0:

@@ -12,11 +12,15 @@
  * Threading: a bz_ctx is not thread-safe (the reference is single-threaded and mutates its oracle
  * structs, src/utilities/auglagfun.jl:11-26).  Use one ctx per host thread / per GPU.
  *
- * Device: the library expects to have the GPU to itself (one process per GPU).  Three kernels make CTAs of one launch
- * wait for each other and are sized to be co-resident on an idle device: the grid-wide dense pass for nx > 16384, the
- * speculative L step that rides on the dense pass, and the slab mode's cross-rank exchanges.  Every such wait is
- * bounded (about 4 s): on a shared device a solve fails with BZ_ERR_CUDA / BZ_ERR_COMM instead of hanging, and the
- * problem object must then be destroyed.
+ * Device: the library expects to have the GPU to itself (one process per GPU).  Some kernels make CTAs of one launch --
+ * or two kernels of one call -- wait for each other and are sized to be co-resident on an idle device: the grid-wide
+ * dense pass for nx > 16384, the speculative L step that rides on the dense pass, the cooperative L kernel, the slab
+ * mode's cross-rank exchanges (in the stencil passes, the fused obstacle kernel and the L kernel), and the persistent
+ * warp-per-instance kernel of bz_batch_solve, which runs beside the thread-per-solve kernel and is fed by it.  Every
+ * such wait is bounded (4 to 20 s): on a shared device a call fails with BZ_ERR_CUDA / BZ_ERR_COMM instead of hanging,
+ * and the problem object must then be destroyed.  Tuning knobs read once per context from the environment (defaults are
+ * the measured best): BZ_LSPEC, BZ_OBSTACLE_FUSED, BZ_OBSTACLE_ROTATE, BZ_SLAB_FUSED, BZ_BATCH_BUDGET,
+ * BZ_BATCH_CONCURRENT, BZ_BATCH_P2CTAS, BZ_BATCH_DRAIN, BZ_PROF_STRIDE.
  */
 #ifndef BAZINGA_B200_H
 #define BAZINGA_B200_H
