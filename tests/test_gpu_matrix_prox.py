@@ -90,3 +90,23 @@ def test_matrix_prox_constructor_errors_and_limits(gpu_ctx):
         bz.SchattenNormLpPower(0.5, -1.0)
     with pytest.raises(bz.BazingaError):
         bz.NuclearNorm().prox(np.zeros((65, 65)), 1.0, ctx=gpu_ctx)     # one CTA per matrix: 64 x 64 at most
+
+
+def test_matrix_prox_against_the_golden_vectors(gpu_ctx):
+    """tests/golden/matrix_prox.json: inputs and LAPACK-based outputs committed with the script that made them (among them a
+    20 x 20 squared-distance matrix of rank <= 7 like demo/distance_matrix_completion.jl's, and a rank-2 matrix)."""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matrix_prox.json")))
+    for ent in G["cases"]:
+        X = np.array(ent["X"])
+        sig = bz.NuclearNorm().svdvals(X, ctx=gpu_ctx)
+        assert np.max(np.abs(sig - np.array(ent["sigma"]))) <= 1e-12 * max(ent["sigma"])
+        for key, f in (("rank", bz.Rank(G["lambda"])), ("nuclear", bz.NuclearNorm(G["lambda"])),
+                       ("schatten", bz.SchattenNormLpPower(G["p"], G["alpha"]))):
+            Y, val = f.prox(X, ent["gamma"], ctx=gpu_ctx)
+            ref = ent["out"][key]
+            assert np.linalg.norm(Y - np.array(ref["Y"])) <= 1e-10 * max(1.0, np.linalg.norm(X)), (ent["name"], key)
+            assert abs(val - ref["value"]) <= 1e-11 * max(1.0, abs(ref["value"])), (ent["name"], key)
+            tol = 1e-12 if key != "schatten" else 1e-6      # sigma^p of a singular value that is zero up to rounding
+            assert abs(f(X, ctx=gpu_ctx) - ref["f_X"]) <= tol * max(1.0, abs(ref["f_X"])), (ent["name"], key)

@@ -341,3 +341,20 @@ def test_matrix_prox_restatement_properties():
                 lambda: bo.check_and_reshape_as_matrix(np.zeros(35))):
         with pytest.raises(ValueError):
             bad()
+
+
+def test_matrix_prox_oracle_reproduces_the_golden_vectors():
+    """tests/golden/matrix_prox.json (made by make_golden_matprox.py): the restatement of rank.jl / nuclearNorm.jl /
+    schattenNormLp.jl still gives these outputs -- a pin against silent changes; the GPU kernel is held to the same file."""
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matrix_prox.json")))
+    for ent in G["cases"]:
+        X = np.array(ent["X"])
+        assert np.allclose(np.linalg.svd(X, compute_uv=False), ent["sigma"], rtol=1e-12, atol=1e-13)
+        for key, g in (("rank", bo.GRank(G["lambda"])), ("nuclear", bo.GNuclearNorm(G["lambda"])),
+                       ("schatten", bo.GSchattenNormLpPower(G["p"], G["alpha"]))):
+            Y = np.empty_like(X)
+            val = g.prox(Y, X, ent["gamma"])
+            ref = ent["out"][key]
+            assert np.max(np.abs(Y - np.array(ref["Y"]))) <= 1e-11 * max(1.0, np.abs(X).max()), (ent["name"], key)
+            assert abs(val - ref["value"]) <= 1e-11 * max(1.0, abs(ref["value"]))
