@@ -120,7 +120,7 @@ def measured_peak_hbm():
 def traffic_from_profile(m, n):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` capture (profiles/); null for other shapes.  NOT measured in this run."""
-    p = os.path.join(ROOT, "profiles", "r1_dense_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2n_dense_traffic.json")
     try:
         d = json.load(open(p))
         return d["traffic_bytes_per_launch"] if d["shape"] == [m, n] else None
@@ -350,7 +350,7 @@ def run_headline(env, args):
     roofline = {"bound": "hbm", "kernel": "k_dense_algrad<true, false> (fused A-pass: r=Ax-b, w, A'w; A read once)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic_from_profile(m, n),
-                "traffic_source": "profiles/r1_dense_traffic.json (ncu --set full capture of the same kernel and shape; not re-measured in this run)",
+                "traffic_source": "profiles/r2n_dense_traffic.json (ncu --set full capture of two consecutive launches of the same kernel and shape, their mean; not re-measured in this run)",
                 "algorithmic_bytes_per_launch": bgrad, "launches_timed": dom_launches,
                 "avg_launch_us": (1e3 * dom_ms / dom_launches) if dom_launches else None,
                 "events_bracket_every_nth_launch": 31,
