@@ -405,7 +405,16 @@ def test_als_whole_solves_match_oracle(gpu_ctx):
     assert out[5] == r.status == "first_order"
     assert np.max(np.abs(A @ out[0] - b)) <= 1e-4 and np.max(np.abs(out[8])) <= 1e-12        # s in D = {0}
     assert abs(np.sum(np.abs(out[0])) - np.sum(np.abs(r.x))) <= 1e-4 * np.sum(np.abs(r.x))
-    assert abs(out[3] - r.tot_inner_it) <= 0.25 * r.tot_inner_it + 10
+    # iteration count: inside the band the ORACLE itself spans when the order of its sums is permuted (rows / columns of A
+    # shuffled: the same problem, the same solution set).  Measured: 980 .. 1232 around the unpermuted 1013 (-3 % / +22 %).
+    counts = [r.tot_inner_it]
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        pc, prm = rng.permutation(100), rng.permutation(20)
+        p2 = bo.problem_basis_pursuit(A[prm][:, pc], b[prm])
+        counts.append(bo.als(p2["f"], p2["g"], p2["c"], p2["D"], np.zeros(100), np.zeros(20), tol=1e-5,
+                             **{k: v for k, v in pr["kw"].items() if k != "tol"}).tot_inner_it)
+    assert min(counts) - 0.05 * r.tot_inner_it <= out[3] <= max(counts) + 0.05 * r.tot_inner_it, (out[3], counts)
     # the same point as alps finds (convex problem)
     o2 = bz.alps(bz.Zero(), bz.NormL1(1.0), bz.ConstraintBasisPursuit(A, b), bz.ZeroSet(), np.zeros(100), np.zeros(20),
                  tol=1e-5, subsolver=sub, subsolver_maxit=100_000, ctx=gpu_ctx)
